@@ -1,0 +1,546 @@
+"""NumPy-fp32 literal restatement of the PaddleXDE integration hot path (generic callable field).
+
+TEST INFRASTRUCTURE ONLY -- never imported by the product package (paddlexde_b200/).
+
+This module follows the reference's Python line by line (paths relative to /root/reference) with
+the minimal repairs R1-R7 of SURVEY.md 8(c).  It accepts *any* ``func(t, y)`` so that the
+reference's own known-answer fixtures (tests/testing_utils.py: Sine/Linear/Constant problems,
+tests/interpolation/test_interpolation.py) can pin it.  The C oracle (xde_oracle.c) is the same
+algorithm specialised to the fused MLP field; tests check the two agree bit for bit when this
+module is handed the C field evaluation.
+
+PARITY STATUS: Paddle is not installable here and the reference at HEAD is not runnable, so
+accept/reject sequences, adjoint gradients, SDE results, HistoryIndex.backward and B>1 behaviour
+are "parity unpinned" -- defined by this restatement, not by reference outputs.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+f32 = np.float32
+
+
+# ----------------------------------------------------------------------------------------------
+# scalar primitives of the arithmetic specification
+# ----------------------------------------------------------------------------------------------
+def root5(r) -> np.float32:
+    """r ** (1/5): deterministic Newton iteration (integer seed + 4 iterations), fp32.
+
+    Stands in for ``error_ratio ** exponent`` (utils/ode_utils.py:92-95) and the ``1/(order+1)``
+    power of select_initial_step (solver/base_adaptive_solver.py:70)."""
+    r = f32(r)
+    u = np.array([r], dtype=np.float32).view(np.uint32)
+    u = (u // np.uint32(5) + np.uint32(0x32CCCCCC)).astype(np.uint32)
+    x = u.view(np.float32)[0]
+    for _ in range(4):
+        x2 = f32(x * x)
+        x4 = f32(x2 * x2)
+        q = f32(r / x4)
+        # fmaf(4, x, q): 4*x is exact in fp32 (power of two), so the fused and unfused forms agree
+        x = f32(f32(f32(4.0) * x + q) * f32(0.2))
+    return x
+
+
+def rms_norm(v: np.ndarray) -> np.float32:
+    """_rms_norm (utils/ode_utils.py:8-9): squares in fp32, mean/sqrt in fp64 (order independent)."""
+    q = (v.astype(np.float32).ravel() * v.astype(np.float32).ravel()).astype(np.float32)
+    if q.size <= 4096:
+        acc = 0.0
+        for e in q:
+            acc += float(e)
+    else:
+        acc = float(np.sum(q.astype(np.float64)))
+    return f32(math.sqrt(acc / q.size))
+
+
+# ----------------------------------------------------------------------------------------------
+# Dormand-Prince tableau (solver/adaptive_solver/dopri5.py:5-55), cast once to fp32
+# ----------------------------------------------------------------------------------------------
+DP_ALPHA = np.array([1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0], dtype=np.float64).astype(f32)
+DP_BETA = [
+    np.array(b, dtype=np.float64).astype(f32)
+    for b in (
+        [1 / 5],
+        [3 / 40, 9 / 40],
+        [44 / 45, -56 / 15, 32 / 9],
+        [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+        [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+        [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+    )
+]
+DP_C_SOL = np.array([35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0], dtype=np.float64).astype(f32)
+DP_C_ERR = np.array(
+    [
+        35 / 384 - 1951 / 21600,
+        0,
+        500 / 1113 - 22642 / 50085,
+        125 / 192 - 451 / 720,
+        -2187 / 6784 - -12231 / 42400,
+        11 / 84 - 649 / 6300,
+        -1.0 / 60.0,
+    ],
+    dtype=np.float64,
+).astype(f32)
+DP_C_MID = np.array(
+    [
+        6025192743 / 30085553152 / 2,
+        0,
+        51252292925 / 65400821598 / 2,
+        -2691868925 / 45128329728 / 2,
+        187940372067 / 1594534317056 / 2,
+        -1776094331 / 19743644256 / 2,
+        11237099 / 235043384 / 2,
+    ],
+    dtype=np.float64,
+).astype(f32)
+
+
+@dataclass
+class AttemptLog:
+    t0: List[float] = field(default_factory=list)
+    dt: List[float] = field(default_factory=list)
+    ratio: List[float] = field(default_factory=list)
+    accepted: List[bool] = field(default_factory=list)
+    nfe: int = 0
+
+
+class Dopri5:
+    """AdaptiveRKSolver + Dopri5 (solver/base_adaptive_solver_rk.py, adaptive_solver/dopri5.py).
+
+    ``func(t, y)`` and ``norm(v)`` operate on fp32 arrays of y0's shape.  A decreasing t_span is
+    integrated as s = -t with f~(s,y) = -f(-s,y) (repair R5)."""
+
+    order = 5
+
+    def __init__(self, func: Callable, y0: np.ndarray, rtol=1e-7, atol=1e-9, norm=rms_norm,
+                 min_step=0.0, max_step=float("inf"), first_step=None, safety=0.9, ifactor=10.0,
+                 dfactor=0.2, max_num_steps=2**31 - 1):
+        self.func = func
+        self.y0 = np.asarray(y0, dtype=f32)
+        self.rtol, self.atol = f32(rtol), f32(atol)
+        self.min_step, self.max_step = f32(min_step), f32(max_step)
+        self.first_step = None if first_step is None else f32(first_step)
+        self.safety, self.ifactor, self.dfactor = f32(safety), f32(ifactor), f32(dfactor)
+        self.max_num_steps = max_num_steps
+        self.norm = norm
+        self.log = AttemptLog()
+        self.rev = False
+
+    # BaseODE.move / fuse (xde/base_ode.py:47-58)
+    def move(self, s, y):
+        self.log.nfe += 1
+        if self.rev:
+            return (-np.asarray(self.func(f32(-s), y), dtype=f32)).astype(f32)
+        return np.asarray(self.func(f32(s), y), dtype=f32)
+
+    @staticmethod
+    def fuse(dy, dt, y0):
+        return (dy * dt + y0).astype(f32)
+
+    # solver/base_adaptive_solver.py:33-72
+    def select_initial_step(self, t0, y0, order):
+        f0 = self.move(t0, y0)
+        scale = (self.atol + np.abs(y0) * self.rtol).astype(f32)
+        d0 = f32(abs(self.norm((y0 / scale).astype(f32))))
+        d1 = f32(abs(self.norm((f0 / scale).astype(f32))))
+        if d0 < f32(1e-5) or d1 < f32(1e-5):
+            h0 = f32(1e-6)
+        else:
+            h0 = f32(f32(f32(0.01) * d0) / d1)
+        h0 = f32(abs(h0))
+        y1 = self.fuse(f0, h0, y0)
+        f1 = self.move(f32(t0 + h0), y1)
+        d2 = f32(abs(f32(self.norm(((f1 - f0).astype(f32) / scale).astype(f32)) / h0)))
+        if d1 <= f32(1e-15) and d2 <= f32(1e-15):
+            h1 = max(f32(1e-6), f32(h0 * f32(1e-3)))
+        else:
+            mx = d2 if d2 > d1 else d1
+            with np.errstate(divide="ignore"):
+                arg = f32(f32(0.01) / mx)
+            h1 = root5(arg) if (arg > 0 and np.isfinite(arg)) else arg
+        h1 = f32(abs(h1))
+        return f32(np.fmin(f32(f32(100.0) * h0), h1))
+
+    # solver/base_adaptive_solver_rk.py:81-114
+    def _before_integrate(self, t_span):
+        t0 = t_span[0]
+        f0 = self.move(t0, self.y0)
+        if self.first_step is None:
+            first = self.select_initial_step(t0, self.y0, self.order - 1)
+        else:
+            first = self.first_step
+        # _RungeKuttaState(y1, f1, t0, t1, dt, interp_coeff)
+        self.rk = [self.y0, f0, t0, t0, first, [self.y0] * 5]
+
+    # solver/base_adaptive_solver_rk.py:129-181
+    def _runge_kutta_step(self, y0, f0, t0, dt, t1):
+        k = [f0]
+        yi = None
+        for i in range(6):
+            ti = t1 if DP_ALPHA[i] == f32(1.0) else f32(t0 + f32(DP_ALPHA[i] * dt))
+            bd = (DP_BETA[i] * dt).astype(f32)
+            s = (k[0] * bd[0]).astype(f32)
+            for j in range(1, i + 1):
+                s = (s + (k[j] * bd[j]).astype(f32)).astype(f32)
+            yi = (y0 + s).astype(f32)
+            k.append(self.move(ti, yi))
+        y1, f1 = yi, k[-1]
+        ce = (dt * DP_C_ERR).astype(f32)
+        err = (k[0] * ce[0]).astype(f32)
+        for j in range(1, 7):
+            err = (err + (k[j] * ce[j]).astype(f32)).astype(f32)
+        return y1, f1, err, k
+
+    # solver/base_adaptive_solver_rk.py:183-284
+    def _adaptive_step(self):
+        y0, f0, _, t0, dt, coeff = self.rk
+        t1 = f32(t0 + dt)
+        if not (f32(t0 + dt) > t0):
+            raise AssertionError("underflow in dt {}".format(dt))
+        if not np.isfinite(y0).all():
+            raise AssertionError("non-finite values in state `y`")
+        y1, f1, err, k = self._runge_kutta_step(y0, f0, t0, dt, t1)
+        # compute_error_ratio (utils/ode_utils.py:80-82)
+        tol = (self.atol + self.rtol * np.fmax(np.abs(y0), np.abs(y1))).astype(f32)
+        with np.errstate(all="ignore"):
+            ratio = f32(abs(self.norm((err / tol).astype(f32))))
+        accept = bool(ratio <= f32(1.0))
+        if dt > self.max_step:
+            accept = False
+        if dt <= self.min_step:
+            accept = True
+        self.log.t0.append(float(-t0 if self.rev else t0))
+        self.log.dt.append(float(-dt if self.rev else dt))
+        self.log.ratio.append(float(ratio))
+        self.log.accepted.append(accept)
+        if accept:
+            t_next, y_next, f_next = t1, y1, f1
+            coeff = self._interp_fit(y0, y1, k, dt)
+        else:
+            t_next, y_next, f_next = t0, y0, f0
+        # optimal_step_size (utils/ode_utils.py:85-97)
+        if ratio == 0:
+            dt_next = f32(dt * self.ifactor)
+        else:
+            dfac = f32(1.0) if ratio < 1 else self.dfactor
+            p = root5(ratio) if (ratio > 0 and np.isfinite(ratio)) else ratio
+            with np.errstate(all="ignore"):
+                factor = np.fmin(self.ifactor, np.fmax(f32(self.safety / p), dfac))
+            dt_next = f32(dt * factor)
+        dt_next = f32(np.fmin(np.fmax(dt_next, self.min_step), self.max_step))
+        self.rk = [y_next, f_next, t0, t_next, dt_next, coeff]
+
+    # _interp_fit :286-292 + interp_fit utils/ode_utils.py:28-49
+    def _interp_fit(self, y0, y1, k, dt):
+        cm = (dt * DP_C_MID).astype(f32)
+        s = (k[0] * cm[0]).astype(f32)
+        for j in range(1, 7):
+            s = (s + (k[j] * cm[j]).astype(f32)).astype(f32)
+        y_mid = (y0 + s).astype(f32)
+        f0, f1 = k[0], k[-1]
+        two_dt = f32(f32(2.0) * dt)
+        a = ((two_dt * (f1 - f0) - f32(8) * (y1 + y0)) + f32(16) * y_mid).astype(f32)
+        b = (((dt * (f32(5) * f0 - f32(3) * f1) + f32(18) * y0) + f32(14) * y1) - f32(32) * y_mid).astype(f32)
+        c = (((dt * (f1 - f32(4) * f0) - f32(11) * y0) - f32(5) * y1) + f32(16) * y_mid).astype(f32)
+        d = (dt * f0).astype(f32)
+        e = y0
+        return [e, d, c, b, a]
+
+    # step :116-127 + interp_evaluate utils/ode_utils.py:52-77
+    def step(self, next_t):
+        n_steps = 0
+        while next_t > self.rk[3]:
+            assert n_steps < self.max_num_steps, "max_num_steps exceeded"
+            self._adaptive_step()
+            n_steps += 1
+        _, _, t0, t1, _, coeff = self.rk
+        assert (t0 <= next_t) and (next_t <= t1), "invalid interpolation"
+        x = f32(f32(next_t - t0) / f32(t1 - t0))
+        total = (coeff[0] + x * coeff[1]).astype(f32)
+        xp = x
+        for cf in coeff[2:]:
+            xp = f32(xp * x)
+            total = (total + xp * cf).astype(f32)
+        return total
+
+    # AdaptiveSolver.integrate (solver/base_adaptive_solver.py:24-31): [T, *y0.shape]
+    def integrate(self, t_span):
+        t_span = np.asarray(t_span, dtype=f32)
+        self.rev = bool(t_span[1] < t_span[0])
+        ts = (-t_span).astype(f32) if self.rev else t_span
+        sol = np.empty((len(ts),) + self.y0.shape, dtype=f32)
+        sol[0] = self.y0
+        self._before_integrate(ts)
+        for i in range(1, len(ts)):
+            sol[i] = self.step(ts[i])
+        return sol
+
+
+class FixedSolver:
+    """FixedSolver.integrate (solver/base_fixed_solver.py:103-144) with grid == t_span and
+    interp == "linear" (identity at t == t1).  Returns concat(axis=-2)."""
+
+    def __init__(self, func, y0, fuse=None):
+        self.func = func
+        self.y0 = np.asarray(y0, dtype=f32)
+        self.fuse = fuse or (lambda dy, dt, y0: (dy * dt + y0).astype(f32))
+
+    def move(self, t, y):
+        return np.asarray(self.func(f32(t), y), dtype=f32)
+
+    def integrate(self, t_span):
+        t_span = np.asarray(t_span, dtype=f32)
+        sol = [self.y0]
+        y0 = self.y0
+        for i in range(1, len(t_span)):
+            y1 = self.step(t_span[i - 1], t_span[i], y0)
+            sol.append(y1)
+            y0 = y1
+        return np.concatenate(sol, axis=-2)
+
+
+class Euler(FixedSolver):
+    order = 1
+
+    def step(self, t0, t1, y0):  # fixed_solver/euler.py:7-11
+        dt = f32(t1 - t0)
+        return self.fuse(self.move(t0, y0), dt, y0)
+
+
+class RK4(FixedSolver):
+    order = 4
+
+    def step(self, t0, t1, y0):  # rk4_alt_step_func solver/base_fixed_solver.py:166-197
+        third = f32(1 / 3)
+        dt = f32(t1 - t0)
+        dt13 = f32(dt * third)
+        dt23 = f32(dt * f32(2 / 3))
+        k1 = self.move(t0, y0)
+        k2 = self.move(f32(t0 + dt13), self.fuse(k1, dt13, y0))
+        k3 = self.move(f32(t0 + dt23), self.fuse((k1 - k2 * third).astype(f32), dt, y0))
+        k4 = self.move(t1, self.fuse(((k1 - k2) + k3).astype(f32), dt, y0))
+        return (
+            (((self.fuse(k1, dt, y0) + f32(3) * self.fuse(k2, dt, y0)) + f32(3) * self.fuse(k3, dt, y0))
+             + self.fuse(k4, dt, y0)) * f32(0.125)
+        ).astype(f32)
+
+
+def odeint(func, y0, t_span, solver, *, rtol=1e-7, atol=1e-9, options=None):
+    """functional/odeint.py:9-35 (repair R1: xde.format == identity)."""
+    options = dict(options or {})
+    if solver is Dopri5:
+        options.setdefault("norm", rms_norm)
+        s = Dopri5(func, y0, rtol=rtol, atol=atol, **options)
+        out = s.integrate(t_span)
+        odeint.last_log = s.log
+        return out
+    options.pop("norm", None)
+    return solver(func, y0, **options).integrate(t_span)
+
+
+def dde_fuse(dy, dt, y0):
+    """BaseDDE.fuse (xde/base_dde.py:55-58)."""
+    dt = f32(dt)
+    y = (dy * dt + y0).astype(f32)
+    return ((dy - f32(0.001) * y) * dt + y0).astype(f32)
+
+
+# ----------------------------------------------------------------------------------------------
+# MLP field in NumPy (example/ode_demo.py:17-33); fp64 option for accuracy cross-checks
+# ----------------------------------------------------------------------------------------------
+class MLPFieldNP:
+    def __init__(self, w1, b1, w2, b2, pre="cube", dtype=np.float32):
+        self.dtype = dtype
+        self.w1, self.b1, self.w2, self.b2 = (np.asarray(a, dtype=dtype) for a in (w1, b1, w2, b2))
+        self.pre = pre
+
+    def _pre(self, y):
+        return y ** 3 if self.pre == "cube" else (y ** 2 if self.pre == "square" else y)
+
+    def _dpre(self, y):
+        return 3 * y ** 2 if self.pre == "cube" else (2 * y if self.pre == "square" else np.ones_like(y))
+
+    def __call__(self, t, y):
+        y = np.asarray(y, dtype=self.dtype)
+        h = np.tanh(self._pre(y) @ self.w1 + self.b1)
+        return (h @ self.w2 + self.b2).astype(self.dtype)
+
+    def vjp(self, t, y, c):
+        """returns f, vjp_y, (gW1, gb1, gW2, gb2) summed over leading batch dims."""
+        y = np.asarray(y, dtype=self.dtype)
+        c = np.asarray(c, dtype=self.dtype)
+        u = self._pre(y)
+        h = np.tanh(u @ self.w1 + self.b1)
+        f = h @ self.w2 + self.b2
+        dh = c @ self.w2.T
+        dz = dh * (1 - h * h)
+        du = dz @ self.w1.T
+        dy = du * self._dpre(y)
+        u2, dz2, h2, c2 = (a.reshape(-1, a.shape[-1]) for a in (u, dz, h, c))
+        return f, dy, (u2.T @ dz2, dz2.sum(0), h2.T @ c2, c2.sum(0))
+
+
+def odeint_adjoint_backward(field, t_span, y_ans, grad_y, *, rtol=1e-7, atol=1e-9, seminorm=True,
+                            vjp=None):
+    """OdeintAdjointMethod.backward (functional/odeint_adjoint.py:47-167), repairs R4-R6, for one
+    flat augmented state covering the whole leading batch of y_ans[0] (reference batch semantics;
+    call with B == 1 slices for the per-trajectory controller).
+
+    ``vjp(t, y, c) -> (f, dy, [g_p...])``; defaults to ``field.vjp``."""
+    vjp = vjp or field.vjp
+    t_span = np.asarray(t_span, dtype=f32)
+    yshape = y_ans[0].shape
+    ny = int(np.prod(yshape))
+    _, _, g0 = vjp(t_span[0], y_ans[0], np.zeros_like(y_ans[0]))
+    pshapes = [np.asarray(g).shape for g in g0]
+    psizes = [int(np.prod(s)) for s in pshapes]
+
+    def unpack(Y):
+        o = 1
+        y = Y[o:o + ny].reshape(yshape); o += ny
+        a = Y[o:o + ny].reshape(yshape); o += ny
+        ps = []
+        for s, n in zip(pshapes, psizes):
+            ps.append(Y[o:o + n].reshape(s)); o += n
+        return Y[0], y, a, ps
+
+    def aug_dyn(t, Y):  # augmented_dynamics :89-124
+        _, y, a, _ = unpack(Y)
+        f, dy, gs = vjp(t, y, (-a).astype(f32))
+        return np.concatenate([np.zeros(1, f32), np.asarray(f, f32).ravel(), np.asarray(dy, f32).ravel()]
+                              + [np.asarray(g, f32).ravel() for g in gs]).astype(f32)
+
+    def norm(V):  # default_adjoint_norm / adjoint_seminorm :284-309
+        gt, y, a, ps = unpack(V)
+        best = f32(abs(gt))
+        for cand in (rms_norm(y), rms_norm(a)):
+            if cand > best:
+                best = cand
+        if not seminorm:
+            pm = None
+            for p in ps:
+                r = rms_norm(p)
+                if pm is None or r > pm:
+                    pm = r
+            if pm is not None and pm > best:
+                best = pm
+        return best
+
+    aug = np.concatenate([np.zeros(1, f32), y_ans[-1].ravel(), grad_y[-1].ravel(),
+                          np.zeros(sum(psizes), f32)]).astype(f32)
+    logs = []
+    for i in range(len(t_span) - 1, 0, -1):
+        s = Dopri5(aug_dyn, aug, rtol=rtol, atol=atol, norm=norm)
+        sol = s.integrate(t_span[i - 1:i + 1][::-1])
+        logs.append(s.log)
+        aug = sol[1].copy()
+        aug[1:1 + ny] = y_ans[i - 1].ravel()
+        aug[1 + ny:1 + 2 * ny] = (aug[1 + ny:1 + 2 * ny] + grad_y[i - 1].ravel()).astype(f32)
+    _, _, a, ps = unpack(aug)
+    return ps, a.copy(), logs
+
+
+# ----------------------------------------------------------------------------------------------
+# Interpolation (interpolation/interpolate_base.py, interpolate.py) and HistoryIndex
+# ----------------------------------------------------------------------------------------------
+class InterpolationBase:
+    def __init__(self, series, t=None):
+        series = np.asarray(series, dtype=f32)
+        if t is None:
+            t = np.linspace(0, series.shape[-2], series.shape[-2] + 1, dtype=f32)
+        t = np.asarray(t, dtype=f32)
+        self._series_arr, self._scale_t = self._make_series(series, t)
+        self._derivs = self._make_derivative(series, t)
+        self._t, self._series = t, series
+
+    def interpolate(self, t, der=False):  # interpolate_base.py:49-75
+        t = np.atleast_1d(np.asarray(t, dtype=f32))
+        maxlen = self._series.shape[-2] - 1
+        index = np.clip(np.searchsorted(self._t, t, side="left") - 1, 0, maxlen)
+        norm_t = (t - self._t[index]).astype(f32)
+        norm_t = (norm_t / self._scale_t[index]).astype(f32)
+        return self.ts(norm_t, der=der), self.ps(index), index
+
+    def evaluate(self, t):  # :77-95
+        ts, ps, index = self.interpolate(t, der=False)
+        result = ((ts @ self._h) @ ps).squeeze(-2)
+        return (result * self._scale_t[index][:, None]).astype(f32)
+
+    def derivative(self, t):  # :97-114
+        ts, ps, index = self.interpolate(t, der=True)
+        return ((ts @ self._h) @ ps).squeeze(-2).astype(f32)
+
+
+def _scaled_series(series, t):  # interpolate.py:40-66 / 134-158
+    scale = t[1:] - t[:-1]
+    scale1 = np.concatenate([scale, scale[-1:]])
+    scale2 = np.concatenate([scale[:1], scale1[:-1]])
+    series2 = np.concatenate([series[..., 1:, :], series[..., -1:, :]], axis=-2)
+    series_r = np.stack([series / scale1[:, None], series2 / scale2[:, None]], axis=-2)
+    return series_r.astype(f32), scale1.astype(f32)
+
+
+class LinearInterpolation(InterpolationBase):
+    _h = np.array([[-1.0, 1.0], [1.0, 0.0]], dtype=f32)  # interpolate.py:35-38
+
+    def _make_series(self, series, t):
+        return _scaled_series(series, t)
+
+    def _make_derivative(self, series, t):
+        return None
+
+    def ts(self, t, der=False):
+        cols = [t, np.ones_like(t)] if not der else [np.ones_like(t), np.zeros_like(t)]
+        return np.stack(cols, axis=-1)[..., None, :].astype(f32)
+
+    def ps(self, index):
+        return np.stack([self._series_arr[..., 0, :][..., index, :],
+                         self._series_arr[..., 1, :][..., index, :]], axis=-2)
+
+
+class CubicHermiteSpline(InterpolationBase):
+    _h = np.array([[2, -2, 1, 1], [-3, 3, -2, -1], [0, 0, 1, 0], [1, 0, 0, 0]], dtype=f32)  # :127-130
+
+    def _make_series(self, series, t):
+        return _scaled_series(series, t)
+
+    def _make_derivative(self, series, t):  # :160-182
+        diffs_t = t[1:] - t[:-1]
+        diffs_t1 = np.concatenate([diffs_t, diffs_t[-1:]])
+        ds = series[..., 1:, :] - series[..., :-1, :]
+        ds = np.concatenate([ds, ds[..., -1:, :]], axis=-2)
+        derivs = ds / diffs_t1[:, None]
+        return np.concatenate([derivs, derivs[..., -1:, :]], axis=-2).astype(f32)
+
+    def ts(self, t, der=False):
+        if not der:
+            cols = [t ** 3, t ** 2, t, np.ones_like(t)]
+        else:
+            cols = [3 * t ** 2, 2 * t, np.ones_like(t), np.zeros_like(t)]
+        return np.stack(cols, axis=-1)[..., None, :].astype(f32)
+
+    def ps(self, index):
+        return np.stack([self._series_arr[..., 0, :][..., index, :],
+                         self._series_arr[..., 1, :][..., index, :],
+                         self._derivs[..., index, :],
+                         self._derivs[..., index + 1, :]], axis=-2)
+
+
+def history_index_forward(lags, his, his_span, interp_method="cubic"):
+    """HistoryIndex.forward (xde/base_dde.py:84-118) -> (y_lags, derivative_lags)."""
+    if interp_method == "linear":
+        interp = LinearInterpolation(his, his_span)
+    elif interp_method == "cubic":
+        interp = CubicHermiteSpline(his, his_span)
+    else:
+        raise NotImplementedError
+    return interp.evaluate(lags), interp.derivative(lags)
+
+
+def history_index_backward(grad_y, derivative_lags):
+    """HistoryIndex.backward (xde/base_dde.py:121-127); 4-D [B,N,L,D] only, like the reference."""
+    return np.sum((grad_y * derivative_lags).astype(np.float64), axis=(0, 1, 3)).astype(f32)

@@ -1,0 +1,146 @@
+/*
+ * xde_oracle.h -- CPU restatement ("oracle") of the PaddleXDE batched DE-integration hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is product code: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ * The product (paddlexde_b200/) never links, imports or falls back to this library.
+ *
+ * PARITY STATUS: the reference is pure Python on PaddlePaddle; Paddle is not installable in the
+ * build container, and the reference at HEAD cannot run even with Paddle (repairs
+ * R1-R7).  This oracle is therefore a *restatement* of the reference algorithm with a fully defined
+ * fp32 arithmetic order (DESIGN.md "Arithmetic specification").  It is pinned against every
+ * known-answer fixture the reference's tests hold for this path (closed-form Sine/Linear/Constant
+ * ODE fixtures, interpolation ramp/sin fixtures; see tests/test_oracle_fixtures.py).  What those
+ * fixtures do NOT pin (accept/reject sequences, adjoint gradients, SDE results, HistoryIndex
+ * backward, B>1) is "parity unpinned": parity there is defined against this oracle.
+ *
+ * Each function cites the reference file:line it follows (paths relative to /root/reference).
+ */
+#ifndef XDE_ORACLE_H
+#define XDE_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* pre-activation applied to the state before the first Linear (example/ode_demo.py:32-33 uses
+ * y**3, example/sde_demo.py:182-183 uses y**2) */
+enum { ORC_PRE_ID = 0, ORC_PRE_SQUARE = 1, ORC_PRE_CUBE = 2 };
+
+/* status codes (mirror the reference's asserts, solver/base_adaptive_solver_rk.py:120-122,200-203,
+ * utils/ode_utils.py:65-67) */
+enum {
+  ORC_OK = 0,
+  ORC_DT_UNDERFLOW = 1,
+  ORC_NONFINITE_STATE = 2,
+  ORC_MAX_STEPS = 3,
+  ORC_BAD_ARG = 4,
+  ORC_INTERP_RANGE = 5
+};
+
+enum { ORC_CTRL_TRAJECTORY = 0, ORC_CTRL_BATCH = 1 };
+enum { ORC_ADJ_NORM_MIXED = 0, ORC_ADJ_NORM_SEMI = 1 };
+enum { ORC_FIXED_EULER = 0, ORC_FIXED_RK4_38 = 1 };
+enum { ORC_SDE_EM = 0, ORC_SDE_MILSTEIN = 1 };
+enum { ORC_INTERP_LINEAR = 0, ORC_INTERP_HERMITE = 1 };
+
+/* f(t,y) = tanh(pre(y) @ W1 + b1) @ W2 + b2 ; weights in Paddle nn.Linear layout [in,out]
+ * (example/ode_demo.py:17-33) */
+typedef struct {
+  int32_t d, h, pre;
+  const float *w1; /* [d,h] */
+  const float *b1; /* [h]   */
+  const float *w2; /* [h,d] */
+  const float *b2; /* [d]   */
+} orc_mlp_t;
+
+/* solver/base_adaptive_solver_rk.py:32-49 keyword arguments */
+typedef struct {
+  float rtol, atol;
+  float min_step, max_step;
+  float first_step; /* NaN => select_initial_step */
+  float safety, ifactor, dfactor;
+  int32_t max_num_steps;
+} orc_opts_t;
+
+typedef struct {
+  int64_t n_attempts, n_accepted, nfe;
+  int32_t status;
+  float min_abs_ratio_m1; /* min |error_ratio - 1| seen: knife-edge indicator */
+} orc_stats_t;
+
+/* one record per step attempt (optional log) */
+typedef struct {
+  float t0, dt, ratio;
+  int32_t accepted;
+} orc_attempt_t;
+
+void orc_default_opts(orc_opts_t *o);
+
+/* scalar primitives of the arithmetic specification (exposed for tests) */
+float orc_tanhf(float x);
+float orc_root5f(float r); /* r^(1/5), deterministic */
+
+/* field evaluation, one trajectory.  hbuf optional [h]. */
+void orc_mlp_eval(const orc_mlp_t *m, const float *y, float *f, float *hbuf);
+/* field + VJP with cotangent c (functional/odeint_adjoint.py:106-114 uses c = -adj_y).
+ * Writes f[d], dy[d], and ACCUMULATES (+=) the per-trajectory parameter VJP into gw1,gb1,gw2,gb2
+ * when they are non-NULL. */
+void orc_mlp_vjp(const orc_mlp_t *m, const float *y, const float *c, float *f, float *dy,
+                 float *gw1, float *gb1, float *gw2, float *gb2);
+/* batched convenience wrappers */
+void orc_mlp_eval_batch(const orc_mlp_t *m, const float *y, int64_t B, float *f);
+
+/* odeint(func=MLP, solver=Dopri5): functional/odeint.py:9-35 -> solver/base_adaptive_solver.py:24-31.
+ * out is time-major [T,B,D].  controller = ORC_CTRL_BATCH is the literal reference (one global RMS
+ * norm / one dt for the batch, utils/ode_utils.py:8-9,80-82); ORC_CTRL_TRAJECTORY runs the reference
+ * with B=1 once per trajectory (north_star "one controller per trajectory").
+ * stats: one entry per trajectory (TRAJECTORY) or a single entry (BATCH); may be NULL.
+ * log/log_cap: attempt log of trajectory `log_traj` (TRAJECTORY) or of the batch (BATCH); may be NULL.
+ * returns the worst status. */
+int orc_dopri5_mlp(const orc_mlp_t *m, const float *y0, int64_t B, const float *t_span, int32_t T,
+                   const orc_opts_t *opts, int32_t controller, float *out, orc_stats_t *stats,
+                   orc_attempt_t *log, int64_t log_cap, int64_t log_traj, int64_t *log_len,
+                   int32_t nthreads);
+
+/* odeint(func=MLP, solver=Euler|RK4): solver/base_fixed_solver.py:103-144, fixed_solver/euler.py:7-11,
+ * fixed_solver/rk4.py:7-10 (3/8 rule, base_fixed_solver.py:166-197).  grid == t_span.
+ * out is [B,T,D] (concat(axis=-2) of [B,1,D] states, base_fixed_solver.py:143). */
+int orc_fixed_mlp(int32_t method, const orc_mlp_t *m, const float *y0, int64_t B,
+                  const float *t_span, int32_t T, float *out, int32_t nthreads);
+
+/* OdeintAdjointMethod.backward (functional/odeint_adjoint.py:47-167) with repairs R4-R6.
+ * y_ans, grad_y: [T,B,D] time-major.  out_gparams: [d*h + h + h*d + d] = (gW1,gb1,gW2,gb2).
+ * out_adj_y0: optional [B,D] (dL/dy0; the reference computes and then discards it, :167).
+ * stats: per trajectory (TRAJECTORY) or single (BATCH). */
+int orc_dopri5_mlp_adjoint(const orc_mlp_t *m, const float *t_span, int32_t T, const float *y_ans,
+                           const float *grad_y, int64_t B, const orc_opts_t *opts,
+                           int32_t controller, int32_t adj_norm, float *out_gparams,
+                           float *out_adj_y0, orc_stats_t *stats, orc_attempt_t *log,
+                           int64_t log_cap, int64_t log_traj, int64_t *log_len, int32_t nthreads);
+
+/* sdeint with Euler(-Maruyama) / Milstein and caller-supplied increments (repairs R2,R3;
+ * xde/base_sde.py:44-61, fixed_solver/euler.py:7-11).  dW: [T-1,B,D].  out: [B,T,D]. */
+int orc_sde_mlp(int32_t scheme, const orc_mlp_t *drift, const orc_mlp_t *diffusion, const float *y0,
+                int64_t B, const float *t_span, int32_t T, const float *dW, float *out,
+                int32_t nthreads);
+
+/* HistoryIndex.forward (xde/base_dde.py:84-118): interp.evaluate(lags) and interp.derivative(lags)
+ * (interpolation/interpolate_base.py:49-114, interpolate.py:6-204).
+ * his: [R, Th, D] with R = prod(leading dims); his_span: [Th]; lags: [L]; out_val, out_der: [R,L,D]. */
+int orc_history_gather(int32_t kind, const float *his, int64_t R, int32_t Th, int32_t D,
+                       const float *his_span, const float *lags, int32_t L, float *out_val,
+                       float *out_der);
+/* HistoryIndex.backward (xde/base_dde.py:121-127): g_lags[l] = sum_{r,d} grad_y * deriv */
+void orc_history_gather_bwd(const float *grad_y, const float *deriv, int64_t R, int32_t L, int32_t D,
+                            float *g_lags);
+
+/* BaseDDE.fuse damped Euler step (xde/base_dde.py:55-58): y=dy*dt+y0; y1=(dy-0.001*y)*dt+y0 */
+void orc_dde_fuse(const float *dy, float dt, const float *y0, int64_t n, float *y1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,155 @@
+"""Pins the oracle against every known-answer fixture the reference's own tests hold for this path
+(SURVEY.md 8(c)): tests/testing_utils.py Sine/Linear/Constant problems with the tolerances of
+tests/functional/test_adaptive_solver.py:36-38,73-75 and test_fixed_solver.py:26-39, and the
+interpolation ramp/sin fixtures of tests/interpolation/test_interpolation.py:13-85."""
+import math
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+from oracle import oracle_np as onp
+
+f32 = np.float32
+
+
+def allclose(a, b, rtol, atol=1e-8):  # paddle.allclose defaults
+    return np.allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
+
+
+# --- tests/testing_utils.py fixtures --------------------------------------------------------------
+def sine_f(t, y):  # SineXDE.forward :30-31
+    t = f32(t)
+    return (f32(2) * y / t + t ** 4 * np.sin(f32(2) * t) - t ** 2 + f32(4) * t ** 3).astype(f32)
+
+
+def sine_exact(t):  # :33-41
+    t = t.astype(np.float64)
+    return (-0.5 * t ** 4 * np.cos(2 * t) + 0.5 * t ** 3 * np.sin(2 * t) + 0.25 * t ** 2 * np.cos(2 * t)
+            - t ** 3 + 2 * t ** 4 + (math.pi - 0.25) * t ** 2)[:, None]
+
+
+def constant_f(t, y):  # ConstantXDE.forward :22-23, a=0.2, b=3
+    a, b = f32(0.2), f32(3.0)
+    return (a + (y - (a * f32(t) + b)) ** 5).astype(f32)
+
+
+def constant_exact(t):
+    return (0.2 * t.astype(np.float64) + 3.0)[:, None]
+
+
+T_POINTS = np.linspace(1, 8, 10).astype(f32)  # construct_problem :86
+
+
+def test_dopri5_sine_fixture():
+    sol = sine_exact(T_POINTS)                       # [T,1]
+    y0 = sol[0].astype(f32)[None]                    # [1,1]
+    y = onp.odeint(sine_f, y0, T_POINTS, onp.Dopri5)  # [T,1,1]
+    assert allclose(sol, y[:, 0], rtol=4e-3)
+    # far tighter than the reference's tolerance: the restatement is a working fp32 dopri5
+    assert np.max(np.abs(y[:, 0] - sol) / np.abs(sol)) < 5e-6
+    log = onp.odeint.last_log
+    assert 30 <= len(log.dt) <= 80 and sum(log.accepted) >= len(log.dt) - 12
+
+
+def test_dopri5_linear_fixture():
+    rng = np.random.default_rng(0)
+    U = rng.standard_normal((10, 10)) * 0.1
+    A = (2 * U - (U + U.T)).astype(f32)              # LinearXDE :48-49
+
+    def f(t, y):
+        return (A @ y.reshape(10, 1)).reshape(-1).astype(f32)
+
+    exact = np.stack([scipy.linalg.expm(A.astype(np.float64) * float(ti)) @ np.ones(10) for ti in T_POINTS])
+    y = onp.odeint(f, exact[0].astype(f32), T_POINTS, onp.Dopri5)
+    assert allclose(exact, y, rtol=4e-3)
+
+
+def test_dopri5_constant_fixture():
+    sol = constant_exact(T_POINTS)
+    y = onp.odeint(constant_f, sol[0].astype(f32)[None], T_POINTS, onp.Dopri5)
+    assert allclose(sol, y[:, 0], rtol=4e-3)
+
+
+@pytest.mark.parametrize("solver", [onp.Euler, onp.RK4])
+def test_fixed_constant_fixture(solver):
+    sol = constant_exact(T_POINTS)                   # test_fixed_solver.py: rtol=1e-2
+    y = onp.odeint(constant_f, sol[0].astype(f32)[None], T_POINTS, solver)  # [T,1]
+    assert y.shape == (10, 1)
+    assert allclose(sol, y, rtol=1e-2)
+
+
+def test_fixed_output_layout():
+    # y0 [B,1,D] -> [B,T,D] (base_fixed_solver.py:143)
+    y0 = np.ones((3, 1, 2), f32)
+    y = onp.odeint(lambda t, y: (0 * y).astype(f32), y0, T_POINTS, onp.RK4)
+    assert y.shape == (3, 10, 2)
+
+
+# --- tests/interpolation/test_interpolation.py fixtures -------------------------------------------
+def _ramp():
+    series = np.stack([np.arange(0, 1000, 0.5, dtype=f32), np.zeros(2000, f32)], axis=-1)[None]
+    return series, np.arange(0, 2000, 1).astype(f32)
+
+
+def _sin():
+    x = np.arange(0, 20, 0.01, dtype=np.float64)[:2000].astype(f32)
+    series = np.sin(np.stack([x, np.zeros(2000, f32)], axis=-1))[None].astype(f32)
+    return series, x
+
+
+@pytest.mark.parametrize("cls", [onp.LinearInterpolation, onp.CubicHermiteSpline])
+def test_interp_fixed_deriv(cls):
+    series, t = _ramp()
+    it = cls(series, t)
+    assert allclose([[[21.12 * 0.5, 0]]], it.evaluate([21.12]), rtol=1e-4)
+    assert allclose([[[0.5, 0]]], it.derivative([21.12]), rtol=1e-4)
+
+
+@pytest.mark.parametrize("cls,vtol", [(onp.LinearInterpolation, 5e-2), (onp.CubicHermiteSpline, 1e-5)])
+def test_interp_dynamic_deriv(cls, vtol):
+    series, t = _sin()
+    it = cls(series, t)
+    assert allclose(np.sin([[[16.5, 0.0]]]), it.evaluate([16.5]), rtol=vtol, atol=1e-6)
+    assert allclose([[[math.cos(16.5), 0.0]]], it.derivative([16.5]), rtol=1e-2, atol=1e-6)
+
+
+# --- C oracle == literal NumPy restatement ---------------------------------------------------------
+def test_c_gather_matches_literal(oracle):
+    rng = np.random.default_rng(3)
+    his = rng.uniform(-1, 1, (2, 5, 40, 3)).astype(f32)
+    span = np.arange(40).astype(f32)
+    lags = np.concatenate([np.arange(0, 12) + rng.uniform(0, 1, 12), [0.0, 7.0, 39.0, 39.5, -1.0, 45.0]]).astype(f32)
+    for kind in ("linear", "cubic"):
+        v_np, d_np = onp.history_index_forward(lags, his, span, kind)
+        v_c, d_c = oracle.history_gather(kind, his, span, lags)
+        np.testing.assert_allclose(v_c, v_np, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(d_c, d_np, rtol=2e-5, atol=2e-5)
+        g = rng.standard_normal(v_c.shape).astype(f32)
+        np.testing.assert_allclose(oracle.history_gather_bwd(g, d_c), onp.history_index_backward(g, d_c),
+                                   rtol=1e-5, atol=1e-5)
+    # non-uniform grid too
+    span2 = np.cumsum(rng.uniform(0.5, 1.5, 40)).astype(f32)
+    lags2 = rng.uniform(span2[0], span2[-1], 9).astype(f32)
+    for kind in ("linear", "cubic"):
+        v_np, d_np = onp.history_index_forward(lags2, his, span2, kind)
+        v_c, d_c = oracle.history_gather(kind, his, span2, lags2)
+        np.testing.assert_allclose(v_c, v_np, rtol=3e-5, atol=3e-6)
+        np.testing.assert_allclose(d_c, d_np, rtol=3e-5, atol=3e-5)
+
+
+def test_c_primitives(oracle):
+    x = np.concatenate([np.linspace(-12, 12, 40001), [0.0, 1e-5, -3e-4, 4e-4, 7.9, 8.0, 1e30]]).astype(f32)
+    err = np.abs(oracle.tanhf(x).astype(np.float64) - np.tanh(x.astype(np.float64)))
+    assert err.max() < 3e-7                           # <= 5 ulp of 1.0
+    assert np.isnan(oracle.tanhf(np.array([np.nan], f32))[0])
+    r = np.exp(np.random.default_rng(0).uniform(-40, 40, 4000)).astype(f32)
+    ref = r.astype(np.float64) ** 0.2
+    assert np.max(np.abs(oracle.root5f(r) - ref) / ref) < 2.5e-7
+    assert all(onp.root5(v) == c for v, c in zip(r[:300], oracle.root5f(r[:300])))
+
+
+def test_dde_fuse(oracle):
+    rng = np.random.default_rng(1)
+    dy, y0 = rng.standard_normal(100).astype(f32), rng.standard_normal(100).astype(f32)
+    assert np.array_equal(oracle.dde_fuse(dy, 1.0, y0), onp.dde_fuse(dy, 1.0, y0))

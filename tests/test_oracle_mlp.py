@@ -1,0 +1,146 @@
+"""C oracle (fused-MLP specialisation) vs the literal NumPy restatement and vs fp64 truths.
+
+No reference test pins any of this (SURVEY.md 8(c) "not pinned"): step sequences, adjoint gradients,
+SDE results and B>1 behaviour are defined by the restated oracle -- "parity unpinned"."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as onp
+from tests.problems import cfg2_tspan, cfg2_y0, fanin_weights, spiral_weights
+
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def spiral(oracle):
+    return oracle.MLP(*spiral_weights(), pre="cube")
+
+
+def test_field_close_to_fp64(oracle, spiral):
+    y = cfg2_y0(64)
+    ref = onp.MLPFieldNP(spiral.w1, spiral.b1, spiral.w2, spiral.b2, "cube", np.float64)(0.0, y)
+    np.testing.assert_allclose(spiral(0.0, y), ref, rtol=2e-5, atol=2e-6)
+    c = np.random.default_rng(2).standard_normal(y.shape).astype(f32)
+    f, dy, gs = spiral.vjp(0.0, y, c)
+    f64 = onp.MLPFieldNP(spiral.w1, spiral.b1, spiral.w2, spiral.b2, "cube", np.float64)
+    f_r, dy_r, gs_r = f64.vjp(0.0, y, c)
+    np.testing.assert_allclose(dy, dy_r, rtol=1e-4, atol=1e-5)
+    for g, gr in zip(gs, gs_r):
+        np.testing.assert_allclose(g, gr, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("controller", ["trajectory", "batch"])
+def test_dopri5_c_equals_literal(oracle, spiral, controller):
+    y0, t = cfg2_y0(12), np.linspace(0, 25, 1000).astype(f32)[:40:4]
+    out, st, log, rc = oracle.dopri5_mlp(spiral, y0, t, controller=controller, log_traj=5)
+    assert rc == 0
+    if controller == "batch":
+        sol = onp.odeint(spiral, y0, t, onp.Dopri5)
+        assert np.array_equal(sol, out)
+    else:
+        sol = onp.odeint(spiral, y0[5:6], t, onp.Dopri5)
+        assert np.array_equal(sol[:, 0], out[:, 5])
+    lg = onp.odeint.last_log
+    assert np.array_equal(np.array(lg.dt, f32), log.dt)
+    assert np.array_equal(np.array(lg.ratio, f32), log.ratio)
+    assert lg.accepted == list(log.accepted.astype(bool))
+    assert lg.nfe == (st.nfe[5] if controller == "trajectory" else st.nfe[0])
+
+
+def test_dopri5_rejections_and_tolerance(oracle):
+    # a stiffer field (fan-in weights, identity pre-activation) so the controller both accepts and rejects
+    m = oracle.MLP(*[3.0 * a for a in fanin_weights(2, 50, seed=5)], pre="id")
+    y0 = np.random.default_rng(1).uniform(-1, 1, (8, 2)).astype(f32)
+    t = np.linspace(0, 4, 9).astype(f32)
+    out, st, log, rc = oracle.dopri5_mlp(m, y0, t, log_traj=0, rtol=1e-6, atol=1e-8)
+    assert rc == 0 and (st.n_attempts > st.n_accepted).any()
+    sol = onp.odeint(m, y0[0:1], t, onp.Dopri5, rtol=1e-6, atol=1e-8)
+    assert np.array_equal(sol[:, 0], out[:, 0])
+    # accuracy vs scipy fp64
+    from scipy.integrate import solve_ivp
+
+    f64 = onp.MLPFieldNP(m.w1, m.b1, m.w2, m.b2, "id", np.float64)
+    ref = solve_ivp(lambda tt, y: f64(tt, y), (0, 4), y0[0].astype(np.float64), t_eval=t.astype(np.float64),
+                    rtol=1e-11, atol=1e-13, method="DOP853").y.T
+    np.testing.assert_allclose(out[:, 0], ref, rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("method,cls", [("euler", onp.Euler), ("rk4", onp.RK4)])
+def test_fixed_c_equals_literal(oracle, spiral, method, cls):
+    y0, t = cfg2_y0(6), np.linspace(0, 25, 1000).astype(f32)[:32]
+    out = oracle.fixed_mlp(method, spiral, y0, t)                 # [B,T,D]
+    sol = onp.odeint(spiral, y0[:, None, :], t, cls)              # [B,T,D]
+    assert np.array_equal(out, sol)
+
+
+def test_adjoint_c_equals_literal_and_fp64(oracle, spiral):
+    import torch
+
+    B = 6
+    y0, t = cfg2_y0(B), cfg2_tspan(6)
+    out, _, _, rc = oracle.dopri5_mlp(spiral, y0, t)
+    gy = np.zeros_like(out)
+    gy[-1] = np.sign(out[-1]) / out[-1].size
+    gy[2] = 0.01                                                   # a mid-trajectory loss term too
+    g, a0, st, log, rc = oracle.dopri5_mlp_adjoint(spiral, t, out, gy, log_traj=2)
+    assert rc == 0
+    gs = np.zeros(spiral.n_params, np.float64)
+    for b in range(B):
+        ps, a, logs = onp.odeint_adjoint_backward(spiral, t, out[:, b:b + 1], gy[:, b:b + 1], seminorm=True)
+        gs += np.concatenate([p.ravel() for p in ps]).astype(np.float64)
+        assert np.array_equal(a[0], a0[b])
+        if b == 2:
+            dts = np.concatenate([np.array(l.dt, f32) for l in logs])
+            assert np.array_equal(dts, log.dt)
+    assert np.array_equal(gs.astype(f32), g)
+    # batch controller + default mixed norm (the literal reference configuration)
+    gb, a0b, stb, logb, rc = oracle.dopri5_mlp_adjoint(spiral, t, out, gy, controller="batch", adj_norm="mixed")
+    ps, a, logs = onp.odeint_adjoint_backward(spiral, t, out, gy, seminorm=False)
+    np.testing.assert_allclose(np.concatenate([p.ravel() for p in ps]), gb, rtol=1e-5, atol=1e-8)
+    # fp64 truth by autograd through a fine RK4
+    W = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (spiral.w1, spiral.b1, spiral.w2, spiral.b2)]
+    y = torch.tensor(y0, dtype=torch.float64)
+    ts = t.astype(np.float64)
+    loss = 0.0
+    for i in range(1, len(ts)):
+        n = 200
+        h = (ts[i] - ts[i - 1]) / n
+        fn = lambda y: torch.tanh((y ** 3) @ W[0] + W[1]) @ W[2] + W[3]
+        for _ in range(n):
+            k1 = fn(y); k2 = fn(y + h / 2 * k1); k3 = fn(y + h / 2 * k2); k4 = fn(y + h * k3)
+            y = y + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        loss = loss + (y * torch.tensor(gy[i], dtype=torch.float64)).sum()
+    loss.backward()
+    gt = np.concatenate([w.grad.numpy().ravel() for w in W])
+    scale = np.max(np.abs(gt))
+    assert np.max(np.abs(g - gt)) / scale < 5e-6
+    assert np.max(np.abs(gb - gt)) / scale < 5e-6
+
+
+def test_sde_em_and_milstein(oracle):
+    D, H, B, T = 4, 16, 10, 9
+    drift = oracle.MLP(*fanin_weights(D, H, seed=2), pre="cube")
+    diff = oracle.MLP(*fanin_weights(D, H, seed=3), pre="square")
+    rng = np.random.default_rng(2)
+    y0 = rng.uniform(-1, 1, (B, D)).astype(f32)
+    t = np.linspace(0, 1, T).astype(f32)
+    dW = (np.sqrt(1 / (T - 1)) * rng.standard_normal((T - 1, B, D))).astype(f32)
+    out = oracle.sde_mlp("em", drift, diff, y0, t, dW)
+    # literal: Euler step with move/fuse of the intended BaseSDE (xde/base_sde.py:44-61)
+    y = y0.copy()
+    for n in range(T - 1):
+        dt = f32(t[n + 1] - t[n])
+        y = ((y + drift(t[n], y) * dt).astype(f32) + (diff(t[n], y) * dW[n]).astype(f32)).astype(f32)
+        assert np.array_equal(out[:, n + 1], y)
+    # Milstein (extension, no reference counterpart): check the analytic diagonal Jacobian by differences
+    outm = oracle.sde_mlp("milstein", drift, diff, y0, t, dW)
+    g64 = onp.MLPFieldNP(diff.w1, diff.b1, diff.w2, diff.b2, "square", np.float64)
+    y = y0[:, :].astype(np.float64)
+    eps = 1e-6
+    gp = np.stack([(g64(0, y + eps * np.eye(D)[d])[:, d] - g64(0, y - eps * np.eye(D)[d])[:, d]) / (2 * eps)
+                   for d in range(D)], axis=1)
+    dt = float(t[1] - t[0])
+    g = g64(0, y)
+    f64 = onp.MLPFieldNP(drift.w1, drift.b1, drift.w2, drift.b2, "cube", np.float64)
+    ref = y + f64(0, y) * dt + g * dW[0] + 0.5 * g * gp * (dW[0].astype(np.float64) ** 2 - dt)
+    np.testing.assert_allclose(outm[:, 1], ref, rtol=2e-5, atol=2e-6)
