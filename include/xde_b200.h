@@ -1,0 +1,175 @@
+/*
+ * xde_b200.h -- C ABI of libxde_b200.so: the B200 (sm_100a) implementation of PaddleXDE's batched
+ * differential-equation integration hot path.
+ *
+ * The reference (DrownFish19/PaddleXDE) is pure Python on Paddle eager ops and has NO FFI / custom-op
+ * boundary of its own; its de-facto extension point is the solver-class protocol
+ *     s = solver(xde=xde, y0=xde.y0, rtol=rtol, atol=atol, **options); s.integrate(t_span)
+ * (paddlexde/functional/odeint.py:30-31) plus the four functional entry points.  Each entry point
+ * below replaces the inner loop that one of those Python call sites runs; the file:line it
+ * replaces is cited on each declaration (paths relative to the reference root).  The Python shim
+ * (paddlexde_b200/) and the reference-side stub shown in INTEGRATION.md bind these with ctypes.
+ *
+ * Conventions
+ *   - plain C, no torch / DLPack types: raw device pointers + sizes.  All tensor arguments are
+ *     DEVICE pointers to contiguous fp32 unless a name ends in _host.  Inputs are borrowed and
+ *     never written; outputs are caller-allocated.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous with respect to the host; no call synchronises the device.
+ *   - return value: XDE_OK or a negative XDE_E_* launch/argument error.  Solver conditions that the
+ *     reference raises as Python asserts (dt underflow, non-finite state, max_num_steps,
+ *     base_adaptive_solver_rk.py:120-122,200-203) are reported through xde_stats_t.status in device
+ *     memory, to be read by the caller after it synchronises the stream.
+ *   - re-entrant: no global mutable state except a monotonically increasing launch counter.
+ */
+#ifndef XDE_B200_H
+#define XDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XDE_ABI_VERSION 1
+
+/* return codes */
+enum {
+  XDE_OK = 0,
+  XDE_E_BAD_ARG = -1,           /* ValueError in the shim */
+  XDE_E_UNSUPPORTED_FIELD = -2, /* field family / shape not covered by a fused kernel: hard error, no fallback */
+  XDE_E_CUDA = -3               /* a CUDA runtime call failed; see xde_last_error() */
+};
+
+/* device-side solver status (xde_stats_t.status): mirrors the reference's asserts */
+enum {
+  XDE_ST_OK = 0,
+  XDE_ST_DT_UNDERFLOW = 1,    /* assert t0 + dt > t0          base_adaptive_solver_rk.py:200 */
+  XDE_ST_NONFINITE_STATE = 2, /* assert isfinite(y0).all()    base_adaptive_solver_rk.py:201-203 */
+  XDE_ST_MAX_STEPS = 3,       /* max_num_steps exceeded       base_adaptive_solver_rk.py:120-122 */
+  XDE_ST_INTERP_RANGE = 5     /* invalid interpolation        utils/ode_utils.py:65-67 */
+};
+
+/* y ** p applied before the first Linear (example/ode_demo.py:33, example/sde_demo.py:183) */
+enum { XDE_PRE_ID = 0, XDE_PRE_SQUARE = 1, XDE_PRE_CUBE = 2 };
+/* error-controller granularity: TRAJECTORY = one controller per trajectory (north star; equals the
+ * reference run with B = 1 per trajectory); BATCH = the reference's single global RMS norm and dt
+ * (utils/ode_utils.py:8-9,80-82). */
+enum { XDE_CTRL_TRAJECTORY = 0, XDE_CTRL_BATCH = 1 };
+/* adjoint error norm (functional/odeint_adjoint.py:284-309) */
+enum { XDE_ADJ_NORM_MIXED = 0, XDE_ADJ_NORM_SEMI = 1 };
+enum { XDE_FIXED_EULER = 0, XDE_FIXED_RK4_38 = 1 };
+enum { XDE_SDE_EM = 0, XDE_SDE_MILSTEIN = 1 };
+enum { XDE_INTERP_LINEAR = 0, XDE_INTERP_HERMITE = 1 };
+
+/* The fused vector-field family: f(t, y) = tanh(pre(y) @ w1 + b1) @ w2 + b2
+ * (example/ode_demo.py:17-33).  Weights in Paddle nn.Linear layout [in, out]. */
+typedef struct {
+  int32_t d;       /* state dim D */
+  int32_t h;       /* hidden width H */
+  int32_t pre;     /* XDE_PRE_* */
+  int32_t _pad;
+  const float *w1; /* [d, h] */
+  const float *b1; /* [h]    */
+  const float *w2; /* [h, d] */
+  const float *b2; /* [d]    */
+} xde_mlp_field_t;
+
+/* keyword arguments of AdaptiveRKSolver.__init__ (solver/base_adaptive_solver_rk.py:32-49) */
+typedef struct {
+  float rtol, atol;
+  float min_step, max_step;
+  float first_step; /* NaN => select_initial_step (solver/base_adaptive_solver.py:33-72) */
+  float safety, ifactor, dfactor;
+  int32_t max_num_steps;
+  int32_t _pad;
+} xde_ctrl_opts_t;
+
+/* written by the kernels (device memory, zeroed by the entry point before the launch) */
+typedef struct {
+  unsigned long long n_attempts; /* step attempts summed over trajectories (= trajectory-steps) */
+  unsigned long long n_accepted;
+  unsigned long long nfe;        /* vector-field evaluations, counted as the reference would issue them */
+  int32_t status;                /* worst XDE_ST_* over trajectories */
+  int32_t _pad;
+} xde_stats_t;
+
+/* optional per-attempt log, one row of `cap` records per trajectory (tests / diagnostics) */
+typedef struct {
+  float t0, dt, ratio;
+  int32_t accepted;
+} xde_attempt_t;
+
+typedef struct {
+  xde_attempt_t *records; /* [B, cap] device, or NULL */
+  int32_t *counts;        /* [B] device attempts recorded per trajectory (counts beyond cap are counted, not stored) */
+  int32_t cap;
+  int32_t _pad;
+} xde_attempt_log_t;
+
+int xde_abi_version(void);
+/* thread-local text of the last XDE_E_CUDA / argument failure */
+const char *xde_last_error(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+unsigned long long xde_launch_count(void);
+void xde_default_ctrl_opts(xde_ctrl_opts_t *o);
+
+/* odeint(func, y0, t_span, solver=Dopri5)            functional/odeint.py:28-35
+ *   -> AdaptiveSolver.integrate                       solver/base_adaptive_solver.py:24-31
+ *   -> AdaptiveRKSolver._adaptive_step/_runge_kutta_step  solver/base_adaptive_solver_rk.py:116-292
+ * One launch integrates every trajectory over the whole t_span (device-resident controller).
+ * y0 [B,D]; t_span [T] strictly increasing or strictly decreasing; out [T,B,D] time-major
+ * (base_adaptive_solver.py:25).  stats / log may be NULL. */
+int xde_dopri5_mlp_f32(const xde_mlp_field_t *field, const float *y0, int64_t B, const float *t_span,
+                       int32_t T, const xde_ctrl_opts_t *opts, int32_t controller, float *out,
+                       xde_stats_t *stats, const xde_attempt_log_t *log, void *stream);
+
+/* OdeintAdjointMethod.backward                        functional/odeint_adjoint.py:47-167
+ * (augmented_dynamics :89-124 integrated backwards segment by segment :134-159).
+ * y_ans, grad_y [T,B,D]; out_gparams [d*h + h + h*d + d] = (gW1, gb1, gW2, gb2) summed over the
+ * B trajectories handed to this call (all-reduce across GPUs is the caller's, 8(e));
+ * out_adj_y0 [B,D] optional (dL/dy0: computed and discarded by the reference, :167). */
+int xde_dopri5_mlp_adjoint_f32(const xde_mlp_field_t *field, const float *t_span, int32_t T,
+                               const float *y_ans, const float *grad_y, int64_t B,
+                               const xde_ctrl_opts_t *opts, int32_t controller, int32_t adj_norm,
+                               float *out_gparams, float *out_adj_y0, xde_stats_t *stats,
+                               const xde_attempt_log_t *log, void *stream);
+
+/* odeint(func, y0, t_span, solver=Euler|RK4)          functional/odeint.py:28-35
+ *   -> FixedSolver.integrate                          solver/base_fixed_solver.py:103-144
+ *   -> Euler.step fixed_solver/euler.py:7-11 | RK4.step fixed_solver/rk4.py:7-10 (3/8 rule,
+ *      base_fixed_solver.py:166-197).  grid == t_span.  out [B,T,D] (base_fixed_solver.py:143).
+ * out_stride_t: write only every out_stride_t-th grid point (1 = all; the last point is always
+ * written); out then has ceil((T-1)/stride)+1 rows per trajectory. */
+int xde_rk_fixed_mlp_f32(int32_t method, const xde_mlp_field_t *field, const float *y0, int64_t B,
+                         const float *t_span, int32_t T, int32_t out_stride_t, float *out,
+                         void *stream);
+
+/* sdeint(drift, diffusion, y0, t, solver=Euler)       functional/sdeint.py:30-37
+ *   -> BaseSDE.move/fuse xde/base_sde.py:44-61 (intended Euler-Maruyama, diagonal noise) with the
+ *      Brownian increments supplied by the caller: dW [T-1,B,D].  out [B,T,D].
+ * XDE_SDE_MILSTEIN is an extension (no reference counterpart). */
+int xde_sde_mlp_f32(int32_t scheme, const xde_mlp_field_t *drift, const xde_mlp_field_t *diffusion,
+                    const float *y0, int64_t B, const float *t_span, int32_t T, const float *dW,
+                    int32_t out_stride_t, float *out, void *stream);
+
+/* HistoryIndex.forward                                xde/base_dde.py:84-118
+ *   -> InterpolationBase.evaluate / derivative        interpolation/interpolate_base.py:49-114
+ *      (LinearInterpolation interpolate.py:6-97, CubicHermiteSpline :100-204).
+ * his [R,Th,D] (R = product of leading dims), his_span [Th], lags [L]; out_val, out_der [R,L,D]. */
+int xde_history_gather_f32(int32_t kind, const float *his, int64_t R, int32_t Th, int32_t D,
+                           const float *his_span, const float *lags, int32_t L, float *out_val,
+                           float *out_der, void *stream);
+/* HistoryIndex.backward                               xde/base_dde.py:121-127
+ * g_lags[l] = sum_{r,d} grad_y[r,l,d] * deriv[r,l,d].  g_lags [L]. */
+int xde_history_gather_bwd_f32(const float *grad_y, const float *deriv, int64_t R, int32_t L, int32_t D,
+                               float *g_lags, void *stream);
+
+/* BaseDDE.fuse (damped Euler update)                  xde/base_dde.py:55-58
+ * y1 = (dy - 0.001*(dy*dt + y0))*dt + y0, elementwise over n values. */
+int xde_dde_fuse_f32(const float *dy, float dt, const float *y0, int64_t n, float *y1, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XDE_B200_H */

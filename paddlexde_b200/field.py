@@ -1,0 +1,88 @@
+"""The fused vector-field family.
+
+The reference accepts any ``func(t, y)`` (xde/base_ode.py:60-62).  A fused kernel cannot run an
+arbitrary Python callable, so the supported family is declared explicitly:
+
+    f(t, y) = tanh(pre(y) @ W1 + b1) @ W2 + b2          (example/ode_demo.py:17-33)
+
+with Paddle ``nn.Linear`` weight layout ``[in, out]`` and ``pre`` one of ``id | square | cube``
+(``y**3`` in ode_demo, ``y**2`` in sde_demo's diffusion).  Anything else is a hard
+``UnsupportedFieldError`` -- there is no fallback path."""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from . import _tensor as T
+from ._lib import PRE, MlpFieldC, UnsupportedFieldError
+
+
+class MLPField:
+    def __init__(self, w1, b1, w2, b2, pre: str = "cube", act: str = "tanh"):
+        if act != "tanh":
+            raise UnsupportedFieldError(f"activation {act!r} has no fused kernel (tanh only)")
+        if pre not in PRE:
+            raise UnsupportedFieldError(f"pre-activation {pre!r} has no fused kernel (id|square|cube)")
+        self.pre = pre
+        self._src = (w1, b1, w2, b2)  # kept so autograd can route gradients to the caller's tensors
+        self.w1, self.b1, self.w2, self.b2 = (T.to_dev(a) for a in (w1, b1, w2, b2))
+        if self.w1.dim() != 2:
+            raise ValueError("w1 must be [D, H] (Paddle nn.Linear layout [in, out])")
+        self.d, self.h = self.w1.shape
+        if tuple(self.w2.shape) != (self.h, self.d) or tuple(self.b1.shape) != (self.h,) \
+                or tuple(self.b2.shape) != (self.d,):
+            raise ValueError("field shapes must be w1[D,H], b1[H], w2[H,D], b2[D]")
+
+    # -- reference-facing surface ---------------------------------------------------------------
+    def parameters(self) -> Sequence:
+        """Like nn.Layer.parameters() (functional/odeint_adjoint.py:276)."""
+        return list(self._src)
+
+    def refresh(self):
+        """Re-read the caller's parameter tensors (after an optimizer step on host/other tensors)."""
+        self.w1, self.b1, self.w2, self.b2 = (T.to_dev(a) for a in self._src)
+        return self
+
+    @property
+    def n_params(self) -> int:
+        return 2 * self.d * self.h + self.h + self.d
+
+    def split_flat(self, flat: torch.Tensor):
+        d, h = self.d, self.h
+        sizes = [d * h, h, h * d, d]
+        shapes = [(d, h), (h,), (h, d), (d,)]
+        return [c.reshape(s) for c, s in zip(torch.split(flat, sizes), shapes)]
+
+    def c_struct(self) -> MlpFieldC:
+        return MlpFieldC(self.d, self.h, PRE[self.pre], 0, self.w1.data_ptr(), self.b1.data_ptr(),
+                         self.w2.data_ptr(), self.b2.data_ptr())
+
+    # -- extraction from a framework module -------------------------------------------------------
+    @classmethod
+    def from_sequential(cls, net, pre: str = "cube", weight_layout: str = "auto") -> "MLPField":
+        """Recognise ``Sequential(Linear, Tanh, Linear)`` of Paddle or torch; hard-fail otherwise."""
+        layers = list(net.children()) if hasattr(net, "children") else list(net)
+        names = [type(l).__name__ for l in layers]
+        if names != ["Linear", "Tanh", "Linear"]:
+            raise UnsupportedFieldError(f"only Sequential(Linear, Tanh, Linear) is fused; got {names}")
+        l1, _, l2 = layers
+        w1, w2 = l1.weight, l2.weight
+        if weight_layout == "auto":
+            weight_layout = "out_in" if isinstance(w1, torch.Tensor) else "in_out"
+        if weight_layout == "out_in":  # torch nn.Linear stores [out, in]
+            w1, w2 = w1.detach().t().contiguous(), w2.detach().t().contiguous()
+        return cls(w1, l1.bias, w2, l2.bias, pre=pre)
+
+
+def as_field(func) -> MLPField:
+    """What `odeint(func, ...)` accepts: an MLPField, or an object carrying one as `.xde_field`."""
+    if isinstance(func, MLPField):
+        return func
+    f = getattr(func, "xde_field", None)
+    if isinstance(f, MLPField):
+        return f
+    raise UnsupportedFieldError(
+        "paddlexde_b200 integrates the fused field family only: pass an MLPField (or an object with an "
+        "`.xde_field` MLPField attribute, e.g. MLPField.from_sequential(func.net, pre='cube')). "
+        "Arbitrary Python callables cannot run inside the CUDA stepper and there is no fallback.")

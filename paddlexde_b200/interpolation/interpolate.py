@@ -1,0 +1,38 @@
+"""LinearInterpolation / CubicHermiteSpline with the reference's evaluate/derivative surface
+(paddlexde/interpolation/interpolate_base.py:77-114, interpolate.py:6-204).  Nothing is
+pre-processed: the gather kernel reads the 2-3 raw neighbours it needs per query."""
+from __future__ import annotations
+
+import torch
+
+from .. import _tensor as T
+from ..xde.base_dde import history_gather
+
+
+class _Interp:
+    kind = None
+
+    def __init__(self, series, t=None):
+        self._series = T.to_dev(series)
+        n = self._series.shape[-2]
+        if t is None:  # interpolate_base.py:21-27
+            t = torch.linspace(0, n, n + 1)
+        self._t = T.to_dev(t)
+
+    @property
+    def grid_points(self):
+        return self._t
+
+    def evaluate(self, t):
+        return history_gather(torch.as_tensor(t, dtype=torch.float32).reshape(-1), self._series, self._t, self.kind)[0]
+
+    def derivative(self, t):
+        return history_gather(torch.as_tensor(t, dtype=torch.float32).reshape(-1), self._series, self._t, self.kind)[1]
+
+
+class LinearInterpolation(_Interp):
+    kind = "linear"
+
+
+class CubicHermiteSpline(_Interp):
+    kind = "cubic"

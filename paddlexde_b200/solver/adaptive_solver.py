@@ -1,0 +1,135 @@
+"""Dopri5 with the reference's solver-class protocol:
+
+    s = Dopri5(xde=xde, y0=xde.y0, rtol=rtol, atol=atol, **options); s.integrate(t_span)
+
+(paddlexde/functional/odeint.py:30-31; constructor keywords solver/base_adaptive_solver_rk.py:32-49).
+`integrate` is ONE kernel launch (csrc/xde_dopri5_fwd.cu); the controller lives on the device."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from .. import _tensor as T
+from .._lib import (CTRL, AttemptLogC, CtrlOptsC, StatsC, UnsupportedFieldError, check, lib,
+                    raise_for_status)
+
+
+@dataclass
+class SolveStats:
+    n_attempts: int = 0
+    n_accepted: int = 0
+    nfe: int = 0
+    status: int = 0
+
+
+def make_ctrl_opts(rtol, atol, min_step=0.0, max_step=float("inf"), first_step=None, safety=0.9,
+                   ifactor=10.0, dfactor=0.2, max_num_steps=2 ** 31 - 1) -> CtrlOptsC:
+    return CtrlOptsC(float(rtol), float(atol), float(min_step), float(max_step),
+                     float("nan") if first_step is None else float(first_step), float(safety),
+                     float(ifactor), float(dfactor), int(min(max_num_steps, 2 ** 31 - 1)), 0)
+
+
+def check_norm(norm):
+    """options["norm"] is a selector here (utils/ode_utils.py): only the RMS norm is fused."""
+    if norm is None or getattr(norm, "xde_norm", None) == "rms":
+        return
+    raise UnsupportedFieldError("only the reference's default `_rms_norm` error norm is fused on the device; "
+                                "a Python norm callable cannot run inside the CUDA controller")
+
+
+def host_tspan(t_span) -> np.ndarray:
+    """fp32 host copy of t_span (solver/base_adaptive_solver.py:27 casts to the fp32 time dtype)."""
+    if isinstance(t_span, torch.Tensor):
+        t = t_span.detach().to("cpu", torch.float32).numpy()
+    else:
+        t = np.asarray(t_span, dtype=np.float32)
+    t = np.ascontiguousarray(t.reshape(-1))
+    d = np.diff(t)
+    if t.size < 2 or not (np.all(d > 0) or np.all(d < 0)):
+        raise ValueError("t_span must be strictly increasing or strictly decreasing with at least 2 points")
+    return t
+
+
+class StatsBuffer:
+    """Device-resident xde_stats_t read back lazily (one tiny D2H copy when asked)."""
+
+    def __init__(self, dev):
+        self.buf = torch.zeros(C.sizeof(StatsC) // 8, dtype=torch.int64, device=dev)
+
+    def read(self) -> SolveStats:
+        raw = self.buf.cpu().numpy().tobytes()
+        s = StatsC.from_buffer_copy(raw)
+        return SolveStats(int(s.n_attempts), int(s.n_accepted), int(s.nfe), int(s.status))
+
+
+class AttemptLog:
+    """Optional per-trajectory attempt log (tests / diagnostics): records [B, cap]."""
+    dtype = np.dtype([("t0", np.float32), ("dt", np.float32), ("ratio", np.float32), ("accepted", np.int32)])
+
+    def __init__(self, B, cap, dev):
+        self.cap = cap
+        self.records = torch.zeros((B, cap, 4), dtype=torch.float32, device=dev)
+        self.counts = torch.zeros(B, dtype=torch.int32, device=dev)
+
+    def c_struct(self):
+        return AttemptLogC(self.records.data_ptr(), self.counts.data_ptr(), self.cap, 0)
+
+    def read(self):
+        rec = self.records.cpu().numpy().view(self.dtype).reshape(self.records.shape[0], self.cap)
+        return rec.view(np.recarray), self.counts.cpu().numpy()
+
+
+class Dopri5:
+    order = 5
+
+    def __init__(self, xde, y0, rtol, atol, min_step=0, max_step=float("inf"), first_step=None, step_t=None,
+                 jump_t=None, safety=0.9, ifactor=10.0, dfactor=0.2, max_num_steps=2 ** 31 - 1, dtype=None,
+                 norm=None, controller="trajectory", log_attempts=0, check_status=True, **unused_kwargs):
+        if step_t is not None or jump_t is not None:
+            raise NotImplementedError("step_t / jump_t are not on the fused path yet (SURVEY 8(f) rank 2)")
+        if getattr(xde, "kind", None) != "ode":
+            raise UnsupportedFieldError("Dopri5 integrates BaseODE problems")
+        check_norm(norm)
+        if controller not in CTRL:
+            raise ValueError("controller must be 'trajectory' or 'batch'")
+        self.xde, self.y0 = xde, y0
+        self.rtol, self.atol = rtol, atol
+        self.opts = make_ctrl_opts(rtol, atol, min_step, max_step, first_step, safety, ifactor, dfactor,
+                                   max_num_steps)
+        self.controller = controller
+        self.log_attempts = int(log_attempts)
+        self.check_status = check_status
+        self.stats = None
+        self.attempt_log = None
+
+    def integrate(self, t_span):
+        """-> [T, *y0.shape] (solver/base_adaptive_solver.py:25-31)."""
+        field = self.xde.field
+        y0 = T.to_dev(self.y0)
+        if y0.shape[-1] != field.d:
+            raise ValueError(f"y0 last dim {y0.shape[-1]} != field state dim {field.d}")
+        B = y0.numel() // field.d
+        t_host = host_tspan(t_span)
+        t_dev = T.to_dev(t_host)
+        out = torch.empty((t_host.size,) + tuple(y0.shape), device=y0.device, dtype=torch.float32)
+        self._stats_buf = StatsBuffer(y0.device)
+        log_c = None
+        if self.log_attempts > 0:
+            self.attempt_log = AttemptLog(B, self.log_attempts, y0.device)
+            log_c = C.byref(self.attempt_log.c_struct())
+        fs = field.c_struct()
+        check(lib().xde_dopri5_mlp_f32(C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), t_host.size, C.byref(self.opts),
+                                       CTRL[self.controller], T.ptr(out), T.ptr(self._stats_buf.buf), log_c,
+                                       T.stream()))
+        if self.check_status:  # the reference asserts synchronously; opt out to stay asynchronous
+            self.stats = self._stats_buf.read()
+            raise_for_status(self.stats.status)
+        return T.like_input(out, self.y0)
+
+    def read_stats(self) -> SolveStats:
+        self.stats = self._stats_buf.read()
+        return self.stats

@@ -1,0 +1,81 @@
+"""Euler / RK4 (3/8 rule) with the reference's FixedSolver protocol
+(paddlexde/solver/base_fixed_solver.py:17-64 constructor, :103-144 integrate; fixed_solver/euler.py,
+fixed_solver/rk4.py).  `integrate` is one kernel launch over the whole grid."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _tensor as T
+from .._lib import FIXED, SDE, UnsupportedFieldError, check, lib
+from .adaptive_solver import host_tspan
+
+
+class FixedSolver:
+    order: int
+    method: str
+
+    def __init__(self, xde, y0, step_size=None, grid_constructor=None, interp="linear", perturb=False,
+                 out_stride=1, **kwargs):
+        if step_size is not None and grid_constructor is not None:
+            raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
+        if step_size is not None or grid_constructor is not None:
+            # the reference's own loop only ever visits len(t_span) grid points: grid == t_span
+            raise NotImplementedError("step_size / grid_constructor grids are not on the fused path (SURVEY 8(f) rank 2)")
+        if interp not in ("linear", "", None):
+            raise NotImplementedError("interp='cubic' is not on the fused path (SURVEY 8(f) rank 2)")
+        for key in ("atol", "rtol"):  # base_fixed_solver.py:45-47 requires them
+            if key not in kwargs:
+                raise KeyError(key)
+        self.xde, self.y0 = xde, y0
+        self.out_stride = int(out_stride)
+
+    def integrate(self, t_span):
+        kind = getattr(self.xde, "kind", None)
+        y0 = T.to_dev(self.y0)
+        t_host = host_tspan(t_span)
+        t_dev = T.to_dev(t_host)
+        Tn = t_host.size
+        D = y0.shape[-1]
+        B = y0.numel() // D
+        n_out = (Tn - 1 + self.out_stride - 1) // self.out_stride + 1
+        out = torch.empty((B, n_out, D), device=y0.device, dtype=torch.float32)
+        if kind == "ode":
+            fs = self.xde.field.c_struct()
+            check(lib().xde_rk_fixed_mlp_f32(FIXED[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), Tn,
+                                             self.out_stride, T.ptr(out), T.stream()))
+        elif kind == "sde":
+            if self.method != "euler" and self.xde.scheme == "em":
+                raise UnsupportedFieldError("sdeint is fused for solver=Euler (Euler-Maruyama) only")
+            dW = T.to_dev(self.xde.bm_increments)
+            if tuple(dW.shape) != (Tn - 1, B, D):
+                raise ValueError(f"bm_increments must be [T-1, B, D] = {(Tn - 1, B, D)}, got {tuple(dW.shape)}")
+            f, g = self.xde.drift.c_struct(), self.xde.diffusion.c_struct()
+            check(lib().xde_sde_mlp_f32(SDE[self.xde.scheme], C.byref(f), C.byref(g), T.ptr(y0), B, T.ptr(t_dev),
+                                        Tn, T.ptr(dW), self.out_stride, T.ptr(out), T.stream()))
+        else:
+            raise UnsupportedFieldError(f"fixed solvers integrate ODE/SDE problems on the device, not {kind!r}")
+        # concat(axis=-2) of the per-time states (base_fixed_solver.py:143)
+        shp = tuple(y0.shape)
+        if len(shp) >= 3 and shp[-2] == 1:          # y0 [..., 1, D] -> [..., T, D]
+            res = out.reshape(shp[:-2] + (n_out, D))
+        elif len(shp) == 2:                          # y0 [B, D] -> [T*B, D] (time-major blocks)
+            res = out.permute(1, 0, 2).reshape(n_out * B, D)
+        elif len(shp) == 1:
+            res = out.reshape(n_out * D)
+        else:                                        # y0 [..., L, D] -> [..., T*L, D]
+            L = shp[-2]
+            lead = shp[:-2]
+            res = out.reshape(lead + (L, n_out, D)).transpose(-3, -2).reshape(lead + (n_out * L, D))
+        return T.like_input(res.contiguous(), self.y0)
+
+
+class Euler(FixedSolver):
+    order = 1
+    method = "euler"
+
+
+class RK4(FixedSolver):
+    order = 4
+    method = "rk4"

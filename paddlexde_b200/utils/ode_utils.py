@@ -1,0 +1,20 @@
+"""Norm selectors with the reference's names (paddlexde/utils/ode_utils.py:4-19).
+
+In the reference these are Python callables applied to tensors; a fused kernel cannot call back
+into Python, so here they are *selectors*: the solver recognises the object and runs the matching
+device-side reduction.  Passing any other callable as options["norm"] raises UnsupportedFieldError."""
+
+
+def _rms_norm(tensor):  # utils/ode_utils.py:8-9
+    import torch
+    return tensor.abs().pow(2).mean().sqrt() if isinstance(tensor, torch.Tensor) else None
+
+
+def _mixed_norm(tensor_tuple):  # utils/ode_utils.py:16-19
+    if len(tensor_tuple) == 0:
+        return 0.0
+    return max([_rms_norm(t) for t in tensor_tuple])
+
+
+_rms_norm.xde_norm = "rms"
+_mixed_norm.xde_norm = "mixed"

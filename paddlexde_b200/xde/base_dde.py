@@ -1,0 +1,81 @@
+from __future__ import annotations
+
+import torch
+
+from .. import _tensor as T
+from .._lib import INTERP, check, lib
+from .base_xde import BaseXDE
+
+
+def history_gather(lags, his, his_span, interp_method="cubic"):
+    """interp.evaluate(lags), interp.derivative(lags) in one gather kernel
+    (interpolation/interpolate_base.py:49-114). his [..., Th, D] -> two [..., L, D] tensors."""
+    if interp_method not in ("linear", "cubic"):
+        raise NotImplementedError(interp_method)  # xde/base_dde.py:110-111 ("bez" is 8(f) next)
+    his_d, span_d, lags_d = T.to_dev(his), T.to_dev(his_span), T.to_dev(lags).reshape(-1)
+    lead, Th, D = his_d.shape[:-2], his_d.shape[-2], his_d.shape[-1]
+    if span_d.numel() != Th:
+        raise ValueError("his_span must have his.shape[-2] entries")
+    R = 1
+    for s in lead:
+        R *= s
+    L = lags_d.numel()
+    val = torch.empty(tuple(lead) + (L, D), device=his_d.device, dtype=torch.float32)
+    der = torch.empty_like(val)
+    check(lib().xde_history_gather_f32(INTERP[interp_method], T.ptr(his_d), R, Th, D, T.ptr(span_d),
+                                       T.ptr(lags_d), L, T.ptr(val), T.ptr(der), T.stream()))
+    return val, der
+
+
+def history_gather_bwd(grad_y, deriv):
+    """sum(grad_y * deriv, axis=[0,1,3]) generalised to all leading dims (xde/base_dde.py:121-127)."""
+    g, d = T.to_dev(grad_y), T.to_dev(deriv)
+    L, D = g.shape[-2], g.shape[-1]
+    R = g.numel() // (L * D)
+    out = torch.empty(L, device=g.device, dtype=torch.float32)
+    check(lib().xde_history_gather_bwd_f32(T.ptr(g), T.ptr(d), R, L, D, T.ptr(out), T.stream()))
+    return out
+
+
+class HistoryIndex(torch.autograd.Function):
+    """xde/base_dde.py:82-127: differentiable (wrt the real-valued lags) resampling of a fixed history."""
+
+    @staticmethod
+    def forward(ctx, lags, his, his_span, interp_method="cubic"):
+        y_lags, deriv = history_gather(lags, his, his_span, interp_method)
+        ctx.save_for_backward(deriv)
+        return y_lags
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        (deriv,) = ctx.saved_tensors
+        return history_gather_bwd(grad_y.contiguous(), deriv), None, None, None
+
+
+class BaseDDE(BaseXDE):
+    """xde/base_dde.py:14-79: one-shot history resampling, then a fixed-step solve with
+    move = func(y_lags, y0) and the damped fuse (lambda = 0.001, :55-58)."""
+    kind = "dde"
+
+    def __init__(self, func, y0, t_span, lags, his, his_span, his_processed=False):
+        super().__init__(name="DDE", var_nums=1, y0=y0, t_span=t_span)
+        self.func = func
+        self.lags = lags
+        if not his_processed:
+            if isinstance(lags, torch.Tensor) and lags.requires_grad:
+                self.y_lags = HistoryIndex.apply(lags, his, his_span)
+            else:
+                self.y_lags = history_gather(lags, his, his_span, "cubic")[0]
+        else:
+            self.y_lags = his
+        self.his, self.his_span = his, his_span
+        self.init_y0(y0)
+
+    def move(self, t0, dt, y0):
+        return self.func(self.y_lags, y0)
+
+    def fuse(self, dy, dt, y0):
+        dy_d, y0_d = T.to_dev(dy), T.to_dev(y0)
+        out = torch.empty_like(y0_d)
+        check(lib().xde_dde_fuse_f32(T.ptr(dy_d), float(dt), T.ptr(y0_d), y0_d.numel(), T.ptr(out), T.stream()))
+        return out
