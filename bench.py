@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- dopri5 trajectory-steps/s of the B200 path on BASELINE.json configs[1] (cfg2):
+
+    odeint_adjoint, Dopri5, rtol 1e-7 / atol 1e-9, MLP 2-50-2 (y**3 pre-activation),
+    B = 2^20 trajectories per GPU, t_span = linspace(0, 25, 1000)[:10], loss = mean|y_T|.
+
+A "step" is one forward solve + one adjoint (backward) solve of the whole batch.  A
+trajectory-step is one solver step ATTEMPT (accepted or rejected) of one trajectory;
+the attempt counts are read from the device-side counters of the kernels.
+
+  value  inputs resident in HBM, kernels only (+ the loss-gradient fill and, for N > 1, the NCCL
+         all-reduce of the 252 parameter gradients); CUDA events, max over ranks.
+  e2e    through the public API (paddlexde_b200.odeint_adjoint + .backward()) from pinned HOST
+         buffers: H2D of y0, forward, loss, backward, D2H of loss + parameter gradients, every step.
+  roofline       dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json), with the
+                 FP32-pipe figures that actually bound this field (D=2, H=50) beside it.
+  cpu_baseline   the CPU oracle (port of the reference algorithm; Paddle is not installable) on all
+                 host cores, on a bounded sample of the same workload.
+
+`--impl reference` times that CPU oracle as the reference arm (the reference is pure Python on
+Paddle, which cannot be installed offline here; DESIGN.md "Reference arm").
+Multi-GPU: launched by torchrun, one rank per GPU, trajectories sharded by batch (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dopri5 trajectory-steps/s (forward + adjoint)"
+UNIT = "trajectory-steps/s"
+BYTES_FWD, BYTES_ADJ = 32, 64          # algorithmic HBM bytes per trajectory-step (SURVEY 8(d), D = 2)
+FLOPS_FWD, FLOPS_ADJ = 2400, 7200      # algorithmic FLOPs per trajectory-step (24DH, 72DH)
+
+
+def workload(B, seed=0, n_t=10):
+    rng = np.random.default_rng(42)
+    w1 = (0.1 * rng.standard_normal((2, 50))).astype(np.float32)
+    w2 = (0.1 * rng.standard_normal((50, 2))).astype(np.float32)
+    w = (w1, np.zeros(50, np.float32), w2, np.zeros(2, np.float32))
+    y0 = (np.array([2.0, 0.0]) + 0.5 * np.random.default_rng(seed).standard_normal((B, 2))).astype(np.float32)
+    t = np.linspace(0.0, 25.0, 1000).astype(np.float32)[:n_t]
+    return w, y0, t
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU oracle legs (cpu_baseline, --impl reference)
+# ---------------------------------------------------------------------------------------------------
+def oracle_pass(xo, om, y0, t, nthreads):
+    """One forward + adjoint pass of the CPU oracle; returns (attempts, seconds)."""
+    t0 = time.perf_counter()
+    sol, st, _, rc = xo.dopri5_mlp(om, y0, t, nthreads=nthreads)
+    gy = np.zeros_like(sol)
+    gy[-1] = np.sign(sol[-1]) / sol[-1].size
+    g, a0, st2, _, rc2 = xo.dopri5_mlp_adjoint(om, t, sol, gy, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    assert rc == 0 and rc2 == 0
+    return int(st.n_attempts.sum() + st2.n_attempts.sum()), dt
+
+
+def cpu_baseline(target_s=12.0):
+    from oracle import xde_oracle as xo
+
+    xo.build()
+    cores = os.cpu_count() or 1
+    w, y0, t = workload(1 << 12)
+    om = xo.MLP(*w, pre="cube")
+    n, dt = oracle_pass(xo, om, y0, t, cores)           # calibration (also warms the threads)
+    Bs = int(min(1 << 20, max(1 << 12, (1 << 12) * target_s / max(dt, 1e-3))))
+    Bs = 1 << int(np.floor(np.log2(Bs)))
+    w, y0, t = workload(Bs)
+    n, dt = oracle_pass(xo, om, y0, t, cores)
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {Bs} trajectories of the cfg2 batch (2^20), forward+adjoint, OpenMP over {cores} threads, "
+                      f"{dt:.1f} s; Paddle CPU reference not installable offline -> C oracle port of the reference algorithm"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's algorithm on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import xde_oracle as xo
+
+    xo.build()
+    cores = os.cpu_count() or 1
+    Bs = args.ref_batch
+    w, y0, t = workload(Bs)
+    om = xo.MLP(*w, pre="cube")
+    for _ in range(args.warmup):
+        oracle_pass(xo, om, y0, t, cores)
+    tot_n, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        n, dt = oracle_pass(xo, om, y0, t, cores)
+        tot_n += n
+        tot_t += dt
+    v = tot_n / tot_t
+    sample = (f"each step = forward+adjoint over the first {Bs} trajectories of the cfg2 batch, "
+              f"OpenMP over {cores} threads (C oracle port; Paddle not installable offline)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(Bs, 1, "host"),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def config_dict(B, n, where):
+    return {"workload": "cfg2: odeint_adjoint dopri5 rtol=1e-7 atol=1e-9, MLP 2-50-2 (y**3), "
+                        "t=linspace(0,25,1000)[:10], loss=mean|y_T|",
+            "batch_per_gpu": B, "global_batch": B * n, "state_dim": 2, "hidden": 50, "n_out_times": 10,
+            "controller": "trajectory", "adjoint_norm": "seminorm", "parallelism": f"batch-sharded x{n}",
+            "l2": "256 MiB buffer written between steps (inside the timed region); working set 168 MiB > 126 MB L2"
+                  if where == "device" else "n/a"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_id):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_id), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.strip().lower() == "active":
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import paddlexde_b200 as px
+    from paddlexde_b200 import _lib, _tensor as T
+    from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    B = args.batch
+    w, y0_np, t = workload(B, seed=rank)
+    field = px.MLPField(*w, pre="cube")
+    y0 = torch.from_numpy(y0_np).to(dev)
+    xde = px.xde.BaseODE(field, y0, t)
+    gy = torch.zeros((t.size, B, 2), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    inv_n = 1.0 / (B * 2)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    k_ev = {"fwd": [], "adj": []}
+
+    def step(timed):
+        flush.zero_()
+        s = px.Dopri5(xde=xde, y0=y0, rtol=1e-7, atol=1e-9, check_status=False)
+        e = [ev() for _ in range(4)] if timed else None
+        if timed:
+            e[0].record()
+        sol = s.integrate(t)
+        if timed:
+            e[1].record()
+        torch.sign(sol[-1], out=gy[-1])
+        gy[-1].mul_(inv_n)
+        if timed:
+            e[2].record()
+        g, _, st, _ = adjoint_backward(field, t, sol, gy, check_status=False)
+        if timed:
+            e[3].record()
+            k_ev["fwd"].append((e[0], e[1]))
+            k_ev["adj"].append((e[2], e[3]))
+        if world > 1:
+            dist.all_reduce(g)
+        return s, st, g
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        s, st, g = step(False)
+    barrier()
+    fwd_stats, adj_stats = s.read_stats(), st.read()
+    assert fwd_stats.status == 0 and adj_stats.status == 0, "solver status != OK"
+    n_traj_steps = fwd_stats.n_attempts + adj_stats.n_attempts
+
+    uuid = None
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        uuid = local
+    sampler = ClockSampler(uuid) if rank == 0 else None
+    n0 = px.launch_count()
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(args.steps):
+        s, st, g = step(True)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = px.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    a2 = st.read()
+    assert a2.n_attempts == adj_stats.n_attempts and s.read_stats().n_attempts == fwd_stats.n_attempts
+    ms_fwd = float(np.mean([a.elapsed_time(b) for a, b in k_ev["fwd"]]))
+    ms_adj = float(np.mean([a.elapsed_time(b) for a, b in k_ev["adj"]]))
+
+    # ---- end to end through the public API, host buffers ----
+    tw = [torch.tensor(a, device=dev, requires_grad=True) for a in w]
+    field_e = px.MLPField(*tw, pre="cube")
+    y0_pin = torch.from_numpy(y0_np).pin_memory()
+    y0_buf = torch.empty_like(y0)
+    t_host = torch.from_numpy(t)
+
+    def e2e_step():
+        flush.zero_()
+        for p in tw:
+            p.grad = None
+        y0_buf.copy_(y0_pin, non_blocking=True)
+        sol = px.odeint_adjoint(field_e, y0_buf, t_host, solver=px.Dopri5)
+        loss = sol[-1].abs().mean()
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in tw])
+            dist.all_reduce(flat)
+        else:
+            flat = torch.cat([p.grad.reshape(-1) for p in tw])
+        return float(loss.item()), flat.cpu()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(args.steps):
+        loss_v, g_host = e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # ---- FP32 pipe ceiling (measured) ----
+    sink = torch.zeros(1, device=dev)
+    nfl = C.c_int64(0)
+    for _ in range(2):
+        _lib.check(lib.xde_probe_ffma_f32(1 << 14, T.ptr(sink), C.byref(nfl), T.stream()))
+    torch.cuda.synchronize()
+    e0, e1 = ev(), ev()
+    e0.record()
+    _lib.check(lib.xde_probe_ffma_f32(1 << 16, T.ptr(sink), C.byref(nfl), T.stream()))
+    e1.record()
+    torch.cuda.synchronize()
+    ffma_tflops = nfl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e, ms_fwd, ms_adj], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, ms_fwd, ms_adj = tt.tolist()
+        cnt = torch.tensor([n_traj_steps, fwd_stats.n_attempts, adj_stats.n_attempts], device=dev, dtype=torch.int64)
+        cnt_local = cnt.clone()
+        dist.all_reduce(cnt)
+        total_steps = int(cnt[0])
+    else:
+        total_steps = n_traj_steps
+    if rank == 0:
+        hbm, which = peaks()
+        value = total_steps * args.steps / (ms * 1e-3)
+        dom = "adj" if ms_adj >= ms_fwd else "fwd"
+        k_attempts = adj_stats.n_attempts if dom == "adj" else fwd_stats.n_attempts
+        k_ms = ms_adj if dom == "adj" else ms_fwd
+        k_bytes = (BYTES_ADJ if dom == "adj" else BYTES_FWD) * k_attempts
+        k_flops = (FLOPS_ADJ if dom == "adj" else FLOPS_FWD) * k_attempts
+        achieved = k_bytes / (k_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(B, world, "device"),
+            "trajectory_steps_per_step": {"forward": fwd_stats.n_attempts, "adjoint": adj_stats.n_attempts,
+                                          "accepted_forward": fwd_stats.n_accepted, "accepted_adjoint": adj_stats.n_accepted,
+                                          "nfe_forward": fwd_stats.nfe, "nfe_adjoint": adj_stats.nfe, "per": "rank 0"},
+            "kernel_ms": {"dopri5_fwd_small_kernel": ms_fwd, "dopri5_adj_kernel(+cast)": ms_adj},
+            "roofline": {"bound": "hbm", "kernel": "dopri5_adj_kernel" if dom == "adj" else "dopri5_fwd_small_kernel",
+                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "peak_source": which,
+                         "algorithmic_bytes_per_launch": k_bytes,
+                         "note": "D=2, H=50: 75-112 FLOP/B of scalar FP32 + 50 tanh per field evaluation, K=2/N=2 "
+                                 "degenerate for MMA -> the FP32 pipe binds, not HBM (SURVEY 8(d)); see fp32"},
+            "fp32": {"achieved_tflops_algorithmic": k_flops / (k_ms * 1e-3) / 1e12,
+                     "ffma_peak_tflops_measured": ffma_tflops,
+                     "frac_algorithmic": k_flops / (k_ms * 1e-3) / 1e12 / ffma_tflops,
+                     "note": "algorithmic FLOPs count the two GEMVs (+VJP) only; each of the 50 tanh per evaluation costs "
+                             "~14 further FP32 issue slots (rational 13/6 + IEEE division) that the count leaves out"},
+            "e2e": {"value": total_steps * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(y0_np.nbytes + t.nbytes), "d2h_bytes_per_step": int(g_host.numel() * 4 + 4 + 64),
+                    "ms_per_step": ms_e2e / args.steps,
+                    "api": "paddlexde_b200.odeint_adjoint(field, y0, t, solver=Dopri5); loss.backward()"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not args.no_cpu and world >= 1:
+            out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1 << 20, help="trajectories per GPU")
+    ap.add_argument("--ref-batch", type=int, default=1 << 14, help="trajectories per reference-arm step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -113,6 +113,10 @@ const char *xde_last_error(void);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 unsigned long long xde_launch_count(void);
 void xde_default_ctrl_opts(xde_ctrl_opts_t *o);
+/* measurement aid (bench.py): saturates the FP32 FMA pipe for `iters` iterations of 8 independent
+ * chains per thread on every SM; *n_flops_host receives the FLOPs the launch performs.  sink: one
+ * device float (never written in practice). */
+int xde_probe_ffma_f32(int32_t iters, float *sink, int64_t *n_flops_host, void *stream);
 
 /* odeint(func, y0, t_span, solver=Dopri5)            functional/odeint.py:28-35
  *   -> AdaptiveSolver.integrate                       solver/base_adaptive_solver.py:24-31

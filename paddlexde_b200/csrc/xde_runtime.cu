@@ -32,7 +32,33 @@ int sm_count() {
   return cached;
 }
 
+// FP32 FMA-pipe ceiling probe: 8 independent fmaf chains per thread, nothing else in the loop.
+__global__ void __launch_bounds__(512) ffma_probe_kernel(float *sink, int iters, float x, float y) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], x, y);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 123456.789f) sink[0] = s;  // never true for the probe's operands; defeats dead-code removal
+}
+
 }  // namespace xde
+
+extern "C" XDE_EXPORT int xde_probe_ffma_f32(int32_t iters, float *sink, int64_t *n_flops_host, void *stream) {
+  using namespace xde;
+  XDE_REQUIRE(iters > 0 && sink && n_flops_host, XDE_E_BAD_ARG, "null argument");
+  const int grid = sm_count() * 4;
+  ffma_probe_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(sink, iters, 0.999f, 0.001f);
+  count_launch();
+  XDE_CUDA_CHECK(cudaGetLastError());
+  *n_flops_host = (int64_t)grid * 512 * (int64_t)iters * 8 * 2;
+  return XDE_OK;
+}
 
 extern "C" XDE_EXPORT int xde_abi_version(void) { return XDE_ABI_VERSION; }
 extern "C" XDE_EXPORT const char *xde_last_error(void) { return xde::g_err; }

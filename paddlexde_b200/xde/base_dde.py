@@ -46,6 +46,10 @@ class HistoryIndex(torch.autograd.Function):
         ctx.save_for_backward(deriv)
         return y_lags
 
+    @classmethod
+    def apply(cls, lags, his, his_span, interp_method="cubic"):
+        return super().apply(lags, his, his_span, interp_method)
+
     @staticmethod
     def backward(ctx, grad_y):
         (deriv,) = ctx.saved_tensors

@@ -1,0 +1,108 @@
+"""CPU-side checks of the drop-in boundary: libxde_b200.so loads and exports every symbol that
+include/xde_b200.h declares, struct layouts agree with the header, and the host logic of the shim
+(option defaulting, argument errors, the no-fallback rule) behaves like the reference's.
+No compute call is made here (no GPU in this suite)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "xde_b200.h")
+
+
+@pytest.fixture(scope="module")
+def so():
+    from paddlexde_b200 import _lib
+
+    if not os.path.exists(_lib.library_path()):
+        import __graft_entry__ as g
+
+        g.build()
+    return _lib
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(xde_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(so):
+    names = declared_functions()
+    assert len(names) >= 11
+    handle = C.CDLL(so.library_path())
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/xde_b200.h but not exported"
+    assert sorted(so.exported_symbols()) == names, "ctypes binding table and header disagree"
+    assert so.lib().xde_abi_version() == 1
+
+
+def test_struct_layouts(so):
+    # sizes implied by the header (LP64): field 4*4 + 4*8; opts 8*4 + 2*4; stats 3*8 + 2*4; log 2*8 + 2*4
+    assert C.sizeof(so.MlpFieldC) == 48
+    assert C.sizeof(so.CtrlOptsC) == 40
+    assert C.sizeof(so.StatsC) == 32
+    assert C.sizeof(so.AttemptLogC) == 24
+    o = so.CtrlOptsC()
+    so.lib().xde_default_ctrl_opts(C.byref(o))
+    # solver/base_adaptive_solver_rk.py:32-49 defaults
+    assert (o.rtol, o.atol) == (np.float32(1e-7), np.float32(1e-9))
+    assert o.min_step == 0.0 and o.max_step == float("inf") and o.first_step != o.first_step
+    assert (o.safety, o.ifactor, o.dfactor) == (np.float32(0.9), 10.0, np.float32(0.2))
+    assert o.max_num_steps == 2 ** 31 - 1
+
+
+def test_null_arguments_are_bad_arg_without_a_device(so):
+    lib = so.lib()
+    rc = lib.xde_dopri5_mlp_f32(None, None, 1, None, 2, None, 0, None, None, None, None)
+    assert rc == so.XDE_E_BAD_ARG
+    with pytest.raises(ValueError):
+        so.check(rc)
+    rc = lib.xde_history_gather_f32(7, None, 1, 2, 1, None, None, 1, None, None, None)
+    assert rc == so.XDE_E_BAD_ARG
+    assert b"null" in lib.xde_last_error()
+    assert lib.xde_dde_fuse_f32(None, 0.1, None, 4, None, None) == so.XDE_E_BAD_ARG
+
+
+def test_status_words_raise_the_reference_asserts(so):
+    so.raise_for_status(0)
+    for st, text in ((1, "underflow"), (2, "non-finite"), (3, "max_num_steps"), (5, "interpolation")):
+        with pytest.raises(AssertionError, match=text):
+            so.raise_for_status(st)
+
+
+def test_no_fallback_for_python_callables():
+    import paddlexde_b200 as px
+
+    with pytest.raises(px.UnsupportedFieldError):
+        px.field.as_field(lambda t, y: -y)
+    with pytest.raises(px.UnsupportedFieldError):
+        px.solver.adaptive_solver.check_norm(lambda x: x.abs().max())
+    px.solver.adaptive_solver.check_norm(px.utils._rms_norm)
+
+
+def test_tspan_validation():
+    from paddlexde_b200.solver.adaptive_solver import host_tspan
+
+    assert host_tspan([0.0, 1.0, 2.0]).dtype == np.float32
+    assert host_tspan([2.0, 1.0]).tolist() == [2.0, 1.0]
+    for bad in ([0.0], [0.0, 0.0, 1.0], [0.0, 2.0, 1.0]):
+        with pytest.raises(ValueError):
+            host_tspan(bad)
+
+
+def test_fixed_solver_ctor_contract():
+    import paddlexde_b200 as px
+
+    class X:
+        kind = "ode"
+
+    with pytest.raises(KeyError):  # base_fixed_solver.py:45-47 requires rtol/atol
+        px.RK4(xde=X(), y0=None)
+    with pytest.raises(ValueError):  # base_fixed_solver.py:58-60
+        px.RK4(xde=X(), y0=None, rtol=1, atol=1, step_size=0.1, grid_constructor=lambda *a: None)
+    with pytest.raises(NotImplementedError):
+        px.ddeint_adjoint()

@@ -1,0 +1,374 @@
+"""GPU parity tests: the sm_100a kernels (called through the C ABI of libxde_b200.so via the shim)
+against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): identical accept/reject step sequences; final states and gradients
+within rtol 1e-5 (fp32).  Because the kernels follow the oracle's arithmetic specification, states
+are in fact compared BIT-EXACT here; parameter gradients (fp64 batch accumulation on both sides, in
+different orders) are compared at rtol 1e-5 / atol 1e-6*max|g|.
+"""
+import numpy as np
+import pytest
+
+from tests.problems import cfg2_tspan, cfg2_y0, fanin_weights, spiral_weights
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def px():
+    import torch
+
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import paddlexde_b200 as px
+
+    px._lib.lib()  # hard failure if the extension is missing: there is no fallback to test
+    return px
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    return torch
+
+
+def both(px, oracle, w, pre):
+    return px.MLPField(*w, pre=pre), oracle.MLP(*w, pre=pre)
+
+
+def solve_fwd(px, torch, field, y0, t, **opt):
+    xde = px.xde.BaseODE(field, torch.from_numpy(y0).cuda(), t)
+    s = px.Dopri5(xde=xde, y0=xde.y0, **{"rtol": 1e-7, "atol": 1e-9, **opt})
+    sol = s.integrate(t)
+    return sol, s
+
+
+# ------------------------------------------------------------------------------------------------
+# dopri5 forward
+# ------------------------------------------------------------------------------------------------
+def test_dopri5_cfg1_bit_exact_and_step_sequence(px, torch, oracle):
+    """cfg1: spiral ODE, MLP 2-50-2, B=20, t = linspace(0,25,1000)[:32]."""
+    field, om = both(px, oracle, spiral_weights(), "cube")
+    rng = np.random.default_rng(42)
+    y0 = (np.array([2.0, 0.0]) + rng.standard_normal((20, 2))).astype(f32)
+    t = cfg2_tspan(32)
+    sol, s = solve_fwd(px, torch, field, y0, t, log_attempts=256)
+    ref, st, _, rc = oracle.dopri5_mlp(om, y0, t)
+    assert rc == 0
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    assert s.stats.n_attempts == int(st.n_attempts.sum())
+    assert s.stats.n_accepted == int(st.n_accepted.sum())
+    assert s.stats.nfe == int(st.nfe.sum())
+    rec, cnt = s.attempt_log.read()
+    for b in range(20):  # identical accept/reject sequence, dt and error ratio, per trajectory
+        _, _, lg, _ = oracle.dopri5_mlp(om, y0, t, log_traj=b)
+        assert cnt[b] == len(lg)
+        r = rec[b, :cnt[b]]
+        assert np.array_equal(r.accepted, lg.accepted)
+        assert np.array_equal(r.dt, lg.dt) and np.array_equal(r.t0, lg.t0)
+        assert np.array_equal(r.ratio, lg.ratio)
+
+
+@pytest.mark.parametrize("d,h,pre", [(1, 16, "id"), (2, 50, "cube"), (3, 20, "square"), (4, 33, "id"), (8, 64, "id")])
+def test_dopri5_shapes(px, torch, oracle, d, h, pre):
+    field, om = both(px, oracle, fanin_weights(d, h, seed=d), pre)
+    y0 = np.random.default_rng(d).uniform(-1, 1, (333, d)).astype(f32)
+    t = np.linspace(0, 2, 7).astype(f32)
+    sol, s = solve_fwd(px, torch, field, y0, t, rtol=1e-6, atol=1e-8)
+    ref, st, _, rc = oracle.dopri5_mlp(om, y0, t, rtol=1e-6, atol=1e-8)
+    assert rc == 0 and np.array_equal(sol.cpu().numpy(), ref)
+    assert s.stats.n_attempts == int(st.n_attempts.sum())
+
+
+def test_dopri5_rejections_reverse_time_and_first_step(px, torch, oracle):
+    w = [3.0 * a for a in fanin_weights(2, 50, seed=5)]
+    field, om = both(px, oracle, w, "id")
+    y0 = np.random.default_rng(1).uniform(-1, 1, (257, 2)).astype(f32)
+    t = np.linspace(0, 4, 9).astype(f32)
+    sol, s = solve_fwd(px, torch, field, y0, t, rtol=1e-6, atol=1e-8)
+    ref, st, _, _ = oracle.dopri5_mlp(om, y0, t, rtol=1e-6, atol=1e-8)
+    assert (st.n_attempts > st.n_accepted).any(), "the case must exercise rejections"
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    assert s.stats.n_accepted == int(st.n_accepted.sum())
+    # decreasing t_span (repair R5: s = -t)
+    tr = t[::-1].copy()
+    sol, _ = solve_fwd(px, torch, field, y0, tr, rtol=1e-6, atol=1e-8)
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0, tr, rtol=1e-6, atol=1e-8)
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    # first_step / max_step / safety options (base_adaptive_solver_rk.py:32-49)
+    kw = dict(rtol=1e-5, atol=1e-7, first_step=0.01, max_step=0.2, safety=0.8, ifactor=5.0, dfactor=0.3)
+    sol, _ = solve_fwd(px, torch, field, y0, t, **kw)
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0, t, **kw)
+    assert np.array_equal(sol.cpu().numpy(), ref)
+
+
+def test_dopri5_ragged_batches(px, torch, oracle):
+    """B = 1, a prime, one-over-a-warp: the per-CTA queue and tail handling."""
+    field, om = both(px, oracle, spiral_weights(), "cube")
+    t = cfg2_tspan(6)
+    for B in (1, 31, 33, 1009):
+        y0 = cfg2_y0(B, seed=B)
+        sol, _ = solve_fwd(px, torch, field, y0, t)
+        ref, _, _, _ = oracle.dopri5_mlp(om, y0, t)
+        assert np.array_equal(sol.cpu().numpy(), ref), B
+
+
+def test_dopri5_status_words(px, torch, oracle):
+    field, _ = both(px, oracle, spiral_weights(), "cube")
+    y0 = cfg2_y0(64)
+    om = oracle.MLP(*spiral_weights(), pre="cube")
+    t5 = np.array([0.0, 5.0], f32)
+    with pytest.raises(AssertionError, match="max_num_steps"):
+        solve_fwd(px, torch, field, y0, t5, max_num_steps=3)
+    assert oracle.dopri5_mlp(om, y0, t5, max_num_steps=3)[3] == 3
+    bad = y0.copy()
+    bad[7, 0] = np.inf
+    with pytest.raises(AssertionError):
+        solve_fwd(px, torch, field, bad, cfg2_tspan(4))
+    sol, s = solve_fwd(px, torch, field, bad, cfg2_tspan(4), check_status=False)
+    ref, _, _, rc = oracle.dopri5_mlp(om, bad, cfg2_tspan(4))
+    assert rc != 0 and s.read_stats().status == rc
+    keep = np.arange(64) != 7  # the other trajectories are unaffected (one controller per trajectory)
+    assert np.array_equal(sol.cpu().numpy()[:, keep], ref[:, keep])
+    with pytest.raises(px.UnsupportedFieldError):  # no fused kernel for D=5: loud, no fallback
+        f5, _ = both(px, oracle, fanin_weights(5, 8), "id")
+        solve_fwd(px, torch, f5, np.zeros((4, 5), f32), cfg2_tspan(4))
+
+
+def test_dopri5_full_size_subset_parity(px, torch, oracle):
+    """cfg2 at BASELINE size (B = 2^20): with one controller per trajectory every trajectory is
+    independent of its neighbours, so a random subset of the full-size GPU result must equal the
+    oracle run on that subset alone -- bit for bit."""
+    field, om = both(px, oracle, spiral_weights(), "cube")
+    B = 1 << 20
+    y0, t = cfg2_y0(B), cfg2_tspan(10)
+    sol, s = solve_fwd(px, torch, field, y0, t)
+    idx = np.random.default_rng(7).choice(B, 4096, replace=False)
+    ref, st, _, rc = oracle.dopri5_mlp(om, y0[idx], t)
+    assert rc == 0
+    got = sol[:, torch.from_numpy(idx).cuda()].cpu().numpy()
+    assert np.array_equal(got, ref)
+    assert s.stats.status == 0 and s.stats.n_accepted >= B and s.stats.nfe == 3 * B + 6 * s.stats.n_attempts
+    assert np.array_equal(sol[0].cpu().numpy(), y0)
+
+
+# ------------------------------------------------------------------------------------------------
+# adjoint
+# ------------------------------------------------------------------------------------------------
+def loss_grad(sol_np):
+    """loss = mean(|y_T|) (cfg2) -> grad_y [T,B,D]"""
+    gy = np.zeros_like(sol_np)
+    gy[-1] = np.sign(sol_np[-1]) / sol_np[-1].size
+    return gy
+
+
+@pytest.mark.parametrize("d,h,pre,B", [(2, 50, "cube", 300), (2, 20, "id", 64), (1, 40, "square", 100), (4, 64, "id", 50)])
+def test_adjoint_parity(px, torch, oracle, d, h, pre, B):
+    from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
+
+    w = spiral_weights() if (d, h) == (2, 50) else fanin_weights(d, h, seed=h)
+    field, om = both(px, oracle, w, pre)
+    y0 = cfg2_y0(B) if d == 2 else np.random.default_rng(3).uniform(-1, 1, (B, d)).astype(f32)
+    t = cfg2_tspan(6) if d == 2 else np.linspace(0, 1, 5).astype(f32)
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0, t)
+    gy = loss_grad(ref)
+    gy[2] = 0.01 * np.random.default_rng(4).standard_normal(gy[2].shape).astype(f32)  # a mid-time cotangent
+    g, a0, stats, log = adjoint_backward(field, t, ref, gy, return_adj_y0=True, log_attempts=512)
+    g_ref, a_ref, st_ref, _, rc = oracle.dopri5_mlp_adjoint(om, t, ref, gy)
+    assert rc == 0
+    s = stats.read()
+    assert s.status == 0
+    assert s.n_attempts == int(st_ref.n_attempts.sum()) and s.n_accepted == int(st_ref.n_accepted.sum())
+    assert s.nfe == int(st_ref.nfe.sum())
+    assert np.array_equal(a0.cpu().numpy(), a_ref), "adjoint state dL/dy0 must be bit-exact"
+    scale = np.abs(g_ref).max()
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-5, atol=1e-6 * scale)
+    rec, cnt = log.read()
+    for b in (0, B // 2, B - 1):
+        _, _, _, lg, _ = oracle.dopri5_mlp_adjoint(om, t, ref, gy, log_traj=b)
+        assert cnt[b] == len(lg)
+        r = rec[b, :cnt[b]]
+        assert np.array_equal(r.accepted, lg.accepted) and np.array_equal(r.dt, lg.dt)
+        assert np.array_equal(r.ratio, lg.ratio)
+
+
+def test_adjoint_gradient_is_the_true_gradient(px, torch, oracle):
+    """Independent of the oracle: finite differences of the GPU forward in fp32 are too noisy, so
+    compare with the fp64 NumPy adjoint-free gradient (discretise-then-differentiate is not the same
+    as the continuous adjoint; at rtol 1e-7 they agree to ~1e-4 relative)."""
+    from oracle import oracle_np as onp
+    from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
+
+    w = spiral_weights()
+    field, om = both(px, oracle, w, "cube")
+    y0, t = cfg2_y0(32), cfg2_tspan(5)
+    sol, _ = solve_fwd(px, torch, field, y0, t)
+    sol_np = sol.cpu().numpy()
+    gy = loss_grad(sol_np)
+    g, _, _, _ = adjoint_backward(field, t, sol, gy)
+    g = g.cpu().numpy()
+    # fp64 central differences on a fixed-step fp64 RK4 of the same field
+    def loss(params):
+        fld = onp.MLPFieldNP(*params, "cube", np.float64)
+        y = y0.astype(np.float64)
+        tt = np.linspace(float(t[0]), float(t[-1]), 401)
+        for i in range(400):
+            hh = tt[i + 1] - tt[i]
+            k1 = fld(tt[i], y)
+            k2 = fld(tt[i] + hh / 2, y + hh / 2 * k1)
+            k3 = fld(tt[i] + hh / 2, y + hh / 2 * k2)
+            k4 = fld(tt[i + 1], y + hh * k3)
+            y = y + hh / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        return np.abs(y).mean()
+
+    params = [a.astype(np.float64) for a in w]
+    flat_idx = [(0, (0, 3)), (0, (1, 17)), (1, (5,)), (2, (9, 1)), (2, (30, 0)), (3, (1,))]
+    off = [0, 100, 150, 250]
+    for pi, ix in flat_idx:
+        e = 1e-5
+        pp = [a.copy() for a in params]
+        pp[pi][ix] += e
+        pm = [a.copy() for a in params]
+        pm[pi][ix] -= e
+        fd = (loss(pp) - loss(pm)) / (2 * e)
+        k = off[pi] + int(np.ravel_multi_index(ix, params[pi].shape))
+        assert abs(g[k] - fd) <= 2e-3 * abs(fd) + 1e-5 * np.abs(g).max(), (pi, ix, g[k], fd)
+
+
+def test_odeint_adjoint_autograd_surface(px, torch, oracle):
+    """odeint_adjoint(...).backward(): grads for the parameters only, y0 gets None
+    (functional/odeint_adjoint.py:167)."""
+    w = spiral_weights()
+    tw = [torch.tensor(a, device="cuda", requires_grad=True) for a in w]
+    field = px.MLPField(*tw, pre="cube")
+    om = oracle.MLP(*w, pre="cube")
+    y0 = torch.from_numpy(cfg2_y0(128)).cuda().requires_grad_(True)
+    t = cfg2_tspan(5)
+    sol = px.odeint_adjoint(field, y0, t, solver=px.Dopri5)
+    assert tuple(sol.shape) == (5, 128, 2)
+    loss = sol[-1].abs().mean()
+    loss.backward()
+    assert y0.grad is None
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0.detach().cpu().numpy(), t)
+    assert np.array_equal(sol.detach().cpu().numpy(), ref)
+    g_ref, _, _, _, _ = oracle.dopri5_mlp_adjoint(om, t, ref, loss_grad(ref))
+    got = np.concatenate([p.grad.cpu().numpy().ravel() for p in tw])
+    np.testing.assert_allclose(got, g_ref, rtol=1e-5, atol=1e-6 * np.abs(g_ref).max())
+
+
+# ------------------------------------------------------------------------------------------------
+# fixed-grid solvers, SDE
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver", ["Euler", "RK4"])
+@pytest.mark.parametrize("d,h,pre", [(2, 50, "cube"), (4, 32, "id"), (8, 48, "square")])
+def test_fixed_solvers_bit_exact(px, torch, oracle, solver, d, h, pre):
+    w = spiral_weights() if d == 2 else fanin_weights(d, h)
+    field, om = both(px, oracle, w, pre)
+    B = 515
+    y0 = cfg2_y0(B) if d == 2 else np.random.default_rng(0).uniform(-1, 1, (B, d)).astype(f32)
+    t = cfg2_tspan(32) if d == 2 else np.linspace(0, 1, 21).astype(f32)
+    y0_3d = torch.from_numpy(y0).cuda().reshape(B, 1, d)  # [B,1,D] -> [B,T,D] (base_fixed_solver.py:143)
+    sol = px.odeint(field, y0_3d, t, getattr(px, solver))
+    ref = oracle.fixed_mlp(solver.lower(), om, y0, t)
+    assert tuple(sol.shape) == (B, t.size, d)
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    # y0 [B,D] -> concat(axis=-2) gives [T*B, D]
+    sol2 = px.odeint(field, torch.from_numpy(y0).cuda(), t, getattr(px, solver))
+    assert np.array_equal(sol2.cpu().numpy().reshape(t.size, B, d), ref.transpose(1, 0, 2))
+
+
+@pytest.mark.parametrize("scheme", ["em", "milstein"])
+def test_sde_supplied_increments_bit_exact(px, torch, oracle, scheme):
+    d, h, B = 4, 32, 700
+    wf, wg = fanin_weights(d, h, seed=2), fanin_weights(d, h, seed=3)
+    f, of = both(px, oracle, wf, "cube")
+    g, og = both(px, oracle, wg, "square")
+    rng = np.random.default_rng(2)
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, 17).astype(f32)
+    dW = (np.sqrt(1 / 16) * rng.standard_normal((16, B, d))).astype(f32)
+    sol = px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler,
+                    options={"bm_increments": torch.from_numpy(dW).cuda(), "scheme": scheme})
+    ref = oracle.sde_mlp(scheme, of, og, y0, t, dW)
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    with pytest.raises(ValueError):  # increments are mandatory: no host Brownian tree on this path
+        px.sdeint(f, g, torch.from_numpy(y0).cuda(), t, px.Euler)
+
+
+# ------------------------------------------------------------------------------------------------
+# history gather / DDE
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["linear", "cubic"])
+def test_history_gather_cfg5(px, torch, oracle, kind):
+    """cfg5 shapes: his [8,307,288,3], 12 real-valued lags (+ edge queries on and off the grid)."""
+    from paddlexde_b200.xde.base_dde import history_gather, history_gather_bwd
+
+    rng = np.random.default_rng(5)
+    his = rng.uniform(-1, 1, (8, 307, 288, 3)).astype(f32)
+    his[..., 1:] = np.round(his[..., 1:] * 10)
+    span = np.arange(288, dtype=f32)
+    lags = (np.arange(12) + rng.uniform(0, 1, 12)).astype(f32)
+    for lg in (lags, np.array([0.0, 1.0, 286.0, 286.5, 287.0, 3.25], f32), np.full(12, 287.0, f32)):
+        v, dv = history_gather(lg, his, span, kind)
+        v_r, d_r = oracle.history_gather(kind, his, span, lg)
+        assert np.array_equal(v.cpu().numpy(), v_r)
+        assert np.array_equal(dv.cpu().numpy(), d_r)
+    gy = rng.standard_normal(v_r.shape).astype(f32)
+    gl = history_gather_bwd(torch.from_numpy(gy).cuda(), dv)
+    gl_r = oracle.history_gather_bwd(gy, d_r)
+    np.testing.assert_allclose(gl.cpu().numpy(), gl_r, rtol=1e-5, atol=1e-5 * np.abs(gl_r).max())
+
+
+def test_history_gather_nonuniform_span_and_reference_fixture(px, torch, oracle):
+    """The reference's own interpolation fixtures (tests/interpolation/test_interpolation.py:13-85):
+    ramp at t=21.12 and sin sampled at 0.01 queried at t=16.5."""
+    ramp = np.arange(100, dtype=f32).reshape(1, 100, 1)
+    for cls, kind in ((px.interpolation.LinearInterpolation, "linear"), (px.interpolation.CubicHermiteSpline, "cubic")):
+        it = cls(ramp, np.arange(100, dtype=f32))
+        np.testing.assert_allclose(it.evaluate([21.12]).cpu().numpy().ravel(), [21.12], rtol=1e-4)
+        np.testing.assert_allclose(it.derivative([21.12]).cpu().numpy().ravel(), [1.0], rtol=1e-4)
+    ts = np.arange(0, 20, 0.01, dtype=f32)
+    series = np.sin(ts).reshape(1, -1, 1).astype(f32)
+    it = px.interpolation.CubicHermiteSpline(series, ts)
+    np.testing.assert_allclose(it.evaluate([16.5]).cpu().numpy().ravel(), [np.sin(16.5)], rtol=1e-5)
+    np.testing.assert_allclose(it.derivative([16.5]).cpu().numpy().ravel(), [np.cos(16.5)], rtol=1e-2)
+    # non-uniform grid vs oracle
+    rng = np.random.default_rng(9)
+    span = np.cumsum(rng.uniform(0.2, 1.5, 40)).astype(f32)
+    his = rng.standard_normal((5, 40, 7)).astype(f32)
+    q = rng.uniform(span[0], span[-1], 33).astype(f32)
+    from paddlexde_b200.xde.base_dde import history_gather
+
+    for kind in ("linear", "cubic"):
+        v, dv = history_gather(q, his, span, kind)
+        v_r, d_r = oracle.history_gather(kind, his, span, q)
+        assert np.array_equal(v.cpu().numpy(), v_r) and np.array_equal(dv.cpu().numpy(), d_r)
+
+
+def test_ddeint_one_damped_euler_step(px, torch, oracle):
+    """D3STN usage (train_dde.py:418-433): lags -> y_lags, one Euler step with the damped fuse;
+    gradient wrt the learnable lags through HistoryIndex.backward."""
+    rng = np.random.default_rng(6)
+    his = rng.uniform(-1, 1, (8, 307, 288, 3)).astype(f32)
+    span = np.arange(288, dtype=f32)
+    lags = torch.tensor((np.arange(12) + rng.uniform(0, 1, 12)).astype(f32), device="cuda", requires_grad=True)
+    y0 = rng.uniform(-1, 1, (8, 307, 12, 3)).astype(f32)
+    V = torch.tensor(rng.standard_normal((3, 3)).astype(f32) * 0.3, device="cuda")
+
+    def func(y_lags, y):  # stand-in field; the real D3STN network is out of scope
+        return torch.tanh(y @ V + y_lags.mean(dim=-2, keepdim=True))
+
+    sol, y_lags = px.ddeint(func, torch.from_numpy(y0).cuda(), np.arange(2, dtype=f32), lags,
+                            torch.from_numpy(his).cuda(), torch.from_numpy(span).cuda(), px.Euler,
+                            fixed_solver_interp="")
+    yl_ref, d_ref = oracle.history_gather("cubic", his, span, lags.detach().cpu().numpy())
+    assert np.array_equal(y_lags.detach().cpu().numpy(), yl_ref)
+    dy = func(torch.from_numpy(yl_ref).cuda(), torch.from_numpy(y0).cuda()).cpu().numpy()
+    y1_ref = oracle.dde_fuse(dy, 1.0, y0)
+    assert tuple(sol.shape) == (8, 307, 24, 3)  # concat(axis=-2) of y0 and y1
+    assert np.array_equal(sol[..., 12:, :].cpu().numpy(), y1_ref)
+    gy = rng.standard_normal(yl_ref.shape).astype(f32)
+    y_lags.backward(torch.from_numpy(gy).cuda())
+    gl_ref = oracle.history_gather_bwd(gy, d_ref)
+    np.testing.assert_allclose(lags.grad.cpu().numpy(), gl_ref, rtol=1e-5, atol=1e-5 * np.abs(gl_ref).max())
