@@ -163,42 +163,15 @@ void orc_mlp_eval_batch(const orc_mlp_t *m, const float *y, int64_t B, float *f)
   for (int64_t b = 0; b < B; ++b) orc_mlp_eval(m, y + b * m->d, f + b * m->d, NULL);
 }
 
-/* Reduction over the hidden axis in the order the adjoint path fixes: 32 interleaved
- * partial fma-chains (partial l covers j = l, l+32, l+64, ...; first term a plain product) combined
- * by a balanced binary tree with partner distance 16, 8, 4, 2, 1.  term(j) = a[j] * b[j*stride]. */
-static float tree32_dot(const float *a, const float *b, int stride, int H) {
-  float p[32];
-  for (int l = 0; l < 32; ++l) {
-    float acc = 0.0f;
-    for (int j = l, q = 0; j < H; j += 32, ++q) {
-      if (q == 0)
-        acc = a[j] * b[(size_t)j * stride];
-      else
-        acc = fmaf(a[j], b[(size_t)j * stride], acc);
-    }
-    p[l] = acc;
-  }
-  for (int dist = 16; dist >= 1; dist >>= 1)
-    for (int i = 0; i < dist; ++i) p[i] = p[i] + p[i + dist];
-  return p[0];
-}
-
 /* paddle.autograd.grad(f, (y, *params), grad_outputs=c)  (functional/odeint_adjoint.py:108-114);
  * SURVEY Appendix B.  dh = c W2^T ; dz = dh*(1-h*h) ; du = dz W1^T ; dy = du * pre'(y);
- * gW2 = h^T c ; gb2 = c ; gW1 = u^T dz ; gb1 = dz.
- * The two reductions over the hidden axis (f = h W2, du = dz W1^T) use tree32_dot: this is the
- * order a warp-cooperative kernel (one hidden unit pair per lane) can reproduce exactly. */
+ * gW2 = h^T c ; gb2 = c ; gW1 = u^T dz ; gb1 = dz. */
 void orc_mlp_vjp(const orc_mlp_t *m, const float *y, const float *c, float *f, float *dy, float *gw1,
                  float *gb1, float *gw2, float *gb2) {
   const int D = m->d, H = m->h;
   float u[ORC_MAX_D], h[ORC_MAX_H], dz[ORC_MAX_H];
   for (int k = 0; k < D; ++k) u[k] = pre_act(m->pre, y[k]);
-  for (int j = 0; j < H; ++j) {
-    float acc = u[0] * m->w1[j];
-    for (int k = 1; k < D; ++k) acc = fmaf(u[k], m->w1[(size_t)k * H + j], acc);
-    h[j] = orc_tanhf(acc + m->b1[j]);
-  }
-  for (int d = 0; d < D; ++d) f[d] = tree32_dot(h, m->w2 + d, D, H) + m->b2[d];
+  orc_mlp_eval(m, y, f, h);
   for (int j = 0; j < H; ++j) {
     float acc = c[0] * m->w2[(size_t)j * D];
     for (int d = 1; d < D; ++d) acc = fmaf(c[d], m->w2[(size_t)j * D + d], acc);
@@ -206,8 +179,11 @@ void orc_mlp_vjp(const orc_mlp_t *m, const float *y, const float *c, float *f, f
     float s = 1.0f - t;
     dz[j] = acc * s;
   }
-  for (int k = 0; k < D; ++k)
-    dy[k] = tree32_dot(dz, m->w1 + (size_t)k * H, 1, H) * pre_act_grad(m->pre, y[k]);
+  for (int k = 0; k < D; ++k) {
+    float acc = dz[0] * m->w1[(size_t)k * H];
+    for (int j = 1; j < H; ++j) acc = fmaf(dz[j], m->w1[(size_t)k * H + j], acc);
+    dy[k] = acc * pre_act_grad(m->pre, y[k]);
+  }
   if (gw1)
     for (int k = 0; k < D; ++k)
       for (int j = 0; j < H; ++j) gw1[(size_t)k * H + j] += u[k] * dz[j];

@@ -5,32 +5,36 @@
 // augmented state (y, a, g_theta), dynamics augmented_dynamics :89-124, then y <- y_ans[i-1],
 // a += grad_y[i-1].  Repairs R4-R6 (flat state, reverse time as s = -t, norm over the flat state).
 //
-// Design.  The parameter-gradient state g_theta (P = 2DH+H+D values) is the problem: it is an outer
-// product per trajectory and stage, summed over the batch, and a rejected step must not contribute.
-// Layout that makes this cheap:
-//   * a warp works on G trajectory "slots" at once; lane l owns hidden units j = l, l+32, ... :
-//     their W1 columns / W2 rows live in registers, so the parameter-gradient accumulators for
-//     those units are lane-private (no cross-lane traffic for g_theta at all);
-//   * per stage, each slot's (pre(y), a) is broadcast by shuffles, every lane evaluates its hidden
-//     units (z, tanh, dh, dz), and the 2D partial sums per slot (f and du) of all G slots are reduced
-//     together by ONE multi-value butterfly (2D*G values in ~2D*G shuffles) that leaves each total
-//     in the lane that owns that state component -- "owner" lanes keep s0, the 7 stages, t, dt and
-//     run the controller for their slot, so there is one controller per trajectory;
-//   * g_theta is not integrated as state: because it never feeds back, its value at the segment
-//     end is sum_i W_i * k_i^theta with scalar weights W_i known when the attempt starts
-//     (dt*c_sol_i, or the dense-output polynomial weights for the last step of a segment); each
-//     lane accumulates a tentative per-slot sum and commits it (fp64) only when the slot's
-//     controller accepts the step.  The stage-0 term reuses the FSAL evaluation: it is seeded into
-//     the next attempt's tentative sum as soon as the next dt is known.
-//   * slots advance as independent state machines (INIT: f0, probe; ATTEMPT: stages 1..6), one
-//     field evaluation per slot per round; finished slots refill from a per-CTA trajectory queue.
+// Design (round 1b; the first version was warp-cooperative and issued ~3x the instructions):
+//   * ONE THREAD OWNS ONE TRAJECTORY: (y, a), the 7 Dormand-Prince stages of both, t, dt and the
+//     accept/reject controller live in registers.  Every lane is an independent state machine that
+//     performs one field+VJP evaluation per "round" (INIT: f0, probe; ATTEMPT: stages 1..6; REPLAY:
+//     see below), so lanes of a warp never wait for each other's controller decisions.
+//   * The parameter-gradient state g_theta (P = 2DH+H+D values) is a per-trajectory outer product
+//     summed over the batch, far too large for per-thread registers.  It is never integrated as
+//     state: since it does not feed back, its value is sum_i W_i * k_i^theta with scalar weights W_i
+//     that are known when an attempt starts (dt*c_sol_i, or the dense-output polynomial weights
+//     when the attempt reaches the segment end).  Each round a lane stores the (h_j, dz_j) of its
+//     evaluation as one column of a per-warp shared-memory tile [H][32] and publishes
+//     (W*u, W, W*a); then the warp TRANSPOSES roles: lane l owns hidden units l and l+32 and folds
+//     all 32 columns into lane-private accumulators (5 FMAs per unit and trajectory).  No shuffles,
+//     no atomics in the loop; tile rows are padded to 33 so both phases are bank-conflict free.
+//   * A rejected attempt has already been folded in.  The owning lane then spends one extra block
+//     of six evaluations (REPLAY) re-evaluating stages 1..5 of the failed attempt with weights -W_i
+//     and the start point with (W_0' - W_0) for the shrunk step; the other lanes keep working.
+//     The cost of a rejection is one attempt of that lane only.
+//   * The FSAL evaluation is folded with W_6 + W_0(next attempt): the controller runs before the
+//     fold of that round.  The f0 column of INIT is kept through the probe evaluation and folded
+//     once select_initial_step has produced dt.
 // Supported norm: the adjoint seminorm (functional/odeint_adjoint.py:301-309) -- with one
 // controller per trajectory g_theta is a per-trajectory partial integral.
 #include "xde_common.cuh"
 
 namespace xde {
 
-constexpr int kAdjThreads = 128;
+constexpr int kAdjThreads = 96;  // 3 warps: 5 CTAs (15 warps) per SM fit the per-warp tiles for H = 50
+constexpr int kAdjWarps = kAdjThreads / 32;
+constexpr int kTileStride = 33;  // float2 elements per hidden-unit row (32 lanes + 1 pad)
 
 struct AdjParams {
   xde_mlp_field_t field;
@@ -47,63 +51,53 @@ struct AdjParams {
   long long chunk;
 };
 
-struct AdjTables {  // shared-memory coefficient tables (per-lane stage lookup)
-  float beta[6][8];  // beta[i][j], stage i+1 input
+struct AdjTables {   // shared-memory coefficient tables (dynamic stage lookup)
+  float beta[6][8];  // beta[i][j], input of stage i+1
   float wsol[8], wa[8], wb[8], wc[8];
 };
 
-enum { AM_IDLE = 0, AM_INIT = 1, AM_ATTEMPT = 2, AM_DONE = 3 };
-// events broadcast from the owner lanes to the hidden-unit role for the theta bookkeeping
-enum { EV_NONE = 0, EV_STAGE = 1, EV_ACCEPT_CONT = 2, EV_ACCEPT_END = 3, EV_REJECT = 4, EV_INIT0 = 5, EV_INIT1 = 6 };
+enum { AM_IDLE = 0, AM_INIT = 1, AM_ATTEMPT = 2, AM_REPLAY = 3, AM_DONE = 4 };
 
-template <int N>
-struct Log2 { static constexpr int v = 1 + Log2<N / 2>::v; };
-template <>
-struct Log2<1> { static constexpr int v = 0; };
+template <int D>
+struct AdjCoef {  // per-lane fold coefficients: {W*u[0..D), W, W*a[0..D)} padded to float4s
+  static constexpr int N = 2 * D + 1;
+  static constexpr int STRIDE = ((N + 3) / 4) * 4;
+};
 
-// Multi-value butterfly: v[0..NV) per lane -> the lane-sum of value (lane >> (5-log2 NV)) in every
-// lane.  Arithmetic tree per value: partner distance 16, 8, 4, 2, 1.
-template <int NV>
-__device__ __forceinline__ float butterfly_reduce(float (&v)[NV], int lane) {
-  constexpr int LOG = Log2<NV>::v;
-  int n = NV;
-#pragma unroll
-  for (int step = 0; step < LOG; ++step) {
-    const int dist = 16 >> step;
-    const bool hi = (lane & dist) != 0;
-    n >>= 1;
-#pragma unroll
-    for (int i = 0; i < NV / 2; ++i) {
-      if (i < n) {
-        const float keep = hi ? v[i + n] : v[i];
-        const float send = hi ? v[i] : v[i + n];
-        v[i] = keep + __shfl_xor_sync(XDE_FULL_MASK, send, dist);
-      }
-    }
+template <int D, int HPL>
+struct AdjSmem {
+  static __host__ __device__ size_t tile_floats(int H) { return (((size_t)2 * H * kTileStride + 3) / 4) * 4; }
+  static __host__ __device__ size_t warp_floats(int H) { return tile_floats(H) + 32 * AdjCoef<D>::STRIDE; }
+  static __host__ __device__ size_t bytes(int H, int T) {
+    size_t fl = SmallRec<D>::floats(H) + (size_t)((T + 3) / 4) * 4 + kAdjWarps * warp_floats(H);
+    size_t red = sizeof(double) * (size_t)(2 * D * H + H + D);
+    size_t b = sizeof(float) * fl;
+    return b > red ? b : red;
   }
-  float r = v[0];
-#pragma unroll
-  for (int step = LOG; step < 5; ++step) r = r + __shfl_xor_sync(XDE_FULL_MASK, r, 16 >> step);
-  return r;
-}
+};
 
-template <int D, int HPL, int PRE, int G>
-__global__ void __launch_bounds__(kAdjThreads) dopri5_adj_kernel(const AdjParams p) {
-  constexpr int C = 2 * D;
-  constexpr int NV = G * C;
-  static_assert(NV == 8 || NV == 16 || NV == 32, "G*2D must be 8, 16 or 32");
-  constexpr int SH = 5 - Log2<NV>::v;  // owner duplication: lane l owns value l >> SH
-  constexpr int NTH = (2 * D + 1) * HPL;  // lane-private theta values
+template <int D, int HPL, int PRE>
+__global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 2) ? 5 : 1) dopri5_adj_kernel(const AdjParams p) {
+  constexpr int C = 2 * D;                 // state components per trajectory: y then a
+  constexpr int NTH = (2 * D + 1) * HPL;   // lane-private theta accumulators
+  constexpr int REC = SmallRec<D>::REC;
+  constexpr int CST = AdjCoef<D>::STRIDE;
 
   extern __shared__ __align__(16) float smem[];
   __shared__ AdjTables tb;
   __shared__ unsigned long long s_next;
   __shared__ unsigned long long s_cnt[3];
   __shared__ int s_status;
-  float *st = smem;  // solver times s_i = tsign * t_i
 
   const int H = p.field.h;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *sw = smem;
+  float *st = sw + SmallRec<D>::floats(H);
+  float *wbase = st + ((p.T + 3) / 4) * 4 + (size_t)warp * AdjSmem<D, HPL>::warp_floats(H);
+  float2 *tile = reinterpret_cast<float2 *>(wbase);                    // [H][33] of (h, dz)
+  float *coef = wbase + AdjSmem<D, HPL>::tile_floats(H);               // [32][CST]
+
+  load_small_field<D>(sw, p.field);
   // direction of the backward sweep: t_span increasing (usual) -> integrate s = -t
   const float tsign = (p.t_span[1] > p.t_span[0]) ? -1.0f : 1.0f;
   for (int i = threadIdx.x; i < p.T; i += blockDim.x) st[i] = tsign * p.t_span[i];
@@ -144,56 +138,43 @@ __global__ void __launch_bounds__(kAdjThreads) dopri5_adj_kernel(const AdjParams
     s_cnt[0] = s_cnt[1] = s_cnt[2] = 0ull;
     s_status = 0;
   }
+  for (int i = lane; i < 32 * CST; i += 32) coef[i] = 0.0f;
   __syncthreads();
 
-  // ---- hidden-unit role: this lane's units j = lane + 32 q (zero weights for j >= H) ----
-  float w1r[D][HPL], b1r[HPL], w2r[HPL][D];
-#pragma unroll
-  for (int q = 0; q < HPL; ++q) {
-    const int j = lane + 32 * q;
-    const bool ok = j < H;
-    b1r[q] = ok ? p.field.b1[j] : 0.0f;
-#pragma unroll
-    for (int k = 0; k < D; ++k) w1r[k][q] = ok ? p.field.w1[k * H + j] : 0.0f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) w2r[q][d] = ok ? p.field.w2[j * D + d] : 0.0f;
-  }
-  double acc[NTH];  // committed parameter-gradient sums of this lane's units (fp64)
-  float S[G][NTH];  // tentative sums of the attempt in flight, per slot
-  float hk[G][HPL], dzk[G][HPL];
-#pragma unroll
-  for (int i = 0; i < NTH; ++i) acc[i] = 0.0;
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-#pragma unroll
-    for (int i = 0; i < NTH; ++i) S[g][i] = 0.0f;
-#pragma unroll
-    for (int q = 0; q < HPL; ++q) hk[g][q] = dzk[g][q] = 0.0f;
-  }
-
-  // ---- owner role: this lane owns state component `cown` of slot `gown` ----
-  const int vown = lane >> SH;
-  const int gown = vown / C, cown = vown % C;
-  const bool is_y = cown < D;
-  const int comp = is_y ? cown : cown - D;
-  const bool primary = (lane & ((1 << SH) - 1)) == 0;
-  const int slot_lead = (gown * C) << SH;          // lane holding component 0 of my slot
-  const int partner_y = (gown * C + comp) << SH;   // lane holding y[comp] of my slot
-  const float b2own = is_y ? p.field.b2[comp] : 0.0f;
   const xde_ctrl_opts_t o = p.o;
 
+  // ---- hidden-unit role (fold phase): this lane's units j = lane + 32 q ----
+  double acc[NTH];  // committed parameter-gradient sums of this lane's units (fp64)
+  float Tt[NTH];    // fp32 running sums, flushed into acc every few rounds
+#pragma unroll
+  for (int i = 0; i < NTH; ++i) {
+    acc[i] = 0.0;
+    Tt[i] = 0.0f;
+  }
+  double gb2acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) gb2acc[d] = 0.0;
+
+  // ---- trajectory role: one controller per thread ----
   int mode = AM_IDLE, stage = 0, seg = 0, n_steps = 0, n_logged = 0;
   long long traj = -1;
-  float s0 = 0.f, kk[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float s0[C], kk[7][C];
+#pragma unroll
+  for (int e = 0; e < C; ++e) {
+    s0[e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) kk[j][e] = 0.f;
+  }
   float t0 = 0.f, dt = 0.f, te = 0.f, xfin = 0.f;
   bool fin = false;  // the attempt in flight reaches the segment end if accepted
-  float scale = 1.f, h0 = 0.f, d1 = 0.f;
-  float Sb2 = 0.f;   // tentative gb2 sum (a-component owners)
-  double accb2 = 0.0;
+  float dt_old = 0.f, xfin_old = 0.f;
+  bool fin_old = false;
+  float h0 = 0.f, d1 = 0.f;
   unsigned n_att = 0, n_acc = 0, n_fe = 0;
   int status = 0;
+  int since_flush = 0;
 
-  // theta weight of the eval at `stg` (0..6) for an attempt (dtv, finv, xv); sign folded in
+  // theta weight of the evaluation at stage `stg` (0..6) of an attempt (dtv, finv, xv); sign folded in
   auto theta_w = [&](int stg, float dtv, bool finv, float xv) -> float {
     float w;
     if (finv) {
@@ -205,35 +186,55 @@ __global__ void __launch_bounds__(kAdjThreads) dopri5_adj_kernel(const AdjParams
     }
     return -tsign * w;  // d g_theta / ds = -tsign * vjp_theta(a)
   };
+  // rms over the y part and over the a part, fp64 accumulation; adjoint seminorm =
+  // max(|g_t| = 0, rms(y), rms(a)) with Python max semantics (functional/odeint_adjoint.py:304-307)
+  auto semi_norm = [&](const float (&v)[C]) -> float {
+    double sy = 0.0, sa = 0.0;
+#pragma unroll
+    for (int e = 0; e < D; ++e) {
+      sy += (double)(v[e] * v[e]);
+      sa += (double)(v[D + e] * v[D + e]);
+    }
+    const float ny = rms_from_sumsq(sy, (double)D), na = rms_from_sumsq(sa, (double)D);
+    float best = 0.0f;
+    if (ny > best) best = ny;
+    if (na > best) best = na;
+    return best;
+  };
+  auto plan_attempt = [&]() {  // (t0, dt, te) -> does the attempt reach the segment end, and where
+    const float t1n = t0 + dt;
+    fin = !(te > t1n);
+    xfin = fin ? __fdiv_rn(te - t0, t1n - t0) : 0.f;
+  };
 
   while (true) {
-    // ================= refill idle slots =================
+    // ================= refill idle lanes from the CTA queue (warp-aggregated) =================
     {
-      const bool need = (mode == AM_IDLE) && (cown == 0) && primary;
+      const bool need = (mode == AM_IDLE);
       const unsigned m = __ballot_sync(XDE_FULL_MASK, need);
-      const unsigned many = __ballot_sync(XDE_FULL_MASK, mode == AM_IDLE);
-      if (many) {
+      if (m) {
         unsigned long long base = 0;
-        if (m) {
-          const int leader = __ffs(m) - 1;
-          if (lane == leader) base = atomicAdd(&s_next, (unsigned long long)__popc(m));
-          base = __shfl_sync(XDE_FULL_MASK, base, leader);
-        }
-        long long cand = (long long)base + __popc(m & ((1u << lane) - 1u));
-        cand = __shfl_sync(XDE_FULL_MASK, cand, slot_lead);
-        if (mode == AM_IDLE) {
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(&s_next, (unsigned long long)__popc(m));
+        base = __shfl_sync(XDE_FULL_MASK, base, leader);
+        if (need) {
+          const long long cand = (long long)base + __popc(m & ((1u << lane) - 1u));
           if (cand < c1) {
             traj = cand;
             seg = p.T - 1;
-            const long long src = ((long long)seg * p.B + traj) * D + comp;
-            s0 = is_y ? p.y_ans[src] : p.grad_y[src];  // aug_state = [y_ans[-1], grad_y[-1]] (:75-82)
+            // aug_state = [y_ans[-1], grad_y[-1]] (functional/odeint_adjoint.py:75-82)
+#pragma unroll
+            for (int e = 0; e < D; ++e) {
+              const long long src = ((long long)seg * p.B + traj) * D + e;
+              s0[e] = p.y_ans[src];
+              s0[D + e] = p.grad_y[src];
+            }
             t0 = st[seg];
             te = st[seg - 1];
             mode = AM_INIT;
             stage = 0;
             n_steps = 0;
             n_logged = 0;
-            Sb2 = 0.f;
           } else {
             mode = AM_DONE;
           }
@@ -242,343 +243,335 @@ __global__ void __launch_bounds__(kAdjThreads) dopri5_adj_kernel(const AdjParams
     }
     if (__all_sync(XDE_FULL_MASK, mode == AM_DONE)) break;
 
-    const bool att = (mode == AM_ATTEMPT), ini = (mode == AM_INIT);
+    const bool att = (mode == AM_ATTEMPT), ini = (mode == AM_INIT), rep = (mode == AM_REPLAY);
 
-    // ================= (1) owner: input of this round's evaluation =================
+    // ================= (1) assertions when an attempt starts =================
+    // _adaptive_step (base_adaptive_solver_rk.py:200-203) + max_num_steps (:120-122)
     float t1 = t0 + dt;
-    bool live = att || ini;
-    {
-      // assertions of _adaptive_step (base_adaptive_solver_rk.py:200-203) + max_num_steps (:120-122),
-      // checked when an attempt starts.  Non-finite state is a slot-wide condition (convergent ballot).
-      const unsigned nf = __ballot_sync(XDE_FULL_MASK, !(fabsf(s0) < INFINITY));
-      const unsigned slot_mask = (((C << SH) == 32) ? 0xffffffffu : ((1u << (C << SH)) - 1u)) << slot_lead;
-      if (att && stage == 1) {
-        int bad = 0;
-        if (!(n_steps < o.max_num_steps)) bad = XDE_ST_MAX_STEPS;
-        else if (!(t0 + dt > t0)) bad = XDE_ST_DT_UNDERFLOW;
-        else if (nf & slot_mask) bad = XDE_ST_NONFINITE_STATE;
-        if (bad) {
-          status = max(status, bad);
-          if (!is_y && p.adj_y0 && primary) p.adj_y0[traj * D + comp] = NAN;
-          if (p.log_counts && cown == 0 && primary) p.log_counts[traj] = n_logged;
-          mode = AM_IDLE;
-          live = false;
-        }
-      }
-    }
-    float yin;
-    {
-      const int bi = (stage >= 1 && stage <= 6) ? stage - 1 : 0;
-      float s = kk[0] * (tb.beta[bi][0] * dt);
-#pragma unroll
-      for (int j = 1; j < 6; ++j)
-        if (j < stage) s = s + kk[j] * (tb.beta[bi][j] * dt);
-      const float y_att = s0 + s;
-      const float y_ini = (stage == 0) ? s0 : (kk[0] * h0 + s0);
-      yin = att ? y_att : y_ini;
-    }
-    const float bc_own = is_y ? pre_act<PRE>(yin) : yin;  // y owners broadcast u = pre(y), a owners a
-    const float ypart = __shfl_sync(XDE_FULL_MASK, yin, partner_y);
-    const float dpre = pre_act_grad<PRE>(ypart);
-
-    // ================= (2) field + VJP evaluation, slot by slot (warp-uniform code) =================
-    float v[NV];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float u[D], a[D];
-#pragma unroll
-      for (int k = 0; k < D; ++k) u[k] = __shfl_sync(XDE_FULL_MASK, bc_own, ((g * C + k) << SH));
-#pragma unroll
-      for (int d = 0; d < D; ++d) a[d] = __shfl_sync(XDE_FULL_MASK, bc_own, ((g * C + D + d) << SH));
-      // the INIT probe must not overwrite the retained (h, dz) of the f0 evaluation
-      const int keepflag = __shfl_sync(XDE_FULL_MASK, (int)(ini && stage == 1), (g * C) << SH);
-      float pf[D], pdu[D];
-#pragma unroll
-      for (int q = 0; q < HPL; ++q) {
-        float z = u[0] * w1r[0][q];
-#pragma unroll
-        for (int k = 1; k < D; ++k) z = fmaf(u[k], w1r[k][q], z);
-        const float h = tanh_rat(z + b1r[q]);
-        float dh = a[0] * w2r[q][0];
-#pragma unroll
-        for (int d = 1; d < D; ++d) dh = fmaf(a[d], w2r[q][d], dh);
-        const float t = h * h;
-        const float sgrad = 1.0f - t;
-        const float dz = dh * sgrad;
-#pragma unroll
-        for (int d = 0; d < D; ++d) pf[d] = (q == 0) ? h * w2r[q][d] : fmaf(h, w2r[q][d], pf[d]);
-#pragma unroll
-        for (int k = 0; k < D; ++k) pdu[k] = (q == 0) ? dz * w1r[k][q] : fmaf(dz, w1r[k][q], pdu[k]);
-        if (!keepflag) {
-          hk[g][q] = h;
-          dzk[g][q] = dz;
-        }
-      }
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        v[g * C + d] = pf[d];
-        v[g * C + D + d] = pdu[d];
-      }
-    }
-    // ================= (3) reduce: totals land in the owner lanes =================
-    const float tot = butterfly_reduce<NV>(v, lane);
-    // solver-time dynamics: dy/ds = tsign * f ; da/ds = -tsign * vjp_y(a)
-    const float fo = is_y ? tsign * (tot + b2own) : (-tsign) * (tot * dpre);
-
-    // ================= (4) owner: state machine =================
-    int ev = EV_NONE;
-    float w_eval = 0.f;  // theta weight of the evaluation just done
-    float w_seed = 0.f;  // theta weight of stage 0 of the next attempt (seeding)
-    float sb2_term = 0.f;
-    // rms over the D components of my group (y or a), fp64 accumulation; mixed seminorm =
-    // max(|g_t| = 0, rms(y), rms(a)) with Python max semantics (functional/odeint_adjoint.py:304-307)
-    auto semi_norm = [&](float val) -> float {
-      double sq = (double)(val * val);
-#pragma unroll
-      for (int off = 1; off < D; off <<= 1) sq += __shfl_xor_sync(XDE_FULL_MASK, sq, off << SH);
-      const float mine = rms_from_sumsq(sq, (double)D);
-      const float other = __shfl_xor_sync(XDE_FULL_MASK, mine, D << SH);
-      const float ny = is_y ? mine : other, na = is_y ? other : mine;
-      float best = 0.0f;
-      if (ny > best) best = ny;
-      if (na > best) best = na;
-      return best;
-    };
-
-    // norm arguments are formed per lane; the reductions themselves run in convergent code
-    float argA = 0.f, argB = 0.f, scale_new = scale;
-    const bool is_init0 = live && ini && stage == 0;
-    const bool is_init1 = live && ini && stage == 1;
-    const bool is_last = live && att && stage == 6;
-    if (is_init0) {
-      scale_new = o.atol + fabsf(s0) * o.rtol;  // select_initial_step (base_adaptive_solver.py:50)
-      argA = __fdiv_rn(s0, scale_new);
-      argB = __fdiv_rn(fo, scale_new);
-    } else if (is_init1) {
-      argA = __fdiv_rn(fo - kk[0], scale);
-    } else if (is_last) {
-      // error estimate and tolerance (base_adaptive_solver_rk.py:180; ode_utils.py:80-82), k6 = fo
-      float e = kk[0] * (dt * DP::cerr(0));
-#pragma unroll
-      for (int j = 1; j < 6; ++j) e = e + kk[j] * (dt * DP::cerr(j));
-      e = e + fo * (dt * DP::cerr(6));
-      const float tol = o.atol + o.rtol * fmaxf(fabsf(s0), fabsf(yin));
-      argA = __fdiv_rn(e, tol);
-    }
-    const float nA = semi_norm(argA);
-    float nB = 0.f;
-    if (__any_sync(XDE_FULL_MASK, is_init0)) nB = semi_norm(argB);
-
-    if (is_init0) {
-      // _before_integrate f0 + select_initial_step part 1 (base_adaptive_solver.py:44-57)
-      kk[0] = fo;
-      scale = scale_new;
-      const float d0 = fabsf(nA);
-      d1 = fabsf(nB);
-      if (d0 < 1e-5f || d1 < 1e-5f) h0 = 1e-6f; else h0 = __fdiv_rn(0.01f * d0, d1);
-      h0 = fabsf(h0);
-      stage = 1;
-      ev = EV_INIT0;
-    } else if (is_init1) {
-      const float d2 = fabsf(__fdiv_rn(nA, h0));
-      float h1;
-      if (d1 <= 1e-15f && d2 <= 1e-15f) {
-        h1 = fmaxf(1e-6f, h0 * 1e-3f);
+    if (att && stage == 1) {
+      int bad = 0;
+      if (!(n_steps < o.max_num_steps)) {
+        bad = XDE_ST_MAX_STEPS;
+      } else if (!(t0 + dt > t0)) {
+        bad = XDE_ST_DT_UNDERFLOW;
       } else {
-        const float mx = (d2 > d1) ? d2 : d1;
-        const float arg = __fdiv_rn(0.01f, mx);
-        h1 = (arg > 0.0f && arg < INFINITY) ? root5(arg) : arg;
+        bool finite = true;
+#pragma unroll
+        for (int e = 0; e < C; ++e) finite = finite && (fabsf(s0[e]) < INFINITY);
+        if (!finite) bad = XDE_ST_NONFINITE_STATE;
       }
-      h1 = fabsf(h1);
-      const bool has_first = (o.first_step == o.first_step);
-      dt = has_first ? o.first_step : fminf(100.0f * h0, h1);
-      if (primary && cown == 0) n_fe += has_first ? 1u : 3u;
-      mode = AM_ATTEMPT;
-      stage = 1;
-      const float t1n = t0 + dt;
-      fin = !(te > t1n);
-      xfin = fin ? __fdiv_rn(te - t0, t1n - t0) : 0.f;
-      w_seed = theta_w(0, dt, fin, xfin);
-      ev = EV_INIT1;
-    } else if (live && att) {
-      w_eval = theta_w(stage, dt, fin, xfin);
-      if (!is_y) sb2_term = w_eval * yin;
-      if (stage < 6) {
+      if (bad) {
+        status = max(status, bad);
+        if (p.adj_y0) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) p.adj_y0[traj * D + d] = NAN;
+        }
+        if (p.log_counts) p.log_counts[traj] = n_logged;
+        mode = AM_IDLE;
+      }
+    }
+    const bool live = (mode == AM_ATTEMPT) || (mode == AM_INIT) || (mode == AM_REPLAY);
+
+    // ================= (2) input of this round's evaluation =================
+    // ATTEMPT stage i: s0 + sum_{j<i} k_j*(beta_ij*dt) (base_adaptive_solver_rk.py:166-168);
+    // REPLAY r: the same for stage r of the rejected attempt (dt_old), r = 0 -> the start point;
+    // INIT 0: s0; INIT 1: the Euler probe k0*h0 + s0 (base_adaptive_solver.py:60).
+    float yin[C];
+    {
+      const int nst = ini ? stage : (rep ? stage : stage);  // number of k terms
+      const int row = (nst >= 1) ? nst - 1 : 0;
+      const float dtv = rep ? dt_old : dt;
+      float cj[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) cj[j] = tb.beta[row][j] * dtv;
+      if (ini) cj[0] = h0;
+#pragma unroll
+      for (int e = 0; e < C; ++e) {
+        float s = kk[0][e] * cj[0];
 #pragma unroll
         for (int j = 1; j < 6; ++j)
-          if (j == stage) kk[j] = fo;
-        stage++;
-        ev = EV_STAGE;
-      } else {
-        kk[6] = fo;
-        const float ratio = fabsf(nA);
-        bool accept = (ratio <= 1.0f);
-        if (dt > o.max_step) accept = false;
-        if (dt <= o.min_step) accept = true;
-        const float dt_next = next_step_size(dt, ratio, o);
-        if (primary && cown == 0) {
+          if (j < nst) s = s + kk[j][e] * cj[j];
+        yin[e] = (nst >= 1) ? (s0[e] + s) : s0[e];
+      }
+    }
+
+    // ================= (3) field + VJP evaluation of this lane's trajectory =================
+    // f = tanh(pre(y) W1 + b1) W2 + b2 ; dh = a W2^T ; dz = dh (1 - h^2) ; du = dz W1^T (Appendix B)
+    const bool wr = live && !(ini && stage == 1);  // the probe must not overwrite the f0 column
+    float fo[C];
+    {
+      float u[D], accf[D], pdu[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        u[k] = pre_act<PRE>(yin[k]);
+        accf[k] = 0.0f;
+        pdu[k] = 0.0f;
+      }
+#pragma unroll 2
+      for (int j = 0; j < H; ++j) {
+        float rec[REC];
+        const float4 *r4 = reinterpret_cast<const float4 *>(sw + j * REC);
+#pragma unroll
+        for (int q = 0; q < REC / 4; ++q) {
+          const float4 v = r4[q];
+          rec[4 * q] = v.x;
+          rec[4 * q + 1] = v.y;
+          rec[4 * q + 2] = v.z;
+          rec[4 * q + 3] = v.w;
+        }
+        float z = u[0] * rec[0];
+#pragma unroll
+        for (int k = 1; k < D; ++k) z = fmaf(u[k], rec[k], z);
+        const float h = tanh_rat(z + rec[D]);
+        float dh = yin[D] * rec[D + 1];
+#pragma unroll
+        for (int d = 1; d < D; ++d) dh = fmaf(yin[D + d], rec[D + 1 + d], dh);
+        const float hh = h * h;
+        const float sg = 1.0f - hh;
+        const float dz = dh * sg;
+#pragma unroll
+        for (int d = 0; d < D; ++d) accf[d] = fmaf(h, rec[D + 1 + d], accf[d]);
+#pragma unroll
+        for (int k = 0; k < D; ++k) pdu[k] = fmaf(dz, rec[k], pdu[k]);  // first term: fma(.,.,0) == product
+        if (wr) tile[j * kTileStride + lane] = make_float2(h, dz);
+      }
+      // solver-time dynamics: dy/ds = tsign * f ; da/ds = -tsign * vjp_y(a)
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        fo[d] = tsign * (accf[d] + sw[H * REC + d]);
+        fo[D + d] = (-tsign) * (pdu[d] * pre_act_grad<PRE>(yin[d]));
+      }
+    }
+
+    // ================= (4) controller / state machine =================
+    float wacc = 0.f;           // fold weight of this lane's tile column
+    bool col_is_start = false;  // the column holds the f0 evaluation at the start point
+    if (live) {
+      if (ini) {
+        if (stage == 0) {
+          // _before_integrate f0 + select_initial_step part 1 (base_adaptive_solver.py:44-57)
+          float v0[C], v1[C];
+#pragma unroll
+          for (int e = 0; e < C; ++e) {
+            kk[0][e] = fo[e];
+            const float sc = o.atol + fabsf(s0[e]) * o.rtol;
+            v0[e] = __fdiv_rn(s0[e], sc);
+            v1[e] = __fdiv_rn(fo[e], sc);
+          }
+          const float d0 = fabsf(semi_norm(v0));
+          d1 = fabsf(semi_norm(v1));
+          if (d0 < 1e-5f || d1 < 1e-5f) h0 = 1e-6f; else h0 = __fdiv_rn(0.01f * d0, d1);
+          h0 = fabsf(h0);
+          stage = 1;
+        } else {
+          float v[C];
+#pragma unroll
+          for (int e = 0; e < C; ++e) {
+            const float sc = o.atol + fabsf(s0[e]) * o.rtol;
+            v[e] = __fdiv_rn(fo[e] - kk[0][e], sc);
+          }
+          const float d2 = fabsf(__fdiv_rn(semi_norm(v), h0));
+          float h1;
+          if (d1 <= 1e-15f && d2 <= 1e-15f) {
+            h1 = fmaxf(1e-6f, h0 * 1e-3f);
+          } else {
+            const float mx = (d2 > d1) ? d2 : d1;
+            const float arg = __fdiv_rn(0.01f, mx);
+            h1 = (arg > 0.0f && arg < INFINITY) ? root5(arg) : arg;
+          }
+          h1 = fabsf(h1);
+          const bool has_first = (o.first_step == o.first_step);
+          dt = has_first ? o.first_step : fminf(100.0f * h0, h1);
+          n_fe += has_first ? 1u : 3u;
+          mode = AM_ATTEMPT;
+          stage = 1;
+          plan_attempt();
+          wacc = theta_w(0, dt, fin, xfin);
+          col_is_start = true;
+        }
+      } else if (att) {
+        const float w_eval = theta_w(stage, dt, fin, xfin);
+        if (stage < 6) {
+#pragma unroll
+          for (int j = 1; j < 6; ++j)
+            if (j == stage) {
+#pragma unroll
+              for (int e = 0; e < C; ++e) kk[j][e] = fo[e];
+            }
+          stage++;
+          wacc = w_eval;
+        } else {
+          // error estimate and ratio (base_adaptive_solver_rk.py:180; ode_utils.py:80-82), k6 = fo
+          float v[C];
+#pragma unroll
+          for (int e = 0; e < C; ++e) {
+            kk[6][e] = fo[e];
+            float er = kk[0][e] * (dt * DP::cerr(0));
+#pragma unroll
+            for (int j = 1; j < 7; ++j) er = er + kk[j][e] * (dt * DP::cerr(j));
+            const float tol = o.atol + o.rtol * fmaxf(fabsf(s0[e]), fabsf(yin[e]));
+            v[e] = __fdiv_rn(er, tol);
+          }
+          const float ratio = fabsf(semi_norm(v));
+          bool accept = (ratio <= 1.0f);
+          if (dt > o.max_step) accept = false;
+          if (dt <= o.min_step) accept = true;
+          const float dt_next = next_step_size(dt, ratio, o);
           n_att++;
           n_fe += 6;
-          if (p.log_records) {
-            if (n_logged < p.log_cap) {
-              xde_attempt_t r;
-              r.t0 = tsign * t0;
-              r.dt = tsign * dt;
-              r.ratio = ratio;
-              r.accepted = accept ? 1 : 0;
-              p.log_records[traj * p.log_cap + n_logged] = r;
-            }
+          if (p.log_records && n_logged < p.log_cap) {
+            xde_attempt_t r;
+            r.t0 = tsign * t0;
+            r.dt = tsign * dt;
+            r.ratio = ratio;
+            r.accepted = accept ? 1 : 0;
+            p.log_records[traj * p.log_cap + n_logged] = r;
           }
-          if (accept) n_acc++;
-        }
-        n_logged++;
-        n_steps++;
-        if (accept) {
-          if (fin) {
-            // dense output at the segment end (interp_fit + interp_evaluate), then
-            // y <- y_ans[i-1], a += grad_y[i-1] (functional/odeint_adjoint.py:153-159)
-            float sm = kk[0] * (dt * DP::cmid(0));
+          n_logged++;
+          n_steps++;
+          if (accept) {
+            n_acc++;
+            if (fin) {
+              // dense output at the segment end (interp_fit + interp_evaluate), then
+              // y <- y_ans[i-1], a += grad_y[i-1] (functional/odeint_adjoint.py:153-159)
+              seg -= 1;
+              const float two_dt = 2.0f * dt;
+              const float x = xfin;
 #pragma unroll
-            for (int j = 1; j < 7; ++j) sm = sm + kk[j] * (dt * DP::cmid(j));
-            const float ym = s0 + sm;
-            const float F0 = kk[0], F1 = kk[6], Y0 = s0, Y1 = yin;
-            const float two_dt = 2.0f * dt;
-            const float ca = (two_dt * (F1 - F0) - 8.0f * (Y1 + Y0)) + 16.0f * ym;
-            const float cb = ((dt * (5.0f * F0 - 3.0f * F1) + 18.0f * Y0) + 14.0f * Y1) - 32.0f * ym;
-            const float cc = ((dt * (F1 - 4.0f * F0) - 11.0f * Y0) - 5.0f * Y1) + 16.0f * ym;
-            const float cd = dt * F0;
-            const float x = xfin;
-            float total = Y0 + x * cd;
-            float xp = x * x;
-            total = total + xp * cc;
-            xp = xp * x;
-            total = total + xp * cb;
-            xp = xp * x;
-            total = total + xp * ca;
-            seg -= 1;
-            const long long src = ((long long)seg * p.B + traj) * D + comp;
-            s0 = is_y ? p.y_ans[src] : (total + p.grad_y[src]);
-            n_steps = 0;
-            if (seg == 0) {
-              if (!is_y && p.adj_y0 && primary) p.adj_y0[traj * D + comp] = s0;
-              if (p.log_counts && cown == 0 && primary) p.log_counts[traj] = n_logged;
-              mode = AM_IDLE;
+              for (int e = 0; e < C; ++e) {
+                float sm = kk[0][e] * (dt * DP::cmid(0));
+#pragma unroll
+                for (int j = 1; j < 7; ++j) sm = sm + kk[j][e] * (dt * DP::cmid(j));
+                const float ym = s0[e] + sm;
+                const float F0 = kk[0][e], F1 = kk[6][e], Y0 = s0[e], Y1 = yin[e];
+                const float ca = (two_dt * (F1 - F0) - 8.0f * (Y1 + Y0)) + 16.0f * ym;
+                const float cb = ((dt * (5.0f * F0 - 3.0f * F1) + 18.0f * Y0) + 14.0f * Y1) - 32.0f * ym;
+                const float cc = ((dt * (F1 - 4.0f * F0) - 11.0f * Y0) - 5.0f * Y1) + 16.0f * ym;
+                const float cd = dt * F0;
+                float total = Y0 + x * cd;
+                float xp = x * x;
+                total = total + xp * cc;
+                xp = xp * x;
+                total = total + xp * cb;
+                xp = xp * x;
+                total = total + xp * ca;
+                const long long src = ((long long)seg * p.B + traj) * D + (e < D ? e : e - D);
+                s0[e] = (e < D) ? p.y_ans[src] : (total + p.grad_y[src]);
+              }
+              n_steps = 0;
+              wacc = w_eval;
+              if (seg == 0) {
+                if (p.adj_y0) {
+#pragma unroll
+                  for (int d = 0; d < D; ++d) p.adj_y0[traj * D + d] = s0[D + d];
+                }
+                if (p.log_counts) p.log_counts[traj] = n_logged;
+                mode = AM_IDLE;
+              } else {
+                t0 = st[seg];
+                te = st[seg - 1];
+                mode = AM_INIT;
+                stage = 0;
+              }
             } else {
-              t0 = st[seg];
-              te = st[seg - 1];
-              mode = AM_INIT;
-              stage = 0;
+#pragma unroll
+              for (int e = 0; e < C; ++e) {
+                s0[e] = yin[e];
+                kk[0][e] = kk[6][e];
+              }
+              t0 = t1;
+              dt = dt_next;
+              stage = 1;
+              plan_attempt();
+              // FSAL: this evaluation is also stage 0 of the next attempt
+              wacc = w_eval + theta_w(0, dt, fin, xfin);
             }
-            ev = EV_ACCEPT_END;
           } else {
-            s0 = yin;
-            kk[0] = kk[6];
-            t0 = t1;
+            // rejected: everything folded for this attempt is taken back by a REPLAY block
+            dt_old = dt;
+            fin_old = fin;
+            xfin_old = xfin;
             dt = dt_next;
-            stage = 1;
-            const float t1n = t0 + dt;
-            fin = !(te > t1n);
-            xfin = fin ? __fdiv_rn(te - t0, t1n - t0) : 0.f;
-            w_seed = theta_w(0, dt, fin, xfin);
-            ev = EV_ACCEPT_CONT;
+            plan_attempt();
+            mode = AM_REPLAY;
+            stage = 0;
+            wacc = 0.f;
           }
-        } else {
-          dt = dt_next;
+        }
+      } else {  // REPLAY
+        if (stage == 0)
+          wacc = theta_w(0, dt, fin, xfin) - theta_w(0, dt_old, fin_old, xfin_old);
+        else
+          wacc = -theta_w(stage, dt_old, fin_old, xfin_old);
+        stage++;
+        if (stage == 6) {
+          mode = AM_ATTEMPT;
           stage = 1;
-          const float t1n = t0 + dt;
-          fin = !(te > t1n);
-          xfin = fin ? __fdiv_rn(te - t0, t1n - t0) : 0.f;
-          w_seed = theta_w(0, dt, fin, xfin);
-          ev = EV_REJECT;
         }
       }
     }
-    // gb2: lane-private to the a-component owners (gb2[d] = sum W * a_d)
-    if (!is_y) {
-      if (ev == EV_STAGE) Sb2 += sb2_term;
-      else if (ev == EV_ACCEPT_CONT || ev == EV_ACCEPT_END) {
-        accb2 += (double)(Sb2 + sb2_term);
-        Sb2 = (ev == EV_ACCEPT_CONT) ? w_seed * s0 : 0.f;
-      } else if (ev == EV_REJECT || ev == EV_INIT1) {
-        Sb2 = w_seed * s0;
-      }
-    }
-    // start-state broadcast values for re-seeding after INIT / reject
-    const float bc_start = is_y ? pre_act<PRE>(s0) : s0;
 
-    // ================= (5) theta bookkeeping, slot by slot (warp-uniform code) =================
+    // ================= (5) fold: transpose roles, lane l <- hidden units l, l+32 =================
+    {
+      // the column's inputs: this round's evaluation point, or the start point for the kept f0 column
+      float cu[D], ca[D];
+      const bool fold = (wacc != 0.0f);
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int lead = (g * C) << SH;
-      const int evg = __shfl_sync(XDE_FULL_MASK, ev, lead);
-      if (evg == EV_NONE || evg == EV_INIT0) continue;
-      const float wev = __shfl_sync(XDE_FULL_MASK, w_eval, lead);
-      const float wsd = __shfl_sync(XDE_FULL_MASK, w_seed, lead);
-      float u[D], a[D];
-#pragma unroll
-      for (int k = 0; k < D; ++k) u[k] = __shfl_sync(XDE_FULL_MASK, bc_own, ((g * C + k) << SH));
-#pragma unroll
-      for (int d = 0; d < D; ++d) a[d] = __shfl_sync(XDE_FULL_MASK, bc_own, ((g * C + D + d) << SH));
-      if (evg == EV_STAGE || evg == EV_ACCEPT_CONT || evg == EV_ACCEPT_END) {
-        // S += W_i * k_i^theta for the evaluation of this round
-#pragma unroll
-        for (int q = 0; q < HPL; ++q) {
-          const float wdz = wev * dzk[g][q], wh = wev * hk[g][q];
-#pragma unroll
-          for (int k = 0; k < D; ++k) S[g][k * HPL + q] = fmaf(u[k], wdz, S[g][k * HPL + q]);
-          S[g][D * HPL + q] += wdz;
-#pragma unroll
-          for (int d = 0; d < D; ++d) S[g][(D + 1) * HPL + q * D + d] = fmaf(a[d], wh, S[g][(D + 1) * HPL + q * D + d]);
-        }
+      for (int d = 0; d < D; ++d) {
+        // col_is_start only happens in INIT, where s0 is unchanged since the f0 evaluation; after a
+        // segment end s0 already holds the next segment's start, so the stage-6 point is read from yin
+        const float yv = col_is_start ? s0[d] : yin[d];
+        const float av = col_is_start ? s0[D + d] : yin[D + d];
+        cu[d] = fold ? wacc * pre_act<PRE>(yv) : 0.0f;
+        ca[d] = fold ? wacc * av : 0.0f;
+        gb2acc[d] += (double)ca[d];
       }
-      if (evg == EV_ACCEPT_CONT || evg == EV_ACCEPT_END) {
+      const unsigned fm = __ballot_sync(XDE_FULL_MASK, fold);
+      if (fm) {
+        float *c = coef + lane * CST;
 #pragma unroll
-        for (int i = 0; i < NTH; ++i) acc[i] += (double)S[g][i];
-      }
-      if (evg == EV_ACCEPT_END) {
-#pragma unroll
-        for (int i = 0; i < NTH; ++i) S[g][i] = 0.0f;
-      } else if (evg == EV_ACCEPT_CONT) {
-        // the stage-6 point is the next attempt's stage 0 (FSAL): seed with its weight
-#pragma unroll
-        for (int q = 0; q < HPL; ++q) {
-          const float wdz = wsd * dzk[g][q], wh = wsd * hk[g][q];
-#pragma unroll
-          for (int k = 0; k < D; ++k) S[g][k * HPL + q] = u[k] * wdz;
-          S[g][D * HPL + q] = wdz;
-#pragma unroll
-          for (int d = 0; d < D; ++d) S[g][(D + 1) * HPL + q * D + d] = a[d] * wh;
+        for (int d = 0; d < D; ++d) {
+          c[d] = cu[d];
+          c[D + 1 + d] = ca[d];
         }
-      } else if (evg == EV_REJECT || evg == EV_INIT1) {
-        // stage-0 term at the (unchanged) start state.  INIT1: (h, dz) of the f0 evaluation were
-        // retained.  REJECT: they were overwritten by stages 1..6 -> re-evaluate this lane's units.
-        float us[D], as[D];
+        c[D] = wacc;
+        __syncwarp();
+        unsigned m = fm;
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          float cb[CST];
+          const float4 *c4 = reinterpret_cast<const float4 *>(coef + b * CST);
 #pragma unroll
-        for (int k = 0; k < D; ++k) us[k] = __shfl_sync(XDE_FULL_MASK, bc_start, ((g * C + k) << SH));
-#pragma unroll
-        for (int d = 0; d < D; ++d) as[d] = __shfl_sync(XDE_FULL_MASK, bc_start, ((g * C + D + d) << SH));
-        if (evg == EV_REJECT) {
+          for (int q = 0; q < CST / 4; ++q) {
+            const float4 v = c4[q];
+            cb[4 * q] = v.x;
+            cb[4 * q + 1] = v.y;
+            cb[4 * q + 2] = v.z;
+            cb[4 * q + 3] = v.w;
+          }
 #pragma unroll
           for (int q = 0; q < HPL; ++q) {
-            float z = us[0] * w1r[0][q];
+            const int j = lane + 32 * q;
+            if (j < H) {
+              const float2 hv = tile[j * kTileStride + b];
 #pragma unroll
-            for (int k = 1; k < D; ++k) z = fmaf(us[k], w1r[k][q], z);
-            const float h = tanh_rat(z + b1r[q]);
-            float dh = as[0] * w2r[q][0];
+              for (int k = 0; k < D; ++k) Tt[k * HPL + q] = fmaf(cb[k], hv.y, Tt[k * HPL + q]);
+              Tt[D * HPL + q] = fmaf(cb[D], hv.y, Tt[D * HPL + q]);
 #pragma unroll
-            for (int d = 1; d < D; ++d) dh = fmaf(as[d], w2r[q][d], dh);
-            hk[g][q] = h;
-            dzk[g][q] = dh * (1.0f - h * h);
+              for (int d = 0; d < D; ++d)
+                Tt[(D + 1) * HPL + q * D + d] = fmaf(cb[D + 1 + d], hv.x, Tt[(D + 1) * HPL + q * D + d]);
+            }
           }
         }
+        __syncwarp();
+        if (++since_flush >= 8) {
+          since_flush = 0;
 #pragma unroll
-        for (int q = 0; q < HPL; ++q) {
-          const float wdz = wsd * dzk[g][q], wh = wsd * hk[g][q];
-#pragma unroll
-          for (int k = 0; k < D; ++k) S[g][k * HPL + q] = us[k] * wdz;
-          S[g][D * HPL + q] = wdz;
-#pragma unroll
-          for (int d = 0; d < D; ++d) S[g][(D + 1) * HPL + q * D + d] = as[d] * wh;
+          for (int i = 0; i < NTH; ++i) {
+            acc[i] += (double)Tt[i];
+            Tt[i] = 0.0f;
+          }
         }
       }
     }
@@ -586,17 +579,30 @@ __global__ void __launch_bounds__(kAdjThreads) dopri5_adj_kernel(const AdjParams
 
   // ================= epilogue: parameter gradients and stats =================
 #pragma unroll
+  for (int i = 0; i < NTH; ++i) acc[i] += (double)Tt[i];
+  __syncthreads();  // every warp is done with its tile: reuse shared memory as the CTA reduction buffer
+  double *red = reinterpret_cast<double *>(smem);
+  const int P = 2 * D * H + H + D;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) red[i] = 0.0;
+  __syncthreads();
+#pragma unroll
   for (int q = 0; q < HPL; ++q) {
     const int j = lane + 32 * q;
     if (j < H) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) atomicAdd(&p.gacc[k * H + j], acc[k * HPL + q]);
-      atomicAdd(&p.gacc[D * H + j], acc[D * HPL + q]);
+      for (int k = 0; k < D; ++k) atomicAdd(&red[k * H + j], acc[k * HPL + q]);
+      atomicAdd(&red[D * H + j], acc[D * HPL + q]);
 #pragma unroll
-      for (int d = 0; d < D; ++d) atomicAdd(&p.gacc[D * H + H + j * D + d], acc[(D + 1) * HPL + q * D + d]);
+      for (int d = 0; d < D; ++d) atomicAdd(&red[D * H + H + j * D + d], acc[(D + 1) * HPL + q * D + d]);
     }
   }
-  if (!is_y && primary) atomicAdd(&p.gacc[D * H + H + H * D + comp], accb2);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double v = gb2acc[d];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(XDE_FULL_MASK, v, off);
+    if (lane == 0) atomicAdd(&red[D * H + H + H * D + d], v);
+  }
   {
     unsigned a = n_att, b = n_acc, c = n_fe;
 #pragma unroll
@@ -612,13 +618,14 @@ __global__ void __launch_bounds__(kAdjThreads) dopri5_adj_kernel(const AdjParams
       atomicAdd(&s_cnt[2], (unsigned long long)c);
       atomicMax(&s_status, status);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && p.stats) {
-      atomicAdd(&p.stats->n_attempts, s_cnt[0]);
-      atomicAdd(&p.stats->n_accepted, s_cnt[1]);
-      atomicAdd(&p.stats->nfe, s_cnt[2]);
-      atomicMax(&p.stats->status, s_status);
-    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) atomicAdd(&p.gacc[i], red[i]);
+  if (threadIdx.x == 0 && p.stats) {
+    atomicAdd(&p.stats->n_attempts, s_cnt[0]);
+    atomicAdd(&p.stats->n_accepted, s_cnt[1]);
+    atomicAdd(&p.stats->nfe, s_cnt[2]);
+    atomicMax(&p.stats->status, s_status);
   }
 }
 
@@ -627,17 +634,17 @@ __global__ void adj_cast_kernel(const double *__restrict__ a, float *__restrict_
   if (i < n) o[i] = (float)a[i];
 }
 
-template <int D, int HPL, int PRE, int G>
+template <int D, int HPL, int PRE>
 static int launch_adj(const AdjParams &p, cudaStream_t stream) {
-  const size_t smem = sizeof(float) * (size_t)p.T;
-  XDE_REQUIRE(smem <= 160 * 1024, XDE_E_UNSUPPORTED_FIELD, "adjoint: t_span too long for shared memory");
-  auto kern = dopri5_adj_kernel<D, HPL, PRE, G>;
+  const size_t smem = AdjSmem<D, HPL>::bytes(p.field.h, p.T);
+  XDE_REQUIRE(smem <= 200 * 1024, XDE_E_UNSUPPORTED_FIELD, "adjoint: field + t_span exceed shared memory");
+  auto kern = dopri5_adj_kernel<D, HPL, PRE>;
   XDE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   XDE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kAdjThreads, smem));
   if (per_sm < 1) per_sm = 1;
-  const long long slots_per_cta = (long long)(kAdjThreads / 32) * G;
-  long long want = (p.B + slots_per_cta - 1) / slots_per_cta;
+  // persistent grid: a whole number of CTAs per SM; each CTA owns a contiguous chunk of trajectories
+  long long want = (p.B + kAdjThreads - 1) / kAdjThreads;
   long long grid = (long long)sm_count() * per_sm;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
@@ -650,15 +657,27 @@ static int launch_adj(const AdjParams &p, cudaStream_t stream) {
   return XDE_OK;
 }
 
-template <int D, int HPL, int G>
+template <int D, int HPL>
 static int adj_pre(const AdjParams &p, cudaStream_t s) {
   switch (p.field.pre) {
-    case XDE_PRE_ID: return launch_adj<D, HPL, XDE_PRE_ID, G>(p, s);
-    case XDE_PRE_SQUARE: return launch_adj<D, HPL, XDE_PRE_SQUARE, G>(p, s);
-    case XDE_PRE_CUBE: return launch_adj<D, HPL, XDE_PRE_CUBE, G>(p, s);
+    case XDE_PRE_ID: return launch_adj<D, HPL, XDE_PRE_ID>(p, s);
+    case XDE_PRE_SQUARE: return launch_adj<D, HPL, XDE_PRE_SQUARE>(p, s);
+    case XDE_PRE_CUBE: return launch_adj<D, HPL, XDE_PRE_CUBE>(p, s);
   }
   set_last_error("unknown pre-activation %d", p.field.pre);
   return XDE_E_BAD_ARG;
+}
+
+template <int D>
+static int adj_hpl(const AdjParams &p, cudaStream_t s) {
+  const int H = p.field.h;
+  if (H <= 32) return adj_pre<D, 1>(p, s);
+  if (H <= 64) return adj_pre<D, 2>(p, s);
+  if constexpr (D <= 2) {
+    if (H <= 128) return adj_pre<D, 4>(p, s);
+  }
+  set_last_error("adjoint: hidden width H=%d has no fused kernel for D=%d (H <= 64; H <= 128 for D <= 2)", H, D);
+  return XDE_E_UNSUPPORTED_FIELD;
 }
 
 }  // namespace xde
@@ -697,13 +716,13 @@ extern "C" XDE_EXPORT int xde_dopri5_mlp_adjoint_f32(const xde_mlp_field_t *fiel
   XDE_CUDA_CHECK(cudaMemsetAsync(p.gacc, 0, sizeof(double) * P, s));
   if (stats) XDE_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(xde_stats_t), s));
   int rc = XDE_E_UNSUPPORTED_FIELD;
-  if (D == 2 && H <= 32) rc = adj_pre<2, 1, 4>(p, s);
-  else if (D == 2 && H <= 64) rc = adj_pre<2, 2, 4>(p, s);
-  else if (D == 1 && H <= 32) rc = adj_pre<1, 1, 8>(p, s);
-  else if (D == 1 && H <= 64) rc = adj_pre<1, 2, 8>(p, s);
-  else if (D == 4 && H <= 32) rc = adj_pre<4, 1, 2>(p, s);
-  else if (D == 4 && H <= 64) rc = adj_pre<4, 2, 2>(p, s);
-  else set_last_error("adjoint: field D=%d H=%d has no fused kernel (D in {1,2,4}, H <= 64)", D, H);
+  switch (D) {
+    case 1: rc = adj_hpl<1>(p, s); break;
+    case 2: rc = adj_hpl<2>(p, s); break;
+    case 3: rc = adj_hpl<3>(p, s); break;
+    case 4: rc = adj_hpl<4>(p, s); break;
+    default: set_last_error("adjoint: state dim D=%d has no fused kernel (D in {1,2,3,4})", D);
+  }
   if (rc == XDE_OK) {
     adj_cast_kernel<<<(P + 255) / 256, 256, 0, s>>>(p.gacc, out_gparams, P);
     count_launch();

@@ -193,6 +193,31 @@ def test_adjoint_parity(px, torch, oracle, d, h, pre, B):
         assert np.array_equal(r.ratio, lg.ratio)
 
 
+def test_adjoint_with_rejections_and_replay(px, torch, oracle):
+    """A stiffer field so that the ADJOINT controller rejects steps: the kernel folds parameter-gradient
+    contributions eagerly and takes a rejected attempt back with a REPLAY block -- the state path must
+    stay bit-exact and the gradients within rtol 1e-5."""
+    from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
+
+    w = [3.0 * a for a in fanin_weights(2, 50, seed=5)]
+    field, om = both(px, oracle, w, "id")
+    B = 500
+    y0 = np.random.default_rng(1).uniform(-1, 1, (B, 2)).astype(f32)
+    t = np.linspace(0, 4, 5).astype(f32)
+    kw = dict(rtol=1e-6, atol=1e-8)
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0, t, **kw)
+    gy = 0.01 * np.random.default_rng(4).standard_normal(ref.shape).astype(f32)
+    g, a0, stats, _ = adjoint_backward(field, t, ref, gy, return_adj_y0=True, **kw)
+    g_ref, a_ref, st_ref, _, rc = oracle.dopri5_mlp_adjoint(om, t, ref, gy, **kw)
+    assert rc == 0
+    n_rej = int((st_ref.n_attempts - st_ref.n_accepted).sum())
+    assert n_rej > B // 10, f"the case must exercise rejections (got {n_rej})"
+    s = stats.read()
+    assert (s.n_attempts, s.n_accepted) == (int(st_ref.n_attempts.sum()), int(st_ref.n_accepted.sum()))
+    assert np.array_equal(a0.cpu().numpy(), a_ref)
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-5, atol=2e-6 * np.abs(g_ref).max())
+
+
 def test_adjoint_gradient_is_the_true_gradient(px, torch, oracle):
     """Independent of the oracle: finite differences of the GPU forward in fp32 are too noisy, so
     compare with the fp64 NumPy adjoint-free gradient (discretise-then-differentiate is not the same
