@@ -117,6 +117,8 @@ void xde_default_ctrl_opts(xde_ctrl_opts_t *o);
  * chains per thread on every SM; *n_flops_host receives the FLOPs the launch performs.  sink: one
  * device float (never written in practice). */
 int xde_probe_ffma_f32(int32_t iters, float *sink, int64_t *n_flops_host, void *stream);
+/* the same with the packed FFMA2 instruction (fma.rn.f32x2, sm_100+): 2 FMAs per lane and issue slot */
+int xde_probe_ffma2_f32(int32_t iters, float *sink, int64_t *n_flops_host, void *stream);
 
 /* odeint(func, y0, t_span, solver=Dopri5)            functional/odeint.py:28-35
  *   -> AdaptiveSolver.integrate                       solver/base_adaptive_solver.py:24-31

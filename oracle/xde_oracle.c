@@ -140,8 +140,22 @@ static inline float pre_act_grad(int pre, float y) {
 #define ORC_MAX_D 256
 #define ORC_MAX_H 1024
 
-/* f = tanh(pre(y) @ W1 + b1) @ W2 + b2.  nn.Linear = matmul then bias add; the matmul is a
- * sequential-k fma chain (first term a plain product). */
+/* Reduction over the hidden axis j = 0..H-1 in the order the arithmetic specification fixes
+ * (DESIGN.md "Arithmetic specification"): two interleaved fma chains -- one over the even hidden
+ * units, one over the odd ones, each started from +0 -- added at the end.  (A matmul's summation
+ * order is implementation-defined in Paddle; this is the order the B200 kernels use, where one
+ * packed FFMA2 instruction advances both chains.)  term(j) = a[j] * b[j*stride]. */
+static float chain2_dot(const float *a, const float *b, int stride, int H) {
+  float acc_e = 0.0f, acc_o = 0.0f;
+  for (int j = 0; j < H; j += 2) {
+    acc_e = fmaf(a[j], b[(size_t)j * stride], acc_e);
+    if (j + 1 < H) acc_o = fmaf(a[j + 1], b[(size_t)(j + 1) * stride], acc_o);
+  }
+  return acc_e + acc_o;
+}
+
+/* f = tanh(pre(y) @ W1 + b1) @ W2 + b2.  nn.Linear = matmul then bias add; the first matmul is a
+ * sequential-k fma chain (first term a plain product), the second one uses chain2_dot. */
 void orc_mlp_eval(const orc_mlp_t *m, const float *y, float *f, float *hbuf) {
   const int D = m->d, H = m->h;
   float u[ORC_MAX_D], hloc[ORC_MAX_H];
@@ -152,11 +166,7 @@ void orc_mlp_eval(const orc_mlp_t *m, const float *y, float *f, float *hbuf) {
     for (int k = 1; k < D; ++k) acc = fmaf(u[k], m->w1[(size_t)k * H + j], acc);
     h[j] = orc_tanhf(acc + m->b1[j]);
   }
-  for (int d = 0; d < D; ++d) {
-    float acc = h[0] * m->w2[d];
-    for (int j = 1; j < H; ++j) acc = fmaf(h[j], m->w2[(size_t)j * D + d], acc);
-    f[d] = acc + m->b2[d];
-  }
+  for (int d = 0; d < D; ++d) f[d] = chain2_dot(h, m->w2 + d, D, H) + m->b2[d];
 }
 
 void orc_mlp_eval_batch(const orc_mlp_t *m, const float *y, int64_t B, float *f) {
@@ -175,15 +185,11 @@ void orc_mlp_vjp(const orc_mlp_t *m, const float *y, const float *c, float *f, f
   for (int j = 0; j < H; ++j) {
     float acc = c[0] * m->w2[(size_t)j * D];
     for (int d = 1; d < D; ++d) acc = fmaf(c[d], m->w2[(size_t)j * D + d], acc);
-    float t = h[j] * h[j];
-    float s = 1.0f - t;
+    float s = fmaf(-h[j], h[j], 1.0f); /* tanh' = 1 - h^2, one rounding (fused, as Paddle's GPU tanh_grad) */
     dz[j] = acc * s;
   }
-  for (int k = 0; k < D; ++k) {
-    float acc = dz[0] * m->w1[(size_t)k * H];
-    for (int j = 1; j < H; ++j) acc = fmaf(dz[j], m->w1[(size_t)k * H + j], acc);
-    dy[k] = acc * pre_act_grad(m->pre, y[k]);
-  }
+  for (int k = 0; k < D; ++k)
+    dy[k] = chain2_dot(dz, m->w1 + (size_t)k * H, 1, H) * pre_act_grad(m->pre, y[k]);
   if (gw1)
     for (int k = 0; k < D; ++k)
       for (int j = 0; j < H; ++j) gw1[(size_t)k * H + j] += u[k] * dz[j];
@@ -781,17 +787,13 @@ static void mlp_eval_diag_jac(const orc_mlp_t *m, const float *y, float *g, floa
   const int D = m->d, H = m->h;
   float h[ORC_MAX_H];
   orc_mlp_eval(m, y, g, h);
+  float sw[ORC_MAX_H];
   for (int d = 0; d < D; ++d) {
-    float acc = 0.0f;
     for (int j = 0; j < H; ++j) {
-      float s = 1.0f - h[j] * h[j];
-      float w = s * m->w1[(size_t)d * H + j];
-      if (j == 0)
-        acc = w * m->w2[d];
-      else
-        acc = fmaf(w, m->w2[(size_t)j * D + d], acc);
+      float s = fmaf(-h[j], h[j], 1.0f);
+      sw[j] = s * m->w1[(size_t)d * H + j];
     }
-    gp[d] = acc * pre_act_grad(m->pre, y[d]);
+    gp[d] = chain2_dot(sw, m->w2 + d, D, H) * pre_act_grad(m->pre, y[d]);
   }
 }
 

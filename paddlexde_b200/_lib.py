@@ -55,6 +55,7 @@ _EXPORTS = {
     "xde_launch_count": (C.c_ulonglong, []),
     "xde_default_ctrl_opts": (None, [C.POINTER(CtrlOptsC)]),
     "xde_probe_ffma_f32": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "xde_probe_ffma2_f32": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "xde_dopri5_mlp_f32": (C.c_int, [C.POINTER(MlpFieldC), C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                      C.POINTER(CtrlOptsC), C.c_int32, C.c_void_p, C.c_void_p,
                                      C.POINTER(AttemptLogC), C.c_void_p]),

@@ -15,10 +15,14 @@
 //     state: since it does not feed back, its value is sum_i W_i * k_i^theta with scalar weights W_i
 //     that are known when an attempt starts (dt*c_sol_i, or the dense-output polynomial weights
 //     when the attempt reaches the segment end).  Each round a lane stores the (h_j, dz_j) of its
-//     evaluation as one column of a per-warp shared-memory tile [H][32] and publishes
-//     (W*u, W, W*a); then the warp TRANSPOSES roles: lane l owns hidden units l and l+32 and folds
-//     all 32 columns into lane-private accumulators (5 FMAs per unit and trajectory).  No shuffles,
-//     no atomics in the loop; tile rows are padded to 33 so both phases are bank-conflict free.
+//     evaluation as one column of a per-warp shared-memory tile [H/2][32] of float4
+//     (h_j, h_j+1, dz_j, dz_j+1) and publishes (W*u, W, W*a); then the warp TRANSPOSES roles: lane l
+//     owns the hidden-unit pair (2l, 2l+1) and folds all 32 columns into lane-private accumulators
+//     (5 packed FFMA2 per pair and trajectory).  No shuffles, no atomics in the loop; tile rows are
+//     padded to 33 so both phases are bank-conflict free.
+//   * The field + VJP is evaluated two hidden units at a time with Blackwell's packed fp32
+//     instructions (FFMA2/FMUL2/FADD2, xde_common.cuh): the kernel is issue-bound, and a packed
+//     instruction does two IEEE operations per issue slot.
 //   * A rejected attempt has already been folded in.  The owning lane then spends one extra block
 //     of six evaluations (REPLAY) re-evaluating stages 1..5 of the failed attempt with weights -W_i
 //     and the start point with (W_0' - W_0) for the shrunk step; the other lanes keep working.
@@ -34,7 +38,7 @@ namespace xde {
 
 constexpr int kAdjThreads = 96;  // 3 warps: 5 CTAs (15 warps) per SM fit the per-warp tiles for H = 50
 constexpr int kAdjWarps = kAdjThreads / 32;
-constexpr int kTileStride = 33;  // float2 elements per hidden-unit row (32 lanes + 1 pad)
+constexpr int kTileStride = 33;  // float4 elements per hidden-unit-pair row (32 lanes + 1 pad)
 
 struct AdjParams {
   xde_mlp_field_t field;
@@ -66,7 +70,7 @@ struct AdjCoef {  // per-lane fold coefficients: {W*u[0..D), W, W*a[0..D)} padde
 
 template <int D, int HPL>
 struct AdjSmem {
-  static __host__ __device__ size_t tile_floats(int H) { return (((size_t)2 * H * kTileStride + 3) / 4) * 4; }
+  static __host__ __device__ size_t tile_floats(int H) { return (size_t)4 * SmallRec<D>::pairs(H) * kTileStride; }
   static __host__ __device__ size_t warp_floats(int H) { return tile_floats(H) + 32 * AdjCoef<D>::STRIDE; }
   static __host__ __device__ size_t bytes(int H, int T) {
     size_t fl = SmallRec<D>::floats(H) + (size_t)((T + 3) / 4) * 4 + kAdjWarps * warp_floats(H);
@@ -77,9 +81,10 @@ struct AdjSmem {
 };
 
 template <int D, int HPL, int PRE>
-__global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 2) ? 5 : 1) dopri5_adj_kernel(const AdjParams p) {
+__global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? 5 : 1) dopri5_adj_kernel(const AdjParams p) {
   constexpr int C = 2 * D;                 // state components per trajectory: y then a
-  constexpr int NTH = (2 * D + 1) * HPL;   // lane-private theta accumulators
+  constexpr int NTP = (2 * D + 1) * HPL;   // lane-private theta accumulator PAIRS (HPL unit pairs per lane)
+  constexpr int NTH = 2 * NTP;
   constexpr int REC = SmallRec<D>::REC;
   constexpr int CST = AdjCoef<D>::STRIDE;
 
@@ -94,7 +99,8 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 2) ? 5 : 1) dop
   float *sw = smem;
   float *st = sw + SmallRec<D>::floats(H);
   float *wbase = st + ((p.T + 3) / 4) * 4 + (size_t)warp * AdjSmem<D, HPL>::warp_floats(H);
-  float2 *tile = reinterpret_cast<float2 *>(wbase);                    // [H][33] of (h, dz)
+  float4 *tile = reinterpret_cast<float4 *>(wbase);                    // [H/2][33] of (h_j, h_j+1, dz_j, dz_j+1)
+  const int NP = SmallRec<D>::pairs(H);
   float *coef = wbase + AdjSmem<D, HPL>::tile_floats(H);               // [32][CST]
 
   load_small_field<D>(sw, p.field);
@@ -144,13 +150,12 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 2) ? 5 : 1) dop
   const xde_ctrl_opts_t o = p.o;
 
   // ---- hidden-unit role (fold phase): this lane's units j = lane + 32 q ----
-  double acc[NTH];  // committed parameter-gradient sums of this lane's units (fp64)
-  float Tt[NTH];    // fp32 running sums, flushed into acc every few rounds
+  double acc[NTH];  // committed parameter-gradient sums of this lane's units (fp64); [2*i + e]: pair i, unit e
+  f32x2 Tt[NTP];    // packed fp32 running sums, flushed into acc every few rounds
 #pragma unroll
-  for (int i = 0; i < NTH; ++i) {
-    acc[i] = 0.0;
-    Tt[i] = 0.0f;
-  }
+  for (int i = 0; i < NTH; ++i) acc[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NTP; ++i) Tt[i] = pk1(0.0f);
   double gb2acc[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) gb2acc[d] = 0.0;
@@ -300,46 +305,46 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 2) ? 5 : 1) dop
     const bool wr = live && !(ini && stage == 1);  // the probe must not overwrite the f0 column
     float fo[C];
     {
-      float u[D], accf[D], pdu[D];
+      float u[D];
+      f32x2 accf[D], pdu[D];
 #pragma unroll
       for (int k = 0; k < D; ++k) {
         u[k] = pre_act<PRE>(yin[k]);
-        accf[k] = 0.0f;
-        pdu[k] = 0.0f;
+        accf[k] = pk1(0.0f);
+        pdu[k] = pk1(0.0f);
       }
 #pragma unroll 2
-      for (int j = 0; j < H; ++j) {
-        float rec[REC];
-        const float4 *r4 = reinterpret_cast<const float4 *>(sw + j * REC);
+      for (int jp = 0; jp < NP; ++jp) {
+        f32x2 w1p[D], b1p, w2p[D];
+        read_pair_rec<D>(sw, jp, w1p, b1p, w2p);
+        f32x2 z = first_layer_seed<D>(u[0], w1p[0]);
 #pragma unroll
-        for (int q = 0; q < REC / 4; ++q) {
-          const float4 v = r4[q];
-          rec[4 * q] = v.x;
-          rec[4 * q + 1] = v.y;
-          rec[4 * q + 2] = v.z;
-          rec[4 * q + 3] = v.w;
+        for (int k = 1; k < D; ++k) z = fma2(pk1(u[k]), w1p[k], z);
+        const f32x2 h = tanh_rat2(add2(z, b1p));
+        f32x2 dh = mul2(pk1(yin[D]), w2p[0]);
+#pragma unroll
+        for (int d = 1; d < D; ++d) dh = fma2(pk1(yin[D + d]), w2p[d], dh);
+        const f32x2 sg = one_minus_sq2(h);
+        const f32x2 dz = mul2(dh, sg);
+#pragma unroll
+        for (int d = 0; d < D; ++d) accf[d] = fma2(h, w2p[d], accf[d]);
+#pragma unroll
+        for (int k = 0; k < D; ++k) pdu[k] = fma2(dz, w1p[k], pdu[k]);
+        if (wr) {
+          float h0, h1, z0, z1;
+          upk(h, h0, h1);
+          upk(dz, z0, z1);
+          tile[jp * kTileStride + lane] = make_float4(h0, h1, z0, z1);
         }
-        float z = u[0] * rec[0];
-#pragma unroll
-        for (int k = 1; k < D; ++k) z = fmaf(u[k], rec[k], z);
-        const float h = tanh_rat(z + rec[D]);
-        float dh = yin[D] * rec[D + 1];
-#pragma unroll
-        for (int d = 1; d < D; ++d) dh = fmaf(yin[D + d], rec[D + 1 + d], dh);
-        const float hh = h * h;
-        const float sg = 1.0f - hh;
-        const float dz = dh * sg;
-#pragma unroll
-        for (int d = 0; d < D; ++d) accf[d] = fmaf(h, rec[D + 1 + d], accf[d]);
-#pragma unroll
-        for (int k = 0; k < D; ++k) pdu[k] = fmaf(dz, rec[k], pdu[k]);  // first term: fma(.,.,0) == product
-        if (wr) tile[j * kTileStride + lane] = make_float2(h, dz);
       }
       // solver-time dynamics: dy/ds = tsign * f ; da/ds = -tsign * vjp_y(a)
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        fo[d] = tsign * (accf[d] + sw[H * REC + d]);
-        fo[D + d] = (-tsign) * (pdu[d] * pre_act_grad<PRE>(yin[d]));
+        float fe, fod, ue, uo;
+        upk(accf[d], fe, fod);
+        upk(pdu[d], ue, uo);
+        fo[d] = tsign * ((fe + fod) + sw[NP * REC + d]);
+        fo[D + d] = (-tsign) * ((ue + uo) * pre_act_grad<PRE>(yin[d]));
       }
     }
 
@@ -552,15 +557,16 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 2) ? 5 : 1) dop
           }
 #pragma unroll
           for (int q = 0; q < HPL; ++q) {
-            const int j = lane + 32 * q;
-            if (j < H) {
-              const float2 hv = tile[j * kTileStride + b];
+            const int jp = lane + 32 * q;
+            if (jp < NP) {
+              const float4 hv = tile[jp * kTileStride + b];
+              const f32x2 hp = pk(hv.x, hv.y), dzp = pk(hv.z, hv.w);
 #pragma unroll
-              for (int k = 0; k < D; ++k) Tt[k * HPL + q] = fmaf(cb[k], hv.y, Tt[k * HPL + q]);
-              Tt[D * HPL + q] = fmaf(cb[D], hv.y, Tt[D * HPL + q]);
+              for (int k = 0; k < D; ++k) Tt[q * (2 * D + 1) + k] = fma2(pk1(cb[k]), dzp, Tt[q * (2 * D + 1) + k]);
+              Tt[q * (2 * D + 1) + D] = fma2(pk1(cb[D]), dzp, Tt[q * (2 * D + 1) + D]);
 #pragma unroll
               for (int d = 0; d < D; ++d)
-                Tt[(D + 1) * HPL + q * D + d] = fmaf(cb[D + 1 + d], hv.x, Tt[(D + 1) * HPL + q * D + d]);
+                Tt[q * (2 * D + 1) + D + 1 + d] = fma2(pk1(cb[D + 1 + d]), hp, Tt[q * (2 * D + 1) + D + 1 + d]);
             }
           }
         }
@@ -568,9 +574,12 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 2) ? 5 : 1) dop
         if (++since_flush >= 8) {
           since_flush = 0;
 #pragma unroll
-          for (int i = 0; i < NTH; ++i) {
-            acc[i] += (double)Tt[i];
-            Tt[i] = 0.0f;
+          for (int i = 0; i < NTP; ++i) {
+            float e0, e1;
+            upk(Tt[i], e0, e1);
+            acc[2 * i] += (double)e0;
+            acc[2 * i + 1] += (double)e1;
+            Tt[i] = pk1(0.0f);
           }
         }
       }
@@ -579,7 +588,12 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 2) ? 5 : 1) dop
 
   // ================= epilogue: parameter gradients and stats =================
 #pragma unroll
-  for (int i = 0; i < NTH; ++i) acc[i] += (double)Tt[i];
+  for (int i = 0; i < NTP; ++i) {
+    float e0, e1;
+    upk(Tt[i], e0, e1);
+    acc[2 * i] += (double)e0;
+    acc[2 * i + 1] += (double)e1;
+  }
   __syncthreads();  // every warp is done with its tile: reuse shared memory as the CTA reduction buffer
   double *red = reinterpret_cast<double *>(smem);
   const int P = 2 * D * H + H + D;
@@ -587,13 +601,17 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 2) ? 5 : 1) dop
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < HPL; ++q) {
-    const int j = lane + 32 * q;
-    if (j < H) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) atomicAdd(&red[k * H + j], acc[k * HPL + q]);
-      atomicAdd(&red[D * H + j], acc[D * HPL + q]);
+    for (int e = 0; e < 2; ++e) {
+      const int j = 2 * (lane + 32 * q) + e;  // hidden unit of accumulator half e of pair q
+      if (j < H) {
+        const int base = q * (2 * D + 1);
 #pragma unroll
-      for (int d = 0; d < D; ++d) atomicAdd(&red[D * H + H + j * D + d], acc[(D + 1) * HPL + q * D + d]);
+        for (int k = 0; k < D; ++k) atomicAdd(&red[k * H + j], acc[2 * (base + k) + e]);
+        atomicAdd(&red[D * H + j], acc[2 * (base + D) + e]);
+#pragma unroll
+        for (int d = 0; d < D; ++d) atomicAdd(&red[D * H + H + j * D + d], acc[2 * (base + D + 1 + d) + e]);
+      }
     }
   }
 #pragma unroll
@@ -671,10 +689,9 @@ static int adj_pre(const AdjParams &p, cudaStream_t s) {
 template <int D>
 static int adj_hpl(const AdjParams &p, cudaStream_t s) {
   const int H = p.field.h;
-  if (H <= 32) return adj_pre<D, 1>(p, s);
-  if (H <= 64) return adj_pre<D, 2>(p, s);
+  if (H <= 64) return adj_pre<D, 1>(p, s);  // HPL = hidden-unit PAIRS per lane in the fold phase
   if constexpr (D <= 2) {
-    if (H <= 128) return adj_pre<D, 4>(p, s);
+    if (H <= 128) return adj_pre<D, 2>(p, s);
   }
   set_last_error("adjoint: hidden width H=%d has no fused kernel for D=%d (H <= 64; H <= 128 for D <= 2)", H, D);
   return XDE_E_UNSUPPORTED_FIELD;

@@ -83,30 +83,36 @@ template <int D, int PRE>
 __device__ __forceinline__ void mlp_eval_diag_small(const float *__restrict__ sw, int H, const float (&y)[D],
                                                     float (&g)[D], float (&gp)[D]) {
   constexpr int REC = SmallRec<D>::REC;
-  float u[D], acc[D], jac[D];
+  const int NP = SmallRec<D>::pairs(H);
+  float u[D];
+  f32x2 acc[D], jac[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     u[k] = pre_act<PRE>(y[k]);
-    acc[k] = 0.0f;
-    jac[k] = 0.0f;
+    acc[k] = pk1(0.0f);
+    jac[k] = pk1(0.0f);
   }
-  for (int j = 0; j < H; ++j) {
-    const float *rec = sw + j * REC;
-    float z = u[0] * rec[0];
+  for (int jp = 0; jp < NP; ++jp) {
+    f32x2 w1p[D], b1p, w2p[D];
+    read_pair_rec<D>(sw, jp, w1p, b1p, w2p);
+    f32x2 z = first_layer_seed<D>(u[0], w1p[0]);
 #pragma unroll
-    for (int k = 1; k < D; ++k) z = fmaf(u[k], rec[k], z);
-    const float h = tanh_rat(z + rec[D]);
-    const float s = 1.0f - h * h;
+    for (int k = 1; k < D; ++k) z = fma2(pk1(u[k]), w1p[k], z);
+    const f32x2 h = tanh_rat2(add2(z, b1p));
+    const f32x2 s = one_minus_sq2(h);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      acc[d] = fmaf(h, rec[D + 1 + d], acc[d]);
-      jac[d] = fmaf(s * rec[d], rec[D + 1 + d], jac[d]);
+      acc[d] = fma2(h, w2p[d], acc[d]);
+      jac[d] = fma2(mul2(s, w1p[d]), w2p[d], jac[d]);
     }
   }
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    g[d] = acc[d] + sw[H * REC + d];
-    gp[d] = jac[d] * pre_act_grad<PRE>(y[d]);
+    float e, o;
+    upk(acc[d], e, o);
+    g[d] = (e + o) + sw[NP * REC + d];
+    upk(jac[d], e, o);
+    gp[d] = (e + o) * pre_act_grad<PRE>(y[d]);
   }
 }
 

@@ -47,7 +47,42 @@ __global__ void __launch_bounds__(512) ffma_probe_kernel(float *sink, int iters,
   if (s == 123456.789f) sink[0] = s;  // never true for the probe's operands; defeats dead-code removal
 }
 
+// The same with Blackwell's packed FFMA2 (fma.rn.f32x2): two IEEE fp32 FMAs per lane and instruction.
+__global__ void __launch_bounds__(512) ffma2_probe_kernel(float *sink, int iters, float x, float y) {
+  unsigned long long a[8];
+  const float2 xv = make_float2(x, x), yv = make_float2(y, y);
+  const unsigned long long xx = *reinterpret_cast<const unsigned long long *>(&xv);
+  const unsigned long long yy = *reinterpret_cast<const unsigned long long *>(&yv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 v = make_float2((float)(threadIdx.x + i), (float)(threadIdx.x + 2 * i));
+    a[i] = *reinterpret_cast<const unsigned long long *>(&v);
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a[i]) : "l"(a[i]), "l"(xx), "l"(yy));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 v = *reinterpret_cast<const float2 *>(&a[i]);
+    s += v.x + v.y;
+  }
+  if (s == 123456.789f) sink[0] = s;
+}
+
 }  // namespace xde
+
+extern "C" XDE_EXPORT int xde_probe_ffma2_f32(int32_t iters, float *sink, int64_t *n_flops_host, void *stream) {
+  using namespace xde;
+  XDE_REQUIRE(iters > 0 && sink && n_flops_host, XDE_E_BAD_ARG, "null argument");
+  const int grid = sm_count() * 4;
+  ffma2_probe_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(sink, iters, 0.999f, 0.001f);
+  count_launch();
+  XDE_CUDA_CHECK(cudaGetLastError());
+  *n_flops_host = (int64_t)grid * 512 * (int64_t)iters * 8 * 4;
+  return XDE_OK;
+}
 
 extern "C" XDE_EXPORT int xde_probe_ffma_f32(int32_t iters, float *sink, int64_t *n_flops_host, void *stream) {
   using namespace xde;
