@@ -1,0 +1,358 @@
+// xde_tile.cu -- fixed-grid steppers for LARGE states (D = 32 / 64, H = 64 / 128 / 256): cfg3 (ensemble
+// RK4, MLP 64-256-64) and cfg4 (Euler-Maruyama, two 32-64-32 nets).
+//   * odeint(..., solver=Euler|RK4): FixedSolver.integrate (solver/base_fixed_solver.py:103-144),
+//     Euler.step (fixed_solver/euler.py:7-11), RK4.step = 3/8 rule (base_fixed_solver.py:166-197);
+//   * sdeint(..., solver=Euler): y1 = y0 + f*dt + g*dW with caller-supplied dW (xde/base_sde.py:44-61).
+//
+// Design.  At these sizes one trajectory no longer fits a thread, and the field is GEMM-shaped:
+//   Z[TM x H] = U[TM x D] W1[D x H],  F[TM x D] = tanh(Z + b1)[TM x H] W2[H x D].
+// A CTA (256 threads) keeps BOTH weight matrices resident in shared memory for the whole solve
+// (64-256-64: 128 KB) and integrates tiles of TM trajectories over the entire time grid; state and
+// RK stages live in registers, only the stage input U and the hidden activations pass through
+// shared memory (k-major, so every operand fetch is a conflict-free LDS.128/LDS.64).  The GEMMs are
+// register-tiled FP32 with Blackwell's packed FFMA2 (two IEEE FMAs per issue slot): layer 1 gives
+// each thread an R1 x C1 block of Z, layer 2 splits the hidden axis between the two half-warps
+// (even / odd hidden units -- exactly the two-chain reduction order of the arithmetic
+// specification) and joins them with one shuffle.  Results are bit-identical to the oracle.
+// Tensor cores (tcgen05, 3xTF32) are the next step for this kernel (DESIGN.md "Next"): they
+// cannot be bit-exact against an fp32 oracle, so this FP32 path is also their reference.
+#include "xde_common.cuh"
+
+namespace xde {
+
+constexpr int kTileThreads = 256;
+
+struct TileParams {
+  xde_mlp_field_t f, g;
+  const float *y0, *t_span, *dW;
+  float *out;
+  long long B;
+  int T, stride, n_out;
+};
+
+__device__ __forceinline__ float pre_rt(int pre, float y) {
+  if (pre == XDE_PRE_CUBE) return (y * y) * y;
+  if (pre == XDE_PRE_SQUARE) return y * y;
+  return y;
+}
+
+template <int D, int H, int TM, int R1, int C1, int R2, int C2>
+struct TileGeom {
+  static constexpr int NRG1 = TM / R1, NCG1 = H / C1;
+  static constexpr int NRG2 = TM / R2, NCG2 = D / C2;
+  static_assert(NRG1 * NCG1 == kTileThreads, "layer-1 thread grid must cover the CTA");
+  static_assert(NRG2 * NCG2 * 2 == kTileThreads, "layer-2 thread grid (x2 hidden parities) must cover the CTA");
+  static_assert(R1 == 4 && R2 == 2 && C1 % 4 == 0 && C2 % 4 == 0 && NRG2 % 16 == 0, "operand fetch widths");
+  static constexpr int net_floats = D * H + H * D + H + ((D + 3) / 4) * 4;
+  // sU (x2: drift / diffusion pre-activations), sH
+  static constexpr int act_floats = 2 * D * TM + H * TM;
+  static size_t bytes(int nets, int T) { return sizeof(float) * ((size_t)nets * net_floats + act_floats + ((T + 3) / 4) * 4); }
+};
+
+template <int D, int H>
+__device__ __forceinline__ void load_net(float *s, const xde_mlp_field_t &f) {
+  float *w1 = s, *w2 = s + D * H, *b1 = w2 + H * D, *b2 = b1 + H;
+  for (int i = threadIdx.x; i < D * H; i += blockDim.x) {
+    w1[i] = f.w1[i];
+    w2[i] = f.w2[i];
+  }
+  for (int i = threadIdx.x; i < H; i += blockDim.x) b1[i] = f.b1[i];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) b2[i] = f.b2[i];
+}
+
+// One field evaluation for the CTA's TM trajectories.  sU holds pre(y) k-major [D][TM]; the result
+// F[R2][C2] (rows rg2*R2.., columns cg2*C2..) is returned in registers, identical on both hidden
+// parities.  Two __syncthreads: the caller has synchronised after writing sU.
+template <int D, int H, int TM, int R1, int C1, int R2, int C2>
+__device__ __forceinline__ void tile_eval(const float *__restrict__ net, const float *__restrict__ sU,
+                                          float *__restrict__ sH, float (&F)[R2][C2]) {
+  using G = TileGeom<D, H, TM, R1, C1, R2, C2>;
+  const float *sW1 = net, *sW2 = net + D * H, *sb1 = sW2 + H * D, *sb2 = sb1 + H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- layer 1: Z = U W1, sequential-k fma chain per element ----
+  {
+    const int rg = tid % G::NRG1, cg = tid / G::NRG1;
+    f32x2 acc[R1][C1 / 2];
+#pragma unroll
+    for (int r = 0; r < R1; ++r)
+#pragma unroll
+      for (int c = 0; c < C1 / 2; ++c) acc[r][c] = pk1(0.0f);
+    const float4 *u4 = reinterpret_cast<const float4 *>(sU + rg * R1);
+    const float4 *w4 = reinterpret_cast<const float4 *>(sW1 + cg * C1);
+#pragma unroll 4
+    for (int k = 0; k < D; ++k) {
+      const float4 uv = u4[k * (TM / 4)];
+      const float ur[4] = {uv.x, uv.y, uv.z, uv.w};
+      f32x2 w[C1 / 2];
+#pragma unroll
+      for (int q = 0; q < C1 / 4; ++q) {
+        const float4 wv = w4[k * (H / 4) + q];
+        w[2 * q] = pk(wv.x, wv.y);
+        w[2 * q + 1] = pk(wv.z, wv.w);
+      }
+#pragma unroll
+      for (int r = 0; r < R1; ++r)
+#pragma unroll
+        for (int c = 0; c < C1 / 2; ++c) acc[r][c] = fma2(pk1(ur[r]), w[c], acc[r][c]);
+    }
+    // bias, tanh, transpose into sH[hidden][trajectory]
+#pragma unroll
+    for (int c = 0; c < C1 / 2; ++c) {
+      const int j = cg * C1 + 2 * c;
+      const f32x2 b = pk(sb1[j], sb1[j + 1]);
+      float h0[R1], h1[R1];
+#pragma unroll
+      for (int r = 0; r < R1; ++r) upk(tanh_rat2(add2(acc[r][c], b)), h0[r], h1[r]);
+      *reinterpret_cast<float4 *>(sH + j * TM + rg * R1) = make_float4(h0[0], h0[1], h0[2], h0[3]);
+      *reinterpret_cast<float4 *>(sH + (j + 1) * TM + rg * R1) = make_float4(h1[0], h1[1], h1[2], h1[3]);
+    }
+  }
+  __syncthreads();
+  // ---- layer 2: F = Hh W2; lanes 0-15 of a warp take the even hidden units, lanes 16-31 the odd ----
+  {
+    const int e = lane >> 4;
+    const int p = warp * 16 + (lane & 15);
+    const int rg2 = p % G::NRG2, cg2 = p / G::NRG2;
+    f32x2 acc[R2][C2 / 2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r)
+#pragma unroll
+      for (int c = 0; c < C2 / 2; ++c) acc[r][c] = pk1(0.0f);
+    const float2 *h2 = reinterpret_cast<const float2 *>(sH + rg2 * R2);
+    const float4 *w4 = reinterpret_cast<const float4 *>(sW2 + cg2 * C2);
+#pragma unroll 4
+    for (int j = e; j < H; j += 2) {
+      const float2 hv = h2[j * (TM / 2)];
+      f32x2 w[C2 / 2];
+#pragma unroll
+      for (int q = 0; q < C2 / 4; ++q) {
+        const float4 wv = w4[j * (D / 4) + q];
+        w[2 * q] = pk(wv.x, wv.y);
+        w[2 * q + 1] = pk(wv.z, wv.w);
+      }
+#pragma unroll
+      for (int c = 0; c < C2 / 2; ++c) {
+        acc[0][c] = fma2(pk1(hv.x), w[c], acc[0][c]);
+        acc[1][c] = fma2(pk1(hv.y), w[c], acc[1][c]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R2; ++r)
+#pragma unroll
+      for (int c = 0; c < C2 / 2; ++c) {
+        const f32x2 other = __shfl_xor_sync(XDE_FULL_MASK, acc[r][c], 16);
+        float s0, s1;
+        upk(add2(acc[r][c], other), s0, s1);  // even chain + odd chain (commutative: same bits on both halves)
+        F[r][2 * c] = s0 + sb2[cg2 * C2 + 2 * c];
+        F[r][2 * c + 1] = s1 + sb2[cg2 * C2 + 2 * c + 1];
+      }
+  }
+}
+
+// KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama
+template <int D, int H, int TM, int R1, int C1, int R2, int C2, int KIND>
+__global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileParams p) {
+  using G = TileGeom<D, H, TM, R1, C1, R2, C2>;
+  extern __shared__ __align__(16) float smem[];
+  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  float *netf = smem;
+  float *netg = smem + G::net_floats;  // only when NETS == 2
+  float *sU = smem + NETS * G::net_floats;
+  float *sUg = sU + D * TM;
+  float *sH = sUg + D * TM;
+  float *st = sH + H * TM;
+  load_net<D, H>(netf, p.f);
+  if (KIND == 2) load_net<D, H>(netg, p.g);
+  for (int i = threadIdx.x; i < p.T; i += blockDim.x) st[i] = p.t_span[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = lane >> 4;
+  const int pidx = warp * 16 + (lane & 15);
+  const int rg2 = pidx % G::NRG2, cg2 = pidx / G::NRG2;
+  const int c0 = cg2 * C2;
+  const float one_third = (float)(1.0 / 3.0);
+  const int pref = p.f.pre, preg = p.g.pre;
+  const long long n_tiles = (p.B + TM - 1) / TM;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long b0 = tile * TM + rg2 * R2;  // first of this thread's R2 trajectories
+    float y[R2][C2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      const long long b = b0 + r;
+      const bool ok = b < p.B;
+#pragma unroll
+      for (int q = 0; q < C2 / 4; ++q) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) v = *reinterpret_cast<const float4 *>(p.y0 + b * D + c0 + 4 * q);
+        y[r][4 * q] = v.x;
+        y[r][4 * q + 1] = v.y;
+        y[r][4 * q + 2] = v.z;
+        y[r][4 * q + 3] = v.w;
+        if (ok && r == e) *reinterpret_cast<float4 *>(p.out + b * (long long)p.n_out * D + c0 + 4 * q) = v;
+      }
+    }
+    // publish a stage input: the half-warp with parity e writes row e of its pair
+    auto put_u = [&](float *dst, int pre, const float (&v)[R2][C2]) {
+#pragma unroll
+      for (int c = 0; c < C2; ++c) dst[(c0 + c) * TM + rg2 * R2 + e] = pre_rt(pre, e ? v[1][c] : v[0][c]);
+    };
+    for (int i = 1; i < p.T; ++i) {
+      const float t0 = st[i - 1], t1 = st[i];
+      const float dt = t1 - t0;
+      float k1[R2][C2];
+      // no barrier needed before put_u: every warp has passed the layer-1/layer-2 barrier of the previous
+      // evaluation (nobody reads sU any more); the barrier below also fences the previous readers of sH
+      put_u(sU, pref, y);
+      if (KIND == 2) put_u(sUg, preg, y);
+      __syncthreads();
+      tile_eval<D, H, TM, R1, C1, R2, C2>(netf, sU, sH, k1);
+      if (KIND == 0) {
+#pragma unroll
+        for (int r = 0; r < R2; ++r)
+#pragma unroll
+          for (int c = 0; c < C2; ++c) y[r][c] = k1[r][c] * dt + y[r][c];
+      } else if (KIND == 1) {
+        float k2[R2][C2], k3[R2][C2], k4[R2][C2], yi[R2][C2];
+        const float dt13 = dt * one_third;
+#pragma unroll
+        for (int r = 0; r < R2; ++r)
+#pragma unroll
+          for (int c = 0; c < C2; ++c) yi[r][c] = k1[r][c] * dt13 + y[r][c];
+        put_u(sU, pref, yi);
+        __syncthreads();
+        tile_eval<D, H, TM, R1, C1, R2, C2>(netf, sU, sH, k2);
+#pragma unroll
+        for (int r = 0; r < R2; ++r)
+#pragma unroll
+          for (int c = 0; c < C2; ++c) yi[r][c] = (k1[r][c] - k2[r][c] * one_third) * dt + y[r][c];
+        put_u(sU, pref, yi);
+        __syncthreads();
+        tile_eval<D, H, TM, R1, C1, R2, C2>(netf, sU, sH, k3);
+#pragma unroll
+        for (int r = 0; r < R2; ++r)
+#pragma unroll
+          for (int c = 0; c < C2; ++c) yi[r][c] = ((k1[r][c] - k2[r][c]) + k3[r][c]) * dt + y[r][c];
+        put_u(sU, pref, yi);
+        __syncthreads();
+        tile_eval<D, H, TM, R1, C1, R2, C2>(netf, sU, sH, k4);
+#pragma unroll
+        for (int r = 0; r < R2; ++r)
+#pragma unroll
+          for (int c = 0; c < C2; ++c) {
+            const float a = k1[r][c] * dt + y[r][c];
+            const float bb = k2[r][c] * dt + y[r][c];
+            const float cc = k3[r][c] * dt + y[r][c];
+            const float dd = k4[r][c] * dt + y[r][c];
+            y[r][c] = (((a + 3.0f * bb) + 3.0f * cc) + dd) * 0.125f;
+          }
+      } else {
+        float g[R2][C2];
+        __syncthreads();  // sH is reused by the second network
+        tile_eval<D, H, TM, R1, C1, R2, C2>(netg, sUg, sH, g);
+#pragma unroll
+        for (int r = 0; r < R2; ++r) {
+          const long long b = b0 + r;
+          const bool ok = b < p.B;
+#pragma unroll
+          for (int q = 0; q < C2 / 4; ++q) {
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) wv = __ldg(reinterpret_cast<const float4 *>(p.dW + ((long long)(i - 1) * p.B + b) * D + c0 + 4 * q));
+            const float w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int z = 0; z < 4; ++z) {
+              const int c = 4 * q + z;
+              y[r][c] = (y[r][c] + k1[r][c] * dt) + g[r][c] * w[z];
+            }
+          }
+        }
+      }
+      // linear_interp at t == t1 is the identity (interpolation/functional/interp_fn.py:4-10)
+      if (i % p.stride == 0 || i == p.T - 1) {
+        const int row = (i == p.T - 1) ? p.n_out - 1 : i / p.stride;
+        const long long b = b0 + e;
+        if (b < p.B) {
+#pragma unroll
+          for (int q = 0; q < C2 / 4; ++q) {
+            const float4 v = e ? make_float4(y[1][4 * q], y[1][4 * q + 1], y[1][4 * q + 2], y[1][4 * q + 3])
+                               : make_float4(y[0][4 * q], y[0][4 * q + 1], y[0][4 * q + 2], y[0][4 * q + 3]);
+            *reinterpret_cast<float4 *>(p.out + (b * (long long)p.n_out + row) * D + c0 + 4 * q) = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int D, int H, int TM, int R1, int C1, int R2, int C2, int KIND>
+static int launch_tile(const TileParams &p, cudaStream_t s) {
+  using G = TileGeom<D, H, TM, R1, C1, R2, C2>;
+  const size_t smem = G::bytes(KIND == 2 ? 2 : 1, p.T);
+  XDE_REQUIRE(smem <= 227 * 1024, XDE_E_UNSUPPORTED_FIELD,
+              "tiled solver: weights + tiles + grid need %zu bytes of shared memory (> 227 KB)", smem);
+  auto kern = fixed_tile_kernel<D, H, TM, R1, C1, R2, C2, KIND>;
+  XDE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  XDE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  long long n_tiles = (p.B + TM - 1) / TM;
+  long long grid = (long long)sm_count() * per_sm;  // persistent: a whole number of CTAs per SM
+  if (grid > n_tiles) grid = n_tiles;
+  kern<<<(unsigned)grid, kTileThreads, smem, s>>>(p);
+  count_launch();
+  XDE_CUDA_CHECK(cudaGetLastError());
+  return XDE_OK;
+}
+
+template <int KIND>
+static int tile_dispatch(const TileParams &p, cudaStream_t s) {
+  const int D = p.f.d, H = p.f.h;
+  if (D == 64 && H == 256) return launch_tile<64, 256, 32, 4, 8, 2, 8, KIND>(p, s);
+  if (D == 64 && H == 128) return launch_tile<64, 128, 32, 4, 4, 2, 8, KIND>(p, s);
+  if (D == 64 && H == 64) return launch_tile<64, 64, 64, 4, 4, 2, 16, KIND>(p, s);
+  if (D == 32 && H == 256) return launch_tile<32, 256, 32, 4, 8, 2, 4, KIND>(p, s);
+  if (D == 32 && H == 128) return launch_tile<32, 128, 64, 4, 8, 2, 8, KIND>(p, s);
+  if (D == 32 && H == 64) return launch_tile<32, 64, 64, 4, 4, 2, 8, KIND>(p, s);
+  if (D == 16 && H == 64) return launch_tile<16, 64, 64, 4, 4, 2, 4, KIND>(p, s);
+  set_last_error("tiled solver: no kernel for D=%d H=%d (D in {16,32,64} x H in {64,128,256}; small states D<=8 any H)", D, H);
+  return XDE_E_UNSUPPORTED_FIELD;
+}
+
+bool tile_covers(int D) { return D >= 16; }
+
+int rk_fixed_tile(int method, const xde_mlp_field_t *f, const float *y0, long long B, const float *t_span,
+                  int T, int stride, float *out, cudaStream_t s) {
+  TileParams p{};
+  p.f = *f;
+  p.g = *f;
+  p.y0 = y0;
+  p.t_span = t_span;
+  p.out = out;
+  p.B = B;
+  p.T = T;
+  p.stride = stride;
+  p.n_out = (T - 1 + stride - 1) / stride + 1;
+  return method == XDE_FIXED_EULER ? tile_dispatch<0>(p, s) : tile_dispatch<1>(p, s);
+}
+
+int sde_tile(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const float *y0, long long B,
+             const float *t_span, int T, const float *dW, int stride, float *out, cudaStream_t s) {
+  XDE_REQUIRE(scheme == XDE_SDE_EM, XDE_E_UNSUPPORTED_FIELD,
+              "Milstein (an extension without a reference counterpart) is fused for small states (D <= 8) only");
+  XDE_REQUIRE(f->h == g->h, XDE_E_UNSUPPORTED_FIELD, "tiled sde: drift and diffusion must share the hidden width");
+  TileParams p{};
+  p.f = *f;
+  p.g = *g;
+  p.y0 = y0;
+  p.t_span = t_span;
+  p.dW = dW;
+  p.out = out;
+  p.B = B;
+  p.T = T;
+  p.stride = stride;
+  p.n_out = (T - 1 + stride - 1) / stride + 1;
+  return tile_dispatch<2>(p, s);
+}
+
+}  // namespace xde

@@ -322,6 +322,59 @@ def test_sde_supplied_increments_bit_exact(px, torch, oracle, scheme):
 
 
 # ------------------------------------------------------------------------------------------------
+# large states: the register-tiled FFMA2 kernels (cfg3: 64-256-64 RK4, cfg4: 32-64-32 Euler-Maruyama)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,h,B", [(64, 256, 100), (64, 128, 33), (64, 64, 130), (32, 256, 31), (32, 128, 65),
+                                   (32, 64, 200), (16, 64, 77)])
+@pytest.mark.parametrize("solver", ["Euler", "RK4"])
+def test_tiled_fixed_solvers_bit_exact(px, torch, oracle, solver, d, h, B):
+    field, om = both(px, oracle, fanin_weights(d, h, seed=d + h), "id" if d == 64 else "cube")
+    y0 = np.random.default_rng(d).uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, 11).astype(f32)
+    sol = px.odeint(field, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, getattr(px, solver))
+    ref = oracle.fixed_mlp(solver.lower(), om, y0, t)
+    assert tuple(sol.shape) == (B, t.size, d)
+    assert np.array_equal(sol.cpu().numpy(), ref)
+
+
+def test_tiled_cfg3_full_size_subset_and_stride(px, torch, oracle):
+    """cfg3 at the per-GPU BASELINE size (B = 2^17, D = 64, MLP 64-256-64, RK4, 100 steps, every 10th
+    point stored): trajectories are independent, so a random subset must equal the oracle bit for bit."""
+    d, h, B = 64, 256, 1 << 17
+    field, om = both(px, oracle, fanin_weights(d, h, seed=1), "id")
+    y0 = np.random.default_rng(1).uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, 101).astype(f32)
+    xde = px.xde.BaseODE(field, torch.from_numpy(y0).cuda().reshape(B, 1, d), t)
+    sol = px.RK4(xde=xde, y0=xde.y0, rtol=1e-7, atol=1e-9, out_stride=10).integrate(t)
+    assert tuple(sol.shape) == (B, 11, d)
+    idx = np.random.default_rng(3).choice(B, 192, replace=False)
+    ref = oracle.fixed_mlp("rk4", om, y0[idx], t)[:, ::10]
+    assert np.array_equal(sol[torch.from_numpy(idx).cuda()].cpu().numpy(), ref)
+    assert np.isfinite(sol.cpu().numpy()).all()
+
+
+def test_tiled_sde_cfg4_shapes(px, torch, oracle):
+    """cfg4: D = 32, two 32-64-32 nets (drift y**3, diffusion y**2), 16 steps, supplied increments."""
+    d, h, B = 32, 64, 1000
+    f, of = both(px, oracle, fanin_weights(d, h, seed=2), "cube")
+    g, og = both(px, oracle, fanin_weights(d, h, seed=3), "square")
+    rng = np.random.default_rng(2)
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, 17).astype(f32)
+    dW = (np.sqrt(1 / 16) * rng.standard_normal((16, B, d))).astype(f32)
+    sol = px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler,
+                    options={"bm_increments": torch.from_numpy(dW).cuda()})
+    ref = oracle.sde_mlp("em", of, og, y0, t, dW)
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    with pytest.raises(px.UnsupportedFieldError):  # Milstein is an extension, fused for small states only
+        px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler,
+                  options={"bm_increments": torch.from_numpy(dW).cuda(), "scheme": "milstein"})
+    with pytest.raises(px.UnsupportedFieldError):  # no kernel for this shape: loud, no fallback
+        f48, _ = both(px, oracle, fanin_weights(48, 64), "id")
+        px.odeint(f48, torch.zeros(4, 1, 48).cuda(), t, px.RK4)
+
+
+# ------------------------------------------------------------------------------------------------
 # history gather / DDE
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["linear", "cubic"])
