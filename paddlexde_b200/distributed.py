@@ -1,0 +1,52 @@
+"""Batch sharding across GPUs.
+
+Trajectories are independent given the field parameters, so the path shards by batch: one process per
+GPU, contiguous rows of ``y0`` (and of ``dW[:, rows]``, ``his[rows]``) per rank, parameters replicated.
+Forward / SDE / gather need no communication.  The ONLY collective is one all-reduce (sum) of the
+adjoint parameter-gradient vector per backward -- the counterpart of the DataParallel gradient
+all-reduce in the reference's example trainer (example/D3STN/train_dde.py:201-202,454-456)."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(n: int, rank: int, world: int):
+    """[start, stop) of the contiguous rows owned by `rank`; the first n % world ranks get one extra row."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def init_from_env(backend: str | None = None):
+    """One process per GPU, launched by torchrun: returns (rank, world, local_rank)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+    return rank, world, local
+
+
+def grad_allreduce(group=None):
+    """The hook for ``options={"grad_allreduce": ...}`` of odeint_adjoint: sums the flat parameter-gradient
+    vector over the ranks in place (NCCL over NVLink on GPUs; a no-op for a single process)."""
+
+    def hook(g: torch.Tensor):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+        return g
+
+    return hook

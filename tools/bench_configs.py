@@ -1,0 +1,82 @@
+"""Secondary measurements (not the bench.py line): cfg3 / cfg4 / cfg5 kernels, device-resident, CUDA events.
+Prints one JSON object per config with throughput and the roofline fractions of SURVEY 8(d)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import paddlexde_b200 as px
+from paddlexde_b200.xde.base_dde import history_gather, history_gather_bwd
+from tests.problems import fanin_weights
+
+HBM = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+FFMA = 72.3  # TFLOP/s, measured by tools/probe_fp32.py on this pool
+
+
+def timeit(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def cfg3(B=1 << 17):
+    d, h = 64, 256
+    field = px.MLPField(*fanin_weights(d, h, seed=1), pre="id")
+    y0 = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, (B, 1, d)).astype(np.float32)).cuda()
+    t = np.linspace(0, 1, 101).astype(np.float32)
+    xde = px.xde.BaseODE(field, y0, t)
+    s = px.RK4(xde=xde, y0=y0, rtol=1e-7, atol=1e-9, out_stride=10)
+    ms = timeit(lambda: s.integrate(t))
+    steps = B * 100
+    flops = steps * 16 * d * h
+    byts = steps * 8 * d + B * 11 * d * 4
+    return {"config": "cfg3 rk4 64-256-64", "B": B, "ms": ms, "traj_steps_per_s": steps / ms * 1e3,
+            "tflops_algorithmic": flops / ms / 1e9, "frac_ffma_peak": flops / ms / 1e9 / FFMA,
+            "hbm_gbs_algorithmic": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / HBM}
+
+
+def cfg4(B=1 << 21):
+    d, h = 32, 64
+    f = px.MLPField(*fanin_weights(d, h, seed=2), pre="cube")
+    g = px.MLPField(*fanin_weights(d, h, seed=3), pre="square")
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    y0 = (torch.rand((B, 1, d), device="cuda", generator=gen) * 2 - 1)
+    t = np.linspace(0, 1, 17).astype(np.float32)
+    dW = torch.randn((16, B, d), device="cuda", generator=gen) * 0.25
+    xde = px.xde.BaseSDE(f, g, y0, t, bm_increments=dW)
+    s = px.Euler(xde=xde, y0=y0, rtol=1e-7, atol=1e-9, out_stride=16)
+    ms = timeit(lambda: s.integrate(t))
+    steps = B * 16
+    flops = steps * (4 * d * h * 2)
+    byts = steps * 4 * d + B * 2 * d * 4 + B * d * 4  # dW read per step + y0 in + 2 rows out
+    return {"config": "cfg4 sde-EM 2x(32-64-32)", "B": B, "ms": ms, "traj_steps_per_s": steps / ms * 1e3,
+            "tflops_algorithmic": flops / ms / 1e9, "frac_ffma_peak": flops / ms / 1e9 / FFMA,
+            "hbm_gbs_algorithmic": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / HBM,
+            "note": "B=2^21 (half of cfg4's 2^22: the full dW table is 8 GiB; fits, but halves the run time)"}
+
+
+def cfg5(Bh=1024, kind="cubic"):
+    rng = np.random.default_rng(5)
+    his = torch.from_numpy(rng.uniform(-1, 1, (Bh, 307, 288, 3)).astype(np.float32)).cuda()
+    span = torch.arange(288, dtype=torch.float32, device="cuda")
+    lags = torch.from_numpy((np.arange(12) + rng.uniform(0, 1, 12)).astype(np.float32)).cuda()
+    ms = timeit(lambda: history_gather(lags, his, span, kind))
+    n = Bh * 307 * 12 * 3
+    v, dv = history_gather(lags, his, span, kind)
+    gy = torch.randn_like(v)
+    ms_b = timeit(lambda: history_gather_bwd(gy, dv))
+    return {"config": f"cfg5 history gather {kind}", "B": Bh, "ms_fwd": ms, "ms_bwd": ms_b, "elements": n,
+            "hbm_gbs_algorithmic_fwd": n * 20 / ms / 1e6, "frac_hbm_fwd": n * 20 / ms / 1e6 / HBM,
+            "hbm_gbs_algorithmic_bwd": n * 8 / ms_b / 1e6, "frac_hbm_bwd": n * 8 / ms_b / 1e6 / HBM,
+            "note": "his is 1.06 GB at B=1024 but only 12 of 288 time rows are touched: 20 B/element algorithmic"}
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["cfg3", "cfg4", "cfg5"]
+    for w in which:
+        print(json.dumps(globals()[w]()), flush=True)
