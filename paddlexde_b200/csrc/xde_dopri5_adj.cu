@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? 5 : 1) dop
     s_status = 0;
   }
   for (int i = lane; i < 32 * CST; i += 32) coef[i] = 0.0f;
+  for (int i = lane; i < NP * kTileStride; i += 32) tile[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
   const xde_ctrl_opts_t o = p.o;
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? 5 : 1) dop
   unsigned n_att = 0, n_acc = 0, n_fe = 0;
   int status = 0;
   int since_flush = 0;
+  bool col_ok = true;  // this lane's tile column holds finite values only (zero-weight columns may be folded)
 
   // theta weight of the evaluation at stage `stg` (0..6) of an attempt (dtv, finv, xv); sign folded in
   auto theta_w = [&](int stg, float dtv, bool finv, float xv) -> float {
@@ -200,7 +202,10 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? 5 : 1) dop
       sy += (double)(v[e] * v[e]);
       sa += (double)(v[D + e] * v[D + e]);
     }
-    const float ny = rms_from_sumsq(sy, (double)D), na = rms_from_sumsq(sa, (double)D);
+    // mean over D: for a power of two the reciprocal multiply is the exact quotient (no fp64 division)
+    constexpr bool kPow2 = (D & (D - 1)) == 0;
+    const float ny = kPow2 ? (float)sqrt(sy * (1.0 / D)) : rms_from_sumsq(sy, (double)D);
+    const float na = kPow2 ? (float)sqrt(sa * (1.0 / D)) : rms_from_sumsq(sa, (double)D);
     float best = 0.0f;
     if (ny > best) best = ny;
     if (na > best) best = na;
@@ -346,6 +351,13 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? 5 : 1) dop
         fo[d] = tsign * ((fe + fod) + sw[NP * REC + d]);
         fo[D + d] = (-tsign) * ((ue + uo) * pre_act_grad<PRE>(yin[d]));
       }
+    }
+
+    if (wr) {
+      bool finite = true;
+#pragma unroll
+      for (int e2 = 0; e2 < C; ++e2) finite = finite && (fabsf(fo[e2]) < INFINITY);
+      col_ok = finite;  // fo finite => every (h, dz) of the column is finite
     }
 
     // ================= (4) controller / state machine =================
@@ -539,12 +551,9 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? 5 : 1) dop
           c[d] = cu[d];
           c[D + 1 + d] = ca[d];
         }
-        c[D] = wacc;
+        c[D] = fold ? wacc : 0.0f;
         __syncwarp();
-        unsigned m = fm;
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
+        auto fold_column = [&](int b) {
           float cb[CST];
           const float4 *c4 = reinterpret_cast<const float4 *>(coef + b * CST);
 #pragma unroll
@@ -568,6 +577,19 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? 5 : 1) dop
               for (int d = 0; d < D; ++d)
                 Tt[q * (2 * D + 1) + D + 1 + d] = fma2(pk1(cb[D + 1 + d]), hp, Tt[q * (2 * D + 1) + D + 1 + d]);
             }
+          }
+        };
+        // Fast path: every column is finite, so columns with zero weight contribute exactly +0 and all 32
+        // can be folded by straight-line code (compile-time shared-memory offsets, no mask arithmetic).
+        if (__all_sync(XDE_FULL_MASK, col_ok)) {
+#pragma unroll
+          for (int b = 0; b < 32; ++b) fold_column(b);
+        } else {
+          unsigned m = fm;
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            fold_column(b);
           }
         }
         __syncwarp();
@@ -729,7 +751,7 @@ extern "C" XDE_EXPORT int xde_dopri5_mlp_adjoint_f32(const xde_mlp_field_t *fiel
   p.log_records = log ? log->records : nullptr;
   p.log_counts = log ? log->counts : nullptr;
   p.log_cap = log ? log->cap : 0;
-  XDE_CUDA_CHECK(cudaMallocAsync(&p.gacc, sizeof(double) * P, s));
+  XDE_CUDA_CHECK(scratch_alloc((void **)&p.gacc, sizeof(double) * P, s));
   XDE_CUDA_CHECK(cudaMemsetAsync(p.gacc, 0, sizeof(double) * P, s));
   if (stats) XDE_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(xde_stats_t), s));
   int rc = XDE_E_UNSUPPORTED_FIELD;

@@ -19,6 +19,26 @@ void set_last_error(const char *fmt, ...) {
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Stream-ordered scratch (fp64 reduction buffers).  The default memory pool returns its memory to the
+// OS at every synchronisation unless a release threshold is set, which makes each call pay a fresh
+// driver allocation (~1 ms): keep the pool warm.  Set once per device; idempotent and thread-safe.
+cudaError_t scratch_alloc(void **ptr, size_t bytes, cudaStream_t s) {
+  static std::atomic<unsigned long long> configured{0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_relaxed) & bit)) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = 64ull << 20;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured.fetch_or(bit, std::memory_order_relaxed);
+  }
+  return cudaMallocAsync(ptr, bytes, s);
+}
+
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
