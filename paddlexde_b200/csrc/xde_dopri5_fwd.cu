@@ -379,6 +379,10 @@ static int dispatch_pre(const FwdParams &p, cudaStream_t s) {
   return XDE_E_BAD_ARG;
 }
 
+int dopri5_fwd_batch(const xde_mlp_field_t *field, const float *y0, long long B, const float *t_span, int T,
+                     const xde_ctrl_opts_t *opts, float *out, xde_stats_t *stats, const xde_attempt_log_t *log,
+                     cudaStream_t s);  // xde_dopri5_batch.cu
+
 }  // namespace xde
 
 extern "C" XDE_EXPORT int xde_dopri5_mlp_f32(const xde_mlp_field_t *field, const float *y0, int64_t B,
@@ -388,9 +392,13 @@ extern "C" XDE_EXPORT int xde_dopri5_mlp_f32(const xde_mlp_field_t *field, const
   using namespace xde;
   XDE_REQUIRE(field && y0 && t_span && opts && out, XDE_E_BAD_ARG, "null argument");
   XDE_REQUIRE(B >= 1 && T >= 2, XDE_E_BAD_ARG, "need B >= 1 and T >= 2 (B=%lld T=%d)", (long long)B, T);
-  XDE_REQUIRE(controller == XDE_CTRL_TRAJECTORY, XDE_E_UNSUPPORTED_FIELD,
-              "controller=BATCH is not implemented on the device yet (use XDE_CTRL_TRAJECTORY)");
+  XDE_REQUIRE(controller == XDE_CTRL_TRAJECTORY || controller == XDE_CTRL_BATCH, XDE_E_BAD_ARG,
+              "unknown controller %d", controller);
   cudaStream_t s = (cudaStream_t)stream;
+  if (controller == XDE_CTRL_BATCH) {
+    if (stats) XDE_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(xde_stats_t), s));
+    return dopri5_fwd_batch(field, y0, B, t_span, T, opts, out, stats, log, s);
+  }
   // strict monotonicity of t_span is the caller's precondition (the shim checks its host copy);
   // the direction is read on the device so that this call never synchronises.
   FwdParams p{};

@@ -136,6 +136,47 @@ def test_dopri5_status_words(px, torch, oracle):
         solve_fwd(px, torch, f5, np.zeros((4, 5), f32), cfg2_tspan(4))
 
 
+@pytest.mark.parametrize("B", [1, 20, 1000, 40000])
+def test_dopri5_batch_controller_reference_faithful(px, torch, oracle, B):
+    """controller="batch": the reference's single global RMS norm and dt (utils/ode_utils.py:8-9).  The
+    accept/reject sequence, every dt and error ratio, and the solution must equal the oracle's literal
+    batch run.  (fp64 partial sums are added in a different -- fixed -- order than the oracle's
+    sequential loop; a flipped fp32 rounding of the ratio is possible in principle and would show here.)"""
+    field, om = both(px, oracle, spiral_weights(), "cube")
+    y0 = cfg2_y0(B, seed=3)
+    t = cfg2_tspan(32 if B <= 1000 else 8)
+    sol, s = solve_fwd(px, torch, field, y0, t, controller="batch", log_attempts=512)
+    ref, st, lg, rc = oracle.dopri5_mlp(om, y0, t, controller="batch")
+    assert rc == 0
+    rec, cnt = s.attempt_log.read()
+    assert cnt[0] == len(lg)
+    r = rec[0, :cnt[0]]
+    assert np.array_equal(r.accepted, lg.accepted)
+    assert np.array_equal(r.dt, lg.dt) and np.array_equal(r.t0, lg.t0)
+    assert np.array_equal(r.ratio, lg.ratio)
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    assert s.stats.n_attempts == int(st.n_attempts[0]) * B and s.stats.nfe == int(st.nfe[0]) * B
+
+
+def test_dopri5_batch_controller_rejections_reverse_and_status(px, torch, oracle):
+    w = [3.0 * a for a in fanin_weights(2, 50, seed=5)]
+    field, om = both(px, oracle, w, "id")
+    y0 = np.random.default_rng(1).uniform(-1, 1, (777, 2)).astype(f32)
+    for t in (np.linspace(0, 4, 9).astype(f32), np.linspace(4, 0, 9).astype(f32)):
+        kw = dict(rtol=1e-6, atol=1e-8)
+        sol, s = solve_fwd(px, torch, field, y0, t, controller="batch", **kw)
+        ref, st, lg, rc = oracle.dopri5_mlp(om, y0, t, controller="batch", **kw)
+        assert rc == 0 and (lg.accepted == 0).any(), "the case must exercise rejections"
+        assert np.array_equal(sol.cpu().numpy(), ref)
+        assert s.stats.n_accepted == int(st.n_accepted[0]) * 777
+    with pytest.raises(AssertionError, match="max_num_steps"):
+        solve_fwd(px, torch, field, y0, np.array([0.0, 50.0], f32), controller="batch", max_num_steps=2)
+    bad = y0.copy()
+    bad[5, 1] = np.nan
+    with pytest.raises(AssertionError, match="non-finite"):  # one bad trajectory aborts the batch, as in the reference
+        solve_fwd(px, torch, field, bad, np.linspace(0, 4, 9).astype(f32), controller="batch", first_step=0.01)
+
+
 def test_dopri5_full_size_subset_parity(px, torch, oracle):
     """cfg2 at BASELINE size (B = 2^20): with one controller per trajectory every trajectory is
     independent of its neighbours, so a random subset of the full-size GPU result must equal the
