@@ -719,6 +719,11 @@ static int adj_hpl(const AdjParams &p, cudaStream_t s) {
   return XDE_E_UNSUPPORTED_FIELD;
 }
 
+int dopri5_adj_batch(const xde_mlp_field_t *field, const float *t_span, int T, const float *y_ans,
+                     const float *grad_y, long long B, const xde_ctrl_opts_t *opts, int adj_norm,
+                     float *out_gparams, float *out_adj_y0, xde_stats_t *stats, const xde_attempt_log_t *log,
+                     cudaStream_t s);  // xde_dopri5_adj_batch.cu
+
 }  // namespace xde
 
 extern "C" XDE_EXPORT int xde_dopri5_mlp_adjoint_f32(const xde_mlp_field_t *field, const float *t_span, int32_t T,
@@ -730,12 +735,19 @@ extern "C" XDE_EXPORT int xde_dopri5_mlp_adjoint_f32(const xde_mlp_field_t *fiel
   using namespace xde;
   XDE_REQUIRE(field && t_span && y_ans && grad_y && opts && out_gparams, XDE_E_BAD_ARG, "null argument");
   XDE_REQUIRE(B >= 1 && T >= 2, XDE_E_BAD_ARG, "need B >= 1 and T >= 2");
-  XDE_REQUIRE(controller == XDE_CTRL_TRAJECTORY, XDE_E_UNSUPPORTED_FIELD,
-              "adjoint: controller=BATCH is not implemented on the device yet");
+  XDE_REQUIRE(controller == XDE_CTRL_TRAJECTORY || controller == XDE_CTRL_BATCH, XDE_E_BAD_ARG,
+              "unknown controller %d", controller);
+  XDE_REQUIRE(adj_norm == XDE_ADJ_NORM_SEMI || adj_norm == XDE_ADJ_NORM_MIXED, XDE_E_BAD_ARG,
+              "unknown adjoint norm %d", adj_norm);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (controller == XDE_CTRL_BATCH) {
+    if (stats) XDE_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(xde_stats_t), s));
+    return dopri5_adj_batch(field, t_span, T, y_ans, grad_y, B, opts, adj_norm, out_gparams, out_adj_y0, stats, log, s);
+  }
   XDE_REQUIRE(adj_norm == XDE_ADJ_NORM_SEMI, XDE_E_UNSUPPORTED_FIELD,
               "adjoint with one controller per trajectory supports the seminorm only "
-              "(adjoint_options={'norm': 'seminorm'}); the mixed norm needs controller=BATCH");
-  cudaStream_t s = (cudaStream_t)stream;
+              "(adjoint_options={'norm': 'seminorm'}); the mixed norm couples all trajectories and needs "
+              "controller=BATCH");
   const int D = field->d, H = field->h;
   const int P = 2 * D * H + H + D;
   AdjParams p{};

@@ -259,6 +259,98 @@ def test_adjoint_with_rejections_and_replay(px, torch, oracle):
     np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-5, atol=2e-6 * np.abs(g_ref).max())
 
 
+@pytest.mark.parametrize("norm", ["seminorm", "mixed"])
+@pytest.mark.parametrize("B,d,h,pre", [(1, 2, 50, "cube"), (300, 2, 50, "cube"), (5000, 2, 50, "cube"), (130, 4, 32, "id"),
+                                       (77, 1, 40, "square")])
+def test_adjoint_batch_controller_reference_default(px, torch, oracle, norm, B, d, h, pre):
+    """controller="batch": one dt / one error norm for the whole augmented state -- with norm="mixed" this is
+    the reference's DEFAULT odeint_adjoint configuration (functional/odeint_adjoint.py:284-291).
+    seminorm: the controller sees only (y, a), whose arithmetic is specified exactly -> bit-exact dt / ratio
+    sequence and dL/dy0.  mixed: at rtol 1e-7 (below fp32 epsilon) the parameter-gradient error estimate is
+    pure rounding noise of the batch sum (ratio ~1e-2) and this kernel sums in another order
+    (fp64 tree vs the oracle's sequential fp32 loop): step sizes inside a segment (and with them the attempt
+    count) are not comparable there -- only each segment's initial step, the results and the gradients are;
+    the looser-tolerance test below compares the whole sequence where truncation error dominates."""
+    from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
+
+    w = spiral_weights() if (d, h) == (2, 50) else fanin_weights(d, h, seed=h)
+    field, om = both(px, oracle, w, pre)
+    y0 = cfg2_y0(B, seed=4) if d == 2 else np.random.default_rng(3).uniform(-1, 1, (B, d)).astype(f32)
+    t = cfg2_tspan(6) if d == 2 else np.linspace(0, 1, 5).astype(f32)
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0, t, controller="batch")
+    gy = loss_grad(ref)
+    gy[2] = 0.01 * np.random.default_rng(4).standard_normal(gy[2].shape).astype(f32)
+    g, a0, stats, log = adjoint_backward(field, t, ref, gy, return_adj_y0=True, log_attempts=1024,
+                                         controller="batch", adj_norm=norm)
+    g_ref, a_ref, st_ref, lg, rc = oracle.dopri5_mlp_adjoint(om, t, ref, gy, controller="batch", adj_norm=norm)
+    assert rc == 0
+    s = stats.read()
+    assert s.status == 0
+    rec, cnt = log.read()
+    r = rec[0, :cnt[0]]
+    scale = np.abs(g_ref).max()
+    if norm == "seminorm":
+        assert cnt[0] == len(lg) and np.array_equal(r.accepted, lg.accepted)
+        assert s.n_attempts == int(st_ref.n_attempts[0]) * B and s.nfe == int(st_ref.nfe[0]) * B
+        assert np.array_equal(r.dt, lg.dt) and np.array_equal(r.ratio, lg.ratio)
+        assert np.array_equal(a0.cpu().numpy(), a_ref)
+    else:
+        # every segment's select_initial_step (its norms include k_0^theta and the probe's k^theta) must agree
+        first = np.flatnonzero(np.isin(r.t0, t))
+        first_ref = np.flatnonzero(np.isin(lg.t0, t))
+        np.testing.assert_allclose(r.dt[first], lg.dt[first_ref], rtol=1e-4)
+        assert r.accepted.all() and lg.accepted.all()
+        np.testing.assert_allclose(a0.cpu().numpy(), a_ref, rtol=1e-5, atol=2e-6 * np.abs(a_ref).max())
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-5, atol=2e-6 * scale)
+
+
+def test_adjoint_batch_mixed_norm_step_sizes_where_truncation_dominates(px, torch, oracle):
+    """Same configuration at rtol 1e-4 / atol 1e-6 on a stiffer field: the error estimate is now truncation
+    error, not rounding noise, so the mixed-norm controller must reproduce the oracle's dt and ratio sequence
+    (to the accuracy the different batch-summation order allows) including its rejections."""
+    from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
+
+    w = [3.0 * a for a in fanin_weights(2, 50, seed=5)]
+    field, om = both(px, oracle, w, "id")
+    B = 400
+    y0 = np.random.default_rng(1).uniform(-1, 1, (B, 2)).astype(f32)
+    t = np.linspace(0, 4, 5).astype(f32)
+    kw = dict(rtol=1e-4, atol=1e-6)
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0, t, controller="batch", **kw)
+    gy = 0.01 * np.random.default_rng(4).standard_normal(ref.shape).astype(f32)
+    g, a0, stats, log = adjoint_backward(field, t, ref, gy, return_adj_y0=True, log_attempts=1024, controller="batch",
+                                         adj_norm="mixed", **kw)
+    g_ref, a_ref, st_ref, lg, rc = oracle.dopri5_mlp_adjoint(om, t, ref, gy, controller="batch", adj_norm="mixed", **kw)
+    assert rc == 0 and stats.read().status == 0
+    rec, cnt = log.read()
+    r = rec[0, :cnt[0]]
+    assert cnt[0] == len(lg) and np.array_equal(r.accepted, lg.accepted)
+    np.testing.assert_allclose(r.dt, lg.dt, rtol=2e-2)
+    np.testing.assert_allclose(r.ratio, lg.ratio, rtol=1e-1, atol=1e-3)
+    np.testing.assert_allclose(a0.cpu().numpy(), a_ref, rtol=1e-3, atol=1e-4 * np.abs(a_ref).max())
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-3, atol=1e-4 * np.abs(g_ref).max())
+
+
+def test_odeint_adjoint_reference_defaults_via_options(px, torch, oracle):
+    """options={"controller": "batch"}: forward with the global controller, backward with the reference's default
+    mixed adjoint norm -- the literal reference configuration, end to end through the public API."""
+    w = spiral_weights()
+    tw = [torch.tensor(a, device="cuda", requires_grad=True) for a in w]
+    field = px.MLPField(*tw, pre="cube")
+    om = oracle.MLP(*w, pre="cube")
+    y0 = cfg2_y0(256, seed=9)
+    t = cfg2_tspan(5)
+    sol = px.odeint_adjoint(field, torch.from_numpy(y0).cuda(), t, solver=px.Dopri5,
+                            options={"norm": px.utils._rms_norm, "controller": "batch"})
+    sol[-1].abs().mean().backward()
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0, t, controller="batch")
+    assert np.array_equal(sol.detach().cpu().numpy(), ref)
+    g_ref, _, _, _, _ = oracle.dopri5_mlp_adjoint(om, t, ref, loss_grad(ref), controller="batch", adj_norm="mixed")
+    got = np.concatenate([p.grad.cpu().numpy().ravel() for p in tw])
+    np.testing.assert_allclose(got, g_ref, rtol=1e-5, atol=2e-6 * np.abs(g_ref).max())
+    assert px.odeint_adjoint.last["adj_norm"] == "mixed"
+
+
 def test_adjoint_gradient_is_the_true_gradient(px, torch, oracle):
     """Independent of the oracle: finite differences of the GPU forward in fp32 are too noisy, so
     compare with the fp64 NumPy adjoint-free gradient (discretise-then-differentiate is not the same
