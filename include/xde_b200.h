@@ -159,6 +159,17 @@ int xde_sde_mlp_f32(int32_t scheme, const xde_mlp_field_t *drift, const xde_mlp_
                     const float *y0, int64_t B, const float *t_span, int32_t T, const float *dW,
                     int32_t out_stride_t, float *out, void *stream);
 
+/* Tensor-core variants of the two fixed-grid entry points above (same arguments, same reference lines):
+ * the dense layers of the field run on tcgen05 (fp16-split three-product GEMMs, fp32 accumulation in
+ * TMEM), for D in {16,32,64} x H in {64,128,256} (sde: H <= 128).  Results agree with the FP32 entry
+ * points to ~1e-6 relative (north star: rtol 1e-5), not bit for bit; anything else returns
+ * XDE_E_UNSUPPORTED_FIELD. */
+int xde_rk_fixed_mlp_tc_f32(int32_t method, const xde_mlp_field_t *field, const float *y0, int64_t B,
+                            const float *t_span, int32_t T, int32_t out_stride_t, float *out, void *stream);
+int xde_sde_mlp_tc_f32(int32_t scheme, const xde_mlp_field_t *drift, const xde_mlp_field_t *diffusion,
+                       const float *y0, int64_t B, const float *t_span, int32_t T, const float *dW,
+                       int32_t out_stride_t, float *out, void *stream);
+
 /* HistoryIndex.forward                                xde/base_dde.py:84-118
  *   -> InterpolationBase.evaluate / derivative        interpolation/interpolate_base.py:49-114
  *      (LinearInterpolation interpolate.py:6-97, CubicHermiteSpline :100-204).

@@ -1,0 +1,619 @@
+// xde_tc.cu -- fixed-grid steppers for LARGE states on the 5th-generation tensor cores (tcgen05 + TMEM).
+//   * odeint(..., solver=Euler|RK4): FixedSolver.integrate (solver/base_fixed_solver.py:103-144),
+//     Euler.step (fixed_solver/euler.py:7-11), RK4.step = 3/8 rule (base_fixed_solver.py:166-197);
+//   * sdeint(..., solver=Euler): y1 = y0 + f*dt + g*dW with caller-supplied dW (xde/base_sde.py:44-61).
+// Same boundary as xde_tile.cu (the FP32 FFMA2 path, bit-exact against the oracle); this file is the
+// tensor-core path: the two dense layers of the field
+//     Z[128 x H] = U[128 x D] W1[D x H],   F[128 x D] = tanh(Z + b1)[128 x H] W2[H x D]
+// run as tcgen05.mma (kind::f16, M = 128, fp32 accumulators in TMEM); everything else (tanh, RK stage
+// combines, the SDE update) stays in fp32 registers.
+//
+// Precision.  fp32 operands are split into two fp16 pieces, x = hi + lo (hi = rn16(x), lo = rn16(x - hi):
+// 22 significant bits), and each GEMM is three MMAs hi*hi + hi*lo + lo*hi accumulated in fp32 -- the
+// dropped lo*lo term and the split error are ~2^-22 relative, the level of fp32 rounding itself.
+// Weights are pre-scaled by a power of two (exact) so that their lo pieces stay normal fp16 numbers.
+// Results agree with the FP32 path / the oracle to ~1e-6 relative (tests: rtol 1e-5), not bit for bit.
+//
+// Data flow (one CTA per SM, persistent over tiles of 128 trajectories; row r of the tile = TMEM lane r):
+//   * all operands of the activations live in TMEM, never in shared memory:
+//       U  (layer-1 A operand): the stage input, written as packed fp16 by the threads that own the
+//          state (tcgen05.st), hi and lo side by side;
+//       Z  (layer-1 accumulator, fp32) is read back 16 columns per thread (tcgen05.ld), bias + tanh in
+//          registers, and the SAME 16 columns are overwritten IN PLACE with the fp16 hi (8 columns) and
+//          lo (8 columns) of tanh -- which is exactly the A operand of layer 2 for one K = 16 step;
+//       F  (layer-2 accumulator) is read back by the state owners.
+//   * shared memory holds only the weights (fp16 hi/lo, K-major, no swizzle: 8 x 16 B core matrices),
+//     64-256-64: 128 KB, resident for the whole solve.
+//   * 16 compute warps (warp w: lane quarter w%4, column group w/4) + 1 warp whose elected thread issues
+//     every MMA.  Hand-offs are mbarriers: u_ready (compute -> MMA), z_ready[c] (tcgen05.commit ->
+//     compute, per 64-wide hidden chunk), h_ready[c] (compute -> MMA), f_ready (commit -> compute).
+//     Layer-1 chunks are issued back to back, so the tanh epilogue of chunk c overlaps the MMAs of
+//     chunk c+1 and the layer-2 MMAs of chunk c-1.  No barrier is ever needed in the other direction:
+//     every buffer's next writer is ordered behind its last reader by the chain itself.
+#include <cuda_fp16.h>
+
+#include "xde_common.cuh"
+
+namespace xde {
+namespace tc {
+
+constexpr int kComputeWarps = 16;
+constexpr int kThreads = (kComputeWarps + 1) * 32;
+constexpr int kTM = 128;
+constexpr int kMaxChunks = 4;
+
+template <int D, int H, int NETS>
+struct Geom {
+  static_assert(D % 16 == 0 && D >= 16 && D <= 64, "state dim: 16, 32, 48, 64");
+  static_assert(H % 64 == 0 && H >= 64 && H <= 256, "hidden width: 64, 128, 192, 256");
+  static constexpr int NC = D / 4;    // state columns per compute thread
+  static constexpr int CH = H / 64;   // 64-wide hidden chunks per network
+  static constexpr int NCHUNK = NETS * CH;
+  static_assert(NCHUNK <= kMaxChunks, "too many hidden chunks");
+  // layer-2 accumulators per network: NFM "main" ones (hi*hi products; chunk c goes to c % NFM) and one
+  // for the hi*lo + lo*hi corrections.  The tensor core truncates the fp32 accumulator once per MMA, an
+  // error of ~0.5 ulp(|accumulator|) each time and always towards zero: keeping the 2^-11-times-smaller
+  // correction products away from the full-size sums, and halving the chain length, keeps that bias at
+  // a few fp32 ulps.  The epilogue adds the partial sums in fp32 (round to nearest).
+  static constexpr int NFM = CH >= 2 ? 2 : 1;
+  static constexpr int FW = (NFM + 1) * D;
+  static constexpr int Z0 = 0, F0 = NETS * H, U0 = NETS * (H + FW);
+  static constexpr int COLS = NETS * (H + FW + D);
+  static_assert(COLS <= 512, "TMEM has 512 columns");
+  static constexpr int ALLOC = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
+  static constexpr int MAT_BYTES = D * H * 2;          // one fp16 copy of one weight matrix
+  static constexpr int NET_W_BYTES = 4 * MAT_BYTES;    // W1hi | W1lo | W2hi | W2lo
+  static constexpr int W_BYTES = NETS * NET_W_BYTES;
+  // shared memory: [barriers + tmem slot: 128 B][weights][b1 NETS*H][b2 NETS*D][sinv NETS*2 (+pad)][t grid]
+  static constexpr int OFF_W = 128;
+  static constexpr int OFF_B1 = OFF_W + W_BYTES;
+  static constexpr int OFF_B2 = OFF_B1 + NETS * H * 4;
+  static constexpr int OFF_SINV = OFF_B2 + NETS * D * 4;
+  static constexpr int OFF_T = OFF_SINV + 16;
+  static size_t bytes(int T) { return (size_t)OFF_T + 4 * (size_t)((T + 3) / 4) * 4; }
+};
+
+struct TcParams {
+  xde_mlp_field_t f, g;
+  const unsigned char *wbuf;  // prepared weights: Geom::W_BYTES, then float sinv[NETS][2]
+  const float *y0, *t_span, *dW;
+  float *out;
+  long long B;
+  int T, stride, n_out;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// completion of every MMA this thread has issued so far -> one arrival on the mbarrier
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem, fp16 packed] * B[smem descriptor], M = 128, K = 16
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d),
+      "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; LBO = byte step between core matrices
+// along K, SBO = byte step between 8-row groups along N (cute::UMMA::SmemDescriptor, version 1).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, A and B K-major, M = 128
+__host__ __device__ constexpr uint32_t instr_desc(int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+}
+
+template <int N>
+struct Tmem;
+template <>
+struct Tmem<2> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a) : "memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[2]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(a), "r"(r[0]), "r"(r[1]) : "memory");
+  }
+};
+template <>
+struct Tmem<4> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(a)
+                 : "memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3])
+                 : "memory");
+  }
+};
+template <>
+struct Tmem<8> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(a)
+                 : "memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(a), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+  }
+};
+template <>
+struct Tmem<16> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(a)
+        : "memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(a),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+  }
+};
+
+// x0, x1 -> packed fp16 hi pieces and packed fp16 lo pieces (element 0 in the low half)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+__device__ __forceinline__ float pre_rt(int pre, float y) {
+  if (pre == XDE_PRE_CUBE) return (y * y) * y;
+  if (pre == XDE_PRE_SQUARE) return y * y;
+  return y;
+}
+
+// ---- weight preparation ---------------------------------------------------------------------------
+// One CTA per (network, layer): power-of-two scale from max|W|, then the scaled matrix as fp16 hi / lo
+// in the K-major core-matrix order the MMA's B descriptor walks:
+//   layer 1 (B rows = hidden unit j, K = input i):  half index (i/8)*(H*8) + j*8 + i%8,  value W1[i*H + j]
+//   layer 2 (B rows = output d,      K = hidden j): half index (j/8)*(D*8) + d*8 + j%8,  value W2[j*D + d]
+__global__ void __launch_bounds__(1024) tc_prep_kernel(xde_mlp_field_t f, xde_mlp_field_t g, unsigned char *wbuf,
+                                                       int nets) {
+  const int net = blockIdx.x >> 1, layer = blockIdx.x & 1;
+  const xde_mlp_field_t &fld = net ? g : f;
+  const int D = fld.d, H = fld.h, n = D * H;
+  const float *W = layer ? fld.w2 : fld.w1;
+  __shared__ float red[32];
+  float m = 0.0f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = fabsf(W[i]);
+    if (a > m && a < INFINITY) m = a;
+  }
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(XDE_FULL_MASK, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = 0.0f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+  int e = 0;
+  if (m > 0.0f) e = 13 - ilogbf(m);  // max|W| * 2^e in [2^13, 2^14): hi never overflows, lo stays normal
+  e = max(-100, min(100, e));
+  const float scale = ldexpf(1.0f, e);
+  const size_t mat = (size_t)n * 2;
+  __half *hi = reinterpret_cast<__half *>(wbuf + (size_t)net * 4 * mat + (size_t)layer * 2 * mat);
+  __half *lo = reinterpret_cast<__half *>(wbuf + (size_t)net * 4 * mat + (size_t)layer * 2 * mat + mat);
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    int k, r, R;  // K index, B-row index, number of B rows
+    if (layer == 0) {
+      k = idx / H;
+      r = idx % H;
+      R = H;
+    } else {
+      k = idx / D;
+      r = idx % D;
+      R = D;
+    }
+    const float v = W[idx] * scale;
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const int dst = (k >> 3) * (R * 8) + r * 8 + (k & 7);
+    hi[dst] = h;
+    lo[dst] = l;
+  }
+  if (threadIdx.x == 0) {
+    float *sinv = reinterpret_cast<float *>(wbuf + (size_t)nets * 4 * mat);
+    sinv[net * 2 + layer] = ldexpf(1.0f, -e);
+  }
+}
+
+// ---- the solver -----------------------------------------------------------------------------------
+// KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama (two networks)
+template <int D, int H, int KIND>
+__global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p) {
+  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  using G = Geom<D, H, NETS>;
+  constexpr int NC = G::NC, CH = G::CH, NCHUNK = G::NCHUNK;
+  constexpr int EVALS = (KIND == 1) ? 4 : 1;  // field evaluations per step
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *u_ready = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *f_ready = u_ready + 1;
+  uint64_t *z_ready = u_ready + 2;
+  uint64_t *h_ready = z_ready + kMaxChunks;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_ready + kMaxChunks);
+  unsigned char *sW = smem + G::OFF_W;
+  const float *sb1 = reinterpret_cast<const float *>(smem + G::OFF_B1);
+  const float *sb2 = reinterpret_cast<const float *>(smem + G::OFF_B2);
+  const float *ssinv = reinterpret_cast<const float *>(smem + G::OFF_SINV);
+  const float *st = reinterpret_cast<const float *>(smem + G::OFF_T);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup ----
+  if (warp == kComputeWarps) {
+    if (lane == 0) {
+      mbar_init(u_ready, kComputeWarps);
+      mbar_init(f_ready, 1);
+      for (int c = 0; c < kMaxChunks; ++c) {
+        mbar_init(z_ready + c, 1);
+        mbar_init(h_ready + c, kComputeWarps);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)G::ALLOC)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.wbuf);
+    uint4 *dst = reinterpret_cast<uint4 *>(sW);
+    for (int i = tid; i < G::W_BYTES / 16; i += kThreads) dst[i] = src[i];
+    float *b1w = reinterpret_cast<float *>(smem + G::OFF_B1);
+    float *b2w = reinterpret_cast<float *>(smem + G::OFF_B2);
+    float *siw = reinterpret_cast<float *>(smem + G::OFF_SINV);
+    float *tw = reinterpret_cast<float *>(smem + G::OFF_T);
+    for (int i = tid; i < NETS * H; i += kThreads) b1w[i] = (i < H ? p.f.b1[i] : p.g.b1[i - H]);
+    for (int i = tid; i < NETS * D; i += kThreads) b2w[i] = (i < D ? p.f.b2[i] : p.g.b2[i - D]);
+    if (tid < NETS * 2) siw[tid] = reinterpret_cast<const float *>(p.wbuf + G::W_BYTES)[tid];
+    for (int i = tid; i < p.T; i += kThreads) tw[i] = p.t_span[i];
+  }
+  // the MMA unit reads shared memory through the async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const long long n_tiles = (p.B + kTM - 1) / kTM;
+  long long my_tiles = 0;
+  if ((long long)blockIdx.x < n_tiles) my_tiles = (n_tiles - 1 - blockIdx.x) / gridDim.x + 1;
+  const long long total_evals = my_tiles * (long long)(p.T - 1) * EVALS;
+
+  if (warp == kComputeWarps) {
+    // =============================== MMA issuer (one thread) ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = instr_desc(64), idesc2 = instr_desc(D);
+      const uint32_t w_addr = smem_u32(sW);
+      for (long long ev = 0; ev < total_evals; ++ev) {
+        const uint32_t par = (uint32_t)(ev & 1);
+        mbar_wait(u_ready, par);
+        tc_fence_after();
+        // layer 1, chunk by chunk: Z[:, 64 c ..] = U W1[:, 64 c ..]
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int net = c / CH, cc = c % CH;
+          const uint32_t d = tmem + G::Z0 + net * H + cc * 64;
+          const uint32_t w1hi = w_addr + net * G::NET_W_BYTES, w1lo = w1hi + G::MAT_BYTES;
+          // corrections first, while the accumulator is still small (see Geom::NFM), then the hi*hi products
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t a_hi = tmem + G::U0 + net * D + 8 * ks, a_lo = a_hi + D / 2;
+            const uint32_t off = (2 * ks) * (H * 16) + (cc * 64) * 16;
+            mma_ts(d, a_hi, smem_desc(w1lo + off, H * 16, 128), idesc1, ks > 0);
+            mma_ts(d, a_lo, smem_desc(w1hi + off, H * 16, 128), idesc1, 1);
+          }
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t a_hi = tmem + G::U0 + net * D + 8 * ks;
+            const uint32_t off = (2 * ks) * (H * 16) + (cc * 64) * 16;
+            mma_ts(d, a_hi, smem_desc(w1hi + off, H * 16, 128), idesc1, 1);
+          }
+          tc_commit(z_ready + c);
+        }
+        // layer 2, as each chunk of tanh lands: F += Hh[:, 64 c ..] W2[64 c .., :]
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int net = c / CH, cc = c % CH;
+          mbar_wait(h_ready + c, par);
+          tc_fence_after();
+          const uint32_t d_main = tmem + G::F0 + net * G::FW + (cc % G::NFM) * D;
+          const uint32_t d_corr = tmem + G::F0 + net * G::FW + G::NFM * D;
+          const uint32_t w2hi = w_addr + net * G::NET_W_BYTES + 2 * G::MAT_BYTES, w2lo = w2hi + G::MAT_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const int s = cc * 4 + ks;  // K step = hidden units 16 s .. 16 s + 15
+            const uint32_t a_hi = tmem + G::Z0 + net * H + 16 * s, a_lo = a_hi + 8;
+            const uint32_t off = (2 * s) * (D * 16);
+            const uint64_t b_hi = smem_desc(w2hi + off, D * 16, 128), b_lo = smem_desc(w2lo + off, D * 16, 128);
+            mma_ts(d_corr, a_hi, b_lo, idesc2, (cc | ks) != 0);
+            mma_ts(d_corr, a_lo, b_hi, idesc2, 1);
+            mma_ts(d_main, a_hi, b_hi, idesc2, !(cc < G::NFM && ks == 0));
+          }
+        }
+        tc_commit(f_ready);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== compute warps ===============================
+    const int q = warp & 3, j = warp >> 2;  // TMEM lane quarter, column group
+    const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
+    const int c0 = j * NC;  // first state column of this thread
+    const int pref = p.f.pre, preg = p.g.pre;
+    const float one_third = (float)(1.0 / 3.0);
+    uint32_t par = 0;
+
+    // one evaluation of the field(s) at yi: kf (and kg) <- f(yi) (, g(yi))
+    auto eval = [&](const float (&yi)[NC], float (&kf)[NC], float (&kg)[NC]) {
+      // 1. stage input -> U (fp16 hi | lo)
+#pragma unroll
+      for (int net = 0; net < NETS; ++net) {
+        uint32_t uh[NC / 2], ul[NC / 2];
+        const int pre = net ? preg : pref;
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) split2(pre_rt(pre, yi[2 * c]), pre_rt(pre, yi[2 * c + 1]), uh[c], ul[c]);
+        Tmem<NC / 2>::st(tl + G::U0 + net * D + j * (NC / 2), uh);
+        Tmem<NC / 2>::st(tl + G::U0 + net * D + D / 2 + j * (NC / 2), ul);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(u_ready);
+      // 2. hidden chunks: Z -> tanh -> fp16 hi | lo, in place
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int net = c / CH, cc = c % CH;
+        const int h0 = net * H + cc * 64 + j * 16;  // first hidden unit (= Z column) of this thread
+        mbar_wait(z_ready + c, par);
+        tc_fence_after();
+        uint32_t z[16];
+        Tmem<16>::ld(tl + G::Z0 + h0, z);
+        tc_wait_ld();
+        const f32x2 s1 = pk1(ssinv[net * 2]);
+        uint32_t o[16];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const float2 b = *reinterpret_cast<const float2 *>(sb1 + h0 + 2 * m);
+          const f32x2 a = fma2(pk(__uint_as_float(z[2 * m]), __uint_as_float(z[2 * m + 1])), s1, pk(b.x, b.y));
+          float t0, t1;
+          upk(tanh_rat2(a), t0, t1);
+          split2(t0, t1, o[m], o[8 + m]);
+        }
+        Tmem<16>::st(tl + G::Z0 + h0, o);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_ready + c);
+      }
+      // 3. F -> registers
+      mbar_wait(f_ready, par);
+      tc_fence_after();
+#pragma unroll
+      for (int net = 0; net < NETS; ++net) {
+        float(&kk)[NC] = net ? kg : kf;
+        const uint32_t fa = tl + G::F0 + net * G::FW + c0;
+        uint32_t r0[NC], r1[NC];
+        Tmem<NC>::ld(fa, r0);
+        Tmem<NC>::ld(fa + D, r1);  // NFM == 1: this is already the correction accumulator
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < NC; ++c) kk[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+        if (G::NFM == 2) {
+          Tmem<NC>::ld(fa + 2 * D, r0);
+          tc_wait_ld();
+#pragma unroll
+          for (int c = 0; c < NC; ++c) kk[c] += __uint_as_float(r0[c]);
+        }
+        const float s2 = ssinv[net * 2 + 1];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) kk[c] = fmaf(kk[c], s2, sb2[net * D + c0 + c]);
+      }
+      par ^= 1u;
+    };
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long b = tile * kTM + 32 * q + lane;
+      const bool ok = b < p.B;
+      float y[NC];
+#pragma unroll
+      for (int v = 0; v < NC / 4; ++v) {
+        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+          t4 = *reinterpret_cast<const float4 *>(p.y0 + b * D + c0 + 4 * v);
+          *reinterpret_cast<float4 *>(p.out + b * (long long)p.n_out * D + c0 + 4 * v) = t4;
+        }
+        y[4 * v] = t4.x;
+        y[4 * v + 1] = t4.y;
+        y[4 * v + 2] = t4.z;
+        y[4 * v + 3] = t4.w;
+      }
+      for (int i = 1; i < p.T; ++i) {
+        const float dt = st[i] - st[i - 1];
+        float k[NC], kg[NC];
+        if (KIND == 0) {
+          eval(y, k, kg);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) y[c] = fmaf(k[c], dt, y[c]);
+        } else if (KIND == 1) {
+          // RK4.step = rk4_alt_step_func (base_fixed_solver.py:166-197), as written there:
+          //   k2 = f(y + dt k1/3), k3 = f(y + dt (k1 - k2/3)), k4 = f(y + dt (k1 - k2 + k3)),
+          //   y1 = y + dt (k1 + 3 k2 + 3 k3 + k4) / 8
+          float yi[NC], A[NC], S[NC];
+          eval(y, k, kg);
+          const float dt13 = dt * one_third;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            A[c] = k[c];
+            yi[c] = fmaf(k[c], dt13, y[c]);
+          }
+          eval(yi, k, kg);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            yi[c] = fmaf(fmaf(-one_third, k[c], A[c]), dt, y[c]);
+            S[c] = fmaf(3.0f, k[c], A[c]);
+            A[c] = A[c] - k[c];
+          }
+          eval(yi, k, kg);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            yi[c] = fmaf(A[c] + k[c], dt, y[c]);
+            S[c] = fmaf(3.0f, k[c], S[c]);
+          }
+          eval(yi, k, kg);
+          const float dt8 = dt * 0.125f;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) y[c] = fmaf(S[c] + k[c], dt8, y[c]);
+        } else {
+          float w[NC];
+#pragma unroll
+          for (int v = 0; v < NC / 4; ++v) {
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) t4 = __ldg(reinterpret_cast<const float4 *>(p.dW + ((long long)(i - 1) * p.B + b) * D + c0 + 4 * v));
+            w[4 * v] = t4.x;
+            w[4 * v + 1] = t4.y;
+            w[4 * v + 2] = t4.z;
+            w[4 * v + 3] = t4.w;
+          }
+          eval(y, k, kg);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) y[c] = fmaf(kg[c], w[c], fmaf(k[c], dt, y[c]));
+        }
+        // linear_interp at t == t1 is the identity (interpolation/functional/interp_fn.py:4-10)
+        if (ok && (i % p.stride == 0 || i == p.T - 1)) {
+          const int row = (i == p.T - 1) ? p.n_out - 1 : i / p.stride;
+#pragma unroll
+          for (int v = 0; v < NC / 4; ++v)
+            *reinterpret_cast<float4 *>(p.out + (b * (long long)p.n_out + row) * D + c0 + 4 * v) =
+                make_float4(y[4 * v], y[4 * v + 1], y[4 * v + 2], y[4 * v + 3]);
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kComputeWarps) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)G::ALLOC)
+                 : "memory");
+  }
+}
+
+template <int D, int H, int KIND>
+static int launch_tc(TcParams p, cudaStream_t s) {
+  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  using G = Geom<D, H, NETS>;
+  const size_t smem = G::bytes(p.T);
+  XDE_REQUIRE(smem <= 227 * 1024, XDE_E_UNSUPPORTED_FIELD,
+              "tensor-core solver: weights + time grid need %zu bytes of shared memory (> 227 KB)", smem);
+  void *wbuf = nullptr;
+  const size_t wbytes = (size_t)G::W_BYTES + 16;
+  XDE_CUDA_CHECK(scratch_alloc(&wbuf, wbytes, s));
+  tc_prep_kernel<<<NETS * 2, 1024, 0, s>>>(p.f, p.g, (unsigned char *)wbuf, NETS);
+  count_launch();
+  p.wbuf = (const unsigned char *)wbuf;
+  auto kern = fixed_tc_kernel<D, H, KIND>;
+  XDE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n_tiles = (p.B + kTM - 1) / kTM;
+  long long grid = sm_count();  // persistent: one CTA (and its 512 TMEM columns) per SM
+  if (grid > n_tiles) grid = n_tiles;
+  kern<<<(unsigned)grid, kThreads, smem, s>>>(p);
+  count_launch();
+  XDE_CUDA_CHECK(cudaGetLastError());
+  XDE_CUDA_CHECK(cudaFreeAsync(wbuf, s));
+  return XDE_OK;
+}
+
+template <int KIND>
+static int tc_dispatch(const TcParams &p, cudaStream_t s) {
+  const int D = p.f.d, H = p.f.h;
+#define XDE_TC_CASE(DD, HH) \
+  if (D == DD && H == HH) return launch_tc<DD, HH, KIND>(p, s);
+  XDE_TC_CASE(64, 64) XDE_TC_CASE(32, 128) XDE_TC_CASE(32, 64) XDE_TC_CASE(16, 128) XDE_TC_CASE(16, 64)
+  if constexpr (KIND != 2) {  // two networks: 2 (H + FW + D) <= 512 TMEM columns
+    XDE_TC_CASE(64, 256) XDE_TC_CASE(64, 128) XDE_TC_CASE(32, 256)
+  }
+#undef XDE_TC_CASE
+  set_last_error("tensor-core solver: no kernel for D=%d H=%d (D in {16,32,64} x H in {64,128,256}; sde: TMEM limits D=64 to H=64, others to H<=128)", D, H);
+  return XDE_E_UNSUPPORTED_FIELD;
+}
+
+}  // namespace tc
+
+int rk_fixed_tc(int method, const xde_mlp_field_t *f, const float *y0, long long B, const float *t_span, int T,
+                int stride, float *out, cudaStream_t s) {
+  tc::TcParams p{};
+  p.f = *f;
+  p.g = *f;
+  p.y0 = y0;
+  p.t_span = t_span;
+  p.out = out;
+  p.B = B;
+  p.T = T;
+  p.stride = stride;
+  p.n_out = (T - 1 + stride - 1) / stride + 1;
+  return method == XDE_FIXED_EULER ? tc::tc_dispatch<0>(p, s) : tc::tc_dispatch<1>(p, s);
+}
+
+int sde_tc(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const float *y0, long long B,
+           const float *t_span, int T, const float *dW, int stride, float *out, cudaStream_t s) {
+  XDE_REQUIRE(scheme == XDE_SDE_EM, XDE_E_UNSUPPORTED_FIELD,
+              "Milstein (an extension without a reference counterpart) is fused for small states (D <= 8) only");
+  XDE_REQUIRE(f->h == g->h, XDE_E_UNSUPPORTED_FIELD, "tensor-core sde: drift and diffusion must share the hidden width");
+  tc::TcParams p{};
+  p.f = *f;
+  p.g = *g;
+  p.y0 = y0;
+  p.t_span = t_span;
+  p.dW = dW;
+  p.out = out;
+  p.B = B;
+  p.T = T;
+  p.stride = stride;
+  p.n_out = (T - 1 + stride - 1) / stride + 1;
+  return tc::tc_dispatch<2>(p, s);
+}
+
+}  // namespace xde

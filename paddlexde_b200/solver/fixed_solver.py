@@ -17,7 +17,7 @@ class FixedSolver:
     method: str
 
     def __init__(self, xde, y0, step_size=None, grid_constructor=None, interp="linear", perturb=False,
-                 out_stride=1, **kwargs):
+                 out_stride=1, math="fp32", **kwargs):
         if step_size is not None and grid_constructor is not None:
             raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
         if step_size is not None or grid_constructor is not None:
@@ -30,6 +30,11 @@ class FixedSolver:
                 raise KeyError(key)
         self.xde, self.y0 = xde, y0
         self.out_stride = int(out_stride)
+        # math="fp32": FFMA path, bit-exact against the oracle's arithmetic specification (default);
+        # math="tensor": tcgen05 path for D in {16,32,64} (fp16-split 3-product GEMMs, ~1e-6 relative)
+        if math not in ("fp32", "tensor"):
+            raise ValueError(f"math must be 'fp32' or 'tensor', got {math!r}")
+        self.math = math
 
     def integrate(self, t_span):
         kind = getattr(self.xde, "kind", None)
@@ -43,8 +48,9 @@ class FixedSolver:
         out = torch.empty((B, n_out, D), device=y0.device, dtype=torch.float32)
         if kind == "ode":
             fs = self.xde.field.c_struct()
-            check(lib().xde_rk_fixed_mlp_f32(FIXED[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), Tn,
-                                             self.out_stride, T.ptr(out), T.stream()))
+            entry = lib().xde_rk_fixed_mlp_tc_f32 if self.math == "tensor" else lib().xde_rk_fixed_mlp_f32
+            check(entry(FIXED[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), Tn,
+                        self.out_stride, T.ptr(out), T.stream()))
         elif kind == "sde":
             if self.method != "euler" and self.xde.scheme == "em":
                 raise UnsupportedFieldError("sdeint is fused for solver=Euler (Euler-Maruyama) only")
@@ -52,8 +58,9 @@ class FixedSolver:
             if tuple(dW.shape) != (Tn - 1, B, D):
                 raise ValueError(f"bm_increments must be [T-1, B, D] = {(Tn - 1, B, D)}, got {tuple(dW.shape)}")
             f, g = self.xde.drift.c_struct(), self.xde.diffusion.c_struct()
-            check(lib().xde_sde_mlp_f32(SDE[self.xde.scheme], C.byref(f), C.byref(g), T.ptr(y0), B, T.ptr(t_dev),
-                                        Tn, T.ptr(dW), self.out_stride, T.ptr(out), T.stream()))
+            entry = lib().xde_sde_mlp_tc_f32 if self.math == "tensor" else lib().xde_sde_mlp_f32
+            check(entry(SDE[self.xde.scheme], C.byref(f), C.byref(g), T.ptr(y0), B, T.ptr(t_dev),
+                        Tn, T.ptr(dW), self.out_stride, T.ptr(out), T.stream()))
         else:
             raise UnsupportedFieldError(f"fixed solvers integrate ODE/SDE problems on the device, not {kind!r}")
         # concat(axis=-2) of the per-time states (base_fixed_solver.py:143)

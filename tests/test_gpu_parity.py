@@ -508,6 +508,98 @@ def test_tiled_sde_cfg4_shapes(px, torch, oracle):
 
 
 # ------------------------------------------------------------------------------------------------
+# large states on the tensor cores (csrc/xde_tc.cu): tcgen05 fp16-split 3-product GEMMs, fp32 accumulate.
+# Not bit-exact by construction; the north-star tolerance (rtol 1e-5, with an atol scaled to the state:
+# SURVEY appendix C take-away 3) is written in every assert.
+# ------------------------------------------------------------------------------------------------
+def _close(a, b, rtol=1e-5):
+    scale = float(np.abs(b).max())
+    return np.allclose(a, b, rtol=rtol, atol=rtol * scale)
+
+
+@pytest.mark.parametrize("d,h,B", [(64, 256, 100), (64, 128, 33), (64, 64, 130), (32, 256, 31), (32, 128, 257),
+                                   (32, 64, 200), (16, 64, 77), (64, 256, 1)])
+@pytest.mark.parametrize("solver", ["Euler", "RK4"])
+def test_tensor_fixed_solvers_match_oracle(px, torch, oracle, solver, d, h, B):
+    field, om = both(px, oracle, fanin_weights(d, h, seed=d + h), "id" if d == 64 else "cube")
+    y0 = np.random.default_rng(d).uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, 11).astype(f32)
+    sol = px.odeint(field, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, getattr(px, solver),
+                    options={"math": "tensor"})
+    ref = oracle.fixed_mlp(solver.lower(), om, y0, t)
+    assert tuple(sol.shape) == (B, t.size, d)
+    got = sol.cpu().numpy()
+    assert np.array_equal(got[:, 0], y0)  # the initial row is copied, not computed
+    assert _close(got, ref, rtol=1e-5)
+
+
+def test_tensor_path_is_as_accurate_as_fp32(px, torch, oracle):
+    """Against an fp64 evaluation of the same scheme the tensor path's error must be of the size of the
+    FP32 path's own rounding error (measured ratio 0.6-1.9; bound 4)."""
+    d, h, B = 64, 256, 512
+    w = fanin_weights(d, h, seed=7)
+    field = px.MLPField(*w, pre="id")
+    y0 = np.random.default_rng(7).uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, 11).astype(f32)
+    w1, b1, w2, b2 = [np.asarray(a, dtype=np.float64) for a in w]
+    f = lambda y: np.tanh(y @ w1 + b1) @ w2 + b2
+    y = y0.astype(np.float64)
+    for i in range(1, t.size):  # rk4_alt_step_func, base_fixed_solver.py:166-197, in fp64
+        dt = float(t[i]) - float(t[i - 1])
+        k1 = f(y); k2 = f(y + dt / 3 * k1); k3 = f(y + dt * (k1 - k2 / 3)); k4 = f(y + dt * (k1 - k2 + k3))
+        y = y + dt * (k1 + 3 * k2 + 3 * k3 + k4) / 8
+    yd = torch.from_numpy(y0).cuda().reshape(B, 1, d)
+    e = {}
+    for math in ("tensor", "fp32"):
+        sol = px.odeint(field, yd, t, px.RK4, options={"math": math}).cpu().numpy()[:, -1]
+        e[math] = np.abs(sol - y).max()
+    assert e["tensor"] <= 4 * e["fp32"] + 1e-7, e
+
+
+def test_tensor_cfg3_full_size_subset_and_stride(px, torch, oracle):
+    """cfg3 at the per-GPU BASELINE size (B = 2^17, 64-256-64, RK4, 100 steps, every 10th point stored)
+    on the tensor path: a random subset against the oracle at rtol 1e-5, and against the FP32 kernel."""
+    d, h, B = 64, 256, 1 << 17
+    field, om = both(px, oracle, fanin_weights(d, h, seed=1), "id")
+    y0 = np.random.default_rng(1).uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, 101).astype(f32)
+    yd = torch.from_numpy(y0).cuda().reshape(B, 1, d)
+    sol = px.odeint(field, yd, t, px.RK4, options={"math": "tensor", "out_stride": 10})
+    assert tuple(sol.shape) == (B, 11, d)
+    idx = np.random.default_rng(3).choice(B, 192, replace=False)
+    ref = oracle.fixed_mlp("rk4", om, y0[idx], t)[:, ::10]
+    assert _close(sol[torch.from_numpy(idx).cuda()].cpu().numpy(), ref, rtol=1e-5)
+    exact = px.odeint(field, yd, t, px.RK4, options={"math": "fp32", "out_stride": 10})
+    scale = float(exact.abs().max())
+    assert float((sol - exact).abs().max()) <= 1e-5 * scale
+    assert bool(torch.isfinite(sol).all())
+
+
+@pytest.mark.parametrize("d,h,B", [(32, 64, 1000), (32, 128, 130), (64, 64, 129), (16, 64, 5)])
+def test_tensor_sde_matches_oracle(px, torch, oracle, d, h, B):
+    """cfg4 shapes on the tensor path: two nets (drift y**3, diffusion y**2), 16 steps, supplied increments."""
+    f, of = both(px, oracle, fanin_weights(d, h, seed=2), "cube")
+    g, og = both(px, oracle, fanin_weights(d, h, seed=3), "square")
+    rng = np.random.default_rng(2)
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, 17).astype(f32)
+    dW = (np.sqrt(1 / 16) * rng.standard_normal((16, B, d))).astype(f32)
+    sol = px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler,
+                    options={"bm_increments": torch.from_numpy(dW).cuda(), "math": "tensor"})
+    ref = oracle.sde_mlp("em", of, og, y0, t, dW)
+    assert _close(sol.cpu().numpy(), ref, rtol=1e-5)
+
+
+def test_tensor_path_is_loud_about_unsupported_shapes(px, torch, oracle):
+    t = np.linspace(0, 1, 5).astype(f32)
+    small, _ = both(px, oracle, fanin_weights(2, 50), "cube")
+    with pytest.raises(px.UnsupportedFieldError):  # K = 2 is degenerate for an MMA: FP32 path only
+        px.odeint(small, torch.zeros(4, 1, 2).cuda(), t, px.RK4, options={"math": "tensor"})
+    with pytest.raises(ValueError):
+        px.odeint(small, torch.zeros(4, 1, 2).cuda(), t, px.RK4, options={"math": "bf16"})
+
+
+# ------------------------------------------------------------------------------------------------
 # history gather / DDE
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["linear", "cubic"])
