@@ -197,6 +197,31 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
+// tanh on a packed pair for the tolerance path: the same 13/6 rational as tanh_rat2 (xde_common.cuh), but
+// the quotient is p * rcp.approx(q) (~2 ulp instead of correctly rounded) and the |a| < 4e-4 -> a select
+// is dropped (there the rational is a * (1 - 1.3e-7)).  10 packed FMA-pipe ops + 2 MUFU + 4 FMNMX per
+// pair instead of 17 + 2 + 4 + 4 (FSETP/FSEL): the epilogue is issue-bound, so this is ~20 % of the step.
+__device__ __forceinline__ f32x2 tanh_fast2(f32x2 a) {
+  const float c = 7.90531110763549805f;
+  float a0, a1;
+  upk(a, a0, a1);
+  const f32x2 x = pk(fminf(fmaxf(a0, -c), c), fminf(fmaxf(a1, -c), c));
+  const f32x2 x2 = mul2(x, x);
+  f32x2 p = fma2(x2, pk1(-2.76076847742355e-16f), pk1(2.00018790482477e-13f));
+  p = fma2(x2, p, pk1(-8.60467152213735e-11f));
+  p = fma2(x2, p, pk1(5.12229709037114e-08f));
+  p = fma2(x2, p, pk1(1.48572235717979e-05f));
+  p = fma2(x2, p, pk1(6.37261928875436e-04f));
+  p = fma2(x2, p, pk1(4.89352455891786e-03f));
+  p = mul2(x, p);
+  f32x2 q = fma2(x2, pk1(1.19825839466702e-06f), pk1(1.18534705686654e-04f));
+  q = fma2(x2, q, pk1(2.26843463243900e-03f));
+  q = fma2(x2, q, pk1(4.89352518554385e-03f));
+  float q0, q1;
+  upk(q, q0, q1);
+  return mul2(p, pk(rcp_approx(q0), rcp_approx(q1)));
+}
+
 __device__ __forceinline__ float pre_rt(int pre, float y) {
   if (pre == XDE_PRE_CUBE) return (y * y) * y;
   if (pre == XDE_PRE_SQUARE) return y * y;
@@ -401,24 +426,32 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(u_ready);
-      // 2. hidden chunks: Z -> tanh -> fp16 hi | lo, in place
+      // 2. hidden chunks: Z -> tanh -> fp16 hi | lo, in place.  The TMEM load of chunk c+1 is issued half
+      // way through the tanh of chunk c (its MMAs were queued right behind chunk c's), so its latency and
+      // the mbarrier round trip are hidden behind arithmetic.
+      uint32_t z[16];
+      mbar_wait(z_ready, par);
+      tc_fence_after();
+      Tmem<16>::ld(tl + G::Z0 + j * 16, z);
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
         const int net = c / CH, cc = c % CH;
         const int h0 = net * H + cc * 64 + j * 16;  // first hidden unit (= Z column) of this thread
-        mbar_wait(z_ready + c, par);
-        tc_fence_after();
-        uint32_t z[16];
-        Tmem<16>::ld(tl + G::Z0 + h0, z);
-        tc_wait_ld();
         const f32x2 s1 = pk1(ssinv[net * 2]);
-        uint32_t o[16];
+        uint32_t o[16], zn[16];
+        tc_wait_ld();
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
+          if (m == 4 && c + 1 < NCHUNK) {
+            const int nnet = (c + 1) / CH, ncc = (c + 1) % CH;
+            mbar_wait(z_ready + c + 1, par);
+            tc_fence_after();
+            Tmem<16>::ld(tl + G::Z0 + nnet * H + ncc * 64 + j * 16, zn);
+          }
           const float2 b = *reinterpret_cast<const float2 *>(sb1 + h0 + 2 * m);
           const f32x2 a = fma2(pk(__uint_as_float(z[2 * m]), __uint_as_float(z[2 * m + 1])), s1, pk(b.x, b.y));
           float t0, t1;
-          upk(tanh_rat2(a), t0, t1);
+          upk(tanh_fast2(a), t0, t1);
           split2(t0, t1, o[m], o[8 + m]);
         }
         Tmem<16>::st(tl + G::Z0 + h0, o);
@@ -426,6 +459,10 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(h_ready + c);
+        if (c + 1 < NCHUNK) {
+#pragma unroll
+          for (int m = 0; m < 16; ++m) z[m] = zn[m];
+        }
       }
       // 3. F -> registers
       mbar_wait(f_ready, par);

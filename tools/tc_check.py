@@ -87,6 +87,11 @@ def sde(d, h, B, time=False):
 
 if __name__ == "__main__":
     quick = "quick" in sys.argv
+    if "bench" in sys.argv:
+        print(json.dumps(ode(64, 256, 512, "RK4", "id")), flush=True)
+        print(json.dumps(ode(64, 256, 1 << 17, "RK4", "id", steps=100, time=True)), flush=True)
+        print(json.dumps(sde(32, 64, 1 << 21, time=True)), flush=True)
+        sys.exit(0)
     print(json.dumps(ode(64, 256, 128, "Euler", "id", steps=1)), flush=True)
     print(json.dumps(ode(64, 256, 4096, "Euler", "id", steps=1)), flush=True)
     print(json.dumps(ode(64, 256, 100, "RK4", "id")), flush=True)
