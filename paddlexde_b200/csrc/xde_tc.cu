@@ -64,8 +64,8 @@ struct Geom {
   static constexpr int MAT_BYTES = D * H * 2;          // one fp16 copy of one weight matrix
   static constexpr int NET_W_BYTES = 4 * MAT_BYTES;    // W1hi | W1lo | W2hi | W2lo
   static constexpr int W_BYTES = NETS * NET_W_BYTES;
-  // shared memory: [barriers + tmem slot: 128 B][weights][b1 NETS*H][b2 NETS*D][sinv NETS*2 (+pad)][t grid]
-  static constexpr int OFF_W = 128;
+  // shared memory: [barriers + tmem slot: 256 B][weights][b1 NETS*H][b2 NETS*D][sinv NETS*2 (+pad)][t grid]
+  static constexpr int OFF_W = 256;
   static constexpr int OFF_B1 = OFF_W + W_BYTES;
   static constexpr int OFF_B2 = OFF_B1 + NETS * H * 4;
   static constexpr int OFF_SINV = OFF_B2 + NETS * D * 4;
@@ -81,6 +81,24 @@ struct TcParams {
   long long B;
   int T, stride, n_out;
 };
+
+// ---- optional phase trace (debug builds only: -DXDE_TC_TRACE, tools/tc_trace.py) ------------------------
+#ifdef XDE_TC_TRACE
+__device__ long long *g_trace = nullptr;  // [2][kTraceCap]: row 0 = compute warp 0, row 1 = MMA thread (CTA 0)
+constexpr int kTraceCap = 4096;
+#define XDE_TRACE(row, tag)                                                              \
+  do {                                                                                   \
+    if (g_trace && blockIdx.x == 0 && trace_n < kTraceCap / 2) {                          \
+      g_trace[(row) * kTraceCap + 2 * trace_n] = (tag);                                  \
+      g_trace[(row) * kTraceCap + 2 * trace_n + 1] = clock64();                          \
+      ++trace_n;                                                                         \
+    }                                                                                    \
+  } while (0)
+#else
+#define XDE_TRACE(row, tag) \
+  do {                      \
+  } while (0)
+#endif
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,6 +128,14 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// one lane of a CONVERGED warp (the MMA warp runs its loop with all 32 lanes; only the elected lane issues:
+// inside a divergent `if (lane == 0)` ptxas wraps every UTCHMMA in an ELECT/BRA.U.ANY waterfall loop,
+// ~65 cycles per MMA instead of the ~34 the tensor pipe needs)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
 }
 // D[tmem] (+)= A[tmem, fp16 packed] * B[smem descriptor], M = 128, K = 16
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -347,20 +373,22 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
   const long long total_evals = my_tiles * (long long)(p.T - 1) * EVALS;
 
   if (warp == kComputeWarps) {
-    // =============================== MMA issuer (one thread) ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = instr_desc(64), idesc2 = instr_desc(D);
-      const uint32_t w_addr = smem_u32(sW);
-      for (long long ev = 0; ev < total_evals; ++ev) {
-        const uint32_t par = (uint32_t)(ev & 1);
-        mbar_wait(u_ready, par);
-        tc_fence_after();
-        // layer 1, chunk by chunk: Z[:, 64 c ..] = U W1[:, 64 c ..]
+    // =============================== MMA issuer (one elected lane of a converged warp) ===============
+    constexpr uint32_t idesc1 = instr_desc(64), idesc2 = instr_desc(D);
+    const uint32_t w_addr = smem_u32(sW);
+    [[maybe_unused]] int trace_n = (lane == 0) ? 0 : (1 << 30);
+    for (long long ev = 0; ev < total_evals; ++ev) {
+      const uint32_t par = (uint32_t)(ev & 1);
+      mbar_wait(u_ready, par);
+      tc_fence_after();
+      XDE_TRACE(1, 100);
+      // layer 1, chunk by chunk: Z[:, 64 c ..] = U W1[:, 64 c ..]
 #pragma unroll
-        for (int c = 0; c < NCHUNK; ++c) {
-          const int net = c / CH, cc = c % CH;
-          const uint32_t d = tmem + G::Z0 + net * H + cc * 64;
-          const uint32_t w1hi = w_addr + net * G::NET_W_BYTES, w1lo = w1hi + G::MAT_BYTES;
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int net = c / CH, cc = c % CH;
+        const uint32_t d = tmem + G::Z0 + net * H + cc * 64;
+        const uint32_t w1hi = w_addr + net * G::NET_W_BYTES, w1lo = w1hi + G::MAT_BYTES;
+        if (elect_one()) {
           // corrections first, while the accumulator is still small (see Geom::NFM), then the hi*hi products
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
@@ -377,15 +405,20 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
           }
           tc_commit(z_ready + c);
         }
-        // layer 2, as each chunk of tanh lands: F += Hh[:, 64 c ..] W2[64 c .., :]
+        __syncwarp();
+        XDE_TRACE(1, 110 + c);
+      }
+      // layer 2, as each chunk of tanh lands: F += Hh[:, 64 c ..] W2[64 c .., :]
 #pragma unroll
-        for (int c = 0; c < NCHUNK; ++c) {
-          const int net = c / CH, cc = c % CH;
-          mbar_wait(h_ready + c, par);
-          tc_fence_after();
-          const uint32_t d_main = tmem + G::F0 + net * G::FW + (cc % G::NFM) * D;
-          const uint32_t d_corr = tmem + G::F0 + net * G::FW + G::NFM * D;
-          const uint32_t w2hi = w_addr + net * G::NET_W_BYTES + 2 * G::MAT_BYTES, w2lo = w2hi + G::MAT_BYTES;
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int net = c / CH, cc = c % CH;
+        const uint32_t d_main = tmem + G::F0 + net * G::FW + (cc % G::NFM) * D;
+        const uint32_t d_corr = tmem + G::F0 + net * G::FW + G::NFM * D;
+        const uint32_t w2hi = w_addr + net * G::NET_W_BYTES + 2 * G::MAT_BYTES, w2lo = w2hi + G::MAT_BYTES;
+        mbar_wait(h_ready + c, par);
+        tc_fence_after();
+        XDE_TRACE(1, 120 + c);
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const int s = cc * 4 + ks;  // K step = hidden units 16 s .. 16 s + 15
@@ -396,11 +429,12 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
             mma_ts(d_corr, a_lo, b_hi, idesc2, 1);
             mma_ts(d_main, a_hi, b_hi, idesc2, !(cc < G::NFM && ks == 0));
           }
+          if (c == NCHUNK - 1) tc_commit(f_ready);
         }
-        tc_commit(f_ready);
+        __syncwarp();
       }
+      XDE_TRACE(1, 130);
     }
-    __syncwarp();
   } else {
     // =============================== compute warps ===============================
     const int q = warp & 3, j = warp >> 2;  // TMEM lane quarter, column group
@@ -409,30 +443,43 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
     const int pref = p.f.pre, preg = p.g.pre;
     const float one_third = (float)(1.0 / 3.0);
     uint32_t par = 0;
+    [[maybe_unused]] int trace_n = (tid == 0) ? 0 : (1 << 30);
 
-    // one evaluation of the field(s) at yi: kf (and kg) <- f(yi) (, g(yi))
-    auto eval = [&](const float (&yi)[NC], float (&kf)[NC], float (&kg)[NC]) {
+    // one evaluation of the field(s) at yi: kf (and kg) <- f(yi) (, g(yi)); state columns travel as packed pairs
+    constexpr int NP = NC / 2;
+    auto eval = [&](const f32x2 (&yi)[NP], f32x2 (&kf)[NP], f32x2 (&kg)[NP]) {
+      XDE_TRACE(0, 0);
       // 1. stage input -> U (fp16 hi | lo)
 #pragma unroll
       for (int net = 0; net < NETS; ++net) {
         uint32_t uh[NC / 2], ul[NC / 2];
         const int pre = net ? preg : pref;
 #pragma unroll
-        for (int c = 0; c < NC / 2; ++c) split2(pre_rt(pre, yi[2 * c]), pre_rt(pre, yi[2 * c + 1]), uh[c], ul[c]);
+        for (int c = 0; c < NP; ++c) {
+          float v0, v1;
+          upk(yi[c], v0, v1);
+          split2(pre_rt(pre, v0), pre_rt(pre, v1), uh[c], ul[c]);
+        }
         Tmem<NC / 2>::st(tl + G::U0 + net * D + j * (NC / 2), uh);
         Tmem<NC / 2>::st(tl + G::U0 + net * D + D / 2 + j * (NC / 2), ul);
       }
+      XDE_TRACE(0, 3);
       tc_wait_st();
+      XDE_TRACE(0, 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(u_ready);
+      XDE_TRACE(0, 1);
       // 2. hidden chunks: Z -> tanh -> fp16 hi | lo, in place.  The TMEM load of chunk c+1 is issued half
       // way through the tanh of chunk c (its MMAs were queued right behind chunk c's), so its latency and
-      // the mbarrier round trip are hidden behind arithmetic.
+      // the mbarrier round trip hide behind arithmetic.  (Deferring the store-completion wait / hand-off
+      // of chunk c into chunk c+1 was measured: no gain -- the phase is issue-bound, the other warps of
+      // the scheduler already cover those latencies.)
       uint32_t z[16];
       mbar_wait(z_ready, par);
       tc_fence_after();
       Tmem<16>::ld(tl + G::Z0 + j * 16, z);
+      XDE_TRACE(0, 2);
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
         const int net = c / CH, cc = c % CH;
@@ -455,10 +502,13 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
           split2(t0, t1, o[m], o[8 + m]);
         }
         Tmem<16>::st(tl + G::Z0 + h0, o);
+        XDE_TRACE(0, 30 + c);
         tc_wait_st();
+        XDE_TRACE(0, 40 + c);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(h_ready + c);
+        XDE_TRACE(0, 10 + c);
         if (c + 1 < NCHUNK) {
 #pragma unroll
           for (int m = 0; m < 16; ++m) z[m] = zn[m];
@@ -467,33 +517,41 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
       // 3. F -> registers
       mbar_wait(f_ready, par);
       tc_fence_after();
+      XDE_TRACE(0, 20);
 #pragma unroll
       for (int net = 0; net < NETS; ++net) {
-        float(&kk)[NC] = net ? kg : kf;
+        f32x2(&kk)[NP] = net ? kg : kf;
         const uint32_t fa = tl + G::F0 + net * G::FW + c0;
         uint32_t r0[NC], r1[NC];
         Tmem<NC>::ld(fa, r0);
         Tmem<NC>::ld(fa + D, r1);  // NFM == 1: this is already the correction accumulator
         tc_wait_ld();
 #pragma unroll
-        for (int c = 0; c < NC; ++c) kk[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+        for (int c = 0; c < NP; ++c)
+          kk[c] = add2(pk(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1])),
+                       pk(__uint_as_float(r1[2 * c]), __uint_as_float(r1[2 * c + 1])));
         if (G::NFM == 2) {
           Tmem<NC>::ld(fa + 2 * D, r0);
           tc_wait_ld();
 #pragma unroll
-          for (int c = 0; c < NC; ++c) kk[c] += __uint_as_float(r0[c]);
+          for (int c = 0; c < NP; ++c)
+            kk[c] = add2(kk[c], pk(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1])));
         }
-        const float s2 = ssinv[net * 2 + 1];
+        const f32x2 s2 = pk1(ssinv[net * 2 + 1]);
 #pragma unroll
-        for (int c = 0; c < NC; ++c) kk[c] = fmaf(kk[c], s2, sb2[net * D + c0 + c]);
+        for (int c = 0; c < NP; ++c) {
+          const float2 bb = *reinterpret_cast<const float2 *>(sb2 + net * D + c0 + 2 * c);
+          kk[c] = fma2(kk[c], s2, pk(bb.x, bb.y));
+        }
       }
       par ^= 1u;
+      XDE_TRACE(0, 21);
     };
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long b = tile * kTM + 32 * q + lane;
       const bool ok = b < p.B;
-      float y[NC];
+      f32x2 y[NP];
 #pragma unroll
       for (int v = 0; v < NC / 4; ++v) {
         float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -501,69 +559,72 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
           t4 = *reinterpret_cast<const float4 *>(p.y0 + b * D + c0 + 4 * v);
           *reinterpret_cast<float4 *>(p.out + b * (long long)p.n_out * D + c0 + 4 * v) = t4;
         }
-        y[4 * v] = t4.x;
-        y[4 * v + 1] = t4.y;
-        y[4 * v + 2] = t4.z;
-        y[4 * v + 3] = t4.w;
+        y[2 * v] = pk(t4.x, t4.y);
+        y[2 * v + 1] = pk(t4.z, t4.w);
       }
       for (int i = 1; i < p.T; ++i) {
         const float dt = st[i] - st[i - 1];
-        float k[NC], kg[NC];
+        const f32x2 dt2 = pk1(dt);
+        f32x2 k[NP], kg[NP];
         if (KIND == 0) {
           eval(y, k, kg);
 #pragma unroll
-          for (int c = 0; c < NC; ++c) y[c] = fmaf(k[c], dt, y[c]);
+          for (int c = 0; c < NP; ++c) y[c] = fma2(k[c], dt2, y[c]);
         } else if (KIND == 1) {
           // RK4.step = rk4_alt_step_func (base_fixed_solver.py:166-197), as written there:
           //   k2 = f(y + dt k1/3), k3 = f(y + dt (k1 - k2/3)), k4 = f(y + dt (k1 - k2 + k3)),
           //   y1 = y + dt (k1 + 3 k2 + 3 k3 + k4) / 8
-          float yi[NC], A[NC], S[NC];
+          f32x2 yi[NP], A[NP], S[NP];
           eval(y, k, kg);
-          const float dt13 = dt * one_third;
+          const f32x2 dt13 = pk1(dt * one_third);
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
+          for (int c = 0; c < NP; ++c) {
             A[c] = k[c];
-            yi[c] = fmaf(k[c], dt13, y[c]);
+            yi[c] = fma2(k[c], dt13, y[c]);
           }
           eval(yi, k, kg);
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            yi[c] = fmaf(fmaf(-one_third, k[c], A[c]), dt, y[c]);
-            S[c] = fmaf(3.0f, k[c], A[c]);
-            A[c] = A[c] - k[c];
+          for (int c = 0; c < NP; ++c) {
+            yi[c] = fma2(fma2(pk1(-one_third), k[c], A[c]), dt2, y[c]);
+            S[c] = fma2(pk1(3.0f), k[c], A[c]);
+            A[c] = sub2(A[c], k[c]);
           }
           eval(yi, k, kg);
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            yi[c] = fmaf(A[c] + k[c], dt, y[c]);
-            S[c] = fmaf(3.0f, k[c], S[c]);
+          for (int c = 0; c < NP; ++c) {
+            yi[c] = fma2(add2(A[c], k[c]), dt2, y[c]);
+            S[c] = fma2(pk1(3.0f), k[c], S[c]);
           }
           eval(yi, k, kg);
-          const float dt8 = dt * 0.125f;
+          const f32x2 dt8 = pk1(dt * 0.125f);
 #pragma unroll
-          for (int c = 0; c < NC; ++c) y[c] = fmaf(S[c] + k[c], dt8, y[c]);
+          for (int c = 0; c < NP; ++c) y[c] = fma2(add2(S[c], k[c]), dt8, y[c]);
         } else {
-          float w[NC];
+          // the increments are requested before the evaluation and first touched after it (packing them
+          // here would stall on the load before the evaluation starts)
+          float4 w4[NC / 4];
 #pragma unroll
           for (int v = 0; v < NC / 4; ++v) {
-            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) t4 = __ldg(reinterpret_cast<const float4 *>(p.dW + ((long long)(i - 1) * p.B + b) * D + c0 + 4 * v));
-            w[4 * v] = t4.x;
-            w[4 * v + 1] = t4.y;
-            w[4 * v + 2] = t4.z;
-            w[4 * v + 3] = t4.w;
+            w4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) w4[v] = __ldg(reinterpret_cast<const float4 *>(p.dW + ((long long)(i - 1) * p.B + b) * D + c0 + 4 * v));
           }
           eval(y, k, kg);
 #pragma unroll
-          for (int c = 0; c < NC; ++c) y[c] = fmaf(kg[c], w[c], fmaf(k[c], dt, y[c]));
+          for (int v = 0; v < NC / 4; ++v) {
+            y[2 * v] = fma2(kg[2 * v], pk(w4[v].x, w4[v].y), fma2(k[2 * v], dt2, y[2 * v]));
+            y[2 * v + 1] = fma2(kg[2 * v + 1], pk(w4[v].z, w4[v].w), fma2(k[2 * v + 1], dt2, y[2 * v + 1]));
+          }
         }
         // linear_interp at t == t1 is the identity (interpolation/functional/interp_fn.py:4-10)
         if (ok && (i % p.stride == 0 || i == p.T - 1)) {
           const int row = (i == p.T - 1) ? p.n_out - 1 : i / p.stride;
 #pragma unroll
-          for (int v = 0; v < NC / 4; ++v)
-            *reinterpret_cast<float4 *>(p.out + (b * (long long)p.n_out + row) * D + c0 + 4 * v) =
-                make_float4(y[4 * v], y[4 * v + 1], y[4 * v + 2], y[4 * v + 3]);
+          for (int v = 0; v < NC / 4; ++v) {
+            float4 t4;
+            upk(y[2 * v], t4.x, t4.y);
+            upk(y[2 * v + 1], t4.z, t4.w);
+            *reinterpret_cast<float4 *>(p.out + (b * (long long)p.n_out + row) * D + c0 + 4 * v) = t4;
+          }
         }
       }
     }
@@ -618,6 +679,12 @@ static int tc_dispatch(const TcParams &p, cudaStream_t s) {
 }
 
 }  // namespace tc
+
+#ifdef XDE_TC_TRACE
+extern "C" XDE_EXPORT int xde_tc_trace_set(long long *buf) {
+  return cudaMemcpyToSymbol(tc::g_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 int rk_fixed_tc(int method, const xde_mlp_field_t *f, const float *y0, long long B, const float *t_span, int T,
                 int stride, float *out, cudaStream_t s) {
