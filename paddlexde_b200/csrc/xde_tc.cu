@@ -32,21 +32,27 @@
 //     every buffer's next writer is ordered behind its last reader by the chain itself.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "xde_common.cuh"
 
 namespace xde {
 namespace tc {
 
-constexpr int kComputeWarps = 16;
-constexpr int kThreads = (kComputeWarps + 1) * 32;
+// compute warps = 4 lane quarters x NJ column groups (NJ = 4 is what is dispatched; see launch_tc_auto)
+__host__ __device__ constexpr int compute_warps(int NJ) { return 4 * NJ; }
+__host__ __device__ constexpr int cta_threads(int NJ) { return (4 * NJ + 1) * 32; }
 constexpr int kTM = 128;
 constexpr int kMaxChunks = 4;
 
-template <int D, int H, int NETS>
+template <int D, int H, int NETS, int NJ>
 struct Geom {
+  static_assert(NJ == 4 || NJ == 2, "column groups");
   static_assert(D % 16 == 0 && D >= 16 && D <= 64, "state dim: 16, 32, 48, 64");
   static_assert(H % 64 == 0 && H >= 64 && H <= 256, "hidden width: 64, 128, 192, 256");
-  static constexpr int NC = D / 4;    // state columns per compute thread
+  static constexpr int NC = D / NJ;   // state columns per compute thread
+  static_assert(NC % 4 == 0 && NC <= 16, "state columns per thread: 4, 8 or 16");
+  static constexpr int SB = 4 / NJ;   // 16-column tanh blocks per thread and hidden chunk
   static constexpr int CH = H / 64;   // 64-wide hidden chunks per network
   static constexpr int NCHUNK = NETS * CH;
   static_assert(NCHUNK <= kMaxChunks, "too many hidden chunks");
@@ -55,8 +61,11 @@ struct Geom {
   // error of ~0.5 ulp(|accumulator|) each time and always towards zero: keeping the 2^-11-times-smaller
   // correction products away from the full-size sums, and halving the chain length, keeps that bias at
   // a few fp32 ulps.  The epilogue adds the partial sums in fp32 (round to nearest).
+  // A single-chunk network (H = 64) has all of its K steps at hand at once: corrections first, then the
+  // hi*hi products, in ONE accumulator (the ordering does what the separate accumulator does).
   static constexpr int NFM = CH >= 2 ? 2 : 1;
-  static constexpr int FW = (NFM + 1) * D;
+  static constexpr bool SPLIT_CORR = CH >= 2;
+  static constexpr int FW = (NFM + (SPLIT_CORR ? 1 : 0)) * D;
   static constexpr int Z0 = 0, F0 = NETS * H, U0 = NETS * (H + FW);
   static constexpr int COLS = NETS * (H + FW + D);
   static_assert(COLS <= 512, "TMEM has 512 columns");
@@ -309,10 +318,11 @@ __global__ void __launch_bounds__(1024) tc_prep_kernel(xde_mlp_field_t f, xde_ml
 
 // ---- the solver -----------------------------------------------------------------------------------
 // KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama (two networks)
-template <int D, int H, int KIND>
-__global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p) {
+template <int D, int H, int KIND, int NJ>
+__global__ void __launch_bounds__(cta_threads(NJ), NJ == 4 ? 1 : 2) fixed_tc_kernel(const TcParams p) {
   constexpr int NETS = (KIND == 2) ? 2 : 1;
-  using G = Geom<D, H, NETS>;
+  constexpr int kComputeWarps = compute_warps(NJ), kThreads = cta_threads(NJ);
+  using G = Geom<D, H, NETS, NJ>;
   constexpr int NC = G::NC, CH = G::CH, NCHUNK = G::NCHUNK;
   constexpr int EVALS = (KIND == 1) ? 4 : 1;  // field evaluations per step
 
@@ -413,21 +423,35 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
       for (int c = 0; c < NCHUNK; ++c) {
         const int net = c / CH, cc = c % CH;
         const uint32_t d_main = tmem + G::F0 + net * G::FW + (cc % G::NFM) * D;
-        const uint32_t d_corr = tmem + G::F0 + net * G::FW + G::NFM * D;
+        const uint32_t d_corr = G::SPLIT_CORR ? tmem + G::F0 + net * G::FW + G::NFM * D : d_main;
         const uint32_t w2hi = w_addr + net * G::NET_W_BYTES + 2 * G::MAT_BYTES, w2lo = w2hi + G::MAT_BYTES;
         mbar_wait(h_ready + c, par);
         tc_fence_after();
         XDE_TRACE(1, 120 + c);
         if (elect_one()) {
+          if (G::SPLIT_CORR) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const int s = cc * 4 + ks;  // K step = hidden units 16 s .. 16 s + 15
-            const uint32_t a_hi = tmem + G::Z0 + net * H + 16 * s, a_lo = a_hi + 8;
-            const uint32_t off = (2 * s) * (D * 16);
-            const uint64_t b_hi = smem_desc(w2hi + off, D * 16, 128), b_lo = smem_desc(w2lo + off, D * 16, 128);
-            mma_ts(d_corr, a_hi, b_lo, idesc2, (cc | ks) != 0);
-            mma_ts(d_corr, a_lo, b_hi, idesc2, 1);
-            mma_ts(d_main, a_hi, b_hi, idesc2, !(cc < G::NFM && ks == 0));
+            for (int ks = 0; ks < 4; ++ks) {
+              const int s = cc * 4 + ks;  // K step = hidden units 16 s .. 16 s + 15
+              const uint32_t a_hi = tmem + G::Z0 + net * H + 16 * s, a_lo = a_hi + 8;
+              const uint32_t off = (2 * s) * (D * 16);
+              const uint64_t b_hi = smem_desc(w2hi + off, D * 16, 128), b_lo = smem_desc(w2lo + off, D * 16, 128);
+              mma_ts(d_corr, a_hi, b_lo, idesc2, (cc | ks) != 0);
+              mma_ts(d_corr, a_lo, b_hi, idesc2, 1);
+              mma_ts(d_main, a_hi, b_hi, idesc2, !(cc < G::NFM && ks == 0));
+            }
+          } else {  // one chunk, one accumulator: corrections first, then the hi*hi products
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t a_hi = tmem + G::Z0 + net * H + 16 * ks, a_lo = a_hi + 8;
+              const uint32_t off = (2 * ks) * (D * 16);
+              mma_ts(d_main, a_hi, smem_desc(w2lo + off, D * 16, 128), idesc2, ks != 0);
+              mma_ts(d_main, a_lo, smem_desc(w2hi + off, D * 16, 128), idesc2, 1);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ts(d_main, tmem + G::Z0 + net * H + 16 * ks, smem_desc(w2hi + (2 * ks) * (D * 16), D * 16, 128),
+                     idesc2, 1);
           }
           if (c == NCHUNK - 1) tc_commit(f_ready);
         }
@@ -475,25 +499,31 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
       // the mbarrier round trip hide behind arithmetic.  (Deferring the store-completion wait / hand-off
       // of chunk c into chunk c+1 was measured: no gain -- the phase is issue-bound, the other warps of
       // the scheduler already cover those latencies.)
+      constexpr int SB = G::SB, NB = NCHUNK * SB;  // 16-column blocks of this thread: SB per chunk
+      auto zcol = [&](int blk) {
+        const int c = blk / SB, sb = blk % SB;
+        return (c / CH) * H + (c % CH) * 64 + (j * SB + sb) * 16;  // first hidden unit (= Z column) of the block
+      };
       uint32_t z[16];
       mbar_wait(z_ready, par);
       tc_fence_after();
-      Tmem<16>::ld(tl + G::Z0 + j * 16, z);
+      Tmem<16>::ld(tl + G::Z0 + zcol(0), z);
       XDE_TRACE(0, 2);
 #pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
-        const int net = c / CH, cc = c % CH;
-        const int h0 = net * H + cc * 64 + j * 16;  // first hidden unit (= Z column) of this thread
+      for (int blk = 0; blk < NB; ++blk) {
+        const int c = blk / SB, net = c / CH;
+        const int h0 = zcol(blk);
         const f32x2 s1 = pk1(ssinv[net * 2]);
         uint32_t o[16], zn[16];
         tc_wait_ld();
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-          if (m == 4 && c + 1 < NCHUNK) {
-            const int nnet = (c + 1) / CH, ncc = (c + 1) % CH;
-            mbar_wait(z_ready + c + 1, par);
-            tc_fence_after();
-            Tmem<16>::ld(tl + G::Z0 + nnet * H + ncc * 64 + j * 16, zn);
+          if (m == 4 && blk + 1 < NB) {
+            if ((blk + 1) % SB == 0) {
+              mbar_wait(z_ready + (blk + 1) / SB, par);
+              tc_fence_after();
+            }
+            Tmem<16>::ld(tl + G::Z0 + zcol(blk + 1), zn);
           }
           const float2 b = *reinterpret_cast<const float2 *>(sb1 + h0 + 2 * m);
           const f32x2 a = fma2(pk(__uint_as_float(z[2 * m]), __uint_as_float(z[2 * m + 1])), s1, pk(b.x, b.y));
@@ -503,13 +533,15 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
         }
         Tmem<16>::st(tl + G::Z0 + h0, o);
         XDE_TRACE(0, 30 + c);
-        tc_wait_st();
-        XDE_TRACE(0, 40 + c);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(h_ready + c);
-        XDE_TRACE(0, 10 + c);
-        if (c + 1 < NCHUNK) {
+        if (blk % SB == SB - 1) {
+          tc_wait_st();
+          XDE_TRACE(0, 40 + c);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(h_ready + c);
+          XDE_TRACE(0, 10 + c);
+        }
+        if (blk + 1 < NB) {
 #pragma unroll
           for (int m = 0; m < 16; ++m) z[m] = zn[m];
         }
@@ -524,14 +556,15 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
         const uint32_t fa = tl + G::F0 + net * G::FW + c0;
         uint32_t r0[NC], r1[NC];
         Tmem<NC>::ld(fa, r0);
-        Tmem<NC>::ld(fa + D, r1);  // NFM == 1: this is already the correction accumulator
+        if (G::SPLIT_CORR) Tmem<NC>::ld(fa + D, r1);  // second main accumulator
         tc_wait_ld();
 #pragma unroll
-        for (int c = 0; c < NP; ++c)
-          kk[c] = add2(pk(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1])),
-                       pk(__uint_as_float(r1[2 * c]), __uint_as_float(r1[2 * c + 1])));
-        if (G::NFM == 2) {
-          Tmem<NC>::ld(fa + 2 * D, r0);
+        for (int c = 0; c < NP; ++c) {
+          kk[c] = pk(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
+          if (G::SPLIT_CORR) kk[c] = add2(kk[c], pk(__uint_as_float(r1[2 * c]), __uint_as_float(r1[2 * c + 1])));
+        }
+        if (G::SPLIT_CORR) {
+          Tmem<NC>::ld(fa + 2 * D, r0);  // corrections
           tc_wait_ld();
 #pragma unroll
           for (int c = 0; c < NP; ++c)
@@ -639,10 +672,10 @@ __global__ void __launch_bounds__(kThreads, 1) fixed_tc_kernel(const TcParams p)
   }
 }
 
-template <int D, int H, int KIND>
+template <int D, int H, int KIND, int NJ>
 static int launch_tc(TcParams p, cudaStream_t s) {
   constexpr int NETS = (KIND == 2) ? 2 : 1;
-  using G = Geom<D, H, NETS>;
+  using G = Geom<D, H, NETS, NJ>;
   const size_t smem = G::bytes(p.T);
   XDE_REQUIRE(smem <= 227 * 1024, XDE_E_UNSUPPORTED_FIELD,
               "tensor-core solver: weights + time grid need %zu bytes of shared memory (> 227 KB)", smem);
@@ -652,23 +685,36 @@ static int launch_tc(TcParams p, cudaStream_t s) {
   tc_prep_kernel<<<NETS * 2, 1024, 0, s>>>(p.f, p.g, (unsigned char *)wbuf, NETS);
   count_launch();
   p.wbuf = (const unsigned char *)wbuf;
-  auto kern = fixed_tc_kernel<D, H, KIND>;
+  auto kern = fixed_tc_kernel<D, H, KIND, NJ>;
   XDE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  XDE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cta_threads(NJ), smem));
+  per_sm = std::max(1, std::min(per_sm, 512 / G::ALLOC));  // each resident CTA owns G::ALLOC TMEM columns
   const long long n_tiles = (p.B + kTM - 1) / kTM;
-  long long grid = sm_count();  // persistent: one CTA (and its 512 TMEM columns) per SM
+  long long grid = (long long)sm_count() * per_sm;  // persistent
   if (grid > n_tiles) grid = n_tiles;
-  kern<<<(unsigned)grid, kThreads, smem, s>>>(p);
+  kern<<<(unsigned)grid, cta_threads(NJ), smem, s>>>(p);
   count_launch();
   XDE_CUDA_CHECK(cudaGetLastError());
   XDE_CUDA_CHECK(cudaFreeAsync(wbuf, s));
   return XDE_OK;
 }
 
+// NJ = 2 (8 compute warps, meant for two CTAs per SM on small fields) is kept compilable but not dispatched:
+// measured on B200, the register file is allocated per 4 warps, so two 9-warp CTAs at > 80 registers per
+// thread do not co-reside (launch__waves_per_multiprocessor stayed 0.5) and the variant is 4 % slower
+// than one 17-warp CTA.  Hiding the per-evaluation bubbles of small fields needs two tiles in flight
+// inside ONE CTA (DESIGN.md "Next").
+template <int D, int H, int KIND>
+static int launch_tc_auto(const TcParams &p, cudaStream_t s) {
+  return launch_tc<D, H, KIND, 4>(p, s);
+}
+
 template <int KIND>
 static int tc_dispatch(const TcParams &p, cudaStream_t s) {
   const int D = p.f.d, H = p.f.h;
 #define XDE_TC_CASE(DD, HH) \
-  if (D == DD && H == HH) return launch_tc<DD, HH, KIND>(p, s);
+  if (D == DD && H == HH) return launch_tc_auto<DD, HH, KIND>(p, s);
   XDE_TC_CASE(64, 64) XDE_TC_CASE(32, 128) XDE_TC_CASE(32, 64) XDE_TC_CASE(16, 128) XDE_TC_CASE(16, 64)
   if constexpr (KIND != 2) {  // two networks: 2 (H + FW + D) <= 512 TMEM columns
     XDE_TC_CASE(64, 256) XDE_TC_CASE(64, 128) XDE_TC_CASE(32, 256)
