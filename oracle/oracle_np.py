@@ -45,6 +45,28 @@ def root5(r) -> np.float32:
     return x
 
 
+def rootp(r, p: int) -> np.float32:
+    """r ** (1/p) for the orders of the supported tableaux, deterministic: p=2 sqrt (IEEE), p=8 three
+    sqrts, p=3 integer seed + 4 Newton steps x <- (2x + r/x^2)/3, p=5 root5."""
+    r = f32(r)
+    if p == 5:
+        return root5(r)
+    if p == 2:
+        return f32(np.sqrt(r))
+    if p == 8:
+        return f32(np.sqrt(f32(np.sqrt(f32(np.sqrt(r))))))
+    if p == 3:
+        u = np.array([r], dtype=np.float32).view(np.uint32)
+        u = (u // np.uint32(3) + np.uint32(0x2A555555)).astype(np.uint32)
+        x = u.view(np.float32)[0]
+        third = f32(1.0 / 3.0)
+        for _ in range(4):
+            q = f32(r / f32(x * x))
+            x = f32(f32(f32(2.0) * x + q) * third)  # 2*x exact: fused == unfused
+        return x
+    raise ValueError(p)
+
+
 def rms_norm(v: np.ndarray) -> np.float32:
     """_rms_norm (utils/ode_utils.py:8-9): squares in fp32, mean/sqrt in fp64 (order independent)."""
     q = (v.astype(np.float32).ravel() * v.astype(np.float32).ravel()).astype(np.float32)
@@ -99,6 +121,61 @@ DP_C_MID = np.array(
 ).astype(f32)
 
 
+def _tab(alpha, beta, c_sol, c_err, c_mid):
+    """float64 tableau -> (fp32 arrays, fsal flag tested on the float64 values like the reference)."""
+    fsal = bool(c_sol[-1] == 0 and list(c_sol[:-1]) == list(beta[-1]))
+    cast = lambda a: np.array(a, dtype=np.float64).astype(f32)
+    return dict(ALPHA=cast(alpha), BETA=[cast(b) for b in beta], C_SOL=cast(c_sol), C_ERR=cast(c_err),
+                C_MID=cast(c_mid), FSAL=fsal)
+
+
+# adaptive_solver/bosh3.py:5-27, fehlberg2.py:5-22, adaptive_heun.py:5-27
+BOSH3_TAB = _tab([1 / 2, 3 / 4, 1.0], [[1 / 2], [0.0, 3 / 4], [2 / 9, 1 / 3, 4 / 9]], [2 / 9, 1 / 3, 4 / 9, 0.0],
+                 [2 / 9 - 7 / 24, 1 / 3 - 1 / 4, 4 / 9 - 1 / 3, -1 / 8], [0.0, 0.5, 0.0, 0.0])
+FEHLBERG2_TAB = _tab([1 / 2, 1.0], [[1 / 2], [1 / 256, 255 / 256]], [1 / 512, 255 / 256, 1 / 512],
+                     [-1 / 512, 0, 1 / 512], [0.0, 0.5, 0.0])
+HEUN_TAB = _tab([1.0], [[1.0]], [0.5, 0.5], [0.5, -0.5], [0.5, 0.0])
+
+
+def _dopri8_tab():
+    """adaptive_solver/dopri8.py:5-252.  Read from the C oracle's table text so that the 120 rationals
+    exist once in oracle/ (xde_oracle.c D8_*); evaluated here in Python float64 exactly like the
+    reference's literals (`a / b`), including the C_mid quintics at h = 1/2."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "xde_oracle.c")).read()
+
+    def block(name):
+        m = re.search(r"static const double " + name + r"[^=]*=\s*\{(.*?)\};", src, re.S)
+        return m.group(1)
+
+    def ev(txt):  # "16016141.0 / 946692911" or "a / b - -c / d" -> Python float64, left to right like Python
+        return float(eval(txt.replace(".0 /", " /").strip(), {"__builtins__": {}}))
+
+    def flat(txt):
+        return [ev(t) for t in txt.replace("\n", " ").split(",") if t.strip()]
+
+    alpha = flat(block("D8_ALPHA64"))
+    rows = re.findall(r"\{([^{}]*)\}", block("D8_BETA64"))
+    beta = [flat(r) for r in rows]
+    beta = [b + [0.0] * (i + 1 - len(b)) for i, b in enumerate(beta)]
+    c_sol, c_err = flat(block("D8_CSOL64")), flat(block("D8_CERR64"))
+    h = 1 / 2
+    c_mid = [0.0] * 14
+    for r in re.findall(r"\{([^{}]*)\}", block("D8_MIDPOLY")):
+        c = flat(r)
+        v = c[1] * (h ** 5) + c[2] * (h ** 4) + c[3] * (h ** 3) + c[4] * (h ** 2) + c[5] * h
+        if c[6] != 0.0:
+            v = v + c[6]
+        c_mid[int(c[0])] = v / (1 / h)
+    assert len(alpha) == 13 and [len(b) for b in beta] == list(range(1, 14)) and len(c_sol) == len(c_err) == 14
+    return _tab(alpha, beta, c_sol, c_err, c_mid)
+
+
+DOPRI8_TAB = _dopri8_tab()
+DOPRI5_TAB = dict(ALPHA=DP_ALPHA, BETA=DP_BETA, C_SOL=DP_C_SOL, C_ERR=DP_C_ERR, C_MID=DP_C_MID, FSAL=True)
+
+
 @dataclass
 class AttemptLog:
     t0: List[float] = field(default_factory=list)
@@ -108,13 +185,14 @@ class AttemptLog:
     nfe: int = 0
 
 
-class Dopri5:
-    """AdaptiveRKSolver + Dopri5 (solver/base_adaptive_solver_rk.py, adaptive_solver/dopri5.py).
+class AdaptiveRK:
+    """AdaptiveRKSolver (solver/base_adaptive_solver_rk.py) over a tableau (subclasses below).
 
     ``func(t, y)`` and ``norm(v)`` operate on fp32 arrays of y0's shape.  A decreasing t_span is
     integrated as s = -t with f~(s,y) = -f(-s,y) (repair R5)."""
 
     order = 5
+    tab = DOPRI5_TAB
 
     def __init__(self, func: Callable, y0: np.ndarray, rtol=1e-7, atol=1e-9, norm=rms_norm,
                  min_step=0.0, max_step=float("inf"), first_step=None, safety=0.9, ifactor=10.0,
@@ -161,7 +239,7 @@ class Dopri5:
             mx = d2 if d2 > d1 else d1
             with np.errstate(divide="ignore"):
                 arg = f32(f32(0.01) / mx)
-            h1 = root5(arg) if (arg > 0 and np.isfinite(arg)) else arg
+            h1 = rootp(arg, order + 1) if (arg > 0 and np.isfinite(arg)) else arg
         h1 = f32(abs(h1))
         return f32(np.fmin(f32(f32(100.0) * h0), h1))
 
@@ -178,21 +256,26 @@ class Dopri5:
 
     # solver/base_adaptive_solver_rk.py:129-181
     def _runge_kutta_step(self, y0, f0, t0, dt, t1):
+        tb = self.tab
+        S = len(tb["ALPHA"])
         k = [f0]
         yi = None
-        for i in range(6):
-            ti = t1 if DP_ALPHA[i] == f32(1.0) else f32(t0 + f32(DP_ALPHA[i] * dt))
-            bd = (DP_BETA[i] * dt).astype(f32)
-            s = (k[0] * bd[0]).astype(f32)
-            for j in range(1, i + 1):
-                s = (s + (k[j] * bd[j]).astype(f32)).astype(f32)
-            yi = (y0 + s).astype(f32)
+
+        def wsum(coef, n):  # paddle.sum(k[..., :n] * coef, axis=-1): products first, left-to-right sum
+            c = (coef[:n] * dt).astype(f32) if coef is not None else None
+            s = (k[0] * c[0]).astype(f32)
+            for j in range(1, n):
+                s = (s + (k[j] * c[j]).astype(f32)).astype(f32)
+            return s
+
+        for i in range(S):
+            ti = t1 if tb["ALPHA"][i] == f32(1.0) else f32(t0 + f32(tb["ALPHA"][i] * dt))
+            yi = (y0 + wsum(tb["BETA"][i], i + 1)).astype(f32)
             k.append(self.move(ti, yi))
+        if not tb["FSAL"]:  # :172-178
+            yi = (y0 + wsum(tb["C_SOL"], S + 1)).astype(f32)
         y1, f1 = yi, k[-1]
-        ce = (dt * DP_C_ERR).astype(f32)
-        err = (k[0] * ce[0]).astype(f32)
-        for j in range(1, 7):
-            err = (err + (k[j] * ce[j]).astype(f32)).astype(f32)
+        err = wsum(tb["C_ERR"], S + 1)
         return y1, f1, err, k
 
     # solver/base_adaptive_solver_rk.py:183-284
@@ -227,7 +310,7 @@ class Dopri5:
             dt_next = f32(dt * self.ifactor)
         else:
             dfac = f32(1.0) if ratio < 1 else self.dfactor
-            p = root5(ratio) if (ratio > 0 and np.isfinite(ratio)) else ratio
+            p = rootp(ratio, self.order) if (ratio > 0 and np.isfinite(ratio)) else ratio
             with np.errstate(all="ignore"):
                 factor = np.fmin(self.ifactor, np.fmax(f32(self.safety / p), dfac))
             dt_next = f32(dt * factor)
@@ -236,9 +319,9 @@ class Dopri5:
 
     # _interp_fit :286-292 + interp_fit utils/ode_utils.py:28-49
     def _interp_fit(self, y0, y1, k, dt):
-        cm = (dt * DP_C_MID).astype(f32)
+        cm = (dt * self.tab["C_MID"]).astype(f32)
         s = (k[0] * cm[0]).astype(f32)
-        for j in range(1, 7):
+        for j in range(1, len(cm)):
             s = (s + (k[j] * cm[j]).astype(f32)).astype(f32)
         y_mid = (y0 + s).astype(f32)
         f0, f1 = k[0], k[-1]
@@ -280,6 +363,26 @@ class Dopri5:
         return sol
 
 
+class Dopri5(AdaptiveRK):  # adaptive_solver/dopri5.py:58-61
+    order, tab = 5, DOPRI5_TAB
+
+
+class Bosh3(AdaptiveRK):  # adaptive_solver/bosh3.py:24-27
+    order, tab = 3, BOSH3_TAB
+
+
+class Fehlberg2(AdaptiveRK):  # adaptive_solver/fehlberg2.py:19-22
+    order, tab = 2, FEHLBERG2_TAB
+
+
+class AdaptiveHeun(AdaptiveRK):  # adaptive_solver/adaptive_heun.py:24-27
+    order, tab = 2, HEUN_TAB
+
+
+class Dopri8(AdaptiveRK):  # adaptive_solver/dopri8.py:249-252
+    order, tab = 8, DOPRI8_TAB
+
+
 class FixedSolver:
     """FixedSolver.integrate (solver/base_fixed_solver.py:103-144) with grid == t_span and
     interp == "linear" (identity at t == t1).  Returns concat(axis=-2)."""
@@ -311,6 +414,16 @@ class Euler(FixedSolver):
         return self.fuse(self.move(t0, y0), dt, y0)
 
 
+class Midpoint(FixedSolver):
+    order = 2
+
+    def step(self, t0, t1, y0):  # fixed_solver/midpoint.py:7-18
+        dt = f32(t1 - t0)
+        half_dt = f32(f32(0.5) * dt)
+        y_half = self.fuse(self.move(t0, y0), half_dt, y0)
+        return self.fuse(self.move(f32(t0 + half_dt), y_half), dt, y0)
+
+
 class RK4(FixedSolver):
     order = 4
 
@@ -332,9 +445,9 @@ class RK4(FixedSolver):
 def odeint(func, y0, t_span, solver, *, rtol=1e-7, atol=1e-9, options=None):
     """functional/odeint.py:9-35 (repair R1: xde.format == identity)."""
     options = dict(options or {})
-    if solver is Dopri5:
+    if isinstance(solver, type) and issubclass(solver, AdaptiveRK):
         options.setdefault("norm", rms_norm)
-        s = Dopri5(func, y0, rtol=rtol, atol=atol, **options)
+        s = solver(func, y0, rtol=rtol, atol=atol, **options)
         out = s.integrate(t_span)
         odeint.last_log = s.log
         return out

@@ -48,19 +48,161 @@ static const double DP_CMID64[7] = {
     11237099.0 / 235043384.0 / 2,
 };
 
+/* ------------------------------------------------------------------------------------------ */
+/* The other embedded Runge-Kutta tableaux of solver/__init__.py:1-6, same driver:  */
+/* Bosh3 adaptive_solver/bosh3.py:5-27, Fehlberg2 fehlberg2.py:5-22, AdaptiveHeun                 */
+/* adaptive_heun.py:5-27, Dopri8 dopri8.py:5-252.  Authored in float64, cast once to fp32.        */
+/* ------------------------------------------------------------------------------------------ */
+#define ORC_MAX_STAGES 13 /* len(alpha) of Dopri8; k has one more column */
 typedef struct {
-  float alpha[6], beta[6][6], cerr[7], cmid[7];
-} dp_tab_t;
+  int S;     /* len(tableau.alpha): field evaluations per attempt */
+  int order; /* solver.order: exponent of optimal_step_size, and of select_initial_step (order-1+1) */
+  int fsal;  /* c_sol[-1] == 0 and c_sol[:-1] == beta[-1]  (base_adaptive_solver_rk.py:172-176) */
+  float alpha[ORC_MAX_STAGES], beta[ORC_MAX_STAGES][ORC_MAX_STAGES];
+  float csol[ORC_MAX_STAGES + 1], cerr[ORC_MAX_STAGES + 1], cmid[ORC_MAX_STAGES + 1];
+} rk_tab_t;
 
-static void dp_tab_init(dp_tab_t *t) {
-  for (int i = 0; i < 6; ++i) {
-    t->alpha[i] = (float)DP_ALPHA64[i];
-    for (int j = 0; j < 6; ++j) t->beta[i][j] = (float)DP_BETA64[i][j];
+static const double BS_ALPHA64[3] = {1.0 / 2, 3.0 / 4, 1.0};
+static const double BS_BETA64[3][3] = {{1.0 / 2, 0, 0}, {0.0, 3.0 / 4, 0}, {2.0 / 9, 1.0 / 3, 4.0 / 9}};
+static const double BS_CSOL64[4] = {2.0 / 9, 1.0 / 3, 4.0 / 9, 0.0};
+static const double BS_CERR64[4] = {2.0 / 9 - 7.0 / 24, 1.0 / 3 - 1.0 / 4, 4.0 / 9 - 1.0 / 3, -1.0 / 8};
+static const double BS_CMID64[4] = {0.0, 0.5, 0.0, 0.0};
+
+static const double FE_ALPHA64[2] = {1.0 / 2, 1.0};
+static const double FE_BETA64[2][2] = {{1.0 / 2, 0}, {1.0 / 256, 255.0 / 256}};
+static const double FE_CSOL64[3] = {1.0 / 512, 255.0 / 256, 1.0 / 512};
+static const double FE_CERR64[3] = {-1.0 / 512, 0, 1.0 / 512};
+static const double FE_CMID64[3] = {0.0, 0.5, 0.0};
+
+static const double AH_ALPHA64[1] = {1.0};
+static const double AH_BETA64[1][1] = {{1.0}};
+static const double AH_CSOL64[2] = {0.5, 0.5};
+static const double AH_CERR64[2] = {0.5, -0.5};
+static const double AH_CMID64[2] = {0.5, 0.0};
+
+static const double D8_ALPHA64[13] = {1.0 / 18, 1.0 / 12, 1.0 / 8, 5.0 / 16, 3.0 / 8, 59.0 / 400, 93.0 / 200,
+                                      5490023248.0 / 9719169821.0, 13.0 / 20, 1201146811.0 / 1299019798.0,
+                                      1.0, 1.0, 1.0};
+static const double D8_BETA64[13][13] = {
+    {1.0 / 18},
+    {1.0 / 48, 1.0 / 16},
+    {1.0 / 32, 0, 3.0 / 32},
+    {5.0 / 16, 0, -75.0 / 64, 75.0 / 64},
+    {3.0 / 80, 0, 0, 3.0 / 16, 3.0 / 20},
+    {29443841.0 / 614563906, 0, 0, 77736538.0 / 692538347, -28693883.0 / 1125000000, 23124283.0 / 1800000000},
+    {16016141.0 / 946692911, 0, 0, 61564180.0 / 158732637, 22789713.0 / 633445777, 545815736.0 / 2771057229,
+     -180193667.0 / 1043307555},
+    {39632708.0 / 573591083, 0, 0, -433636366.0 / 683701615, -421739975.0 / 2616292301,
+     100302831.0 / 723423059, 790204164.0 / 839813087, 800635310.0 / 3783071287},
+    {246121993.0 / 1340847787, 0, 0, -37695042795.0 / 15268766246, -309121744.0 / 1061227803,
+     -12992083.0 / 490766935, 6005943493.0 / 2108947869, 393006217.0 / 1396673457,
+     123872331.0 / 1001029789},
+    {-1028468189.0 / 846180014, 0, 0, 8478235783.0 / 508512852, 1311729495.0 / 1432422823,
+     -10304129995.0 / 1701304382, -48777925059.0 / 3047939560, 15336726248.0 / 1032824649,
+     -45442868181.0 / 3398467696, 3065993473.0 / 597172653},
+    {185892177.0 / 718116043, 0, 0, -3185094517.0 / 667107341, -477755414.0 / 1098053517,
+     -703635378.0 / 230739211, 5731566787.0 / 1027545527, 5232866602.0 / 850066563,
+     -4093664535.0 / 808688257, 3962137247.0 / 1805957418, 65686358.0 / 487910083},
+    {403863854.0 / 491063109, 0, 0, -5068492393.0 / 434740067, -411421997.0 / 543043805,
+     652783627.0 / 914296604, 11173962825.0 / 925320556, -13158990841.0 / 6184727034,
+     3936647629.0 / 1978049680, -160528059.0 / 685178525, 248638103.0 / 1413531060, 0},
+    {14005451.0 / 335480064, 0, 0, 0, 0, -59238493.0 / 1068277825, 181606767.0 / 758867731,
+     561292985.0 / 797845732, -1041891430.0 / 1371343529, 760417239.0 / 1151165299,
+     118820643.0 / 751138087, -528747749.0 / 2220607170, 1.0 / 4},
+};
+static const double D8_CSOL64[14] = {14005451.0 / 335480064, 0, 0, 0, 0, -59238493.0 / 1068277825,
+                                     181606767.0 / 758867731, 561292985.0 / 797845732,
+                                     -1041891430.0 / 1371343529, 760417239.0 / 1151165299,
+                                     118820643.0 / 751138087, -528747749.0 / 2220607170, 1.0 / 4, 0};
+static const double D8_CERR64[14] = {14005451.0 / 335480064 - 13451932.0 / 455176623, 0, 0, 0, 0,
+                                     -59238493.0 / 1068277825 - -808719846.0 / 976000145,
+                                     181606767.0 / 758867731 - 1757004468.0 / 5645159321,
+                                     561292985.0 / 797845732 - 656045339.0 / 265891186,
+                                     -1041891430.0 / 1371343529 - -3867574721.0 / 1518517206,
+                                     760417239.0 / 1151165299 - 465885868.0 / 322736535,
+                                     118820643.0 / 751138087 - 53011238.0 / 667516719,
+                                     -528747749.0 / 2220607170 - 2.0 / 45, 1.0 / 4, 0};
+/* dopri8.py:149-238: C_mid[j] = (quintic in h, without / with the constant 1) / (1/h) at h = 1/2;
+ * rows: column j, coefficients of h^5 .. h^1, constant */
+static const double D8_MIDPOLY[10][7] = {
+    {0, -6.3448349392860401388, 22.1396504998094068976, -30.0610568289666450593, 19.9990069333683970610,
+     -6.6910181737837595697, 1.0},
+    {5, -39.6107919852202505218, 116.4422149550342161651, -121.4999627731334642623, 52.2273532792945524050,
+     -7.6142658045872677172, 0.0},
+    {6, 20.3761213808791436958, -67.1451318825957197185, 83.1721004639847717481, -46.8919164181093621583,
+     10.7281392630428866124, 0.0},
+    {7, 7.3347098826795362023, -16.5672243527496524646, 9.5724507555993664382, -0.1890893225010595467,
+     0.5526637063753648783, 0.0},
+    {8, 32.8801774352459155182, -89.9916014847245016028, 87.8406057677205645007, -35.7075975946222072821,
+     4.2186562625665153803, 0.0},
+    {9, -10.1588990526426760954, 22.6237489648532849093, -17.4152107770762969005, 6.2736448083240352160,
+     -0.6627209125361597559, 0.0},
+    {10, -12.5401268098782561200, 32.2362340167355370113, -28.5903289514790976966, 10.3160881272450748458,
+     -1.2636789001135462218, 0.0},
+    {11, 29.5553001484516038033, -82.1020315488359848644, 81.6630950584341412934, -34.7650769866611817349,
+     5.4106037898590422230, 0.0},
+    {12, -41.7923486424390588923, 116.2662185791119533462, -114.9375291377009418170, 47.7457971078225540396,
+     -7.0321379067945741781, 0.0},
+    {13, 20.3006925822100825485, -53.9020777466385396792, 50.2558364226176017553, -19.0082099341608028453,
+     2.3537586759714983486, 0.0},
+};
+
+static void tab_fill(rk_tab_t *t, int S, int order, const double *alpha, const double *beta, int ldb,
+                     const double *csol, const double *cerr, const double *cmid) {
+  memset(t, 0, sizeof(*t));
+  t->S = S;
+  t->order = order;
+  for (int i = 0; i < S; ++i) {
+    t->alpha[i] = (float)alpha[i];
+    for (int j = 0; j <= i; ++j) t->beta[i][j] = (float)beta[i * ldb + j];
   }
-  for (int j = 0; j < 7; ++j) {
-    t->cerr[j] = (float)DP_CERR64[j];
-    t->cmid[j] = (float)DP_CMID64[j];
+  for (int j = 0; j <= S; ++j) {
+    t->csol[j] = (float)csol[j];
+    t->cerr[j] = (float)cerr[j];
+    t->cmid[j] = (float)cmid[j];
   }
+  /* the FSAL test of base_adaptive_solver_rk.py:172-176, on the float64 tableau like the reference */
+  t->fsal = (csol[S] == 0.0);
+  for (int j = 0; j < S; ++j)
+    if (csol[j] != beta[(S - 1) * ldb + j]) t->fsal = 0;
+}
+
+static int rk_tab_init(rk_tab_t *t, int method) {
+  switch (method) {
+    case ORC_RK_DOPRI5: {
+      double csol[7];
+      for (int j = 0; j < 6; ++j) csol[j] = DP_BETA64[5][j];
+      csol[6] = 0.0;
+      tab_fill(t, 6, 5, DP_ALPHA64, &DP_BETA64[0][0], 6, csol, DP_CERR64, DP_CMID64);
+      return 0;
+    }
+    case ORC_RK_BOSH3:
+      tab_fill(t, 3, 3, BS_ALPHA64, &BS_BETA64[0][0], 3, BS_CSOL64, BS_CERR64, BS_CMID64);
+      return 0;
+    case ORC_RK_FEHLBERG2:
+      tab_fill(t, 2, 2, FE_ALPHA64, &FE_BETA64[0][0], 2, FE_CSOL64, FE_CERR64, FE_CMID64);
+      return 0;
+    case ORC_RK_ADAPTIVE_HEUN:
+      tab_fill(t, 1, 2, AH_ALPHA64, &AH_BETA64[0][0], 1, AH_CSOL64, AH_CERR64, AH_CMID64);
+      return 0;
+    case ORC_RK_DOPRI8: {
+      double cmid[14] = {0};
+      const double h = 0.5;
+      for (int r = 0; r < 10; ++r) {
+        const double *c = D8_MIDPOLY[r];
+        /* Python: c5*h**5 + c4*h**4 + c3*h**3 + c2*h**2 + c1*h (+ 1.0), left to right, then / (1/h) */
+        double v = c[1] * (h * h * h * h * h) + c[2] * (h * h * h * h);
+        v = v + c[3] * (h * h * h);
+        v = v + c[4] * (h * h);
+        v = v + c[5] * h;
+        if (c[6] != 0.0) v = v + c[6];
+        cmid[(int)c[0]] = v / (1.0 / h);
+      }
+      tab_fill(t, 13, 8, D8_ALPHA64, &D8_BETA64[0][0], 13, D8_CSOL64, D8_CERR64, cmid);
+      return 0;
+    }
+  }
+  return -1;
 }
 
 void orc_default_opts(orc_opts_t *o) {
@@ -122,6 +264,30 @@ float orc_root5f(float r) {
     x = fmaf(4.0f, x, q) * 0.2f;
   }
   return x;
+}
+
+/* r ** (1/p) for the orders of the supported tableaux (same deterministic style as orc_root5f):
+ * p = 2: sqrtf (IEEE); p = 8: sqrtf three times; p = 3: integer seed + 4 Newton steps
+ * x <- (2x + r/x^2)/3; p = 5: orc_root5f.  Caller guarantees r finite and > 0. */
+float orc_rootpf(float r, int32_t p) {
+  if (p == 5) return orc_root5f(r);
+  if (p == 2) return sqrtf(r);
+  if (p == 8) return sqrtf(sqrtf(sqrtf(r)));
+  if (p == 3) {
+    union {
+      float f;
+      uint32_t u;
+    } v;
+    v.f = r;
+    v.u = v.u / 3u + 0x2A555555u;
+    float x = v.f;
+    for (int it = 0; it < 4; ++it) {
+      float q = r / (x * x);
+      x = fmaf(2.0f, x, q) * (float)(1.0 / 3.0);
+    }
+    return x;
+  }
+  return powf(r, 1.0f / (float)p);
 }
 
 static inline float pre_act(int pre, float y) {
@@ -215,12 +381,12 @@ typedef struct {
   void *ctx;
   const orc_opts_t *o;
   int rev; /* repair R5: integrate s = -t with f~(s,y) = -f(-s,y) */
-  dp_tab_t tab;
+  rk_tab_t tab;
   /* _RungeKuttaState (solver/base_adaptive_solver_rk.py:22-24) */
   float *y1, *f1, *coef[5];
   float t0, t1, dt;
   /* work */
-  float *k; /* [7][n] */
+  float *k; /* [S+1][n], S <= 13 */
   float *yi, *err, *v, *ymid, *ynew;
   orc_stats_t *st;
   orc_attempt_t *log;
@@ -231,18 +397,19 @@ static int drv_alloc(drv_t *d, int64_t n) {
   size_t nn = (size_t)n;
   memset(d, 0, sizeof(*d));
   d->n = n;
-  float *blk = (float *)malloc(sizeof(float) * nn * (2 + 5 + 7 + 5));
+  const size_t K = ORC_MAX_STAGES + 1;
+  float *blk = (float *)malloc(sizeof(float) * nn * (2 + 5 + K + 5));
   if (!blk) return -1;
   d->y1 = blk;
   d->f1 = blk + nn;
   for (int i = 0; i < 5; ++i) d->coef[i] = blk + nn * (2 + i);
   d->k = blk + nn * 7;
-  d->yi = blk + nn * 14;
-  d->err = blk + nn * 15;
-  d->v = blk + nn * 16;
-  d->ymid = blk + nn * 17;
-  d->ynew = blk + nn * 18;
-  dp_tab_init(&d->tab);
+  d->yi = blk + nn * (7 + K);
+  d->err = blk + nn * (8 + K);
+  d->v = blk + nn * (9 + K);
+  d->ymid = blk + nn * (10 + K);
+  d->ynew = blk + nn * (11 + K);
+  rk_tab_init(&d->tab, ORC_RK_DOPRI5); /* callers of other tableaux overwrite d->tab */
   return 0;
 }
 static void drv_free(drv_t *d) { free(d->y1); }
@@ -257,8 +424,8 @@ static void drv_rhs(drv_t *d, float s, const float *y, float *dy) {
   if (d->st) d->st->nfe++;
 }
 
-/* solver/base_adaptive_solver.py:33-72 (Hairer II.4), called with order = self.order - 1 = 4
- * (solver/base_adaptive_solver_rk.py:85-87). */
+/* solver/base_adaptive_solver.py:33-72 (Hairer II.4), called with order = self.order - 1
+ * (solver/base_adaptive_solver_rk.py:85-87), i.e. the exponent is 1/self.order. */
 static float drv_select_initial_step(drv_t *d, float t0, const float *y0) {
   const orc_opts_t *o = d->o;
   const int64_t n = d->n;
@@ -287,7 +454,7 @@ static float drv_select_initial_step(drv_t *d, float t0, const float *y0) {
   } else {
     float mx = (d2 > d1) ? d2 : d1; /* python max(d1, d2) */
     float arg = 0.01f / mx;
-    h1 = (arg > 0.0f && arg < INFINITY) ? orc_root5f(arg) : arg;
+    h1 = (arg > 0.0f && arg < INFINITY) ? orc_rootpf(arg, d->tab.order) : arg;
   }
   h1 = fabsf(h1);
   return fminf(100.0f * h0, h1);
@@ -313,7 +480,8 @@ static void drv_before_integrate(drv_t *d, float t0, const float *y0) {
  * utils/ode_utils.py:80-82, optimal_step_size :85-97, _interp_fit :286-292 + interp_fit :28-49 */
 static int drv_adaptive_step(drv_t *d) {
   const orc_opts_t *o = d->o;
-  const dp_tab_t *tb = &d->tab;
+  const rk_tab_t *tb = &d->tab;
+  const int S = tb->S;
   const int64_t n = d->n;
   float *y0 = d->y1, *f0 = d->f1;
   const float t0 = d->t1, dt = d->dt;
@@ -324,9 +492,9 @@ static int drv_adaptive_step(drv_t *d) {
 
   float *k = d->k;
   memcpy(k, f0, sizeof(float) * n);
-  for (int i = 0; i < 6; ++i) {
+  for (int i = 0; i < S; ++i) {
     float ti = (tb->alpha[i] == 1.0f) ? t1 : t0 + tb->alpha[i] * dt;
-    float bd[6];
+    float bd[ORC_MAX_STAGES];
     for (int j = 0; j <= i; ++j) bd[j] = tb->beta[i][j] * dt;
     for (int64_t e = 0; e < n; ++e) {
       float s = k[e] * bd[0];
@@ -335,14 +503,24 @@ static int drv_adaptive_step(drv_t *d) {
     }
     drv_rhs(d, ti, d->yi, k + (size_t)(i + 1) * n);
   }
-  /* FSAL shortcut holds for Dormand-Prince: y1 = yi, f1 = k[...,-1] (:172-179) */
+  /* FSAL shortcut (true for Dormand-Prince, Bosh3): y1 = yi; otherwise y1 = y0 + sum k (dt c_sol)
+   * (:172-179); f1 = k[...,-1] either way */
   float *y1 = d->yi;
-  float *f1 = k + (size_t)6 * n;
-  float ce[7];
-  for (int j = 0; j < 7; ++j) ce[j] = dt * tb->cerr[j];
+  float *f1 = k + (size_t)S * n;
+  if (!tb->fsal) {
+    float cs[ORC_MAX_STAGES + 1];
+    for (int j = 0; j <= S; ++j) cs[j] = dt * tb->csol[j];
+    for (int64_t e = 0; e < n; ++e) {
+      float s = k[e] * cs[0];
+      for (int j = 1; j <= S; ++j) s = s + k[(size_t)j * n + e] * cs[j];
+      y1[e] = y0[e] + s;
+    }
+  }
+  float ce[ORC_MAX_STAGES + 1];
+  for (int j = 0; j <= S; ++j) ce[j] = dt * tb->cerr[j];
   for (int64_t e = 0; e < n; ++e) {
     float s = k[e] * ce[0];
-    for (int j = 1; j < 7; ++j) s = s + k[(size_t)j * n + e] * ce[j];
+    for (int j = 1; j <= S; ++j) s = s + k[(size_t)j * n + e] * ce[j];
     d->err[e] = s;
   }
   for (int64_t e = 0; e < n; ++e) {
@@ -370,12 +548,12 @@ static int drv_adaptive_step(drv_t *d) {
   }
 
   if (accept) {
-    float cm[7];
-    for (int j = 0; j < 7; ++j) cm[j] = dt * tb->cmid[j];
+    float cm[ORC_MAX_STAGES + 1];
+    for (int j = 0; j <= S; ++j) cm[j] = dt * tb->cmid[j];
     const float two_dt = 2.0f * dt;
     for (int64_t e = 0; e < n; ++e) {
       float s = k[e] * cm[0];
-      for (int j = 1; j < 7; ++j) s = s + k[(size_t)j * n + e] * cm[j];
+      for (int j = 1; j <= S; ++j) s = s + k[(size_t)j * n + e] * cm[j];
       float ym = y0[e] + s;
       float F0 = k[e], F1 = f1[e], Y0 = y0[e], Y1 = y1[e];
       float a = (two_dt * (F1 - F0) - 8.0f * (Y1 + Y0)) + 16.0f * ym;
@@ -392,13 +570,13 @@ static int drv_adaptive_step(drv_t *d) {
     memcpy(d->y1, d->ynew, sizeof(float) * n);
     memcpy(d->f1, f1, sizeof(float) * n);
   }
-  /* optimal_step_size(dt, error_ratio, safety, ifactor, dfactor, order=5) */
+  /* optimal_step_size(dt, error_ratio, safety, ifactor, dfactor, self.order) */
   float dt_next;
   if (ratio == 0.0f) {
     dt_next = dt * o->ifactor;
   } else {
     float dfac = (ratio < 1.0f) ? 1.0f : o->dfactor;
-    float p = (ratio > 0.0f && ratio < INFINITY) ? orc_root5f(ratio) : ratio;
+    float p = (ratio > 0.0f && ratio < INFINITY) ? orc_rootpf(ratio, tb->order) : ratio;
     float factor = fminf(o->ifactor, fmaxf(o->safety / p, dfac));
     dt_next = dt * factor;
   }
@@ -489,12 +667,22 @@ int orc_dopri5_mlp(const orc_mlp_t *m, const float *y0, int64_t B, const float *
                    const orc_opts_t *opts, int32_t controller, float *out, orc_stats_t *stats,
                    orc_attempt_t *log, int64_t log_cap, int64_t log_traj, int64_t *log_len,
                    int32_t nthreads) {
+  return orc_adaptive_rk_mlp(ORC_RK_DOPRI5, m, y0, B, t_span, T, opts, controller, out, stats, log, log_cap,
+                             log_traj, log_len, nthreads);
+}
+
+int orc_adaptive_rk_mlp(int32_t method, const orc_mlp_t *m, const float *y0, int64_t B, const float *t_span,
+                        int32_t T, const orc_opts_t *opts, int32_t controller, float *out,
+                        orc_stats_t *stats, orc_attempt_t *log, int64_t log_cap, int64_t log_traj,
+                        int64_t *log_len, int32_t nthreads) {
   const int D = m->d;
-  if (D > ORC_MAX_D || m->h > ORC_MAX_H || T < 2 || B < 1) return ORC_BAD_ARG;
+  rk_tab_t tab;
+  if (D > ORC_MAX_D || m->h > ORC_MAX_H || T < 2 || B < 1 || rk_tab_init(&tab, method)) return ORC_BAD_ARG;
   if (log_len) *log_len = 0;
   if (controller == ORC_CTRL_BATCH) {
     drv_t d;
     if (drv_alloc(&d, B * D)) return ORC_BAD_ARG;
+    d.tab = tab;
     fwd_ctx_t c = {m, B};
     orc_stats_t st;
     stats_reset(&st);
@@ -521,6 +709,7 @@ int orc_dopri5_mlp(const orc_mlp_t *m, const float *y0, int64_t B, const float *
     drv_t d;
     float *tmp = (float *)malloc(sizeof(float) * (size_t)T * D);
     int ok = (drv_alloc(&d, D) == 0) && tmp;
+    if (ok) d.tab = tab;
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 64)
 #endif
@@ -580,6 +769,13 @@ int orc_fixed_mlp(int32_t method, const orc_mlp_t *m, const float *y0, int64_t B
         /* fixed_solver/euler.py:7-11 ; BaseODE.fuse xde/base_ode.py:58 */
         orc_mlp_eval(m, y, k1, NULL);
         for (int e = 0; e < D; ++e) y[e] = k1[e] * dt + y[e];
+      } else if (method == ORC_FIXED_MIDPOINT) {
+        /* fixed_solver/midpoint.py:7-18: y_half = fuse(f(y0), dt/2, y0); y1 = fuse(f(y_half), dt, y0) */
+        const float half_dt = 0.5f * dt;
+        orc_mlp_eval(m, y, k1, NULL);
+        for (int e = 0; e < D; ++e) yi[e] = k1[e] * half_dt + y[e];
+        orc_mlp_eval(m, yi, k2, NULL);
+        for (int e = 0; e < D; ++e) y[e] = k2[e] * dt + y[e];
       } else {
         /* rk4_alt_step_func solver/base_fixed_solver.py:166-197 */
         const float dt13 = dt * one_third;

@@ -42,7 +42,9 @@ enum {
 
 enum { ORC_CTRL_TRAJECTORY = 0, ORC_CTRL_BATCH = 1 };
 enum { ORC_ADJ_NORM_MIXED = 0, ORC_ADJ_NORM_SEMI = 1 };
-enum { ORC_FIXED_EULER = 0, ORC_FIXED_RK4_38 = 1 };
+enum { ORC_FIXED_EULER = 0, ORC_FIXED_RK4_38 = 1, ORC_FIXED_MIDPOINT = 2 };
+/* embedded Runge-Kutta tableaux (the modules under solver/adaptive_solver/) */
+enum { ORC_RK_DOPRI5 = 0, ORC_RK_BOSH3 = 1, ORC_RK_FEHLBERG2 = 2, ORC_RK_ADAPTIVE_HEUN = 3, ORC_RK_DOPRI8 = 4 };
 enum { ORC_SDE_EM = 0, ORC_SDE_MILSTEIN = 1 };
 enum { ORC_INTERP_LINEAR = 0, ORC_INTERP_HERMITE = 1 };
 
@@ -82,6 +84,7 @@ void orc_default_opts(orc_opts_t *o);
 /* scalar primitives of the arithmetic specification (exposed for tests) */
 float orc_tanhf(float x);
 float orc_root5f(float r); /* r^(1/5), deterministic */
+float orc_rootpf(float r, int32_t p); /* r^(1/p) for p in {2,3,5,8}, deterministic */
 
 /* field evaluation, one trajectory.  hbuf optional [h]. */
 void orc_mlp_eval(const orc_mlp_t *m, const float *y, float *f, float *hbuf);
@@ -105,7 +108,14 @@ int orc_dopri5_mlp(const orc_mlp_t *m, const float *y0, int64_t B, const float *
                    orc_attempt_t *log, int64_t log_cap, int64_t log_traj, int64_t *log_len,
                    int32_t nthreads);
 
-/* odeint(func=MLP, solver=Euler|RK4): solver/base_fixed_solver.py:103-144, fixed_solver/euler.py:7-11,
+/* The same driver with any of the reference's embedded tableaux (solver/__init__.py:1-6):
+ * method = ORC_RK_*; orc_dopri5_mlp(...) == orc_adaptive_rk_mlp(ORC_RK_DOPRI5, ...). */
+int orc_adaptive_rk_mlp(int32_t method, const orc_mlp_t *m, const float *y0, int64_t B, const float *t_span,
+                        int32_t T, const orc_opts_t *opts, int32_t controller, float *out,
+                        orc_stats_t *stats, orc_attempt_t *log, int64_t log_cap, int64_t log_traj,
+                        int64_t *log_len, int32_t nthreads);
+
+/* odeint(func=MLP, solver=Euler|RK4|Midpoint; fixed_solver/midpoint.py:7-18): solver/base_fixed_solver.py:103-144, fixed_solver/euler.py:7-11,
  * fixed_solver/rk4.py:7-10 (3/8 rule, base_fixed_solver.py:166-197).  grid == t_span.
  * out is [B,T,D] (concat(axis=-2) of [B,1,D] states, base_fixed_solver.py:143). */
 int orc_fixed_mlp(int32_t method, const orc_mlp_t *m, const float *y0, int64_t B,

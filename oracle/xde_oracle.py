@@ -19,7 +19,8 @@ _SO = os.path.join(_HERE, "libxde_oracle.so")
 PRE = {"id": 0, "identity": 0, "square": 1, "cube": 2}
 CTRL = {"trajectory": 0, "batch": 1}
 ADJ_NORM = {"mixed": 0, "default": 0, "seminorm": 1}
-FIXED = {"euler": 0, "rk4": 1}
+FIXED = {"euler": 0, "rk4": 1, "midpoint": 2}
+RK = {"dopri5": 0, "bosh3": 1, "fehlberg2": 2, "adaptive_heun": 3, "dopri8": 4}
 SDE = {"em": 0, "euler": 0, "milstein": 1}
 INTERP = {"linear": 0, "cubic": 1, "hermite": 1}
 STATUS = {0: "OK", 1: "DT_UNDERFLOW", 2: "NONFINITE_STATE", 3: "MAX_STEPS", 4: "BAD_ARG", 5: "INTERP_RANGE"}
@@ -62,6 +63,8 @@ def lib():
         _lib.orc_tanhf.argtypes = [C.c_float]
         _lib.orc_root5f.restype = C.c_float
         _lib.orc_root5f.argtypes = [C.c_float]
+        _lib.orc_rootpf.restype = C.c_float
+        _lib.orc_rootpf.argtypes = [C.c_float, C.c_int32]
     return _lib
 
 
@@ -140,9 +143,19 @@ def root5f(x):
     return np.array([lib().orc_root5f(float(v)) for v in np.asarray(x, np.float32).ravel()], np.float32).reshape(np.shape(x))
 
 
-def dopri5_mlp(mlp: MLP, y0, t_span, *, controller="trajectory", log_traj: Optional[int] = None,
-               log_cap=100000, nthreads=0, **opt_kw):
+def rootpf(x, p):
+    return np.array([lib().orc_rootpf(float(v), int(p)) for v in np.asarray(x, np.float32).ravel()],
+                    np.float32).reshape(np.shape(x))
+
+
+def dopri5_mlp(mlp: MLP, y0, t_span, **kw):
     """-> (out [T,B,D], stats recarray, log recarray|None, status)"""
+    return adaptive_rk_mlp("dopri5", mlp, y0, t_span, **kw)
+
+
+def adaptive_rk_mlp(method: str, mlp: MLP, y0, t_span, *, controller="trajectory", log_traj: Optional[int] = None,
+                    log_cap=100000, nthreads=0, **opt_kw):
+    """Any embedded tableau of the reference (RK keys) -> (out [T,B,D], stats, log|None, status)"""
     y0, t_span = _f32(y0), _f32(t_span)
     B, D = y0.shape
     T = t_span.size
@@ -153,10 +166,10 @@ def dopri5_mlp(mlp: MLP, y0, t_span, *, controller="trajectory", log_traj: Optio
     log = np.zeros(log_cap if want_log else 0, ATTEMPT_DTYPE)
     log_len = C.c_int64(0)
     m, o = mlp.c(), make_opts(**opt_kw)
-    rc = lib().orc_dopri5_mlp(C.byref(m), _p(y0), C.c_int64(B), _p(t_span), C.c_int32(T), C.byref(o),
-                              C.c_int32(CTRL[controller]), _p(out), _p(stats),
-                              _p(log) if want_log else None, C.c_int64(log_cap),
-                              C.c_int64(log_traj or 0), C.byref(log_len), C.c_int32(nthreads))
+    rc = lib().orc_adaptive_rk_mlp(C.c_int32(RK[method]), C.byref(m), _p(y0), C.c_int64(B), _p(t_span),
+                                   C.c_int32(T), C.byref(o), C.c_int32(CTRL[controller]), _p(out), _p(stats),
+                                   _p(log) if want_log else None, C.c_int64(log_cap),
+                                   C.c_int64(log_traj or 0), C.byref(log_len), C.c_int32(nthreads))
     return out, stats.view(np.recarray), (log[:log_len.value].view(np.recarray) if want_log else None), rc
 
 

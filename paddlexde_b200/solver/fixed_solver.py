@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from .. import _tensor as T
-from .._lib import FIXED, SDE, UnsupportedFieldError, check, lib
+from .._lib import FIXED, SDE, XDE_E_UNSUPPORTED_FIELD, UnsupportedFieldError, check, lib
 from .adaptive_solver import host_tspan
 
 
@@ -17,7 +17,7 @@ class FixedSolver:
     method: str
 
     def __init__(self, xde, y0, step_size=None, grid_constructor=None, interp="linear", perturb=False,
-                 out_stride=1, math="fp32", **kwargs):
+                 out_stride=1, math="auto", **kwargs):
         if step_size is not None and grid_constructor is not None:
             raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
         if step_size is not None or grid_constructor is not None:
@@ -30,11 +30,24 @@ class FixedSolver:
                 raise KeyError(key)
         self.xde, self.y0 = xde, y0
         self.out_stride = int(out_stride)
-        # math="fp32": FFMA path, bit-exact against the oracle's arithmetic specification (default);
-        # math="tensor": tcgen05 path for D in {16,32,64} (fp16-split 3-product GEMMs, ~1e-6 relative)
-        if math not in ("fp32", "tensor"):
-            raise ValueError(f"math must be 'fp32' or 'tensor', got {math!r}")
+        # math="tensor": tcgen05 path (csrc/xde_tc.cu) for D in {16,32,64}: fp16-split 3-product GEMMs with
+        #   fp32 accumulation, as accurate against fp64 as the FP32 kernels, not bit-identical to them;
+        # math="fp32": FFMA kernels, bit-exact against the oracle's arithmetic specification;
+        # math="auto" (default): the tensor path where a kernel exists for the shape, the FP32 kernels
+        #   otherwise (small states are always FP32: K = 2 is degenerate for an MMA).
+        if math not in ("auto", "fp32", "tensor"):
+            raise ValueError(f"math must be 'auto', 'fp32' or 'tensor', got {math!r}")
         self.math = math
+
+    def _launch(self, tensor_entry, fp32_entry, args):
+        """Both entries are CUDA kernels of libxde_b200; "auto" asks the tensor-core one first and takes
+        the FP32 one when it reports that it has no kernel for the shape (XDE_E_UNSUPPORTED_FIELD)."""
+        if self.math == "fp32":
+            return check(fp32_entry(*args))
+        rc = tensor_entry(*args)
+        if rc == XDE_E_UNSUPPORTED_FIELD and self.math == "auto":
+            return check(fp32_entry(*args))
+        return check(rc)
 
     def integrate(self, t_span):
         kind = getattr(self.xde, "kind", None)
@@ -48,9 +61,9 @@ class FixedSolver:
         out = torch.empty((B, n_out, D), device=y0.device, dtype=torch.float32)
         if kind == "ode":
             fs = self.xde.field.c_struct()
-            entry = lib().xde_rk_fixed_mlp_tc_f32 if self.math == "tensor" else lib().xde_rk_fixed_mlp_f32
-            check(entry(FIXED[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), Tn,
-                        self.out_stride, T.ptr(out), T.stream()))
+            args = (FIXED[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), Tn, self.out_stride, T.ptr(out),
+                    T.stream())
+            self._launch(lib().xde_rk_fixed_mlp_tc_f32, lib().xde_rk_fixed_mlp_f32, args)
         elif kind == "sde":
             if self.method != "euler" and self.xde.scheme == "em":
                 raise UnsupportedFieldError("sdeint is fused for solver=Euler (Euler-Maruyama) only")
@@ -58,9 +71,9 @@ class FixedSolver:
             if tuple(dW.shape) != (Tn - 1, B, D):
                 raise ValueError(f"bm_increments must be [T-1, B, D] = {(Tn - 1, B, D)}, got {tuple(dW.shape)}")
             f, g = self.xde.drift.c_struct(), self.xde.diffusion.c_struct()
-            entry = lib().xde_sde_mlp_tc_f32 if self.math == "tensor" else lib().xde_sde_mlp_f32
-            check(entry(SDE[self.xde.scheme], C.byref(f), C.byref(g), T.ptr(y0), B, T.ptr(t_dev),
-                        Tn, T.ptr(dW), self.out_stride, T.ptr(out), T.stream()))
+            args = (SDE[self.xde.scheme], C.byref(f), C.byref(g), T.ptr(y0), B, T.ptr(t_dev), Tn, T.ptr(dW),
+                    self.out_stride, T.ptr(out), T.stream())
+            self._launch(lib().xde_sde_mlp_tc_f32, lib().xde_sde_mlp_f32, args)
         else:
             raise UnsupportedFieldError(f"fixed solvers integrate ODE/SDE problems on the device, not {kind!r}")
         # concat(axis=-2) of the per-time states (base_fixed_solver.py:143)

@@ -464,7 +464,8 @@ def test_tiled_fixed_solvers_bit_exact(px, torch, oracle, solver, d, h, B):
     field, om = both(px, oracle, fanin_weights(d, h, seed=d + h), "id" if d == 64 else "cube")
     y0 = np.random.default_rng(d).uniform(-1, 1, (B, d)).astype(f32)
     t = np.linspace(0, 1, 11).astype(f32)
-    sol = px.odeint(field, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, getattr(px, solver))
+    sol = px.odeint(field, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, getattr(px, solver),
+                    options={"math": "fp32"})
     ref = oracle.fixed_mlp(solver.lower(), om, y0, t)
     assert tuple(sol.shape) == (B, t.size, d)
     assert np.array_equal(sol.cpu().numpy(), ref)
@@ -478,7 +479,7 @@ def test_tiled_cfg3_full_size_subset_and_stride(px, torch, oracle):
     y0 = np.random.default_rng(1).uniform(-1, 1, (B, d)).astype(f32)
     t = np.linspace(0, 1, 101).astype(f32)
     xde = px.xde.BaseODE(field, torch.from_numpy(y0).cuda().reshape(B, 1, d), t)
-    sol = px.RK4(xde=xde, y0=xde.y0, rtol=1e-7, atol=1e-9, out_stride=10).integrate(t)
+    sol = px.RK4(xde=xde, y0=xde.y0, rtol=1e-7, atol=1e-9, out_stride=10, math="fp32").integrate(t)
     assert tuple(sol.shape) == (B, 11, d)
     idx = np.random.default_rng(3).choice(B, 192, replace=False)
     ref = oracle.fixed_mlp("rk4", om, y0[idx], t)[:, ::10]
@@ -496,9 +497,12 @@ def test_tiled_sde_cfg4_shapes(px, torch, oracle):
     t = np.linspace(0, 1, 17).astype(f32)
     dW = (np.sqrt(1 / 16) * rng.standard_normal((16, B, d))).astype(f32)
     sol = px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler,
-                    options={"bm_increments": torch.from_numpy(dW).cuda()})
+                    options={"bm_increments": torch.from_numpy(dW).cuda(), "math": "fp32"})
     ref = oracle.sde_mlp("em", of, og, y0, t, dW)
     assert np.array_equal(sol.cpu().numpy(), ref)
+    auto = px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler,
+                     options={"bm_increments": torch.from_numpy(dW).cuda()})  # default: tensor cores
+    assert _close(auto.cpu().numpy(), ref, rtol=1e-5) and not np.array_equal(auto.cpu().numpy(), ref)
     with pytest.raises(px.UnsupportedFieldError):  # Milstein is an extension, fused for small states only
         px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler,
                   options={"bm_increments": torch.from_numpy(dW).cuda(), "scheme": "milstein"})

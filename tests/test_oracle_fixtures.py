@@ -71,7 +71,50 @@ def test_dopri5_constant_fixture():
     assert allclose(sol, y[:, 0], rtol=4e-3)
 
 
-@pytest.mark.parametrize("solver", [onp.Euler, onp.RK4])
+# tests/functional/test_adaptive_solver.py:32-50: every embedded tableau against the Sine / Constant
+# fixtures at the reference's rtol = 4e-3
+@pytest.mark.parametrize("solver", [onp.Bosh3, onp.Fehlberg2, onp.AdaptiveHeun, onp.Dopri8])
+def test_other_tableaux_sine_and_constant_fixtures(solver):
+    sol = sine_exact(T_POINTS)
+    # the reference's default tolerances (1e-7 / 1e-9) cost the 2nd-order pairs ~1e5 python steps;
+    # its own assertion is at 4e-3, reached with room to spare at 1e-5 / 1e-7
+    y = onp.odeint(sine_f, sol[0].astype(f32)[None], T_POINTS, solver, rtol=1e-5, atol=1e-7)
+    assert allclose(sol, y[:, 0], rtol=4e-3)
+    solc = constant_exact(T_POINTS)
+    yc = onp.odeint(constant_f, solc[0].astype(f32)[None], T_POINTS, solver, rtol=1e-5, atol=1e-7)
+    assert allclose(solc, yc[:, 0], rtol=4e-3)
+
+
+def test_dopri8_tableau_is_eighth_order():
+    """The 120 rationals of adaptive_solver/dopri8.py as restated in oracle/: exact row sums and the
+    convergence order of one step of y' = y in float64 (fp32 runs are rounding-limited at 1e-7)."""
+    keep = lambda a, b, cs, ce, cm: dict(ALPHA=np.array(a), BETA=[np.array(r) for r in b], C_SOL=np.array(cs),
+                                          C_ERR=np.array(ce), C_MID=np.array(cm))
+    orig, onp._tab = onp._tab, keep
+    try:
+        tb = onp._dopri8_tab()
+    finally:
+        onp._tab = orig
+    assert max(abs(sum(b) - a) for a, b in zip(tb["ALPHA"], tb["BETA"])) < 1e-15
+    assert abs(sum(tb["C_SOL"]) - 1) < 1e-15 and abs(sum(tb["C_MID"]) - 0.5) < 1e-15
+
+    def one_step(h):
+        k = [1.0]
+        for i in range(13):
+            k.append(1.0 + h * sum(tb["BETA"][i][j] * k[j] for j in range(i + 1)))
+        y1 = 1.0 + h * sum(tb["C_SOL"][j] * k[j] for j in range(14))
+        y_mid = 1.0 + h * sum(tb["C_MID"][j] * k[j] for j in range(14))
+        return abs(y1 - math.exp(h)), abs(y_mid - math.exp(h / 2))
+
+    (e1, m1), (e2, _) = one_step(0.8), one_step(0.4)
+    assert math.log2(e1 / e2) > 8.5 and m1 < 1e-6   # local error O(h^9); dense midpoint consistent
+    # and the fp32 run still meets the reference's own tolerance with room
+    sol = sine_exact(T_POINTS)
+    y = onp.odeint(sine_f, sol[0].astype(f32)[None], T_POINTS, onp.Dopri8)
+    assert np.max(np.abs(y[:, 0] - sol) / np.abs(sol)) < 1e-4
+
+
+@pytest.mark.parametrize("solver", [onp.Euler, onp.RK4, onp.Midpoint])
 def test_fixed_constant_fixture(solver):
     sol = constant_exact(T_POINTS)                   # test_fixed_solver.py: rtol=1e-2
     y = onp.odeint(constant_f, sol[0].astype(f32)[None], T_POINTS, solver)  # [T,1]

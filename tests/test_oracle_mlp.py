@@ -65,7 +65,34 @@ def test_dopri5_rejections_and_tolerance(oracle):
     np.testing.assert_allclose(out[:, 0], ref, rtol=2e-5, atol=2e-6)
 
 
-@pytest.mark.parametrize("method,cls", [("euler", onp.Euler), ("rk4", onp.RK4)])
+@pytest.mark.parametrize("method,cls,rtol", [("bosh3", onp.Bosh3, 1e-6), ("fehlberg2", onp.Fehlberg2, 1e-4),
+                                             ("adaptive_heun", onp.AdaptiveHeun, 1e-4),
+                                             ("dopri8", onp.Dopri8, 1e-7), ("dopri5", onp.Dopri5, 1e-7)])
+def test_other_tableaux_c_equals_literal(oracle, spiral, method, cls, rtol):
+    """The C driver with each embedded tableau == the literal NumPy restatement, bit for bit (results
+    and the whole accept/reject log), per-trajectory controller."""
+    y0 = np.array([[2.0, 0.0], [1.5, -0.5], [-0.3, 1.1]], np.float32)
+    t = np.linspace(0, 1.5, 7).astype(np.float32)
+    out, st, log, rc = oracle.adaptive_rk_mlp(method, spiral, y0, t, log_traj=1, rtol=rtol, atol=rtol * 1e-2)
+    assert rc == 0
+    sol = onp.odeint(spiral, y0[1:2], t, cls, rtol=rtol, atol=rtol * 1e-2)
+    lg = onp.odeint.last_log
+    assert np.array_equal(out[:, 1:2], sol)
+    assert len(lg.dt) == len(log) and np.array_equal(np.array(lg.dt, np.float32), log.dt)
+    assert np.array_equal(np.array(lg.accepted), log.accepted.astype(bool))
+    assert st.n_attempts[1] == len(log) and st.nfe[1] == lg.nfe
+
+
+@pytest.mark.parametrize("p", [2, 3, 5, 8])
+def test_rootp(oracle, p):
+    r = np.exp(np.random.default_rng(p).uniform(-30, 30, 2000)).astype(np.float32)
+    ref = r.astype(np.float64) ** (1.0 / p)
+    got = oracle.rootpf(r, p)
+    assert np.max(np.abs(got - ref) / ref) < 3e-7
+    assert all(onp.rootp(v, p) == c for v, c in zip(r[:200], got[:200]))
+
+
+@pytest.mark.parametrize("method,cls", [("euler", onp.Euler), ("rk4", onp.RK4), ("midpoint", onp.Midpoint)])
 def test_fixed_c_equals_literal(oracle, spiral, method, cls):
     y0, t = cfg2_y0(6), np.linspace(0, 25, 1000).astype(f32)[:32]
     out = oracle.fixed_mlp(method, spiral, y0, t)                 # [B,T,D]

@@ -7,8 +7,10 @@ import paddlexde_b200 as px
 from paddlexde_b200.xde.base_dde import history_gather, history_gather_bwd
 from tests.problems import fanin_weights
 
-HBM = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] \
-    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+_PEAKS = os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")
+_P = json.load(open(_PEAKS)) if os.path.exists(_PEAKS) else {}
+HBM = _P.get("hbm_gbs", 6650.0)
+TENSOR = _P.get("bf16_tflops_sustained", 1371.6)  # dense 16-bit tensor TFLOP/s (the tensor path runs kind::f16)
 FFMA = 72.3  # TFLOP/s, measured by tools/probe_fp32.py on this pool
 
 
@@ -24,23 +26,30 @@ def timeit(fn, n=5, warm=2):
     return float(np.median(ts))
 
 
-def cfg3(B=1 << 17):
+def cfg3(B=1 << 17, math="tensor"):
     d, h = 64, 256
     field = px.MLPField(*fanin_weights(d, h, seed=1), pre="id")
     y0 = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, (B, 1, d)).astype(np.float32)).cuda()
     t = np.linspace(0, 1, 101).astype(np.float32)
     xde = px.xde.BaseODE(field, y0, t)
-    s = px.RK4(xde=xde, y0=y0, rtol=1e-7, atol=1e-9, out_stride=10)
+    s = px.RK4(xde=xde, y0=y0, rtol=1e-7, atol=1e-9, out_stride=10, math=math)
     ms = timeit(lambda: s.integrate(t))
     steps = B * 100
     flops = steps * 16 * d * h
     byts = steps * 8 * d + B * 11 * d * 4
-    return {"config": "cfg3 rk4 64-256-64", "B": B, "ms": ms, "traj_steps_per_s": steps / ms * 1e3,
-            "tflops_algorithmic": flops / ms / 1e9, "frac_ffma_peak": flops / ms / 1e9 / FFMA,
-            "hbm_gbs_algorithmic": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / HBM}
+    r = {"config": "cfg3 rk4 64-256-64", "math": math, "B": B, "ms": ms, "traj_steps_per_s": steps / ms * 1e3,
+         "tflops_algorithmic": flops / ms / 1e9, "hbm_gbs_algorithmic": byts / ms / 1e6,
+         "frac_hbm": byts / ms / 1e6 / HBM}
+    if math == "tensor":  # three fp16 MMAs per algorithmic product (hi*hi + hi*lo + lo*hi)
+        r.update({"frac_tensor_peak_algorithmic": flops / ms / 1e9 / TENSOR,
+                  "frac_tensor_peak_issued": 3 * flops / ms / 1e9 / TENSOR, "tensor_peak_tflops": TENSOR,
+                  "bound": "FP32/ALU issue of the tanh epilogue (1 tanh per 256 algorithmic FLOP), see DESIGN 5.4b"})
+    else:
+        r["frac_ffma_peak"] = flops / ms / 1e9 / FFMA
+    return r
 
 
-def cfg4(B=1 << 21):
+def cfg4(B=1 << 21, math="tensor"):
     d, h = 32, 64
     f = px.MLPField(*fanin_weights(d, h, seed=2), pre="cube")
     g = px.MLPField(*fanin_weights(d, h, seed=3), pre="square")
@@ -49,14 +58,16 @@ def cfg4(B=1 << 21):
     t = np.linspace(0, 1, 17).astype(np.float32)
     dW = torch.randn((16, B, d), device="cuda", generator=gen) * 0.25
     xde = px.xde.BaseSDE(f, g, y0, t, bm_increments=dW)
-    s = px.Euler(xde=xde, y0=y0, rtol=1e-7, atol=1e-9, out_stride=16)
+    s = px.Euler(xde=xde, y0=y0, rtol=1e-7, atol=1e-9, out_stride=16, math=math)
     ms = timeit(lambda: s.integrate(t))
     steps = B * 16
     flops = steps * (4 * d * h * 2)
-    byts = steps * 4 * d + B * 2 * d * 4 + B * d * 4  # dW read per step + y0 in + 2 rows out
-    return {"config": "cfg4 sde-EM 2x(32-64-32)", "B": B, "ms": ms, "traj_steps_per_s": steps / ms * 1e3,
-            "tflops_algorithmic": flops / ms / 1e9, "frac_ffma_peak": flops / ms / 1e9 / FFMA,
+    byts = steps * 12 * d  # read y, read dW, write y per trajectory-step
+    moved = steps * 4 * d + B * 2 * d * 4 + B * d * 4  # what the fused kernel really moves: dW + y0 in + 2 rows out
+    return {"config": "cfg4 sde-EM 2x(32-64-32)", "math": math, "B": B, "ms": ms,
+            "traj_steps_per_s": steps / ms * 1e3, "tflops_algorithmic": flops / ms / 1e9,
             "hbm_gbs_algorithmic": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / HBM,
+            "hbm_gbs_moved": moved / ms / 1e6,
             "note": "B=2^21 (half of cfg4's 2^22: the full dW table is 8 GiB; fits, but halves the run time)"}
 
 
@@ -79,4 +90,8 @@ def cfg5(Bh=1024, kind="cubic"):
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg3", "cfg4", "cfg5"]
     for w in which:
-        print(json.dumps(globals()[w]()), flush=True)
+        if w in ("cfg3", "cfg4"):
+            for math in ("tensor", "fp32"):
+                print(json.dumps(globals()[w](math=math)), flush=True)
+        else:
+            print(json.dumps(globals()[w]()), flush=True)
