@@ -58,7 +58,17 @@ enum { XDE_PRE_ID = 0, XDE_PRE_SQUARE = 1, XDE_PRE_CUBE = 2 };
 enum { XDE_CTRL_TRAJECTORY = 0, XDE_CTRL_BATCH = 1 };
 /* adjoint error norm (functional/odeint_adjoint.py:284-309) */
 enum { XDE_ADJ_NORM_MIXED = 0, XDE_ADJ_NORM_SEMI = 1 };
-enum { XDE_FIXED_EULER = 0, XDE_FIXED_RK4_38 = 1 };
+enum { XDE_FIXED_EULER = 0, XDE_FIXED_RK4_38 = 1, XDE_FIXED_MIDPOINT = 2 };
+/* embedded Runge-Kutta pairs exported by solver/__init__.py:1-6.  XDE_RK_DOPRI5_TABLE (diagnostics) runs
+ * the table-driven kernel with the Dormand-Prince tableau: it must equal XDE_RK_DOPRI5 bit for bit. */
+enum {
+  XDE_RK_DOPRI5 = 0,
+  XDE_RK_BOSH3 = 1,
+  XDE_RK_FEHLBERG2 = 2,
+  XDE_RK_ADAPTIVE_HEUN = 3,
+  XDE_RK_DOPRI8 = 4,
+  XDE_RK_DOPRI5_TABLE = 100
+};
 enum { XDE_SDE_EM = 0, XDE_SDE_MILSTEIN = 1 };
 enum { XDE_INTERP_LINEAR = 0, XDE_INTERP_HERMITE = 1 };
 
@@ -130,6 +140,15 @@ int xde_dopri5_mlp_f32(const xde_mlp_field_t *field, const float *y0, int64_t B,
                        int32_t T, const xde_ctrl_opts_t *opts, int32_t controller, float *out,
                        xde_stats_t *stats, const xde_attempt_log_t *log, void *stream);
 
+/* odeint(func, y0, t_span, solver=Bosh3|Fehlberg2|AdaptiveHeun|Dopri8|Dopri5): the same driver with the
+ * tableau as data (stage count, FSAL shortcut base_adaptive_solver_rk.py:172-176, controller order):
+ *   adaptive_solver/bosh3.py:5-27, fehlberg2.py:5-22, adaptive_heun.py:5-27, dopri8.py:5-252.
+ * method = XDE_RK_*; XDE_RK_DOPRI5 forwards to xde_dopri5_mlp_f32.  The other pairs run the per-trajectory
+ * controller (controller = XDE_CTRL_BATCH returns XDE_E_UNSUPPORTED_FIELD).  Same layouts as above. */
+int xde_adaptive_rk_mlp_f32(int32_t method, const xde_mlp_field_t *field, const float *y0, int64_t B,
+                            const float *t_span, int32_t T, const xde_ctrl_opts_t *opts, int32_t controller,
+                            float *out, xde_stats_t *stats, const xde_attempt_log_t *log, void *stream);
+
 /* OdeintAdjointMethod.backward                        functional/odeint_adjoint.py:47-167
  * (augmented_dynamics :89-124 integrated backwards segment by segment :134-159).
  * y_ans, grad_y [T,B,D]; out_gparams [d*h + h + h*d + d] = (gW1, gb1, gW2, gb2) summed over the
@@ -141,10 +160,10 @@ int xde_dopri5_mlp_adjoint_f32(const xde_mlp_field_t *field, const float *t_span
                                float *out_gparams, float *out_adj_y0, xde_stats_t *stats,
                                const xde_attempt_log_t *log, void *stream);
 
-/* odeint(func, y0, t_span, solver=Euler|RK4)          functional/odeint.py:28-35
+/* odeint(func, y0, t_span, solver=Euler|RK4|Midpoint) functional/odeint.py:28-35
  *   -> FixedSolver.integrate                          solver/base_fixed_solver.py:103-144
  *   -> Euler.step fixed_solver/euler.py:7-11 | RK4.step fixed_solver/rk4.py:7-10 (3/8 rule,
- *      base_fixed_solver.py:166-197).  grid == t_span.  out [B,T,D] (base_fixed_solver.py:143).
+ *      base_fixed_solver.py:166-197) | Midpoint.step fixed_solver/midpoint.py:7-18.  grid == t_span.  out [B,T,D] (base_fixed_solver.py:143).
  * out_stride_t: write only every out_stride_t-th grid point (1 = all; the last point is always
  * written); out then has ceil((T-1)/stride)+1 rows per trajectory. */
 int xde_rk_fixed_mlp_f32(int32_t method, const xde_mlp_field_t *field, const float *y0, int64_t B,

@@ -16,7 +16,8 @@ ST_OK, ST_DT_UNDERFLOW, ST_NONFINITE_STATE, ST_MAX_STEPS, ST_INTERP_RANGE = 0, 1
 PRE = {"id": 0, "identity": 0, None: 0, "square": 1, "cube": 2}
 CTRL = {"trajectory": 0, "batch": 1}
 ADJ_NORM = {"mixed": 0, "default": 0, "seminorm": 1}
-FIXED = {"euler": 0, "rk4": 1}
+FIXED = {"euler": 0, "rk4": 1, "midpoint": 2}
+RK = {"dopri5": 0, "bosh3": 1, "fehlberg2": 2, "adaptive_heun": 3, "dopri8": 4, "dopri5_table": 100}
 SDE = {"em": 0, "euler": 0, "milstein": 1}
 INTERP = {"linear": 0, "cubic": 1, "hermite": 1}
 
@@ -59,6 +60,9 @@ _EXPORTS = {
     "xde_dopri5_mlp_f32": (C.c_int, [C.POINTER(MlpFieldC), C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                      C.POINTER(CtrlOptsC), C.c_int32, C.c_void_p, C.c_void_p,
                                      C.POINTER(AttemptLogC), C.c_void_p]),
+    "xde_adaptive_rk_mlp_f32": (C.c_int, [C.c_int32, C.POINTER(MlpFieldC), C.c_void_p, C.c_int64, C.c_void_p,
+                                          C.c_int32, C.POINTER(CtrlOptsC), C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.POINTER(AttemptLogC), C.c_void_p]),
     "xde_dopri5_mlp_adjoint_f32": (C.c_int, [C.POINTER(MlpFieldC), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                              C.c_int64, C.POINTER(CtrlOptsC), C.c_int32, C.c_int32, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.POINTER(AttemptLogC), C.c_void_p]),

@@ -23,7 +23,8 @@ extern "C" XDE_EXPORT int xde_rk_fixed_mlp_f32(int32_t method, const xde_mlp_fie
   using namespace xde;
   XDE_REQUIRE(field && y0 && t_span && out, XDE_E_BAD_ARG, "null argument");
   XDE_REQUIRE(B >= 1 && T >= 1 && out_stride_t >= 1, XDE_E_BAD_ARG, "need B>=1, T>=1, out_stride_t>=1");
-  XDE_REQUIRE(method == XDE_FIXED_EULER || method == XDE_FIXED_RK4_38, XDE_E_BAD_ARG, "unknown method %d", method);
+  XDE_REQUIRE(method == XDE_FIXED_EULER || method == XDE_FIXED_RK4_38 || method == XDE_FIXED_MIDPOINT, XDE_E_BAD_ARG,
+              "unknown method %d", method);
   if (tile_covers(field->d)) return rk_fixed_tile(method, field, y0, B, t_span, T, out_stride_t, out, (cudaStream_t)stream);
   return rk_fixed_small(method, field, y0, B, t_span, T, out_stride_t, out, (cudaStream_t)stream);
 }
@@ -48,7 +49,8 @@ extern "C" XDE_EXPORT int xde_rk_fixed_mlp_tc_f32(int32_t method, const xde_mlp_
   using namespace xde;
   XDE_REQUIRE(field && y0 && t_span && out, XDE_E_BAD_ARG, "null argument");
   XDE_REQUIRE(B >= 1 && T >= 1 && out_stride_t >= 1, XDE_E_BAD_ARG, "need B>=1, T>=1, out_stride_t>=1");
-  XDE_REQUIRE(method == XDE_FIXED_EULER || method == XDE_FIXED_RK4_38, XDE_E_BAD_ARG, "unknown method %d", method);
+  XDE_REQUIRE(method == XDE_FIXED_EULER || method == XDE_FIXED_RK4_38 || method == XDE_FIXED_MIDPOINT, XDE_E_BAD_ARG,
+              "unknown method %d", method);
   return rk_fixed_tc(method, field, y0, B, t_span, T, out_stride_t, out, (cudaStream_t)stream);
 }
 

@@ -1,5 +1,5 @@
 // xde_fixed_small.cu -- fixed-grid steppers for small states (D <= 8), one thread per trajectory:
-//   * odeint(..., solver=Euler|RK4): FixedSolver.integrate (solver/base_fixed_solver.py:103-144),
+//   * odeint(..., solver=Euler|RK4|Midpoint): FixedSolver.integrate (solver/base_fixed_solver.py:103-144),
 //     Euler.step (fixed_solver/euler.py:7-11), RK4.step = 3/8 rule (base_fixed_solver.py:166-197),
 //     BaseODE.fuse = dy*dt + y0 (xde/base_ode.py:58);
 //   * sdeint(..., solver=Euler): Euler-Maruyama y1 = y0 + f*dt + g*dW with caller-supplied dW
@@ -47,6 +47,15 @@ __global__ void __launch_bounds__(kFixThreads) rk_fixed_small_kernel(const FixPa
       if (METHOD == XDE_FIXED_EULER) {
 #pragma unroll
         for (int e = 0; e < D; ++e) y[e] = k1[e] * dt + y[e];
+      } else if (METHOD == XDE_FIXED_MIDPOINT) {
+        // fixed_solver/midpoint.py:7-18: y_half = fuse(f(y0), dt/2, y0); y1 = fuse(f(y_half), dt, y0)
+        float k2[D], yi[D];
+        const float half_dt = 0.5f * dt;
+#pragma unroll
+        for (int e = 0; e < D; ++e) yi[e] = k1[e] * half_dt + y[e];
+        mlp_eval_small<D, PRE>(sw, H, yi, k2);
+#pragma unroll
+        for (int e = 0; e < D; ++e) y[e] = k2[e] * dt + y[e];
       } else {
         float k2[D], k3[D], k4[D], yi[D];
         const float dt13 = dt * one_third;
@@ -181,8 +190,9 @@ static int launch_fixed(const FixParams &p, cudaStream_t s) {
 
 template <int D, int PRE>
 static int fixed_method(const FixParams &p, cudaStream_t s) {
-  return p.method == XDE_FIXED_EULER ? launch_fixed<D, PRE, XDE_FIXED_EULER>(p, s)
-                                     : launch_fixed<D, PRE, XDE_FIXED_RK4_38>(p, s);
+  if (p.method == XDE_FIXED_EULER) return launch_fixed<D, PRE, XDE_FIXED_EULER>(p, s);
+  if (p.method == XDE_FIXED_MIDPOINT) return launch_fixed<D, PRE, XDE_FIXED_MIDPOINT>(p, s);
+  return launch_fixed<D, PRE, XDE_FIXED_RK4_38>(p, s);
 }
 template <int D>
 static int fixed_pre(const FixParams &p, cudaStream_t s) {

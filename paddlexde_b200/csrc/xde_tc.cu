@@ -317,14 +317,14 @@ __global__ void __launch_bounds__(1024) tc_prep_kernel(xde_mlp_field_t f, xde_ml
 }
 
 // ---- the solver -----------------------------------------------------------------------------------
-// KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama (two networks)
+// KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama (two networks), 3: ODE Midpoint
 template <int D, int H, int KIND, int NJ>
 __global__ void __launch_bounds__(cta_threads(NJ), NJ == 4 ? 1 : 2) fixed_tc_kernel(const TcParams p) {
   constexpr int NETS = (KIND == 2) ? 2 : 1;
   constexpr int kComputeWarps = compute_warps(NJ), kThreads = cta_threads(NJ);
   using G = Geom<D, H, NETS, NJ>;
   constexpr int NC = G::NC, CH = G::CH, NCHUNK = G::NCHUNK;
-  constexpr int EVALS = (KIND == 1) ? 4 : 1;  // field evaluations per step
+  constexpr int EVALS = (KIND == 1) ? 4 : (KIND == 3) ? 2 : 1;  // field evaluations per step
 
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *u_ready = reinterpret_cast<uint64_t *>(smem);
@@ -603,6 +603,16 @@ __global__ void __launch_bounds__(cta_threads(NJ), NJ == 4 ? 1 : 2) fixed_tc_ker
           eval(y, k, kg);
 #pragma unroll
           for (int c = 0; c < NP; ++c) y[c] = fma2(k[c], dt2, y[c]);
+        } else if (KIND == 3) {
+          // Midpoint.step (fixed_solver/midpoint.py:7-18)
+          f32x2 yi[NP];
+          eval(y, k, kg);
+          const f32x2 half_dt = pk1(0.5f * dt);
+#pragma unroll
+          for (int c = 0; c < NP; ++c) yi[c] = fma2(k[c], half_dt, y[c]);
+          eval(yi, k, kg);
+#pragma unroll
+          for (int c = 0; c < NP; ++c) y[c] = fma2(k[c], dt2, y[c]);
         } else if (KIND == 1) {
           // RK4.step = rk4_alt_step_func (base_fixed_solver.py:166-197), as written there:
           //   k2 = f(y + dt k1/3), k3 = f(y + dt (k1 - k2/3)), k4 = f(y + dt (k1 - k2 + k3)),
@@ -744,7 +754,9 @@ int rk_fixed_tc(int method, const xde_mlp_field_t *f, const float *y0, long long
   p.T = T;
   p.stride = stride;
   p.n_out = (T - 1 + stride - 1) / stride + 1;
-  return method == XDE_FIXED_EULER ? tc::tc_dispatch<0>(p, s) : tc::tc_dispatch<1>(p, s);
+  if (method == XDE_FIXED_EULER) return tc::tc_dispatch<0>(p, s);
+  if (method == XDE_FIXED_MIDPOINT) return tc::tc_dispatch<3>(p, s);
+  return tc::tc_dispatch<1>(p, s);
 }
 
 int sde_tc(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const float *y0, long long B,

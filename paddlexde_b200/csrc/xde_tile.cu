@@ -149,7 +149,7 @@ __device__ __forceinline__ void tile_eval(const float *__restrict__ net, const f
   }
 }
 
-// KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama
+// KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama, 3: ODE Midpoint (fixed_solver/midpoint.py:7-18)
 template <int D, int H, int TM, int R1, int C1, int R2, int C2, int KIND>
 __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileParams p) {
   using G = TileGeom<D, H, TM, R1, C1, R2, C2>;
@@ -213,6 +213,20 @@ __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileP
         for (int r = 0; r < R2; ++r)
 #pragma unroll
           for (int c = 0; c < C2; ++c) y[r][c] = k1[r][c] * dt + y[r][c];
+      } else if (KIND == 3) {
+        float k2[R2][C2], yi[R2][C2];
+        const float half_dt = 0.5f * dt;
+#pragma unroll
+        for (int r = 0; r < R2; ++r)
+#pragma unroll
+          for (int c = 0; c < C2; ++c) yi[r][c] = k1[r][c] * half_dt + y[r][c];
+        put_u(sU, pref, yi);
+        __syncthreads();
+        tile_eval<D, H, TM, R1, C1, R2, C2>(netf, sU, sH, k2);
+#pragma unroll
+        for (int r = 0; r < R2; ++r)
+#pragma unroll
+          for (int c = 0; c < C2; ++c) y[r][c] = k2[r][c] * dt + y[r][c];
       } else if (KIND == 1) {
         float k2[R2][C2], k3[R2][C2], k4[R2][C2], yi[R2][C2];
         const float dt13 = dt * one_third;
@@ -333,7 +347,9 @@ int rk_fixed_tile(int method, const xde_mlp_field_t *f, const float *y0, long lo
   p.T = T;
   p.stride = stride;
   p.n_out = (T - 1 + stride - 1) / stride + 1;
-  return method == XDE_FIXED_EULER ? tile_dispatch<0>(p, s) : tile_dispatch<1>(p, s);
+  if (method == XDE_FIXED_EULER) return tile_dispatch<0>(p, s);
+  if (method == XDE_FIXED_MIDPOINT) return tile_dispatch<3>(p, s);
+  return tile_dispatch<1>(p, s);
 }
 
 int sde_tile(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const float *y0, long long B,

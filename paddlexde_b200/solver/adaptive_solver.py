@@ -1,9 +1,11 @@
-"""Dopri5 with the reference's solver-class protocol:
+"""The embedded Runge-Kutta solvers (Dopri5, Bosh3, Fehlberg2, AdaptiveHeun, Dopri8) with the
+reference's solver-class protocol:
 
     s = Dopri5(xde=xde, y0=xde.y0, rtol=rtol, atol=atol, **options); s.integrate(t_span)
 
 (paddlexde/functional/odeint.py:30-31; constructor keywords solver/base_adaptive_solver_rk.py:32-49).
-`integrate` is ONE kernel launch (csrc/xde_dopri5_fwd.cu); the controller lives on the device."""
+`integrate` is ONE kernel launch (csrc/xde_dopri5_fwd.cu for Dopri5, the table-driven
+csrc/xde_adaptive_rk.cu for the other tableaux); the controller lives on the device."""
 from __future__ import annotations
 
 import ctypes as C
@@ -14,7 +16,7 @@ import numpy as np
 import torch
 
 from .. import _tensor as T
-from .._lib import (CTRL, AttemptLogC, CtrlOptsC, StatsC, UnsupportedFieldError, check, lib,
+from .._lib import (CTRL, RK, AttemptLogC, CtrlOptsC, StatsC, UnsupportedFieldError, check, lib,
                     raise_for_status)
 
 
@@ -83,8 +85,11 @@ class AttemptLog:
         return rec.view(np.recarray), self.counts.cpu().numpy()
 
 
-class Dopri5:
+class AdaptiveRKSolver:
+    """solver/base_adaptive_solver_rk.py:26-49; subclasses name the tableau (`method`) like the reference's
+    adaptive_solver/*.py name theirs."""
     order = 5
+    method = "dopri5"
 
     def __init__(self, xde, y0, rtol, atol, min_step=0, max_step=float("inf"), first_step=None, step_t=None,
                  jump_t=None, safety=0.9, ifactor=10.0, dfactor=0.2, max_num_steps=2 ** 31 - 1, dtype=None,
@@ -92,7 +97,7 @@ class Dopri5:
         if step_t is not None or jump_t is not None:
             raise NotImplementedError("step_t / jump_t are not on the fused path yet (SURVEY 8(f) rank 2)")
         if getattr(xde, "kind", None) != "ode":
-            raise UnsupportedFieldError("Dopri5 integrates BaseODE problems")
+            raise UnsupportedFieldError(f"{type(self).__name__} integrates BaseODE problems")
         check_norm(norm)
         if controller not in CTRL:
             raise ValueError("controller must be 'trajectory' or 'batch'")
@@ -122,9 +127,9 @@ class Dopri5:
             self.attempt_log = AttemptLog(B, self.log_attempts, y0.device)
             log_c = C.byref(self.attempt_log.c_struct())
         fs = field.c_struct()
-        check(lib().xde_dopri5_mlp_f32(C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), t_host.size, C.byref(self.opts),
-                                       CTRL[self.controller], T.ptr(out), T.ptr(self._stats_buf.buf), log_c,
-                                       T.stream()))
+        check(lib().xde_adaptive_rk_mlp_f32(RK[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), t_host.size,
+                                            C.byref(self.opts), CTRL[self.controller], T.ptr(out),
+                                            T.ptr(self._stats_buf.buf), log_c, T.stream()))
         if self.check_status:  # the reference asserts synchronously; opt out to stay asynchronous
             self.stats = self._stats_buf.read()
             raise_for_status(self.stats.status)
@@ -133,3 +138,28 @@ class Dopri5:
     def read_stats(self) -> SolveStats:
         self.stats = self._stats_buf.read()
         return self.stats
+
+
+class Dopri5(AdaptiveRKSolver):          # adaptive_solver/dopri5.py:58-61
+    order, method = 5, "dopri5"
+
+
+class Bosh3(AdaptiveRKSolver):           # adaptive_solver/bosh3.py:24-27
+    order, method = 3, "bosh3"
+
+
+class Fehlberg2(AdaptiveRKSolver):       # adaptive_solver/fehlberg2.py:19-22
+    order, method = 2, "fehlberg2"
+
+
+class AdaptiveHeun(AdaptiveRKSolver):    # adaptive_solver/adaptive_heun.py:24-27
+    order, method = 2, "adaptive_heun"
+
+
+class Dopri8(AdaptiveRKSolver):          # adaptive_solver/dopri8.py:249-252
+    order, method = 8, "dopri8"
+
+
+class _Dopri5Table(AdaptiveRKSolver):
+    """Diagnostics: the table-driven kernel with the Dormand-Prince tableau (== Dopri5 bit for bit)."""
+    order, method = 5, "dopri5_table"

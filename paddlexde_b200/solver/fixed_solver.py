@@ -99,3 +99,8 @@ class Euler(FixedSolver):
 class RK4(FixedSolver):
     order = 4
     method = "rk4"
+
+
+class Midpoint(FixedSolver):  # fixed_solver/midpoint.py:4-18
+    order = 2
+    method = "midpoint"

@@ -455,6 +455,89 @@ def test_sde_supplied_increments_bit_exact(px, torch, oracle, scheme):
 
 
 # ------------------------------------------------------------------------------------------------
+# the other embedded Runge-Kutta pairs: table-driven kernel, csrc/xde_adaptive_rk.cu
+# ------------------------------------------------------------------------------------------------
+def test_table_driven_kernel_equals_tuned_dopri5(px, torch, oracle):
+    """The generic kernel handed the Dormand-Prince tableau == the tuned Dopri5 kernel, bit for bit:
+    states, counters and every record of the attempt logs."""
+    from paddlexde_b200.solver.adaptive_solver import _Dopri5Table
+
+    field, _ = both(px, oracle, spiral_weights(), "cube")
+    y0 = cfg2_y0(777)
+    t = cfg2_tspan(12)
+    res = []
+    for cls in (px.Dopri5, _Dopri5Table):
+        xde = px.xde.BaseODE(field, torch.from_numpy(y0).cuda(), t)
+        s = cls(xde=xde, y0=xde.y0, rtol=1e-7, atol=1e-9, log_attempts=64)
+        sol = s.integrate(t).cpu().numpy()
+        rec, cnt = s.attempt_log.read()
+        res.append((sol, s.stats, rec, cnt))
+    (a, sa, ra, ca), (b, sb, rb, cb) = res
+    assert np.array_equal(a, b) and sa == sb and np.array_equal(ca, cb)
+    for i in range(0, 777, 37):
+        assert ra[i, :ca[i]].tobytes() == rb[i, :cb[i]].tobytes()
+
+
+@pytest.mark.parametrize("name,rtol", [("Bosh3", 1e-6), ("Fehlberg2", 1e-4), ("AdaptiveHeun", 1e-4), ("Dopri8", 1e-7),
+                                       ("Dopri8", 1e-5)])
+@pytest.mark.parametrize("d,h,pre,B", [(2, 50, "cube", 333), (4, 32, "id", 65), (1, 16, "square", 31)])
+def test_other_tableaux_bit_exact_and_step_sequence(px, torch, oracle, name, rtol, d, h, pre, B):
+    w = spiral_weights() if d == 2 else fanin_weights(d, h, seed=d)
+    field, om = both(px, oracle, w, pre)
+    rng = np.random.default_rng(d + B)
+    y0 = (cfg2_y0(B) if d == 2 else rng.uniform(-1, 1, (B, d))).astype(f32)
+    t = np.linspace(0, 1.0, 6).astype(f32)
+    method = {"Bosh3": "bosh3", "Fehlberg2": "fehlberg2", "AdaptiveHeun": "adaptive_heun", "Dopri8": "dopri8"}[name]
+    xde = px.xde.BaseODE(field, torch.from_numpy(y0).cuda(), t)
+    s = getattr(px, name)(xde=xde, y0=xde.y0, rtol=rtol, atol=rtol * 1e-2, log_attempts=4096)
+    sol = s.integrate(t)
+    ref, st, _, rc = oracle.adaptive_rk_mlp(method, om, y0, t, rtol=rtol, atol=rtol * 1e-2)
+    assert rc == 0
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    assert s.stats.n_attempts == int(st.n_attempts.sum()) and s.stats.n_accepted == int(st.n_accepted.sum())
+    assert s.stats.nfe == int(st.nfe.sum())
+    rec, cnt = s.attempt_log.read()
+    for b in (0, B // 2, B - 1):  # identical accept/reject sequence, dt and error ratio
+        _, _, lg, _ = oracle.adaptive_rk_mlp(method, om, y0, t, log_traj=b, rtol=rtol, atol=rtol * 1e-2)
+        assert cnt[b] == len(lg) <= 4096
+        r = rec[b, :cnt[b]]
+        assert np.array_equal(r.accepted, lg.accepted) and np.array_equal(r.dt, lg.dt)
+        assert np.array_equal(r.ratio, lg.ratio)
+
+
+def test_other_tableaux_reverse_time_first_step_and_status(px, torch, oracle):
+    field, om = both(px, oracle, spiral_weights(), "cube")
+    y0 = cfg2_y0(50)
+    t = np.linspace(0.5, 0.0, 5).astype(f32)  # decreasing: repair R5
+    sol = px.odeint(field, torch.from_numpy(y0).cuda(), t, px.Bosh3, rtol=1e-5, atol=1e-7,
+                    options={"first_step": 0.01})
+    ref, _, _, rc = oracle.adaptive_rk_mlp("bosh3", om, y0, t, rtol=1e-5, atol=1e-7, first_step=0.01)
+    assert rc == 0 and np.array_equal(sol.cpu().numpy(), ref)
+    with pytest.raises(AssertionError, match="max_num_steps"):
+        px.odeint(field, torch.from_numpy(y0).cuda(), np.linspace(0, 5, 3).astype(f32), px.AdaptiveHeun,
+                  rtol=1e-6, atol=1e-8, options={"max_num_steps": 5})
+    with pytest.raises(px.UnsupportedFieldError):  # reference-faithful global controller: Dopri5 only
+        px.odeint(field, torch.from_numpy(y0).cuda(), np.linspace(0, 1, 3).astype(f32), px.Bosh3,
+                  options={"controller": "batch"})
+
+
+@pytest.mark.parametrize("d,h,pre,B", [(2, 50, "cube", 100), (8, 48, "square", 33), (64, 256, "id", 70), (32, 64, "cube", 129)])
+def test_midpoint_fixed_solver(px, torch, oracle, d, h, pre, B):
+    """fixed_solver/midpoint.py:7-18 on all three fixed-grid kernels: bit-exact on the FP32 ones
+    (small-state and register-tiled), rtol 1e-5 on the tensor-core one."""
+    field, om = both(px, oracle, fanin_weights(d, h, seed=d + 1), pre)
+    y0 = np.random.default_rng(d).uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, 9).astype(f32)
+    yd = torch.from_numpy(y0).cuda().reshape(B, 1, d)
+    ref = oracle.fixed_mlp("midpoint", om, y0, t)
+    sol = px.odeint(field, yd, t, px.Midpoint, options={"math": "fp32"})
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    if d >= 16:
+        tens = px.odeint(field, yd, t, px.Midpoint, options={"math": "tensor"})
+        assert _close(tens.cpu().numpy(), ref, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
 # large states: the register-tiled FFMA2 kernels (cfg3: 64-256-64 RK4, cfg4: 32-64-32 Euler-Maruyama)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("d,h,B", [(64, 256, 100), (64, 128, 33), (64, 64, 130), (32, 256, 31), (32, 128, 65),
