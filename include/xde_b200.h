@@ -149,6 +149,17 @@ int xde_adaptive_rk_mlp_f32(int32_t method, const xde_mlp_field_t *field, const 
                             const float *t_span, int32_t T, const xde_ctrl_opts_t *opts, int32_t controller,
                             float *out, xde_stats_t *stats, const xde_attempt_log_t *log, void *stream);
 
+/* ... with the solver's step_t / jump_t keyword arguments (solver/base_adaptive_solver_rk.py:38-46 ctor,
+ * :94-114 setup, :209-224 clamping of the attempt to the next forced point, :263-273 index advance and the
+ * re-evaluation of f after a jump).  step_t / jump_t: device arrays in t_span's time, sorted in integration
+ * order and filtered to lie at or after t_span[0] (sort_tvals, utils/ode_utils.py:22-25, is the caller's);
+ * null / 0 = none.  Any method, per-trajectory controller; Dopri5 with forced points runs on the
+ * table-driven kernel (bit-identical arithmetic). */
+int xde_adaptive_rk_mlp_grid_f32(int32_t method, const xde_mlp_field_t *field, const float *y0, int64_t B,
+                                 const float *t_span, int32_t T, const xde_ctrl_opts_t *opts, int32_t controller,
+                                 const float *step_t, int32_t n_step, const float *jump_t, int32_t n_jump,
+                                 float *out, xde_stats_t *stats, const xde_attempt_log_t *log, void *stream);
+
 /* OdeintAdjointMethod.backward                        functional/odeint_adjoint.py:47-167
  * (augmented_dynamics :89-124 integrated backwards segment by segment :134-159).
  * y_ans, grad_y [T,B,D]; out_gparams [d*h + h + h*d + d] = (gW1, gb1, gW2, gb2) summed over the

@@ -196,7 +196,8 @@ class AdaptiveRK:
 
     def __init__(self, func: Callable, y0: np.ndarray, rtol=1e-7, atol=1e-9, norm=rms_norm,
                  min_step=0.0, max_step=float("inf"), first_step=None, safety=0.9, ifactor=10.0,
-                 dfactor=0.2, max_num_steps=2**31 - 1):
+                 dfactor=0.2, max_num_steps=2**31 - 1, step_t=None, jump_t=None):
+        self.step_t_arg, self.jump_t_arg = step_t, jump_t
         self.func = func
         self.y0 = np.asarray(y0, dtype=f32)
         self.rtol, self.atol = f32(rtol), f32(atol)
@@ -253,6 +254,19 @@ class AdaptiveRK:
             first = self.first_step
         # _RungeKuttaState(y1, f1, t0, t1, dt, interp_coeff)
         self.rk = [self.y0, f0, t0, t0, first, [self.y0] * 5]
+        # step_t / jump_t (:94-114): sort_tvals (utils/ode_utils.py:22-25), in solver time
+        import bisect
+
+        def prep(tv):
+            if tv is None:
+                return np.zeros(0, f32)
+            v = np.asarray(tv, f32).reshape(-1)
+            v = (-v).astype(f32) if self.rev else v
+            return np.sort(v[v >= t0]).astype(f32)
+
+        self.step_t, self.jump_t = prep(self.step_t_arg), prep(self.jump_t_arg)
+        self.next_step_index = min(bisect.bisect(self.step_t.tolist(), t0), len(self.step_t) - 1)
+        self.next_jump_index = min(bisect.bisect(self.jump_t.tolist(), t0), len(self.jump_t) - 1)
 
     # solver/base_adaptive_solver_rk.py:129-181
     def _runge_kutta_step(self, y0, f0, t0, dt, t1):
@@ -286,6 +300,21 @@ class AdaptiveRK:
             raise AssertionError("underflow in dt {}".format(dt))
         if not np.isfinite(y0).all():
             raise AssertionError("non-finite values in state `y`")
+        # make step, respecting prescribed grid points (:209-224)
+        on_step_t = on_jump_t = False
+        if len(self.step_t):
+            nxt = self.step_t[self.next_step_index]
+            on_step_t = bool(t0 < nxt < f32(t0 + dt))
+            if on_step_t:
+                t1 = nxt
+                dt = f32(t1 - t0)
+        if len(self.jump_t):
+            nxt = self.jump_t[self.next_jump_index]
+            on_jump_t = bool(t0 < nxt < f32(t0 + dt))
+            if on_jump_t:
+                on_step_t = False
+                t1 = nxt
+                dt = f32(t1 - t0)
         y1, f1, err, k = self._runge_kutta_step(y0, f0, t0, dt, t1)
         # compute_error_ratio (utils/ode_utils.py:80-82)
         tol = (self.atol + self.rtol * np.fmax(np.abs(y0), np.abs(y1))).astype(f32)
@@ -303,6 +332,12 @@ class AdaptiveRK:
         if accept:
             t_next, y_next, f_next = t1, y1, f1
             coeff = self._interp_fit(y0, y1, k, dt)
+            if on_step_t and self.next_step_index != len(self.step_t) - 1:
+                self.next_step_index += 1
+            if on_jump_t:
+                if self.next_jump_index != len(self.jump_t) - 1:
+                    self.next_jump_index += 1
+                f_next = self.move(t_next, y_next)  # :269-273
         else:
             t_next, y_next, f_next = t0, y0, f0
         # optimal_step_size (utils/ode_utils.py:85-97)

@@ -382,6 +382,9 @@ typedef struct {
   const orc_opts_t *o;
   int rev; /* repair R5: integrate s = -t with f~(s,y) = -f(-s,y) */
   rk_tab_t tab;
+  /* step_t / jump_t (base_adaptive_solver_rk.py:94-114): sorted, >= t0, in solver time; may be empty */
+  const float *step_t, *jump_t;
+  int n_step, n_jump, step_idx, jump_idx;
   /* _RungeKuttaState (solver/base_adaptive_solver_rk.py:22-24) */
   float *y1, *f1, *coef[5];
   float t0, t1, dt;
@@ -474,6 +477,12 @@ static void drv_before_integrate(drv_t *d, float t0, const float *y0) {
   d->t1 = t0;
   d->dt = first;
   for (int i = 0; i < 5; ++i) memcpy(d->coef[i], y0, sizeof(float) * n);
+  /* next_*_index = min(bisect.bisect(list, t_span[0]), len - 1)  (:109-114) */
+  d->step_idx = d->jump_idx = 0;
+  while (d->step_idx < d->n_step && !(t0 < d->step_t[d->step_idx])) d->step_idx++;
+  if (d->step_idx > d->n_step - 1) d->step_idx = d->n_step - 1;
+  while (d->jump_idx < d->n_jump && !(t0 < d->jump_t[d->jump_idx])) d->jump_idx++;
+  if (d->jump_idx > d->n_jump - 1) d->jump_idx = d->n_jump - 1;
 }
 
 /* solver/base_adaptive_solver_rk.py:183-284 with _runge_kutta_step :129-181, compute_error_ratio
@@ -484,11 +493,32 @@ static int drv_adaptive_step(drv_t *d) {
   const int S = tb->S;
   const int64_t n = d->n;
   float *y0 = d->y1, *f0 = d->f1;
-  const float t0 = d->t1, dt = d->dt;
-  const float t1 = t0 + dt;
+  const float t0 = d->t1;
+  float dt = d->dt;
+  float t1 = t0 + dt;
   if (!(t0 + dt > t0)) return ORC_DT_UNDERFLOW;
   for (int64_t e = 0; e < n; ++e)
     if (!isfinite(y0[e])) return ORC_NONFINITE_STATE;
+  /* "Make step, respecting prescribed grid points" (:209-224): all the step_t handling, then all the
+   * jump_t handling */
+  int on_step = 0, on_jump = 0;
+  if (d->n_step > 0) {
+    const float nt = d->step_t[d->step_idx];
+    on_step = (t0 < nt) && (nt < t0 + dt);
+    if (on_step) {
+      t1 = nt;
+      dt = t1 - t0;
+    }
+  }
+  if (d->n_jump > 0) {
+    const float nj = d->jump_t[d->jump_idx];
+    on_jump = (t0 < nj) && (nj < t0 + dt);
+    if (on_jump) {
+      on_step = 0;
+      t1 = nj;
+      dt = t1 - t0;
+    }
+  }
 
   float *k = d->k;
   memcpy(k, f0, sizeof(float) * n);
@@ -569,6 +599,11 @@ static int drv_adaptive_step(drv_t *d) {
     memcpy(d->ynew, y1, sizeof(float) * n);
     memcpy(d->y1, d->ynew, sizeof(float) * n);
     memcpy(d->f1, f1, sizeof(float) * n);
+    if (on_step && d->step_idx != d->n_step - 1) d->step_idx++;
+    if (on_jump) {
+      if (d->jump_idx != d->n_jump - 1) d->jump_idx++;
+      drv_rhs(d, t1, d->y1, d->f1); /* f1 = self.func(t_next, y_next) past a discontinuity (:269-273) */
+    }
   }
   /* optimal_step_size(dt, error_ratio, safety, ifactor, dfactor, self.order) */
   float dt_next;
@@ -675,6 +710,15 @@ int orc_adaptive_rk_mlp(int32_t method, const orc_mlp_t *m, const float *y0, int
                         int32_t T, const orc_opts_t *opts, int32_t controller, float *out,
                         orc_stats_t *stats, orc_attempt_t *log, int64_t log_cap, int64_t log_traj,
                         int64_t *log_len, int32_t nthreads) {
+  return orc_adaptive_rk_mlp_grid(method, m, y0, B, t_span, T, opts, controller, NULL, 0, NULL, 0, out, stats,
+                                  log, log_cap, log_traj, log_len, nthreads);
+}
+
+int orc_adaptive_rk_mlp_grid(int32_t method, const orc_mlp_t *m, const float *y0, int64_t B,
+                             const float *t_span, int32_t T, const orc_opts_t *opts, int32_t controller,
+                             const float *step_t, int32_t n_step, const float *jump_t, int32_t n_jump,
+                             float *out, orc_stats_t *stats, orc_attempt_t *log, int64_t log_cap,
+                             int64_t log_traj, int64_t *log_len, int32_t nthreads) {
   const int D = m->d;
   rk_tab_t tab;
   if (D > ORC_MAX_D || m->h > ORC_MAX_H || T < 2 || B < 1 || rk_tab_init(&tab, method)) return ORC_BAD_ARG;
@@ -683,6 +727,7 @@ int orc_adaptive_rk_mlp(int32_t method, const orc_mlp_t *m, const float *y0, int
     drv_t d;
     if (drv_alloc(&d, B * D)) return ORC_BAD_ARG;
     d.tab = tab;
+    d.step_t = step_t, d.n_step = n_step, d.jump_t = jump_t, d.n_jump = n_jump;
     fwd_ctx_t c = {m, B};
     orc_stats_t st;
     stats_reset(&st);
@@ -709,7 +754,10 @@ int orc_adaptive_rk_mlp(int32_t method, const orc_mlp_t *m, const float *y0, int
     drv_t d;
     float *tmp = (float *)malloc(sizeof(float) * (size_t)T * D);
     int ok = (drv_alloc(&d, D) == 0) && tmp;
-    if (ok) d.tab = tab;
+    if (ok) {
+      d.tab = tab;
+      d.step_t = step_t, d.n_step = n_step, d.jump_t = jump_t, d.n_jump = n_jump;
+    }
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 64)
 #endif

@@ -115,6 +115,15 @@ int orc_adaptive_rk_mlp(int32_t method, const orc_mlp_t *m, const float *y0, int
                         orc_stats_t *stats, orc_attempt_t *log, int64_t log_cap, int64_t log_traj,
                         int64_t *log_len, int32_t nthreads);
 
+/* ... with the solver's step_t / jump_t forced grid points (solver/base_adaptive_solver_rk.py:94-114,
+ * 209-224, 263-273).  step_t, jump_t: sorted ascending in SOLVER time (negated for a decreasing t_span)
+ * and filtered to >= t_span[0] (sort_tvals, utils/ode_utils.py:22-25, is the caller's); NULL / 0 = none. */
+int orc_adaptive_rk_mlp_grid(int32_t method, const orc_mlp_t *m, const float *y0, int64_t B,
+                             const float *t_span, int32_t T, const orc_opts_t *opts, int32_t controller,
+                             const float *step_t, int32_t n_step, const float *jump_t, int32_t n_jump,
+                             float *out, orc_stats_t *stats, orc_attempt_t *log, int64_t log_cap,
+                             int64_t log_traj, int64_t *log_len, int32_t nthreads);
+
 /* odeint(func=MLP, solver=Euler|RK4|Midpoint; fixed_solver/midpoint.py:7-18): solver/base_fixed_solver.py:103-144, fixed_solver/euler.py:7-11,
  * fixed_solver/rk4.py:7-10 (3/8 rule, base_fixed_solver.py:166-197).  grid == t_span.
  * out is [B,T,D] (concat(axis=-2) of [B,1,D] states, base_fixed_solver.py:143). */

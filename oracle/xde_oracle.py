@@ -153,8 +153,20 @@ def dopri5_mlp(mlp: MLP, y0, t_span, **kw):
     return adaptive_rk_mlp("dopri5", mlp, y0, t_span, **kw)
 
 
+def sort_tvals(tvals, t_span):
+    """sort_tvals (utils/ode_utils.py:22-25) in solver time: keep values >= t_span[0], ascending; a decreasing
+    t_span is integrated as s = -t (repair R5)."""
+    if tvals is None:
+        return np.zeros(0, np.float32)
+    v = _f32(tvals).reshape(-1)
+    t0 = np.float32(t_span[0])
+    if t_span[1] < t_span[0]:
+        v, t0 = -v, -t0
+    return np.sort(v[v >= t0]).astype(np.float32)
+
+
 def adaptive_rk_mlp(method: str, mlp: MLP, y0, t_span, *, controller="trajectory", log_traj: Optional[int] = None,
-                    log_cap=100000, nthreads=0, **opt_kw):
+                    log_cap=100000, nthreads=0, step_t=None, jump_t=None, **opt_kw):
     """Any embedded tableau of the reference (RK keys) -> (out [T,B,D], stats, log|None, status)"""
     y0, t_span = _f32(y0), _f32(t_span)
     B, D = y0.shape
@@ -166,10 +178,13 @@ def adaptive_rk_mlp(method: str, mlp: MLP, y0, t_span, *, controller="trajectory
     log = np.zeros(log_cap if want_log else 0, ATTEMPT_DTYPE)
     log_len = C.c_int64(0)
     m, o = mlp.c(), make_opts(**opt_kw)
-    rc = lib().orc_adaptive_rk_mlp(C.c_int32(RK[method]), C.byref(m), _p(y0), C.c_int64(B), _p(t_span),
-                                   C.c_int32(T), C.byref(o), C.c_int32(CTRL[controller]), _p(out), _p(stats),
-                                   _p(log) if want_log else None, C.c_int64(log_cap),
-                                   C.c_int64(log_traj or 0), C.byref(log_len), C.c_int32(nthreads))
+    st_, jt_ = sort_tvals(step_t, t_span), sort_tvals(jump_t, t_span)
+    rc = lib().orc_adaptive_rk_mlp_grid(C.c_int32(RK[method]), C.byref(m), _p(y0), C.c_int64(B), _p(t_span),
+                                        C.c_int32(T), C.byref(o), C.c_int32(CTRL[controller]),
+                                        _p(st_) if st_.size else None, C.c_int32(st_.size),
+                                        _p(jt_) if jt_.size else None, C.c_int32(jt_.size), _p(out), _p(stats),
+                                        _p(log) if want_log else None, C.c_int64(log_cap),
+                                        C.c_int64(log_traj or 0), C.byref(log_len), C.c_int32(nthreads))
     return out, stats.view(np.recarray), (log[:log_len.value].view(np.recarray) if want_log else None), rc
 
 

@@ -63,6 +63,10 @@ _EXPORTS = {
     "xde_adaptive_rk_mlp_f32": (C.c_int, [C.c_int32, C.POINTER(MlpFieldC), C.c_void_p, C.c_int64, C.c_void_p,
                                           C.c_int32, C.POINTER(CtrlOptsC), C.c_int32, C.c_void_p, C.c_void_p,
                                           C.POINTER(AttemptLogC), C.c_void_p]),
+    "xde_adaptive_rk_mlp_grid_f32": (C.c_int, [C.c_int32, C.POINTER(MlpFieldC), C.c_void_p, C.c_int64, C.c_void_p,
+                                               C.c_int32, C.POINTER(CtrlOptsC), C.c_int32, C.c_void_p, C.c_int32,
+                                               C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                               C.POINTER(AttemptLogC), C.c_void_p]),
     "xde_dopri5_mlp_adjoint_f32": (C.c_int, [C.POINTER(MlpFieldC), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                              C.c_int64, C.POINTER(CtrlOptsC), C.c_int32, C.c_int32, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.POINTER(AttemptLogC), C.c_void_p]),

@@ -38,6 +38,10 @@ struct RkParams {
   xde_attempt_t *log_records;
   int *log_counts;
   int log_cap;
+  // step_t / jump_t (base_adaptive_solver_rk.py:94-114): sorted in integration order, already filtered to
+  // lie at or after t_span[0] (sort_tvals is the shim's), in t_span's own time; may be null / 0
+  const float *step_t, *jump_t;
+  int n_step, n_jump;
   RkTab tab;
 };
 
@@ -306,6 +310,13 @@ __global__ void __launch_bounds__(kRkThreads) adaptive_rk_small_kernel(const RkP
     }
 
     int i_out = 1, n_steps = 0, n_logged = 0;
+    // next_*_index = min(bisect.bisect(list, t_span[0]), len - 1)  (:109-114); values in solver time
+    const float gsign = rev ? -1.0f : 1.0f;
+    int step_idx = 0, jump_idx = 0;
+    while (step_idx < p.n_step && !(t0 < gsign * p.step_t[step_idx])) step_idx++;
+    if (step_idx > p.n_step - 1) step_idx = p.n_step - 1;
+    while (jump_idx < p.n_jump && !(t0 < gsign * p.jump_t[jump_idx])) jump_idx++;
+    if (jump_idx > p.n_jump - 1) jump_idx = p.n_jump - 1;
     while (i_out < p.T) {
       // assertions of step / _adaptive_step (base_adaptive_solver_rk.py:120-122, 200-203)
       int bad = 0;
@@ -323,7 +334,26 @@ __global__ void __launch_bounds__(kRkThreads) adaptive_rk_small_kernel(const RkP
           for (int e = 0; e < D; ++e) p.out[((long long)i * p.B + traj) * D + e] = NAN;
         break;
       }
-      const float t1 = t0 + dt;
+      float t1 = t0 + dt;
+      // "Make step, respecting prescribed grid points" (:209-224): step_t first, then jump_t
+      bool on_step = false, on_jump = false;
+      if (p.n_step > 0) {
+        const float nt = gsign * p.step_t[step_idx];
+        on_step = (t0 < nt) && (nt < t0 + dt);
+        if (on_step) {
+          t1 = nt;
+          dt = t1 - t0;
+        }
+      }
+      if (p.n_jump > 0) {
+        const float nj = gsign * p.jump_t[jump_idx];
+        on_jump = (t0 < nj) && (nj < t0 + dt);
+        if (on_jump) {
+          on_step = false;
+          t1 = nj;
+          dt = t1 - t0;
+        }
+      }
       // _runge_kutta_step (:129-181): stage input y0 + sum_j k_j (beta_ij dt), products first
       for (int i = 0; i < S; ++i) {
 #pragma unroll
@@ -419,6 +449,14 @@ __global__ void __launch_bounds__(kRkThreads) adaptive_rk_small_kernel(const RkP
           K(0, e) = K(S, e);
         }
         t0 = t1;
+        if (on_step && step_idx != p.n_step - 1) step_idx++;
+        if (on_jump) {  // past a discontinuity: f1 = self.func(t_next, y_next)  (:263-273)
+          if (jump_idx != p.n_jump - 1) jump_idx++;
+          mlp_eval_small<D, PRE>(sw, H, y0, fo);
+#pragma unroll
+          for (int e = 0; e < D; ++e) K(0, e) = fo[e] * fsign;
+          n_fe += 1;
+        }
       }
       dt = dt_next;
     }
@@ -473,20 +511,26 @@ static int rk_dispatch_pre(const RkParams &p, cudaStream_t s) {
 
 }  // namespace xde
 
-extern "C" XDE_EXPORT int xde_adaptive_rk_mlp_f32(int32_t method, const xde_mlp_field_t *field, const float *y0,
-                                                  int64_t B, const float *t_span, int32_t T,
-                                                  const xde_ctrl_opts_t *opts, int32_t controller, float *out,
-                                                  xde_stats_t *stats, const xde_attempt_log_t *log, void *stream) {
+extern "C" XDE_EXPORT int xde_adaptive_rk_mlp_grid_f32(int32_t method, const xde_mlp_field_t *field,
+                                                       const float *y0, int64_t B, const float *t_span, int32_t T,
+                                                       const xde_ctrl_opts_t *opts, int32_t controller,
+                                                       const float *step_t, int32_t n_step, const float *jump_t,
+                                                       int32_t n_jump, float *out, xde_stats_t *stats,
+                                                       const xde_attempt_log_t *log, void *stream) {
   using namespace xde;
-  if (method == XDE_RK_DOPRI5)  // the tuned kernels (both controllers)
+  const bool grid_pts = (n_step > 0 || n_jump > 0);
+  if (method == XDE_RK_DOPRI5 && !grid_pts)  // the tuned kernels (both controllers)
     return xde_dopri5_mlp_f32(field, y0, B, t_span, T, opts, controller, out, stats, log, stream);
+  if (method == XDE_RK_DOPRI5) method = XDE_RK_DOPRI5_TABLE;  // same arithmetic, table-driven
   XDE_REQUIRE(field && y0 && t_span && opts && out, XDE_E_BAD_ARG, "null argument");
   XDE_REQUIRE(B >= 1 && T >= 2, XDE_E_BAD_ARG, "need B >= 1 and T >= 2 (B=%lld T=%d)", (long long)B, T);
+  XDE_REQUIRE(n_step >= 0 && n_jump >= 0 && (n_step == 0 || step_t) && (n_jump == 0 || jump_t), XDE_E_BAD_ARG,
+              "step_t / jump_t: negative count or null pointer");
   RkParams p{};
   XDE_REQUIRE(make_tab(method, p.tab), XDE_E_BAD_ARG, "unknown Runge-Kutta method %d", method);
   XDE_REQUIRE(controller == XDE_CTRL_TRAJECTORY, XDE_E_UNSUPPORTED_FIELD,
-              "the table-driven adaptive kernel has the per-trajectory controller only (controller='batch' is "
-              "fused for Dopri5)");
+              "the table-driven adaptive kernel (other tableaux, step_t / jump_t) has the per-trajectory "
+              "controller only; controller='batch' is fused for plain Dopri5");
   cudaStream_t s = (cudaStream_t)stream;
   p.field = *field;
   p.y0 = y0;
@@ -499,6 +543,10 @@ extern "C" XDE_EXPORT int xde_adaptive_rk_mlp_f32(int32_t method, const xde_mlp_
   p.log_records = log ? log->records : nullptr;
   p.log_counts = log ? log->counts : nullptr;
   p.log_cap = log ? log->cap : 0;
+  p.step_t = step_t;
+  p.n_step = n_step;
+  p.jump_t = jump_t;
+  p.n_jump = n_jump;
   if (stats) XDE_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(xde_stats_t), s));
   switch (field->d) {
     case 1: return rk_dispatch_pre<1>(p, s);
@@ -510,4 +558,12 @@ extern "C" XDE_EXPORT int xde_adaptive_rk_mlp_f32(int32_t method, const xde_mlp_
       set_last_error("adaptive RK: state dim D=%d has no fused kernel (supported: 1,2,3,4,8)", field->d);
       return XDE_E_UNSUPPORTED_FIELD;
   }
+}
+
+extern "C" XDE_EXPORT int xde_adaptive_rk_mlp_f32(int32_t method, const xde_mlp_field_t *field, const float *y0,
+                                                  int64_t B, const float *t_span, int32_t T,
+                                                  const xde_ctrl_opts_t *opts, int32_t controller, float *out,
+                                                  xde_stats_t *stats, const xde_attempt_log_t *log, void *stream) {
+  return xde_adaptive_rk_mlp_grid_f32(method, field, y0, B, t_span, T, opts, controller, nullptr, 0, nullptr, 0, out,
+                                      stats, log, stream);
 }

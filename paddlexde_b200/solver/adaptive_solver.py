@@ -94,8 +94,7 @@ class AdaptiveRKSolver:
     def __init__(self, xde, y0, rtol, atol, min_step=0, max_step=float("inf"), first_step=None, step_t=None,
                  jump_t=None, safety=0.9, ifactor=10.0, dfactor=0.2, max_num_steps=2 ** 31 - 1, dtype=None,
                  norm=None, controller="trajectory", log_attempts=0, check_status=True, **unused_kwargs):
-        if step_t is not None or jump_t is not None:
-            raise NotImplementedError("step_t / jump_t are not on the fused path yet (SURVEY 8(f) rank 2)")
+        self.step_t, self.jump_t = step_t, jump_t
         if getattr(xde, "kind", None) != "ode":
             raise UnsupportedFieldError(f"{type(self).__name__} integrates BaseODE problems")
         check_norm(norm)
@@ -127,13 +126,31 @@ class AdaptiveRKSolver:
             self.attempt_log = AttemptLog(B, self.log_attempts, y0.device)
             log_c = C.byref(self.attempt_log.c_struct())
         fs = field.c_struct()
-        check(lib().xde_adaptive_rk_mlp_f32(RK[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), t_host.size,
-                                            C.byref(self.opts), CTRL[self.controller], T.ptr(out),
-                                            T.ptr(self._stats_buf.buf), log_c, T.stream()))
+        step_t, jump_t = (self._sort_tvals(v, t_host, y0.device) for v in (self.step_t, self.jump_t))
+        check(lib().xde_adaptive_rk_mlp_grid_f32(
+            RK[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), t_host.size, C.byref(self.opts),
+            CTRL[self.controller], T.ptr(step_t) if step_t is not None else None, 0 if step_t is None else step_t.numel(),
+            T.ptr(jump_t) if jump_t is not None else None, 0 if jump_t is None else jump_t.numel(), T.ptr(out),
+            T.ptr(self._stats_buf.buf), log_c, T.stream()))
         if self.check_status:  # the reference asserts synchronously; opt out to stay asynchronous
             self.stats = self._stats_buf.read()
             raise_for_status(self.stats.status)
         return T.like_input(out, self.y0)
+
+    @staticmethod
+    def _sort_tvals(tvals, t_host, dev):
+        """sort_tvals (utils/ode_utils.py:22-25): drop the points before t_span[0], sort in integration
+        order (ascending for an increasing t_span, descending for a decreasing one: repair R5)."""
+        if tvals is None:
+            return None
+        v = (tvals.detach().cpu().numpy() if isinstance(tvals, torch.Tensor) else np.asarray(tvals)).astype(np.float32).reshape(-1)
+        if t_host[1] < t_host[0]:
+            v = np.sort(v[v <= t_host[0]])[::-1]
+        else:
+            v = np.sort(v[v >= t_host[0]])
+        if v.size == 0:
+            return None
+        return torch.from_numpy(np.ascontiguousarray(v)).to(dev)
 
     def read_stats(self) -> SolveStats:
         self.stats = self._stats_buf.read()

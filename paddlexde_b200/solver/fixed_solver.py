@@ -23,8 +23,11 @@ class FixedSolver:
         if step_size is not None or grid_constructor is not None:
             # the reference's own loop only ever visits len(t_span) grid points: grid == t_span
             raise NotImplementedError("step_size / grid_constructor grids are not on the fused path (SURVEY 8(f) rank 2)")
-        if interp not in ("linear", "", None):
-            raise NotImplementedError("interp='cubic' is not on the fused path (SURVEY 8(f) rank 2)")
+        # Output interpolation (base_fixed_solver.py:133-139).  The grid IS t_span, so every output time is the
+        # end of its step: linear_interp returns y1 (interp_fn.py:7-8) and cubic_hermite_interp evaluates at
+        # h = 1, i.e. h00 = h10 = h11 = 0, h01 = 1 -> y1 as well (interp_fn.py:13-20).  Both run the same kernel.
+        if interp not in ("linear", "cubic", "", None):
+            raise ValueError(f"interp must be 'linear' or 'cubic', got {interp!r}")
         for key in ("atol", "rtol"):  # base_fixed_solver.py:45-47 requires them
             if key not in kwargs:
                 raise KeyError(key)

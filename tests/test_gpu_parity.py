@@ -521,6 +521,47 @@ def test_other_tableaux_reverse_time_first_step_and_status(px, torch, oracle):
                   options={"controller": "batch"})
 
 
+@pytest.mark.parametrize("name", ["Dopri5", "Bosh3", "Fehlberg2", "Dopri8"])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_step_t_and_jump_t_forced_grid_points(px, torch, oracle, name, reverse):
+    """solver kwargs step_t / jump_t (base_adaptive_solver_rk.py:94-114, 209-224, 263-273): attempts are
+    clamped to the next forced point, a jump re-evaluates f; bit-exact incl. the attempt log and nfe."""
+    field, om = both(px, oracle, spiral_weights(), "cube")
+    y0 = cfg2_y0(200)
+    t = (np.linspace(1.0, 0.0, 4) if reverse else np.linspace(0, 1.5, 5)).astype(f32)
+    step_t, jump_t = [0.33, 0.9, -1.0, 0.05, 7.0], [0.5, 1.2, 0.051]
+    method = {"Dopri5": "dopri5", "Bosh3": "bosh3", "Fehlberg2": "fehlberg2", "Dopri8": "dopri8"}[name]
+    xde = px.xde.BaseODE(field, torch.from_numpy(y0).cuda(), t)
+    s = getattr(px, name)(xde=xde, y0=xde.y0, rtol=1e-5, atol=1e-7, step_t=torch.tensor(step_t), jump_t=jump_t,
+                          log_attempts=512)
+    sol = s.integrate(t)
+    ref, st, _, rc = oracle.adaptive_rk_mlp(method, om, y0, t, rtol=1e-5, atol=1e-7, step_t=step_t, jump_t=jump_t)
+    plain, stp, _, _ = oracle.adaptive_rk_mlp(method, om, y0, t, rtol=1e-5, atol=1e-7)
+    assert rc == 0 and np.array_equal(sol.cpu().numpy(), ref)
+    assert s.stats.n_attempts == int(st.n_attempts.sum()) > int(stp.n_attempts.sum())  # the points cost steps
+    assert s.stats.nfe == int(st.nfe.sum())
+    rec, cnt = s.attempt_log.read()
+    _, _, lg, _ = oracle.adaptive_rk_mlp(method, om, y0, t, log_traj=17, rtol=1e-5, atol=1e-7, step_t=step_t,
+                                         jump_t=jump_t)
+    r = rec[17, :cnt[17]]
+    assert cnt[17] == len(lg) and np.array_equal(r.dt, lg.dt) and np.array_equal(r.t0, lg.t0)
+    assert np.array_equal(r.accepted, lg.accepted)
+    ends = np.round((r.t0 + r.dt)[r.accepted == 1], 5)   # an accepted attempt ends on every forced point in range
+    inside = [v for v in step_t + jump_t if min(t[0], t[-1]) < v < max(t[0], t[-1])]
+    assert all(np.any(np.isclose(ends, v, atol=2e-6)) for v in inside)
+
+
+def test_fixed_interp_cubic_is_the_same_kernel(px, torch, oracle):
+    field, om = both(px, oracle, spiral_weights(), "cube")
+    y0 = cfg2_y0(64)
+    t = np.linspace(0, 1, 9).astype(f32)
+    yd = torch.from_numpy(y0).cuda().reshape(64, 1, 2)
+    a = px.odeint(field, yd, t, px.RK4, options={"interp": "cubic"})
+    assert np.array_equal(a.cpu().numpy(), oracle.fixed_mlp("rk4", om, y0, t))
+    with pytest.raises(NotImplementedError):  # the reference's own loop never visits a finer grid (SURVEY 3.2)
+        px.odeint(field, yd, t, px.RK4, options={"step_size": 0.01})
+
+
 @pytest.mark.parametrize("d,h,pre,B", [(2, 50, "cube", 100), (8, 48, "square", 33), (64, 256, "id", 70), (32, 64, "cube", 129)])
 def test_midpoint_fixed_solver(px, torch, oracle, d, h, pre, B):
     """fixed_solver/midpoint.py:7-18 on all three fixed-grid kernels: bit-exact on the FP32 ones
