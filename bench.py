@@ -138,20 +138,59 @@ def config_dict(B, n, where):
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / power / throttle reasons sampled DURING the timed region.  NVML from a thread every ~4 ms
+    (the timed region of the default run is ~0.1 s: `nvidia-smi -lms` takes longer than that to print its
+    first row); `nvidia-smi` is the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_id):
+        self.rows, self.p, self.thr, self.stop_flag = [], None, None, False
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByUUID(gpu_id.encode() if isinstance(gpu_id, str) else gpu_id) \
+                if str(gpu_id).startswith("GPU-") else N.nvmlDeviceGetHandleByIndex(int(gpu_id))
+            mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                N.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        r = int(reasons_fn(h))
+                        self.rows.append((float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), mx,
+                                          N.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                          [k for k, b in bits.items() if r & b]))
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+
+            import threading
+            self.thr = threading.Thread(target=loop, daemon=True)
+            self.thr.start()
+            return
+        except Exception:
+            self.thr = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_id), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
     def stop(self):
+        if self.thr is not None:
+            self.stop_flag = True
+            self.thr.join(timeout=2)
+            if not self.rows:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            sm = [r[0] for r in self.rows]
+            return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][1]),
+                    "power_w_max": float(max(r[2] for r in self.rows)), "samples": len(sm),
+                    "reasons": sorted({k for r in self.rows for k in r[3]}), "source": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -176,7 +215,28 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# secondary configs (not the headline): BASELINE.json configs[2] (cfg3) and [3] (cfg4), device-resident
+# ---------------------------------------------------------------------------------------------------
+def secondary_configs():
+    """Kernel timings of the large-state fixed-grid paths, tensor-core (tcgen05) and FP32, with the
+    roofline fractions of SURVEY 8(d).  Reported next to the headline, never instead of it."""
+    try:
+        import torch
+
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs as bc
+        res = []
+        for fn, kw in ((bc.cfg3, {"math": "tensor"}), (bc.cfg3, {"math": "fp32"}), (bc.cfg4, {"math": "tensor"}),
+                       (bc.cfg4, {"math": "fp32"})):
+            res.append(fn(**kw))
+            torch.cuda.empty_cache()
+        return res
+    except Exception as e:  # never lose the headline line over a secondary measurement
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -352,8 +412,16 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if args.batch == 1 << 20:
+            # dram__bytes_read.sum + dram__bytes_write.sum of dopri5_adj_kernel, one launch at this batch:
+            # profiles/r1i_ncu_full_adjoint.md (170.96 MB + 4.92 MB).  Below the algorithmic 64 B/attempt
+            # because the fused kernel keeps (y, a) in registers across the attempts of a segment.
+            out["roofline"]["traffic"] = 175887616
+            out["roofline"]["traffic_source"] = "ncu --set full, profiles/r1i_ncu_full_adjoint.md"
         if not args.no_cpu and world >= 1:
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        if world == 1 and not args.no_secondary:
+            out["secondary"] = secondary_configs()
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -370,6 +438,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=1 << 14, help="trajectories per reference-arm step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg3/cfg4 kernel timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
