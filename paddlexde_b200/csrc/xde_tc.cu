@@ -682,6 +682,387 @@ __global__ void __launch_bounds__(cta_threads(NJ), NJ == 4 ? 1 : 2) fixed_tc_ker
   }
 }
 
+// ---- two tiles in flight (small fields) ----------------------------------------------------------------
+// For H = 64 networks one tile needs <= 256 TMEM columns and the tensor-core work per evaluation is tiny:
+// in fixed_tc_kernel almost half of an evaluation is then exposed latency (first layer-1 chunk, last layer-2
+// chunk, mbarrier / commit / TMEM round trips; phase trace of cfg4: ~3 000 of ~6 300 cycles).  Two 9-warp CTAs
+// per SM do not co-reside (register file granularity), so this kernel keeps TWO tiles (slots A, B; 256 TMEM
+// columns and one set of mbarriers each) in flight inside one CTA and software-pipelines them:
+//     compute warps:  H(A) H(B) | F(A) update(A) U(A) | F(B) update(B) U(B) | H(A) H(B) | ...
+//     MMA warp:       L1(A) L1(B) | L2(A) | L2(B) | L1(A) L1(B) | ...
+// U(x) = stage input to TMEM, L1/L2 = the layers' MMAs, H(x) = tanh epilogue, F(x) = read the field value.
+// Whenever the compute warps wait on a barrier of one slot, the MMAs it stands for were issued a whole phase
+// of the other slot earlier.  Same arithmetic, same TMEM layouts per slot as fixed_tc_kernel.
+template <int D, int H, int KIND>
+__global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcParams p) {
+  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  constexpr int kComputeWarps = compute_warps(4), kThreads = cta_threads(4);
+  using G = Geom<D, H, NETS, 4>;
+  static_assert(G::COLS <= 256 && G::NC <= 8, "two tiles in flight: <= 256 TMEM columns and <= 8 state columns per thread");
+  constexpr int NC = G::NC, NP = NC / 2, CH = G::CH, NCHUNK = G::NCHUNK;
+  constexpr int EVALS = (KIND == 1) ? 4 : (KIND == 3) ? 2 : 1;
+  constexpr uint32_t SLOT = 256;  // TMEM columns per tile slot
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *u_ready = reinterpret_cast<uint64_t *>(smem);  // [2]
+  uint64_t *f_ready = u_ready + 2;                           // [2]
+  uint64_t *z_ready = u_ready + 4;                           // [2][kMaxChunks]
+  uint64_t *h_ready = z_ready + 2 * kMaxChunks;              // [2][kMaxChunks]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_ready + 2 * kMaxChunks);
+  static_assert((4 + 4 * kMaxChunks) * 8 + 4 <= G::OFF_W, "barrier block");
+  unsigned char *sW = smem + G::OFF_W;
+  const float *sb1 = reinterpret_cast<const float *>(smem + G::OFF_B1);
+  const float *sb2 = reinterpret_cast<const float *>(smem + G::OFF_B2);
+  const float *ssinv = reinterpret_cast<const float *>(smem + G::OFF_SINV);
+  const float *st = reinterpret_cast<const float *>(smem + G::OFF_T);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == kComputeWarps) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(u_ready + s, kComputeWarps);
+        mbar_init(f_ready + s, 1);
+        for (int c = 0; c < kMaxChunks; ++c) {
+          mbar_init(z_ready + s * kMaxChunks + c, 1);
+          mbar_init(h_ready + s * kMaxChunks + c, kComputeWarps);
+        }
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(2 * SLOT)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.wbuf);
+    uint4 *dst = reinterpret_cast<uint4 *>(sW);
+    for (int i = tid; i < G::W_BYTES / 16; i += kThreads) dst[i] = src[i];
+    float *b1w = reinterpret_cast<float *>(smem + G::OFF_B1);
+    float *b2w = reinterpret_cast<float *>(smem + G::OFF_B2);
+    float *siw = reinterpret_cast<float *>(smem + G::OFF_SINV);
+    float *tw = reinterpret_cast<float *>(smem + G::OFF_T);
+    for (int i = tid; i < NETS * H; i += kThreads) b1w[i] = (i < H ? p.f.b1[i] : p.g.b1[i - H]);
+    for (int i = tid; i < NETS * D; i += kThreads) b2w[i] = (i < D ? p.f.b2[i] : p.g.b2[i - D]);
+    if (tid < NETS * 2) siw[tid] = reinterpret_cast<const float *>(p.wbuf + G::W_BYTES)[tid];
+    for (int i = tid; i < p.T; i += kThreads) tw[i] = p.t_span[i];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const long long n_tiles = (p.B + kTM - 1) / kTM;
+  const long long stride = 2LL * gridDim.x;  // a CTA takes tiles (t, t + gridDim.x) together
+  long long my_pairs = 0;
+  if ((long long)blockIdx.x < n_tiles) my_pairs = (n_tiles - 1 - blockIdx.x) / stride + 1;
+  const long long rounds = my_pairs * (long long)(p.T - 1) * EVALS;
+
+  if (warp == kComputeWarps) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc1 = instr_desc(64), idesc2 = instr_desc(D);
+    const uint32_t w_addr = smem_u32(sW);
+    for (long long r = 0; r < rounds; ++r) {
+      const uint32_t par = (uint32_t)(r & 1);
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {  // layer 1 of both slots
+        const uint32_t tm = tmem + s * SLOT;
+        mbar_wait(u_ready + s, par);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int net = c / CH, cc = c % CH;
+          const uint32_t d = tm + G::Z0 + net * H + cc * 64;
+          const uint32_t w1hi = w_addr + net * G::NET_W_BYTES, w1lo = w1hi + G::MAT_BYTES;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks) {
+              const uint32_t a_hi = tm + G::U0 + net * D + 8 * ks, a_lo = a_hi + D / 2;
+              const uint32_t off = (2 * ks) * (H * 16) + (cc * 64) * 16;
+              mma_ts(d, a_hi, smem_desc(w1lo + off, H * 16, 128), idesc1, ks > 0);
+              mma_ts(d, a_lo, smem_desc(w1hi + off, H * 16, 128), idesc1, 1);
+            }
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks) {
+              const uint32_t a_hi = tm + G::U0 + net * D + 8 * ks;
+              const uint32_t off = (2 * ks) * (H * 16) + (cc * 64) * 16;
+              mma_ts(d, a_hi, smem_desc(w1hi + off, H * 16, 128), idesc1, 1);
+            }
+            tc_commit(z_ready + s * kMaxChunks + c);
+          }
+          __syncwarp();
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {  // layer 2 of both slots, as their tanh chunks land
+        const uint32_t tm = tmem + s * SLOT;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int net = c / CH, cc = c % CH;
+          const uint32_t d_main = tm + G::F0 + net * G::FW + (cc % G::NFM) * D;
+          const uint32_t d_corr = G::SPLIT_CORR ? tm + G::F0 + net * G::FW + G::NFM * D : d_main;
+          const uint32_t w2hi = w_addr + net * G::NET_W_BYTES + 2 * G::MAT_BYTES, w2lo = w2hi + G::MAT_BYTES;
+          mbar_wait(h_ready + s * kMaxChunks + c, par);
+          tc_fence_after();
+          if (elect_one()) {
+            if (G::SPLIT_CORR) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const int kk = cc * 4 + ks;
+                const uint32_t a_hi = tm + G::Z0 + net * H + 16 * kk, a_lo = a_hi + 8;
+                const uint32_t off = (2 * kk) * (D * 16);
+                mma_ts(d_corr, a_hi, smem_desc(w2lo + off, D * 16, 128), idesc2, (cc | ks) != 0);
+                mma_ts(d_corr, a_lo, smem_desc(w2hi + off, D * 16, 128), idesc2, 1);
+                mma_ts(d_main, a_hi, smem_desc(w2hi + off, D * 16, 128), idesc2, !(cc < G::NFM && ks == 0));
+              }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t a_hi = tm + G::Z0 + net * H + 16 * ks, a_lo = a_hi + 8;
+                const uint32_t off = (2 * ks) * (D * 16);
+                mma_ts(d_main, a_hi, smem_desc(w2lo + off, D * 16, 128), idesc2, ks != 0);
+                mma_ts(d_main, a_lo, smem_desc(w2hi + off, D * 16, 128), idesc2, 1);
+              }
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_ts(d_main, tm + G::Z0 + net * H + 16 * ks, smem_desc(w2hi + (2 * ks) * (D * 16), D * 16, 128),
+                       idesc2, 1);
+            }
+            if (c == NCHUNK - 1) tc_commit(f_ready + s);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // =============================== compute warps ===============================
+    const int q = warp & 3, j = warp >> 2;
+    const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
+    const int c0 = j * NC;
+    const int pref = p.f.pre, preg = p.g.pre;
+    const float one_third = (float)(1.0 / 3.0);
+    uint32_t par = 0;
+    [[maybe_unused]] int trace_n = (tid == 0) ? 0 : (1 << 30);
+
+    auto phaseU = [&](int s, const f32x2(&yi)[NP]) {  // stage input -> U of slot s (fp16 hi | lo)
+      const uint32_t ts = tl + s * SLOT;
+#pragma unroll
+      for (int net = 0; net < NETS; ++net) {
+        uint32_t uh[NP], ul[NP];
+        const int pre = net ? preg : pref;
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+          float v0, v1;
+          upk(yi[c], v0, v1);
+          split2(pre_rt(pre, v0), pre_rt(pre, v1), uh[c], ul[c]);
+        }
+        Tmem<NP>::st(ts + G::U0 + net * D + j * NP, uh);
+        Tmem<NP>::st(ts + G::U0 + net * D + D / 2 + j * NP, ul);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(u_ready + s);
+    };
+    auto phaseH = [&](int s) {  // Z -> tanh -> fp16 hi | lo, in place, chunk by chunk
+      const uint32_t ts = tl + s * SLOT;
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int net = c / CH, cc = c % CH;
+        const int h0 = net * H + cc * 64 + j * 16;
+        mbar_wait(z_ready + s * kMaxChunks + c, par);
+        tc_fence_after();
+        uint32_t z[16], o[16];
+        Tmem<16>::ld(ts + G::Z0 + h0, z);
+        tc_wait_ld();
+        const f32x2 s1 = pk1(ssinv[net * 2]);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const float2 b = *reinterpret_cast<const float2 *>(sb1 + h0 + 2 * m);
+          const f32x2 a = fma2(pk(__uint_as_float(z[2 * m]), __uint_as_float(z[2 * m + 1])), s1, pk(b.x, b.y));
+          float t0, t1;
+          upk(tanh_fast2(a), t0, t1);
+          split2(t0, t1, o[m], o[8 + m]);
+        }
+        Tmem<16>::st(ts + G::Z0 + h0, o);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_ready + s * kMaxChunks + c);
+      }
+    };
+    auto phaseF = [&](int s, f32x2(&kf)[NP], f32x2(&kg)[NP]) {  // F of slot s -> registers
+      const uint32_t ts = tl + s * SLOT;
+      mbar_wait(f_ready + s, par);
+      tc_fence_after();
+#pragma unroll
+      for (int net = 0; net < NETS; ++net) {
+        f32x2(&kk)[NP] = net ? kg : kf;
+        const uint32_t fa = ts + G::F0 + net * G::FW + c0;
+        uint32_t r0[NC], r1[NC];
+        Tmem<NC>::ld(fa, r0);
+        if (G::SPLIT_CORR) Tmem<NC>::ld(fa + D, r1);
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+          kk[c] = pk(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
+          if (G::SPLIT_CORR) kk[c] = add2(kk[c], pk(__uint_as_float(r1[2 * c]), __uint_as_float(r1[2 * c + 1])));
+        }
+        if (G::SPLIT_CORR) {
+          Tmem<NC>::ld(fa + 2 * D, r0);
+          tc_wait_ld();
+#pragma unroll
+          for (int c = 0; c < NP; ++c)
+            kk[c] = add2(kk[c], pk(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1])));
+        }
+        const f32x2 s2 = pk1(ssinv[net * 2 + 1]);
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+          const float2 bb = *reinterpret_cast<const float2 *>(sb2 + net * D + c0 + 2 * c);
+          kk[c] = fma2(kk[c], s2, pk(bb.x, bb.y));
+        }
+      }
+    };
+
+    for (long long t0 = blockIdx.x; t0 < n_tiles; t0 += stride) {
+      long long b[2];
+      bool ok[2];
+      f32x2 y[2][NP], A[2][NP], S[2][NP];
+      float4 w4[2][NC / 4];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const long long tile = t0 + (long long)s * gridDim.x;
+        b[s] = tile * kTM + 32 * q + lane;
+        ok[s] = tile < n_tiles && b[s] < p.B;  // slot B of the last pair may be empty: it runs on zeros
+#pragma unroll
+        for (int v = 0; v < NC / 4; ++v) {
+          float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok[s]) {
+            t4 = *reinterpret_cast<const float4 *>(p.y0 + b[s] * D + c0 + 4 * v);
+            *reinterpret_cast<float4 *>(p.out + b[s] * (long long)p.n_out * D + c0 + 4 * v) = t4;
+          }
+          y[s][2 * v] = pk(t4.x, t4.y);
+          y[s][2 * v + 1] = pk(t4.z, t4.w);
+          w4[s][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (KIND == 2 && ok[s])
+            w4[s][v] = __ldg(reinterpret_cast<const float4 *>(p.dW + b[s] * D + c0 + 4 * v));  // increments of step 1
+        }
+#pragma unroll
+        for (int c = 0; c < NP; ++c) A[s][c] = S[s][c] = pk1(0.0f);
+        phaseU(s, y[s]);
+      }
+      for (int i = 1; i < p.T; ++i) {
+        const float dt = st[i] - st[i - 1];
+        const f32x2 dt2 = pk1(dt);
+#pragma unroll
+        for (int e = 0; e < EVALS; ++e) {
+          XDE_TRACE(0, 200);
+          phaseH(0);
+          XDE_TRACE(0, 201);
+          phaseH(1);
+          XDE_TRACE(0, 202);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            f32x2 k[NP], kg[NP], yi[NP];
+            phaseF(s, k, kg);
+            XDE_TRACE(0, 210 + s);
+            if (KIND == 0) {
+#pragma unroll
+              for (int c = 0; c < NP; ++c) y[s][c] = fma2(k[c], dt2, y[s][c]);
+            } else if (KIND == 3) {  // Midpoint.step (fixed_solver/midpoint.py:7-18)
+#pragma unroll
+              for (int c = 0; c < NP; ++c) {
+                if (e == 0) yi[c] = fma2(k[c], pk1(0.5f * dt), y[s][c]);
+                else y[s][c] = fma2(k[c], dt2, y[s][c]);
+              }
+            } else if (KIND == 1) {  // rk4_alt_step_func (base_fixed_solver.py:166-197), see fixed_tc_kernel
+#pragma unroll
+              for (int c = 0; c < NP; ++c) {
+                if (e == 0) {
+                  A[s][c] = k[c];
+                  yi[c] = fma2(k[c], pk1(dt * one_third), y[s][c]);
+                } else if (e == 1) {
+                  yi[c] = fma2(fma2(pk1(-one_third), k[c], A[s][c]), dt2, y[s][c]);
+                  S[s][c] = fma2(pk1(3.0f), k[c], A[s][c]);
+                  A[s][c] = sub2(A[s][c], k[c]);
+                } else if (e == 2) {
+                  yi[c] = fma2(add2(A[s][c], k[c]), dt2, y[s][c]);
+                  S[s][c] = fma2(pk1(3.0f), k[c], S[s][c]);
+                } else {
+                  y[s][c] = fma2(add2(S[s][c], k[c]), pk1(dt * 0.125f), y[s][c]);
+                }
+              }
+            } else {  // Euler-Maruyama
+#pragma unroll
+              for (int v = 0; v < NC / 4; ++v) {
+                y[s][2 * v] = fma2(kg[2 * v], pk(w4[s][v].x, w4[s][v].y), fma2(k[2 * v], dt2, y[s][2 * v]));
+                y[s][2 * v + 1] = fma2(kg[2 * v + 1], pk(w4[s][v].z, w4[s][v].w), fma2(k[2 * v + 1], dt2, y[s][2 * v + 1]));
+              }
+            }
+            if (e == EVALS - 1) {
+              if (ok[s] && (i % p.stride == 0 || i == p.T - 1)) {
+                const int row = (i == p.T - 1) ? p.n_out - 1 : i / p.stride;
+#pragma unroll
+                for (int v = 0; v < NC / 4; ++v) {
+                  float4 t4;
+                  upk(y[s][2 * v], t4.x, t4.y);
+                  upk(y[s][2 * v + 1], t4.z, t4.w);
+                  *reinterpret_cast<float4 *>(p.out + (b[s] * (long long)p.n_out + row) * D + c0 + 4 * v) = t4;
+                }
+              }
+              if (i < p.T - 1) {  // next step's increments (first touched after its evaluation), then its input
+                if (KIND == 2) {
+#pragma unroll
+                  for (int v = 0; v < NC / 4; ++v)
+                    if (ok[s])
+                      w4[s][v] = __ldg(reinterpret_cast<const float4 *>(p.dW + ((long long)i * p.B + b[s]) * D + c0 + 4 * v));
+                }
+                phaseU(s, y[s]);
+              }
+            } else {
+              phaseU(s, yi);
+            }
+            XDE_TRACE(0, 220 + s);
+          }
+          par ^= 1u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kComputeWarps) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * SLOT) : "memory");
+  }
+}
+
+template <int D, int H, int KIND>
+static int launch_tc2(TcParams p, cudaStream_t s) {
+  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  using G = Geom<D, H, NETS, 4>;
+  const size_t smem = G::bytes(p.T);
+  XDE_REQUIRE(smem <= 227 * 1024, XDE_E_UNSUPPORTED_FIELD,
+              "tensor-core solver: weights + time grid need %zu bytes of shared memory (> 227 KB)", smem);
+  void *wbuf = nullptr;
+  XDE_CUDA_CHECK(scratch_alloc(&wbuf, (size_t)G::W_BYTES + 16, s));
+  tc_prep_kernel<<<NETS * 2, 1024, 0, s>>>(p.f, p.g, (unsigned char *)wbuf, NETS);
+  count_launch();
+  p.wbuf = (const unsigned char *)wbuf;
+  auto kern = fixed_tc2_kernel<D, H, KIND>;
+  XDE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n_tiles = (p.B + kTM - 1) / kTM;
+  long long grid = sm_count();  // persistent: one CTA, two tile slots, all 512 TMEM columns per SM
+  if (grid > (n_tiles + 1) / 2) grid = (n_tiles + 1) / 2;
+  kern<<<(unsigned)grid, cta_threads(4), smem, s>>>(p);
+  count_launch();
+  XDE_CUDA_CHECK(cudaGetLastError());
+  XDE_CUDA_CHECK(cudaFreeAsync(wbuf, s));
+  return XDE_OK;
+}
+
 template <int D, int H, int KIND, int NJ>
 static int launch_tc(TcParams p, cudaStream_t s) {
   constexpr int NETS = (KIND == 2) ? 2 : 1;
@@ -713,10 +1094,16 @@ static int launch_tc(TcParams p, cudaStream_t s) {
 // NJ = 2 (8 compute warps, meant for two CTAs per SM on small fields) is kept compilable but not dispatched:
 // measured on B200, the register file is allocated per 4 warps, so two 9-warp CTAs at > 80 registers per
 // thread do not co-reside (launch__waves_per_multiprocessor stayed 0.5) and the variant is 4 % slower
-// than one 17-warp CTA.  Hiding the per-evaluation bubbles of small fields needs two tiles in flight
-// inside ONE CTA (DESIGN.md "Next").
+// than one 17-warp CTA.  Small fields use fixed_tc2_kernel (two tiles in flight inside one CTA) instead,
+// whenever every SM gets at least one PAIR of tiles.
 template <int D, int H, int KIND>
 static int launch_tc_auto(const TcParams &p, cudaStream_t s) {
+  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  using G = Geom<D, H, NETS, 4>;
+  if constexpr (G::COLS <= 256 && G::NC <= 8) {
+    const long long n_tiles = (p.B + kTM - 1) / kTM;
+    if (n_tiles >= 2LL * sm_count()) return launch_tc2<D, H, KIND>(p, s);
+  }
   return launch_tc<D, H, KIND, 4>(p, s);
 }
 

@@ -718,26 +718,28 @@ def test_tensor_sde_matches_oracle(px, torch, oracle, d, h, B):
     assert _close(sol.cpu().numpy(), ref, rtol=1e-5)
 
 
-@pytest.mark.parametrize("kind", ["ode", "sde"])
-def test_tensor_many_tiles_per_cta(px, torch, oracle, kind):
-    """More tiles than SMs (every persistent CTA walks several tiles; ragged last tile): whole batch
-    against the FP32 kernel, a subset against the oracle."""
-    d, h, B = 32, 64, 148 * 128 * 2 + 77
+@pytest.mark.parametrize("kind,d,h", [("RK4", 32, 64), ("sde", 32, 64), ("Midpoint", 16, 64), ("Euler", 32, 128),
+                                      ("sde", 16, 64), ("RK4", 64, 64)])
+def test_tensor_many_tiles_per_cta(px, torch, oracle, kind, d, h):
+    """More tile pairs than SMs: small fields (<= 256 TMEM columns, D <= 32) run fixed_tc2_kernel, two tiles
+    in flight per CTA, the last pair half empty and the last tile ragged; (64, 64) stays on the one-tile
+    kernel with several tiles per CTA.  Whole batch against the FP32 kernel, a subset against the oracle."""
+    B = 148 * 128 * 2 + 77
     rng = np.random.default_rng(11)
     y0 = rng.uniform(-1, 1, (B, d)).astype(f32)
     yd = torch.from_numpy(y0).cuda().reshape(B, 1, d)
     idx = rng.choice(B, 160, replace=False)
-    if kind == "ode":
+    t = np.linspace(0, 1, 6).astype(f32)
+    if kind != "sde":
         field, om = both(px, oracle, fanin_weights(d, h, seed=5), "cube")
-        t = np.linspace(0, 1, 9).astype(f32)
-        sol = px.odeint(field, yd, t, px.RK4, options={"math": "tensor"})
-        exact = px.odeint(field, yd, t, px.RK4, options={"math": "fp32"})
-        ref = oracle.fixed_mlp("rk4", om, y0[idx], t)
+        S = getattr(px, kind)
+        sol = px.odeint(field, yd, t, S, options={"math": "tensor"})
+        exact = px.odeint(field, yd, t, S, options={"math": "fp32"})
+        ref = oracle.fixed_mlp(kind.lower(), om, y0[idx], t)
     else:
         f, of = both(px, oracle, fanin_weights(d, h, seed=2), "cube")
         g, og = both(px, oracle, fanin_weights(d, h, seed=3), "square")
-        t = np.linspace(0, 1, 9).astype(f32)
-        dW = (np.sqrt(1 / 8) * rng.standard_normal((8, B, d))).astype(f32)
+        dW = (np.sqrt(1 / 5) * rng.standard_normal((5, B, d))).astype(f32)
         dWd = torch.from_numpy(dW).cuda()
         sol = px.sdeint(f, g, yd, t, px.Euler, options={"bm_increments": dWd, "math": "tensor"})
         exact = px.sdeint(f, g, yd, t, px.Euler, options={"bm_increments": dWd, "math": "fp32"})

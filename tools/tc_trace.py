@@ -22,7 +22,7 @@ if which == "cfg3":
     t = np.linspace(0, 1, 21).astype(np.float32)
     px.odeint(field, y0, t, px.RK4, options={"math": "tensor", "out_stride": 20})
 else:
-    d, hh, B = 32, 64, 148 * 128 * 4
+    d, hh, B = 32, 64, 148 * 128 * 8
     f = px.MLPField(*fanin_weights(d, hh, seed=2), pre="cube")
     g = px.MLPField(*fanin_weights(d, hh, seed=3), pre="square")
     y0 = torch.rand((B, 1, d), device="cuda") * 2 - 1
@@ -33,7 +33,8 @@ torch.cuda.synchronize()
 tr = buf.cpu().numpy().reshape(2, CAP // 2, 2)
 names = {0: "eval start", 1: "u stored+arrived", 2: "z0 ready, ld issued", 20: "f_ready seen", 21: "F read, eval end",
          100: "MMA: u_ready seen", 130: "MMA: L2 issued + commit f"}
-names.update({3: "u STTM issued", 4: "u wait::st done"})
+names.update({3: "u STTM issued", 4: "u wait::st done", 200: "round start", 201: "H(A) done", 202: "H(B) done",
+              210: "F(A) read", 211: "F(B) read", 220: "update+U(A) done", 221: "update+U(B) done"})
 for c in range(4):
     names[30 + c] = f"chunk {c} STTM issued"; names[40 + c] = f"chunk {c} wait::st done"
     names[10 + c] = f"chunk {c} tanh stored+arrived"; names[110 + c] = f"MMA: L1 chunk {c} issued+commit"
@@ -41,7 +42,7 @@ for c in range(4):
 ev = [(int(tag), int(clk), r) for r in range(2) for tag, clk in tr[r] if clk]
 ev.sort(key=lambda x: x[1])
 # print evaluations 8..10 of compute warp 0 (steady state) merged with the MMA thread's events
-starts = [clk for tag, clk, r in ev if tag == 0]
+starts = [clk for tag, clk, r in ev if tag in (0, 200)]
 lo, hi = starts[8], starts[11]
 prev = lo
 for tag, clk, r in ev:
