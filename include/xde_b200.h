@@ -70,7 +70,7 @@ enum {
   XDE_RK_DOPRI5_TABLE = 100
 };
 enum { XDE_SDE_EM = 0, XDE_SDE_MILSTEIN = 1 };
-enum { XDE_INTERP_LINEAR = 0, XDE_INTERP_HERMITE = 1 };
+enum { XDE_INTERP_LINEAR = 0, XDE_INTERP_HERMITE = 1, XDE_INTERP_BEZIER = 2 };
 
 /* The fused vector-field family: f(t, y) = tanh(pre(y) @ w1 + b1) @ w2 + b2
  * (example/ode_demo.py:17-33).  Weights in Paddle nn.Linear layout [in, out]. */
@@ -202,7 +202,8 @@ int xde_sde_mlp_tc_f32(int32_t scheme, const xde_mlp_field_t *drift, const xde_m
 
 /* HistoryIndex.forward                                xde/base_dde.py:84-118
  *   -> InterpolationBase.evaluate / derivative        interpolation/interpolate_base.py:49-114
- *      (LinearInterpolation interpolate.py:6-97, CubicHermiteSpline :100-204).
+ *      (LinearInterpolation interpolate.py:6-97, CubicHermiteSpline :100-204, BezierSpline :207-298;
+ *      interp_method "linear" | "cubic" | "bez", xde/base_dde.py:104-111).
  * his [R,Th,D] (R = product of leading dims), his_span [Th], lags [L]; out_val, out_der [R,L,D]. */
 int xde_history_gather_f32(int32_t kind, const float *his, int64_t R, int32_t Th, int32_t D,
                            const float *his_span, const float *lags, int32_t L, float *out_val,

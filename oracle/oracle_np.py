@@ -678,12 +678,47 @@ class CubicHermiteSpline(InterpolationBase):
                          self._derivs[..., index + 1, :]], axis=-2)
 
 
+class BezierSpline(InterpolationBase):
+    """interpolation/interpolate.py:207-298, literally: four consecutive samples as the control polygon of a
+    cubic Bezier segment, each divided by its own (shifted) 3-interval span; Bernstein matrix :240-245."""
+    _h = np.array([[-1, 3, -3, 1], [3, -6, 3, 0], [-3, 3, 0, 0], [1, 0, 0, 0]], dtype=f32)
+
+    def _make_series(self, series, t):  # :247-273
+        scale = (t[3:] - t[:-3]).astype(f32)
+        scale1 = np.concatenate([scale, scale[-1:], scale[-1:], scale[-1:]])
+        scale2 = np.concatenate([scale[:1], scale1[:-1]])
+        scale3 = np.concatenate([scale[:1], scale2[:-1]])
+        scale4 = np.concatenate([scale[:1], scale3[:-1]])
+        s1 = series
+        s2 = np.concatenate([s1[..., 1:, :], series[..., -1:, :]], axis=-2)
+        s3 = np.concatenate([s2[..., 1:, :], series[..., -1:, :]], axis=-2)
+        s4 = np.concatenate([s3[..., 1:, :], series[..., -1:, :]], axis=-2)
+        arr = np.stack([s1 / scale1[:, None], s2 / scale2[:, None], s3 / scale3[:, None], s4 / scale4[:, None]],
+                       axis=-2).astype(f32)
+        return arr, scale1
+
+    def _make_derivative(self, series, t):  # :275-276
+        return None
+
+    def ts(self, t, der=False):  # :278-285
+        if not der:
+            cols = [t ** 3, t ** 2, t, np.ones_like(t)]
+        else:
+            cols = [3 * t ** 2, 2 * t, np.ones_like(t), np.zeros_like(t)]
+        return np.stack(cols, axis=-1)[..., None, :].astype(f32)
+
+    def ps(self, index):  # :287-298
+        return np.stack([self._series_arr[..., m, :][..., index, :] for m in range(4)], axis=-2)
+
+
 def history_index_forward(lags, his, his_span, interp_method="cubic"):
     """HistoryIndex.forward (xde/base_dde.py:84-118) -> (y_lags, derivative_lags)."""
     if interp_method == "linear":
         interp = LinearInterpolation(his, his_span)
     elif interp_method == "cubic":
         interp = CubicHermiteSpline(his, his_span)
+    elif interp_method == "bez":
+        interp = BezierSpline(his, his_span)
     else:
         raise NotImplementedError
     return interp.evaluate(lags), interp.derivative(lags)

@@ -1082,7 +1082,7 @@ int orc_sde_mlp(int32_t scheme, const orc_mlp_t *drift, const orc_mlp_t *diffusi
 int orc_history_gather(int32_t kind, const float *his, int64_t R, int32_t Th, int32_t D,
                        const float *span, const float *lags, int32_t L, float *out_val,
                        float *out_der) {
-  if (Th < 2) return ORC_BAD_ARG;
+  if (Th < 2 || (kind == ORC_INTERP_BEZIER && Th < 4)) return ORC_BAD_ARG;
   for (int l = 0; l < L; ++l) {
     const float t = lags[l];
     /* paddle.bucketize(t, _t) (right=False) = #{_t < t}; index = clip(. - 1, 0, maxlen)
@@ -1095,6 +1095,41 @@ int orc_history_gather(int32_t kind, const float *his, int64_t R, int32_t Th, in
     /* _make_series scale1/scale2 (interpolation/interpolate.py:52-54,147-149) */
 #define SCALE1(i) (((i) < Th - 1) ? (span[(i) + 1] - span[(i)]) : (span[Th - 1] - span[Th - 2]))
 #define SCALE2(i) (((i) == 0) ? (span[1] - span[0]) : SCALE1((i) - 1))
+    if (kind == ORC_INTERP_BEZIER) {
+      /* BezierSpline (interpolation/interpolate.py:207-298): control points p_i .. p_{i+3} (clamped to the
+       * last sample, :258-261), each divided by its own shifted 3-interval span scale_m[i] =
+       * scale1[max(i-(m-1),0)], scale1[i] = t[min(i,Th-4)+3] - t[min(i,Th-4)] (:252-256); Bernstein matrix
+       * :240-245; value rescaled by scale1[i], derivative not (interpolate_base.py:89-114). */
+#define BSC1(i) (span[((i) < Th - 4 ? (i) : Th - 4) + 3] - span[((i) < Th - 4 ? (i) : Th - 4)])
+#define BSCM(i, m) BSC1(((i) - (m)) > 0 ? ((i) - (m)) : 0)
+      const float b1 = BSC1(idx);
+      float sb = t - span[idx];
+      sb = sb / b1;
+      const float s2 = sb * sb, s3 = s2 * sb;
+      const float tv[4] = {s3, s2, sb, 1.0f};
+      const float td[4] = {3.0f * s2, 2.0f * sb, 1.0f, 0.0f};
+      static const float Bm[4][4] = {
+          {-1.0f, 3.0f, -3.0f, 1.0f}, {3.0f, -6.0f, 3.0f, 0}, {-3.0f, 3.0f, 0, 0}, {1.0f, 0, 0, 0}};
+      float cv[4], cd[4], scm[4];
+      int im[4];
+      for (int c = 0; c < 4; ++c) {
+        cv[c] = ((tv[0] * Bm[0][c] + tv[1] * Bm[1][c]) + tv[2] * Bm[2][c]) + tv[3] * Bm[3][c];
+        cd[c] = ((td[0] * Bm[0][c] + td[1] * Bm[1][c]) + td[2] * Bm[2][c]) + td[3] * Bm[3][c];
+        scm[c] = BSCM(idx, c);
+        im[c] = (idx + c < Th) ? idx + c : Th - 1;
+      }
+      for (int64_t r = 0; r < R; ++r) {
+        const float *base = his + (size_t)r * Th * D;
+        for (int e = 0; e < D; ++e) {
+          float a[4];
+          for (int c = 0; c < 4; ++c) a[c] = base[(size_t)im[c] * D + e] / scm[c];
+          size_t o = ((size_t)r * L + l) * D + e;
+          out_val[o] = (((cv[0] * a[0] + cv[1] * a[1]) + cv[2] * a[2]) + cv[3] * a[3]) * b1;
+          out_der[o] = ((cd[0] * a[0] + cd[1] * a[1]) + cd[2] * a[2]) + cd[3] * a[3];
+        }
+      }
+      continue;
+    }
     const float sc1 = SCALE1(idx), sc2 = SCALE2(idx);
     float s = t - span[idx];
     s = s / sc1;

@@ -46,7 +46,7 @@ enum { ORC_FIXED_EULER = 0, ORC_FIXED_RK4_38 = 1, ORC_FIXED_MIDPOINT = 2 };
 /* embedded Runge-Kutta tableaux (the modules under solver/adaptive_solver/) */
 enum { ORC_RK_DOPRI5 = 0, ORC_RK_BOSH3 = 1, ORC_RK_FEHLBERG2 = 2, ORC_RK_ADAPTIVE_HEUN = 3, ORC_RK_DOPRI8 = 4 };
 enum { ORC_SDE_EM = 0, ORC_SDE_MILSTEIN = 1 };
-enum { ORC_INTERP_LINEAR = 0, ORC_INTERP_HERMITE = 1 };
+enum { ORC_INTERP_LINEAR = 0, ORC_INTERP_HERMITE = 1, ORC_INTERP_BEZIER = 2 };
 
 /* f(t,y) = tanh(pre(y) @ W1 + b1) @ W2 + b2 ; weights in Paddle nn.Linear layout [in,out]
  * (example/ode_demo.py:17-33) */

@@ -22,7 +22,7 @@ ADJ_NORM = {"mixed": 0, "default": 0, "seminorm": 1}
 FIXED = {"euler": 0, "rk4": 1, "midpoint": 2}
 RK = {"dopri5": 0, "bosh3": 1, "fehlberg2": 2, "adaptive_heun": 3, "dopri8": 4}
 SDE = {"em": 0, "euler": 0, "milstein": 1}
-INTERP = {"linear": 0, "cubic": 1, "hermite": 1}
+INTERP = {"linear": 0, "cubic": 1, "hermite": 1, "bez": 2, "bezier": 2}
 STATUS = {0: "OK", 1: "DT_UNDERFLOW", 2: "NONFINITE_STATE", 3: "MAX_STEPS", 4: "BAD_ARG", 5: "INTERP_RANGE"}
 
 

@@ -19,7 +19,7 @@ ADJ_NORM = {"mixed": 0, "default": 0, "seminorm": 1}
 FIXED = {"euler": 0, "rk4": 1, "midpoint": 2}
 RK = {"dopri5": 0, "bosh3": 1, "fehlberg2": 2, "adaptive_heun": 3, "dopri8": 4, "dopri5_table": 100}
 SDE = {"em": 0, "euler": 0, "milstein": 1}
-INTERP = {"linear": 0, "cubic": 1, "hermite": 1}
+INTERP = {"linear": 0, "cubic": 1, "hermite": 1, "bez": 2, "bezier": 2}
 
 
 class XdeError(RuntimeError):

@@ -1,1 +1,1 @@
-from .interpolate import CubicHermiteSpline, LinearInterpolation  # noqa: F401
+from .interpolate import BezierSpline, CubicHermiteSpline, LinearInterpolation  # noqa: F401

@@ -1,6 +1,6 @@
-"""LinearInterpolation / CubicHermiteSpline with the reference's evaluate/derivative surface
-(paddlexde/interpolation/interpolate_base.py:77-114, interpolate.py:6-204).  Nothing is
-pre-processed: the gather kernel reads the 2-3 raw neighbours it needs per query."""
+"""LinearInterpolation / CubicHermiteSpline / BezierSpline with the reference's evaluate/derivative surface
+(paddlexde/interpolation/interpolate_base.py:77-114, interpolate.py:6-298).  Nothing is
+pre-processed: the gather kernel reads the 2-4 raw neighbours it needs per query."""
 from __future__ import annotations
 
 import torch
@@ -36,3 +36,7 @@ class LinearInterpolation(_Interp):
 
 class CubicHermiteSpline(_Interp):
     kind = "cubic"
+
+
+class BezierSpline(_Interp):
+    kind = "bez"

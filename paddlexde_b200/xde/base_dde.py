@@ -10,8 +10,8 @@ from .base_xde import BaseXDE
 def history_gather(lags, his, his_span, interp_method="cubic"):
     """interp.evaluate(lags), interp.derivative(lags) in one gather kernel
     (interpolation/interpolate_base.py:49-114). his [..., Th, D] -> two [..., L, D] tensors."""
-    if interp_method not in ("linear", "cubic"):
-        raise NotImplementedError(interp_method)  # xde/base_dde.py:110-111 ("bez" is 8(f) next)
+    if interp_method not in ("linear", "cubic", "bez"):
+        raise NotImplementedError(interp_method)  # xde/base_dde.py:104-111
     his_d, span_d, lags_d = T.to_dev(his), T.to_dev(his_span), T.to_dev(lags).reshape(-1)
     lead, Th, D = his_d.shape[:-2], his_d.shape[-2], his_d.shape[-1]
     if span_d.numel() != Th:

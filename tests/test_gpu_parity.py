@@ -761,7 +761,7 @@ def test_tensor_path_is_loud_about_unsupported_shapes(px, torch, oracle):
 # ------------------------------------------------------------------------------------------------
 # history gather / DDE
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kind", ["linear", "cubic"])
+@pytest.mark.parametrize("kind", ["linear", "cubic", "bez"])
 def test_history_gather_cfg5(px, torch, oracle, kind):
     """cfg5 shapes: his [8,307,288,3], 12 real-valued lags (+ edge queries on and off the grid)."""
     from paddlexde_b200.xde.base_dde import history_gather, history_gather_bwd
@@ -786,7 +786,8 @@ def test_history_gather_nonuniform_span_and_reference_fixture(px, torch, oracle)
     """The reference's own interpolation fixtures (tests/interpolation/test_interpolation.py:13-85):
     ramp at t=21.12 and sin sampled at 0.01 queried at t=16.5."""
     ramp = np.arange(100, dtype=f32).reshape(1, 100, 1)
-    for cls, kind in ((px.interpolation.LinearInterpolation, "linear"), (px.interpolation.CubicHermiteSpline, "cubic")):
+    for cls, kind in ((px.interpolation.LinearInterpolation, "linear"), (px.interpolation.CubicHermiteSpline, "cubic"),
+                      (px.interpolation.BezierSpline, "bez")):
         it = cls(ramp, np.arange(100, dtype=f32))
         np.testing.assert_allclose(it.evaluate([21.12]).cpu().numpy().ravel(), [21.12], rtol=1e-4)
         np.testing.assert_allclose(it.derivative([21.12]).cpu().numpy().ravel(), [1.0], rtol=1e-4)
@@ -795,6 +796,9 @@ def test_history_gather_nonuniform_span_and_reference_fixture(px, torch, oracle)
     it = px.interpolation.CubicHermiteSpline(series, ts)
     np.testing.assert_allclose(it.evaluate([16.5]).cpu().numpy().ravel(), [np.sin(16.5)], rtol=1e-5)
     np.testing.assert_allclose(it.derivative([16.5]).cpu().numpy().ravel(), [np.cos(16.5)], rtol=1e-2)
+    it = px.interpolation.BezierSpline(series, ts)  # test_interpolation.py:82-85
+    np.testing.assert_allclose(it.evaluate([16.5]).cpu().numpy().ravel(), [np.sin(16.5)], rtol=5e-2)
+    np.testing.assert_allclose(it.derivative([16.5]).cpu().numpy().ravel(), [np.cos(16.5)], rtol=1e-2)
     # non-uniform grid vs oracle
     rng = np.random.default_rng(9)
     span = np.cumsum(rng.uniform(0.2, 1.5, 40)).astype(f32)
@@ -802,10 +806,12 @@ def test_history_gather_nonuniform_span_and_reference_fixture(px, torch, oracle)
     q = rng.uniform(span[0], span[-1], 33).astype(f32)
     from paddlexde_b200.xde.base_dde import history_gather
 
-    for kind in ("linear", "cubic"):
+    for kind in ("linear", "cubic", "bez"):
         v, dv = history_gather(q, his, span, kind)
         v_r, d_r = oracle.history_gather(kind, his, span, q)
         assert np.array_equal(v.cpu().numpy(), v_r) and np.array_equal(dv.cpu().numpy(), d_r)
+    with pytest.raises(ValueError):  # a Bezier segment needs four samples
+        history_gather(q[:3], his[:, :3], span[:3], "bez")
 
 
 def test_ddeint_one_damped_euler_step(px, torch, oracle):

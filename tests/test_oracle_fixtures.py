@@ -157,13 +157,25 @@ def test_interp_dynamic_deriv(cls, vtol):
     assert allclose([[[math.cos(16.5), 0.0]]], it.derivative([16.5]), rtol=1e-2, atol=1e-6)
 
 
+def test_bezier_fixtures():
+    """tests/interpolation/test_interpolation.py:43-46, 82-85 (BezierSpline on the ramp and sin series)."""
+    series, t = _ramp()
+    it = onp.BezierSpline(series, t)
+    assert allclose([[[21.12 * 0.5, 0]]], it.evaluate([21.12]), rtol=1e-4)
+    assert allclose([[[0.5, 0]]], it.derivative([21.12]), rtol=1e-4)
+    series, t = _sin()
+    it = onp.BezierSpline(series, t)
+    assert allclose(np.sin([[[16.5, 0.0]]]), it.evaluate([16.5]), rtol=5e-2, atol=1e-6)
+    assert allclose([[[math.cos(16.5), 0.0]]], it.derivative([16.5]), rtol=1e-2, atol=1e-6)
+
+
 # --- C oracle == literal NumPy restatement ---------------------------------------------------------
 def test_c_gather_matches_literal(oracle):
     rng = np.random.default_rng(3)
     his = rng.uniform(-1, 1, (2, 5, 40, 3)).astype(f32)
     span = np.arange(40).astype(f32)
     lags = np.concatenate([np.arange(0, 12) + rng.uniform(0, 1, 12), [0.0, 7.0, 39.0, 39.5, -1.0, 45.0]]).astype(f32)
-    for kind in ("linear", "cubic"):
+    for kind in ("linear", "cubic", "bez"):
         v_np, d_np = onp.history_index_forward(lags, his, span, kind)
         v_c, d_c = oracle.history_gather(kind, his, span, lags)
         np.testing.assert_allclose(v_c, v_np, rtol=2e-5, atol=2e-6)
@@ -174,7 +186,7 @@ def test_c_gather_matches_literal(oracle):
     # non-uniform grid too
     span2 = np.cumsum(rng.uniform(0.5, 1.5, 40)).astype(f32)
     lags2 = rng.uniform(span2[0], span2[-1], 9).astype(f32)
-    for kind in ("linear", "cubic"):
+    for kind in ("linear", "cubic", "bez"):
         v_np, d_np = onp.history_index_forward(lags2, his, span2, kind)
         v_c, d_c = oracle.history_gather(kind, his, span2, lags2)
         np.testing.assert_allclose(v_c, v_np, rtol=3e-5, atol=3e-6)
