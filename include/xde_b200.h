@@ -70,6 +70,7 @@ enum {
   XDE_RK_DOPRI5_TABLE = 100
 };
 enum { XDE_SDE_EM = 0, XDE_SDE_MILSTEIN = 1 };
+enum { XDE_MATH_FP32 = 0, XDE_MATH_TENSOR = 1 };
 enum { XDE_INTERP_LINEAR = 0, XDE_INTERP_HERMITE = 1, XDE_INTERP_BEZIER = 2 };
 
 /* The fused vector-field family: f(t, y) = tanh(pre(y) @ w1 + b1) @ w2 + b2
@@ -199,6 +200,22 @@ int xde_rk_fixed_mlp_tc_f32(int32_t method, const xde_mlp_field_t *field, const 
 int xde_sde_mlp_tc_f32(int32_t scheme, const xde_mlp_field_t *drift, const xde_mlp_field_t *diffusion,
                        const float *y0, int64_t B, const float *t_span, int32_t T, const float *dW,
                        int32_t out_stride_t, float *out, void *stream);
+
+/* Brownian increments without a table.  The reference draws them on the host from
+ * BrownianInterval (utils/brownian/brownian_interval.py:178-240; xde/base_sde.py:35-37); on a fixed grid the
+ * solver only ever asks for W(t[n+1]) - W(t[n]), so a counter-based generator addressed by
+ * (step n, GLOBAL trajectory index b + traj_offset, component) gives the same thing without state:
+ * Philox4x32-10 keyed by `seed`, Box-Muller, dW[n,b,d] = sqrt(|t[n+1]-t[n]|) * N(0,1).  A batch shard that
+ * passes its first global row as traj_offset sees exactly the increments of the unsharded run.
+ *   xde_brownian_increments_f32 writes the table dW [T-1,B,D] (the parity bridge: feed it to the `dW`
+ *   entries above, or to the oracle);  xde_sde_mlp_philox_f32 = xde_sde_mlp_f32 / _tc_f32 (math =
+ *   XDE_MATH_FP32 / XDE_MATH_TENSOR) generating the same increments on the fly -- bit-identical results. */
+int xde_brownian_increments_f32(uint64_t seed, int64_t traj_offset, const float *t_span, int32_t T, int64_t B,
+                                int32_t D, float *dW, void *stream);
+int xde_sde_mlp_philox_f32(int32_t scheme, int32_t math, const xde_mlp_field_t *drift,
+                           const xde_mlp_field_t *diffusion, const float *y0, int64_t B, const float *t_span,
+                           int32_t T, uint64_t seed, int64_t traj_offset, int32_t out_stride_t, float *out,
+                           void *stream);
 
 /* HistoryIndex.forward                                xde/base_dde.py:84-118
  *   -> InterpolationBase.evaluate / derivative        interpolation/interpolate_base.py:49-114

@@ -14,7 +14,8 @@ constexpr int kFixThreads = 128;
 
 struct FixParams {
   xde_mlp_field_t f, g;
-  const float *y0, *t_span, *dW;
+  const float *y0, *t_span;
+  BmSource bm;
   float *out;
   long long B;
   int T, stride, n_out, method;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(kFixThreads) sde_small_kernel(const FixParams 
       const float dt = st[i] - st[i - 1];
       float w[D], f[D], g[D], gp[D];
 #pragma unroll
-      for (int e = 0; e < D; ++e) w[e] = p.dW[((long long)(i - 1) * p.B + b) * D + e];
+      for (int e = 0; e < D; ++e) w[e] = bm_increment1(p.bm, i - 1, b, p.B, D, e, sqrtf(fabsf(dt)));
       mlp_eval_small<D, PREF>(swf, p.f.h, y, f);
       if (SCHEME == XDE_SDE_MILSTEIN)
         mlp_eval_diag_small<D, PREG>(swg, p.g.h, y, g, gp);
@@ -266,13 +267,13 @@ int rk_fixed_small(int method, const xde_mlp_field_t *f, const float *y0, long l
 }
 
 int sde_small(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const float *y0, long long B,
-              const float *t_span, int T, const float *dW, int stride, float *out, cudaStream_t s) {
+              const float *t_span, int T, const BmSource &bm, int stride, float *out, cudaStream_t s) {
   FixParams p{};
   p.f = *f;
   p.g = *g;
   p.y0 = y0;
   p.t_span = t_span;
-  p.dW = dW;
+  p.bm = bm;
   p.out = out;
   p.B = B;
   p.T = T;

@@ -85,7 +85,8 @@ struct Geom {
 struct TcParams {
   xde_mlp_field_t f, g;
   const unsigned char *wbuf;  // prepared weights: Geom::W_BYTES, then float sinv[NETS][2]
-  const float *y0, *t_span, *dW;
+  const float *y0, *t_span;
+  BmSource bm;
   float *out;
   long long B;
   int T, stride, n_out;
@@ -649,7 +650,7 @@ __global__ void __launch_bounds__(cta_threads(NJ), NJ == 4 ? 1 : 2) fixed_tc_ker
 #pragma unroll
           for (int v = 0; v < NC / 4; ++v) {
             w4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) w4[v] = __ldg(reinterpret_cast<const float4 *>(p.dW + ((long long)(i - 1) * p.B + b) * D + c0 + 4 * v));
+            if (ok) w4[v] = bm_increment4(p.bm, i - 1, b, p.B, D, c0 / 4 + v, sqrtf(fabsf(dt)));
           }
           eval(y, k, kg);
 #pragma unroll
@@ -946,8 +947,8 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
           y[s][2 * v] = pk(t4.x, t4.y);
           y[s][2 * v + 1] = pk(t4.z, t4.w);
           w4[s][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (KIND == 2 && ok[s])
-            w4[s][v] = __ldg(reinterpret_cast<const float4 *>(p.dW + b[s] * D + c0 + 4 * v));  // increments of step 1
+          if (KIND == 2 && ok[s] && p.T > 1)  // increments of step 1
+            w4[s][v] = bm_increment4(p.bm, 0, b[s], p.B, D, c0 / 4 + v, sqrtf(fabsf(st[1] - st[0])));
         }
 #pragma unroll
         for (int c = 0; c < NP; ++c) A[s][c] = S[s][c] = pk1(0.0f);
@@ -1017,7 +1018,7 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
 #pragma unroll
                   for (int v = 0; v < NC / 4; ++v)
                     if (ok[s])
-                      w4[s][v] = __ldg(reinterpret_cast<const float4 *>(p.dW + ((long long)i * p.B + b[s]) * D + c0 + 4 * v));
+                      w4[s][v] = bm_increment4(p.bm, i, b[s], p.B, D, c0 / 4 + v, sqrtf(fabsf(st[i + 1] - st[i])));
                 }
                 phaseU(s, y[s]);
               }
@@ -1147,7 +1148,7 @@ int rk_fixed_tc(int method, const xde_mlp_field_t *f, const float *y0, long long
 }
 
 int sde_tc(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const float *y0, long long B,
-           const float *t_span, int T, const float *dW, int stride, float *out, cudaStream_t s) {
+           const float *t_span, int T, const BmSource &bm, int stride, float *out, cudaStream_t s) {
   XDE_REQUIRE(scheme == XDE_SDE_EM, XDE_E_UNSUPPORTED_FIELD,
               "Milstein (an extension without a reference counterpart) is fused for small states (D <= 8) only");
   XDE_REQUIRE(f->h == g->h, XDE_E_UNSUPPORTED_FIELD, "tensor-core sde: drift and diffusion must share the hidden width");
@@ -1156,7 +1157,7 @@ int sde_tc(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const
   p.g = *g;
   p.y0 = y0;
   p.t_span = t_span;
-  p.dW = dW;
+  p.bm = bm;
   p.out = out;
   p.B = B;
   p.T = T;

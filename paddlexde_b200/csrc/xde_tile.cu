@@ -24,7 +24,8 @@ constexpr int kTileThreads = 256;
 
 struct TileParams {
   xde_mlp_field_t f, g;
-  const float *y0, *t_span, *dW;
+  const float *y0, *t_span;
+  BmSource bm;
   float *out;
   long long B;
   int T, stride, n_out;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileP
 #pragma unroll
           for (int q = 0; q < C2 / 4; ++q) {
             float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) wv = __ldg(reinterpret_cast<const float4 *>(p.dW + ((long long)(i - 1) * p.B + b) * D + c0 + 4 * q));
+            if (ok) wv = bm_increment4(p.bm, i - 1, b, p.B, D, c0 / 4 + q, sqrtf(fabsf(dt)));
             const float w[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
             for (int z = 0; z < 4; ++z) {
@@ -353,7 +354,7 @@ int rk_fixed_tile(int method, const xde_mlp_field_t *f, const float *y0, long lo
 }
 
 int sde_tile(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const float *y0, long long B,
-             const float *t_span, int T, const float *dW, int stride, float *out, cudaStream_t s) {
+             const float *t_span, int T, const BmSource &bm, int stride, float *out, cudaStream_t s) {
   XDE_REQUIRE(scheme == XDE_SDE_EM, XDE_E_UNSUPPORTED_FIELD,
               "Milstein (an extension without a reference counterpart) is fused for small states (D <= 8) only");
   XDE_REQUIRE(f->h == g->h, XDE_E_UNSUPPORTED_FIELD, "tiled sde: drift and diffusion must share the hidden width");
@@ -362,7 +363,7 @@ int sde_tile(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, con
   p.g = *g;
   p.y0 = y0;
   p.t_span = t_span;
-  p.dW = dW;
+  p.bm = bm;
   p.out = out;
   p.B = B;
   p.T = T;

@@ -70,13 +70,23 @@ class FixedSolver:
         elif kind == "sde":
             if self.method != "euler" and self.xde.scheme == "em":
                 raise UnsupportedFieldError("sdeint is fused for solver=Euler (Euler-Maruyama) only")
-            dW = T.to_dev(self.xde.bm_increments)
-            if tuple(dW.shape) != (Tn - 1, B, D):
-                raise ValueError(f"bm_increments must be [T-1, B, D] = {(Tn - 1, B, D)}, got {tuple(dW.shape)}")
             f, g = self.xde.drift.c_struct(), self.xde.diffusion.c_struct()
-            args = (SDE[self.xde.scheme], C.byref(f), C.byref(g), T.ptr(y0), B, T.ptr(t_dev), Tn, T.ptr(dW),
-                    self.out_stride, T.ptr(out), T.stream())
-            self._launch(lib().xde_sde_mlp_tc_f32, lib().xde_sde_mlp_f32, args)
+            if self.xde.bm_seed is not None:  # device-side Philox increments: no [T-1, B, D] table at all
+                def philox(math):
+                    return lib().xde_sde_mlp_philox_f32(SDE[self.xde.scheme], math, C.byref(f), C.byref(g), T.ptr(y0), B,
+                                                        T.ptr(t_dev), Tn, int(self.xde.bm_seed) & (2 ** 64 - 1),
+                                                        self.xde.bm_offset, self.out_stride, T.ptr(out), T.stream())
+                rc = philox(0) if self.math == "fp32" else philox(1)
+                if rc == XDE_E_UNSUPPORTED_FIELD and self.math == "auto":
+                    rc = philox(0)
+                check(rc)
+            else:
+                dW = T.to_dev(self.xde.bm_increments)
+                if tuple(dW.shape) != (Tn - 1, B, D):
+                    raise ValueError(f"bm_increments must be [T-1, B, D] = {(Tn - 1, B, D)}, got {tuple(dW.shape)}")
+                args = (SDE[self.xde.scheme], C.byref(f), C.byref(g), T.ptr(y0), B, T.ptr(t_dev), Tn, T.ptr(dW),
+                        self.out_stride, T.ptr(out), T.stream())
+                self._launch(lib().xde_sde_mlp_tc_f32, lib().xde_sde_mlp_f32, args)
         else:
             raise UnsupportedFieldError(f"fixed solvers integrate ODE/SDE problems on the device, not {kind!r}")
         # concat(axis=-2) of the per-time states (base_fixed_solver.py:143)

@@ -579,6 +579,58 @@ def test_midpoint_fixed_solver(px, torch, oracle, d, h, pre, B):
 
 
 # ------------------------------------------------------------------------------------------------
+# device-side Brownian increments (Philox4x32-10 + Box-Muller)
+# ------------------------------------------------------------------------------------------------
+def test_brownian_increments_generator(px, torch, oracle):
+    from oracle.philox_np import brownian_increments as ref_inc
+    from paddlexde_b200.utils.brownian import brownian_increments
+
+    t = np.array([0.0, 0.1, 0.35, 1.0], f32)
+    for D in (1, 2, 6, 32):
+        dev = brownian_increments(11, t, 500, D).cpu().numpy()
+        ref = ref_inc(11, t, 500, D)
+        assert dev.shape == ref.shape == (3, 500, D)
+        np.testing.assert_allclose(dev, ref, rtol=2e-5, atol=2e-6)  # same uint32 stream, libm vs CUDA log/sincos
+    whole = brownian_increments(5, t, 1000, 8)
+    part = brownian_increments(5, t, 300, 8, offset=700)
+    assert torch.equal(part, whole[:, 700:])                         # shard == slice of the whole batch
+    big = brownian_increments(1, np.array([0.0, 0.25], f32), 1 << 20, 8)[0]
+    assert abs(float(big.mean())) < 1e-3 and abs(float(big.var()) - 0.25) < 1e-3
+    c = float((big[:, 0] * big[:, 1]).mean())
+    assert abs(c) < 1e-3                                             # components are independent
+
+
+@pytest.mark.parametrize("d,h,B,math,scheme", [(4, 32, 700, "fp32", "em"), (4, 32, 300, "fp32", "milstein"),
+                                               (32, 64, 1000, "fp32", "em"), (32, 64, 1000, "tensor", "em"),
+                                               (32, 64, 148 * 256 + 5, "tensor", "em"), (16, 64, 130, "tensor", "em")])
+def test_sdeint_with_generated_increments(px, torch, oracle, d, h, B, math, scheme):
+    """options={"bm_seed": s}: increments generated inside the kernel == the same increments written to a
+    table and supplied (bit for bit, every kernel family); the FP32 kernels then equal the oracle run on that
+    table; a sharded run with bm_offset equals the unsharded one."""
+    from paddlexde_b200.utils.brownian import brownian_increments
+
+    f, of = both(px, oracle, fanin_weights(d, h, seed=2), "cube")
+    g, og = both(px, oracle, fanin_weights(d, h, seed=3), "square")
+    y0 = np.random.default_rng(4).uniform(-1, 1, (B, d)).astype(f32)
+    yd = torch.from_numpy(y0).cuda().reshape(B, 1, d)
+    t = np.linspace(0, 1, 9).astype(f32)
+    opt = {"math": math, "scheme": scheme}
+    gen = px.sdeint(f, g, yd, t, px.Euler, options={"bm_seed": 2024, **opt})
+    table = brownian_increments(2024, t, B, d)
+    sup = px.sdeint(f, g, yd, t, px.Euler, options={"bm_increments": table, **opt})
+    assert torch.equal(gen, sup)
+    if math == "fp32" and B <= 2000:
+        ref = oracle.sde_mlp(scheme, of, og, y0, t, table.cpu().numpy())
+        assert np.array_equal(gen.cpu().numpy(), ref)
+    h0 = B // 3
+    parts = [px.sdeint(f, g, yd[a:b], t, px.Euler, options={"bm_seed": 2024, "bm_offset": a, **opt})
+             for a, b in ((0, h0), (h0, B))]
+    assert torch.equal(torch.cat(parts), gen)
+    with pytest.raises(ValueError):
+        px.sdeint(f, g, yd, t, px.Euler, options={"bm_seed": 1, "bm_increments": table})
+
+
+# ------------------------------------------------------------------------------------------------
 # large states: the register-tiled FFMA2 kernels (cfg3: 64-256-64 RK4, cfg4: 32-64-32 Euler-Maruyama)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("d,h,B", [(64, 256, 100), (64, 128, 33), (64, 64, 130), (32, 256, 31), (32, 128, 65),

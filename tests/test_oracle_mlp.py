@@ -171,3 +171,24 @@ def test_sde_em_and_milstein(oracle):
     f64 = onp.MLPFieldNP(drift.w1, drift.b1, drift.w2, drift.b2, "cube", np.float64)
     ref = y + f64(0, y) * dt + g * dW[0] + 0.5 * g * gp * (dW[0].astype(np.float64) ** 2 - dt)
     np.testing.assert_allclose(outm[:, 1], ref, rtol=2e-5, atol=2e-6)
+
+
+def test_philox_known_answers_and_increment_layout():
+    """Random123 known-answer vectors for Philox4x32-10 pin the generator restatement (oracle/philox_np.py)
+    that the device-side Brownian increments are checked against."""
+    from oracle.philox_np import brownian_increments, philox4x32_10
+
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(v) for v in philox4x32_10(*ctr, *key)) == want
+    t = np.linspace(0, 1, 5).astype(np.float32)
+    a = brownian_increments(7, t, 64, 6)
+    assert a.shape == (4, 64, 6) and np.isfinite(a).all()
+    # counter-based: a shard that passes its global offset sees the increments of the whole batch
+    assert np.array_equal(brownian_increments(7, t, 24, 6, offset=40), a[:, 40:])
+    assert not np.array_equal(brownian_increments(8, t, 64, 6), a)
+    big = brownian_increments(3, np.array([0, 0.25], np.float32), 40000, 8)
+    assert abs(big.mean()) < 3e-3 and abs(big.var() - 0.25) < 3e-3
