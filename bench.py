@@ -231,7 +231,7 @@ def secondary_configs():
         import bench_configs as bc
         res = []
         for fn, kw in ((bc.cfg3, {"math": "tensor"}), (bc.cfg3, {"math": "fp32"}), (bc.cfg4, {"math": "tensor"}),
-                       (bc.cfg4, {"math": "fp32"})):
+                       (bc.cfg4, {"math": "fp32"}), (bc.cfg4, {"math": "tensor", "generated": True})):
             res.append(fn(**kw))
             torch.cuda.empty_cache()
         return res

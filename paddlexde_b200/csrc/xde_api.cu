@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) brownian_table_kernel(BmSource bm, const 
     const long long nb = i / G4;
     const long long b = nb % B;
     const int n = (int)(nb / B);
-    const float sq = sqrtf(fabsf(t_span[n + 1] - t_span[n]));
+    const float sq = __fsqrt_rn(fabsf(t_span[n + 1] - t_span[n]));
     const float4 z = bm_normal4(bm.seed, n, b + bm.traj_offset, d4);
     const float v[4] = {z.x * sq, z.y * sq, z.z * sq, z.w * sq};
     float *o = dW + ((long long)n * B + b) * D + 4 * d4;

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kFixThreads) sde_small_kernel(const FixParams 
       const float dt = st[i] - st[i - 1];
       float w[D], f[D], g[D], gp[D];
 #pragma unroll
-      for (int e = 0; e < D; ++e) w[e] = bm_increment1(p.bm, i - 1, b, p.B, D, e, sqrtf(fabsf(dt)));
+      for (int e = 0; e < D; ++e) w[e] = bm_increment1(p.bm, i - 1, b, p.B, D, e, dt);
       mlp_eval_small<D, PREF>(swf, p.f.h, y, f);
       if (SCHEME == XDE_SDE_MILSTEIN)
         mlp_eval_diag_small<D, PREG>(swg, p.g.h, y, g, gp);

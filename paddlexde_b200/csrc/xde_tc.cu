@@ -318,10 +318,11 @@ __global__ void __launch_bounds__(1024) tc_prep_kernel(xde_mlp_field_t f, xde_ml
 }
 
 // ---- the solver -----------------------------------------------------------------------------------
-// KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama (two networks), 3: ODE Midpoint
+// KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama (two networks; increments from the caller's
+// table), 3: ODE Midpoint, 4: SDE Euler-Maruyama with the increments generated in the kernel (BmSource)
 template <int D, int H, int KIND, int NJ>
 __global__ void __launch_bounds__(cta_threads(NJ), NJ == 4 ? 1 : 2) fixed_tc_kernel(const TcParams p) {
-  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  constexpr int NETS = (KIND == 2 || KIND == 4) ? 2 : 1;
   constexpr int kComputeWarps = compute_warps(NJ), kThreads = cta_threads(NJ);
   using G = Geom<D, H, NETS, NJ>;
   constexpr int NC = G::NC, CH = G::CH, NCHUNK = G::NCHUNK;
@@ -650,7 +651,7 @@ __global__ void __launch_bounds__(cta_threads(NJ), NJ == 4 ? 1 : 2) fixed_tc_ker
 #pragma unroll
           for (int v = 0; v < NC / 4; ++v) {
             w4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) w4[v] = bm_increment4(p.bm, i - 1, b, p.B, D, c0 / 4 + v, sqrtf(fabsf(dt)));
+            if (ok) w4[v] = bm_increment4<KIND == 4>(p.bm, i - 1, b, p.B, D, c0 / 4 + v, dt);
           }
           eval(y, k, kg);
 #pragma unroll
@@ -696,7 +697,7 @@ __global__ void __launch_bounds__(cta_threads(NJ), NJ == 4 ? 1 : 2) fixed_tc_ker
 // of the other slot earlier.  Same arithmetic, same TMEM layouts per slot as fixed_tc_kernel.
 template <int D, int H, int KIND>
 __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcParams p) {
-  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  constexpr int NETS = (KIND == 2 || KIND == 4) ? 2 : 1;
   constexpr int kComputeWarps = compute_warps(4), kThreads = cta_threads(4);
   using G = Geom<D, H, NETS, 4>;
   static_assert(G::COLS <= 256 && G::NC <= 8, "two tiles in flight: <= 256 TMEM columns and <= 8 state columns per thread");
@@ -947,8 +948,8 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
           y[s][2 * v] = pk(t4.x, t4.y);
           y[s][2 * v + 1] = pk(t4.z, t4.w);
           w4[s][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (KIND == 2 && ok[s] && p.T > 1)  // increments of step 1
-            w4[s][v] = bm_increment4(p.bm, 0, b[s], p.B, D, c0 / 4 + v, sqrtf(fabsf(st[1] - st[0])));
+          if ((KIND == 2 || KIND == 4) && ok[s] && p.T > 1)  // increments of step 1
+            w4[s][v] = bm_increment4<KIND == 4>(p.bm, 0, b[s], p.B, D, c0 / 4 + v, st[1] - st[0]);
         }
 #pragma unroll
         for (int c = 0; c < NP; ++c) A[s][c] = S[s][c] = pk1(0.0f);
@@ -1014,11 +1015,11 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
                 }
               }
               if (i < p.T - 1) {  // next step's increments (first touched after its evaluation), then its input
-                if (KIND == 2) {
+                if (KIND == 2 || KIND == 4) {
 #pragma unroll
                   for (int v = 0; v < NC / 4; ++v)
                     if (ok[s])
-                      w4[s][v] = bm_increment4(p.bm, i, b[s], p.B, D, c0 / 4 + v, sqrtf(fabsf(st[i + 1] - st[i])));
+                      w4[s][v] = bm_increment4<KIND == 4>(p.bm, i, b[s], p.B, D, c0 / 4 + v, st[i + 1] - st[i]);
                 }
                 phaseU(s, y[s]);
               }
@@ -1042,7 +1043,7 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
 
 template <int D, int H, int KIND>
 static int launch_tc2(TcParams p, cudaStream_t s) {
-  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  constexpr int NETS = (KIND == 2 || KIND == 4) ? 2 : 1;
   using G = Geom<D, H, NETS, 4>;
   const size_t smem = G::bytes(p.T);
   XDE_REQUIRE(smem <= 227 * 1024, XDE_E_UNSUPPORTED_FIELD,
@@ -1066,7 +1067,7 @@ static int launch_tc2(TcParams p, cudaStream_t s) {
 
 template <int D, int H, int KIND, int NJ>
 static int launch_tc(TcParams p, cudaStream_t s) {
-  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  constexpr int NETS = (KIND == 2 || KIND == 4) ? 2 : 1;
   using G = Geom<D, H, NETS, NJ>;
   const size_t smem = G::bytes(p.T);
   XDE_REQUIRE(smem <= 227 * 1024, XDE_E_UNSUPPORTED_FIELD,
@@ -1099,7 +1100,7 @@ static int launch_tc(TcParams p, cudaStream_t s) {
 // whenever every SM gets at least one PAIR of tiles.
 template <int D, int H, int KIND>
 static int launch_tc_auto(const TcParams &p, cudaStream_t s) {
-  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  constexpr int NETS = (KIND == 2 || KIND == 4) ? 2 : 1;
   using G = Geom<D, H, NETS, 4>;
   if constexpr (G::COLS <= 256 && G::NC <= 8) {
     const long long n_tiles = (p.B + kTM - 1) / kTM;
@@ -1114,7 +1115,7 @@ static int tc_dispatch(const TcParams &p, cudaStream_t s) {
 #define XDE_TC_CASE(DD, HH) \
   if (D == DD && H == HH) return launch_tc_auto<DD, HH, KIND>(p, s);
   XDE_TC_CASE(64, 64) XDE_TC_CASE(32, 128) XDE_TC_CASE(32, 64) XDE_TC_CASE(16, 128) XDE_TC_CASE(16, 64)
-  if constexpr (KIND != 2) {  // two networks: 2 (H + FW + D) <= 512 TMEM columns
+  if constexpr (KIND != 2 && KIND != 4) {  // two networks: 2 (H + FW + D) <= 512 TMEM columns
     XDE_TC_CASE(64, 256) XDE_TC_CASE(64, 128) XDE_TC_CASE(32, 256)
   }
 #undef XDE_TC_CASE
@@ -1163,7 +1164,7 @@ int sde_tc(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const
   p.T = T;
   p.stride = stride;
   p.n_out = (T - 1 + stride - 1) / stride + 1;
-  return tc::tc_dispatch<2>(p, s);
+  return bm.table ? tc::tc_dispatch<2>(p, s) : tc::tc_dispatch<4>(p, s);
 }
 
 }  // namespace xde

@@ -150,12 +150,14 @@ __device__ __forceinline__ void tile_eval(const float *__restrict__ net, const f
   }
 }
 
-// KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama, 3: ODE Midpoint (fixed_solver/midpoint.py:7-18)
+// KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama (increments from the caller's table),
+// 3: ODE Midpoint (fixed_solver/midpoint.py:7-18), 4: SDE Euler-Maruyama, increments generated (BmSource)
 template <int D, int H, int TM, int R1, int C1, int R2, int C2, int KIND>
 __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileParams p) {
   using G = TileGeom<D, H, TM, R1, C1, R2, C2>;
   extern __shared__ __align__(16) float smem[];
-  constexpr int NETS = (KIND == 2) ? 2 : 1;
+  constexpr bool SDE = (KIND == 2 || KIND == 4);
+  constexpr int NETS = SDE ? 2 : 1;
   float *netf = smem;
   float *netg = smem + G::net_floats;  // only when NETS == 2
   float *sU = smem + NETS * G::net_floats;
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileP
   float *sH = sUg + D * TM;
   float *st = sH + H * TM;
   load_net<D, H>(netf, p.f);
-  if (KIND == 2) load_net<D, H>(netg, p.g);
+  if (SDE) load_net<D, H>(netg, p.g);
   for (int i = threadIdx.x; i < p.T; i += blockDim.x) st[i] = p.t_span[i];
   __syncthreads();
 
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileP
       // no barrier needed before put_u: every warp has passed the layer-1/layer-2 barrier of the previous
       // evaluation (nobody reads sU any more); the barrier below also fences the previous readers of sH
       put_u(sU, pref, y);
-      if (KIND == 2) put_u(sUg, preg, y);
+      if (SDE) put_u(sUg, preg, y);
       __syncthreads();
       tile_eval<D, H, TM, R1, C1, R2, C2>(netf, sU, sH, k1);
       if (KIND == 0) {
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileP
 #pragma unroll
           for (int q = 0; q < C2 / 4; ++q) {
             float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) wv = bm_increment4(p.bm, i - 1, b, p.B, D, c0 / 4 + q, sqrtf(fabsf(dt)));
+            if (ok) wv = bm_increment4<KIND == 4>(p.bm, i - 1, b, p.B, D, c0 / 4 + q, dt);
             const float w[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
             for (int z = 0; z < 4; ++z) {
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileP
 template <int D, int H, int TM, int R1, int C1, int R2, int C2, int KIND>
 static int launch_tile(const TileParams &p, cudaStream_t s) {
   using G = TileGeom<D, H, TM, R1, C1, R2, C2>;
-  const size_t smem = G::bytes(KIND == 2 ? 2 : 1, p.T);
+  const size_t smem = G::bytes((KIND == 2 || KIND == 4) ? 2 : 1, p.T);
   XDE_REQUIRE(smem <= 227 * 1024, XDE_E_UNSUPPORTED_FIELD,
               "tiled solver: weights + tiles + grid need %zu bytes of shared memory (> 227 KB)", smem);
   auto kern = fixed_tile_kernel<D, H, TM, R1, C1, R2, C2, KIND>;
@@ -369,7 +371,7 @@ int sde_tile(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, con
   p.T = T;
   p.stride = stride;
   p.n_out = (T - 1 + stride - 1) / stride + 1;
-  return tile_dispatch<2>(p, s);
+  return bm.table ? tile_dispatch<2>(p, s) : tile_dispatch<4>(p, s);
 }
 
 }  // namespace xde

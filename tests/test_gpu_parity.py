@@ -590,7 +590,7 @@ def test_brownian_increments_generator(px, torch, oracle):
         dev = brownian_increments(11, t, 500, D).cpu().numpy()
         ref = ref_inc(11, t, 500, D)
         assert dev.shape == ref.shape == (3, 500, D)
-        np.testing.assert_allclose(dev, ref, rtol=2e-5, atol=2e-6)  # same uint32 stream, libm vs CUDA log/sincos
+        np.testing.assert_allclose(dev, ref, rtol=1e-3, atol=2e-5)  # same uint32 stream; MUFU vs libm log/sin/cos
     whole = brownian_increments(5, t, 1000, 8)
     part = brownian_increments(5, t, 300, 8, offset=700)
     assert torch.equal(part, whole[:, 700:])                         # shard == slice of the whole batch

@@ -49,22 +49,23 @@ def cfg3(B=1 << 17, math="tensor"):
     return r
 
 
-def cfg4(B=1 << 21, math="tensor"):
+def cfg4(B=1 << 21, math="tensor", generated=False):
     d, h = 32, 64
     f = px.MLPField(*fanin_weights(d, h, seed=2), pre="cube")
     g = px.MLPField(*fanin_weights(d, h, seed=3), pre="square")
     gen = torch.Generator(device="cuda").manual_seed(2)
     y0 = (torch.rand((B, 1, d), device="cuda", generator=gen) * 2 - 1)
     t = np.linspace(0, 1, 17).astype(np.float32)
-    dW = torch.randn((16, B, d), device="cuda", generator=gen) * 0.25
-    xde = px.xde.BaseSDE(f, g, y0, t, bm_increments=dW)
+    dW = None if generated else torch.randn((16, B, d), device="cuda", generator=gen) * 0.25
+    xde = px.xde.BaseSDE(f, g, y0, t, bm_seed=2) if generated else px.xde.BaseSDE(f, g, y0, t, bm_increments=dW)
     s = px.Euler(xde=xde, y0=y0, rtol=1e-7, atol=1e-9, out_stride=16, math=math)
     ms = timeit(lambda: s.integrate(t))
     steps = B * 16
     flops = steps * (4 * d * h * 2)
     byts = steps * 12 * d  # read y, read dW, write y per trajectory-step
     moved = steps * 4 * d + B * 2 * d * 4 + B * d * 4  # what the fused kernel really moves: dW + y0 in + 2 rows out
-    return {"config": "cfg4 sde-EM 2x(32-64-32)", "math": math, "B": B, "ms": ms,
+    return {"config": "cfg4 sde-EM 2x(32-64-32)" + (" increments generated in-kernel (Philox)" if generated else ""),
+            "math": math, "B": B, "ms": ms,
             "traj_steps_per_s": steps / ms * 1e3, "tflops_algorithmic": flops / ms / 1e9,
             "hbm_gbs_algorithmic": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / HBM,
             "hbm_gbs_moved": moved / ms / 1e6,
@@ -93,5 +94,8 @@ if __name__ == "__main__":
         if w in ("cfg3", "cfg4"):
             for math in ("tensor", "fp32"):
                 print(json.dumps(globals()[w](math=math)), flush=True)
+            if w == "cfg4":
+                print(json.dumps(cfg4(math="tensor", generated=True)), flush=True)
+                print(json.dumps(cfg4(B=1 << 22, math="tensor", generated=True)), flush=True)
         else:
             print(json.dumps(globals()[w]()), flush=True)
