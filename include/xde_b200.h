@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define XDE_ABI_VERSION 1
+#define XDE_ABI_VERSION 2 /* 2: + tensor-core, table-driven adaptive RK, forced grid points, Philox, Bezier */
 
 /* return codes */
 enum {

@@ -110,7 +110,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the ABI is incomplete
             fn.restype = res
             fn.argtypes = args
-        if handle.xde_abi_version() != 1:
+        if handle.xde_abi_version() != 2:
             raise ImportError("libxde_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -63,6 +63,24 @@ def test_shard_rows_partition():
         shard_rows(4, 2, 2)
 
 
+def test_sde_shard_options_reproduce_the_global_increment_stream():
+    """The counter-based Brownian generator is addressed by the global trajectory index: the increments of
+    every shard (NumPy restatement of the device generator) tile the unsharded table exactly."""
+    from oracle.philox_np import brownian_increments
+    from paddlexde_b200.distributed import sde_shard_options, shard_rows
+
+    t = np.linspace(0, 1, 4).astype(np.float32)
+    whole = brownian_increments(99, t, 37, 5)
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_rows(37, r, world)
+            o = sde_shard_options(99, 37, r, world)
+            assert o == {"bm_seed": 99, "bm_offset": lo}
+            parts.append(brownian_increments(o["bm_seed"], t, hi - lo, 5, offset=o["bm_offset"]))
+        assert np.array_equal(np.concatenate(parts, axis=1), whole)
+
+
 @pytest.mark.timeout(300)
 def test_two_rank_gradient_allreduce_equals_single_process(tmp_path, oracle):
     from tests.problems import cfg2_tspan, cfg2_y0, spiral_weights
