@@ -3,6 +3,9 @@ device, error statistics and timings per shape.  Usage: python tools/tc_check.py
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+import paddlexde_b200._lib as _L
+if os.environ.get("XDE_LIB"):  # kernel tuning experiments: an alternative build of the library
+    _L._SO = os.path.abspath(os.environ["XDE_LIB"])
 import paddlexde_b200 as px
 from tests.problems import fanin_weights
 
