@@ -224,11 +224,14 @@ struct Tmem<16> {
   }
 };
 
-// x0, x1 -> packed fp16 hi pieces and packed fp16 lo pieces (element 0 in the low half)
+// x0, x1 -> packed fp16 hi pieces and packed fp16 lo pieces (element 0 in the low half).  The residual is one
+// packed subtraction: the split is a quarter of the epilogue's instructions.
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  float l0, l1;
+  upk(sub2(pk(x0, x1), pk(hf.x, hf.y)), l0, l1);
+  const __half2 l = __floats2half2_rn(l0, l1);
   hi = *reinterpret_cast<const uint32_t *>(&h);
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
@@ -282,6 +285,11 @@ __device__ __forceinline__ f32x2 tanh_mixed2(f32x2 a, int m) {
   return ((XDE_TC_EXP_MASK >> m) & 1) ? tanh_sfu2(a) : tanh_fast2(a);
 }
 
+__device__ __forceinline__ f32x2 pre_rt2(int pre, f32x2 y) {  // the same on a packed pair
+  if (pre == XDE_PRE_CUBE) return mul2(mul2(y, y), y);
+  if (pre == XDE_PRE_SQUARE) return mul2(y, y);
+  return y;
+}
 __device__ __forceinline__ float pre_rt(int pre, float y) {
   if (pre == XDE_PRE_CUBE) return (y * y) * y;
   if (pre == XDE_PRE_SQUARE) return y * y;
@@ -872,7 +880,7 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
     uint32_t par = 0;
     [[maybe_unused]] int trace_n = (tid == 0) ? 0 : (1 << 30);
 
-    auto phaseU = [&](int s, const f32x2(&yi)[NP]) {  // stage input -> U of slot s (fp16 hi | lo)
+    auto phaseU_issue = [&](int s, const f32x2(&yi)[NP]) {  // stage input -> U of slot s (fp16 hi | lo)
       const uint32_t ts = tl + s * SLOT;
 #pragma unroll
       for (int net = 0; net < NETS; ++net) {
@@ -881,12 +889,14 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
 #pragma unroll
         for (int c = 0; c < NP; ++c) {
           float v0, v1;
-          upk(yi[c], v0, v1);
-          split2(pre_rt(pre, v0), pre_rt(pre, v1), uh[c], ul[c]);
+          upk(pre_rt2(pre, yi[c]), v0, v1);
+          split2(v0, v1, uh[c], ul[c]);
         }
         Tmem<NP>::st(ts + G::U0 + net * D + j * NP, uh);
         Tmem<NP>::st(ts + G::U0 + net * D + D / 2 + j * NP, ul);
       }
+    };
+    auto phaseU_finish = [&](int s) {  // stores complete -> hand the slot to the MMA warp
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -919,29 +929,33 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
         if (lane == 0) mbar_arrive(h_ready + s * kMaxChunks + c);
       }
     };
-    auto phaseF = [&](int s, f32x2(&kf)[NP], f32x2(&kg)[NP]) {  // F of slot s -> registers
+    // F of slot s -> registers, in two halves so that the TMEM load of slot B can be in flight while slot A's
+    // stage input is being stored (and the store's completion wait overlaps the load's)
+    auto phaseF_issue = [&](int s, uint32_t(&r)[NETS][NC]) {
       const uint32_t ts = tl + s * SLOT;
       mbar_wait(f_ready + s, par);
       tc_fence_after();
 #pragma unroll
+      for (int net = 0; net < NETS; ++net) Tmem<NC>::ld(ts + G::F0 + net * G::FW + c0, r[net]);
+    };
+    auto phaseF_finish = [&](int s, uint32_t(&r)[NETS][NC], f32x2(&kf)[NP], f32x2(&kg)[NP]) {
+      const uint32_t ts = tl + s * SLOT;
+      tc_wait_ld();
+#pragma unroll
       for (int net = 0; net < NETS; ++net) {
         f32x2(&kk)[NP] = net ? kg : kf;
-        const uint32_t fa = ts + G::F0 + net * G::FW + c0;
-        uint32_t r0[NC], r1[NC];
-        Tmem<NC>::ld(fa, r0);
-        if (G::SPLIT_CORR) Tmem<NC>::ld(fa + D, r1);
-        tc_wait_ld();
 #pragma unroll
-        for (int c = 0; c < NP; ++c) {
-          kk[c] = pk(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
-          if (G::SPLIT_CORR) kk[c] = add2(kk[c], pk(__uint_as_float(r1[2 * c]), __uint_as_float(r1[2 * c + 1])));
-        }
-        if (G::SPLIT_CORR) {
-          Tmem<NC>::ld(fa + 2 * D, r0);
+        for (int c = 0; c < NP; ++c) kk[c] = pk(__uint_as_float(r[net][2 * c]), __uint_as_float(r[net][2 * c + 1]));
+        if (G::SPLIT_CORR) {  // second main accumulator and the corrections
+          const uint32_t fa = ts + G::F0 + net * G::FW + c0;
+          uint32_t r1[NC], r2[NC];
+          Tmem<NC>::ld(fa + D, r1);
+          Tmem<NC>::ld(fa + 2 * D, r2);
           tc_wait_ld();
 #pragma unroll
           for (int c = 0; c < NP; ++c)
-            kk[c] = add2(kk[c], pk(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1])));
+            kk[c] = add2(add2(kk[c], pk(__uint_as_float(r1[2 * c]), __uint_as_float(r1[2 * c + 1]))),
+                         pk(__uint_as_float(r2[2 * c]), __uint_as_float(r2[2 * c + 1])));
         }
         const f32x2 s2 = pk1(ssinv[net * 2 + 1]);
 #pragma unroll
@@ -977,7 +991,8 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
         }
 #pragma unroll
         for (int c = 0; c < NP; ++c) A[s][c] = S[s][c] = pk1(0.0f);
-        phaseU(s, y[s]);
+        phaseU_issue(s, y[s]);
+        phaseU_finish(s);
       }
       for (int i = 1; i < p.T; ++i) {
         const float dt = st[i] - st[i - 1];
@@ -989,11 +1004,14 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
           XDE_TRACE(0, 201);
           phaseH(1);
           XDE_TRACE(0, 202);
+          uint32_t fr[NETS][NC];
+          phaseF_issue(0, fr);
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             f32x2 k[NP], kg[NP], yi[NP];
-            phaseF(s, k, kg);
+            phaseF_finish(s, fr, k, kg);
             XDE_TRACE(0, 210 + s);
+            bool stored = false;
             if (KIND == 0) {
 #pragma unroll
               for (int c = 0; c < NP; ++c) y[s][c] = fma2(k[c], dt2, y[s][c]);
@@ -1045,11 +1063,15 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
                     if (ok[s])
                       w4[s][v] = bm_increment4<KIND == 4>(p.bm, i, b[s], p.B, D, c0 / 4 + v, st[i + 1] - st[i]);
                 }
-                phaseU(s, y[s]);
+                phaseU_issue(s, y[s]);
+                stored = true;
               }
             } else {
-              phaseU(s, yi);
+              phaseU_issue(s, yi);
+              stored = true;
             }
+            if (s == 0) phaseF_issue(1, fr);  // slot B's field value: its load flies while slot A's store completes
+            if (stored) phaseU_finish(s);
             XDE_TRACE(0, 220 + s);
           }
           par ^= 1u;
