@@ -47,7 +47,10 @@ enum {
   XDE_ST_DT_UNDERFLOW = 1,    /* assert t0 + dt > t0          base_adaptive_solver_rk.py:200 */
   XDE_ST_NONFINITE_STATE = 2, /* assert isfinite(y0).all()    base_adaptive_solver_rk.py:201-203 */
   XDE_ST_MAX_STEPS = 3,       /* max_num_steps exceeded       base_adaptive_solver_rk.py:120-122 */
-  XDE_ST_INTERP_RANGE = 5     /* invalid interpolation        utils/ode_utils.py:65-67 */
+  XDE_ST_INTERP_RANGE = 5,    /* invalid interpolation        utils/ode_utils.py:65-67 */
+  XDE_ST_TC_RANGE = 6         /* tensor-core entries only: a stage input pre(y) was non-finite or >= 65504 in
+                                 magnitude (not representable in the fp16 operand split): discard the result and
+                                 use the FP32 entry (no reference counterpart) */
 };
 
 /* y ** p applied before the first Linear (example/ode_demo.py:33, example/sde_demo.py:183) */
@@ -194,12 +197,14 @@ int xde_sde_mlp_f32(int32_t scheme, const xde_mlp_field_t *drift, const xde_mlp_
  * the dense layers of the field run on tcgen05 (fp16-split three-product GEMMs, fp32 accumulation in
  * TMEM), for D in {16,32,64} x H in {64,128,256} (sde: H <= 128).  Results agree with the FP32 entry
  * points to ~1e-6 relative (north star: rtol 1e-5), not bit for bit; anything else returns
- * XDE_E_UNSUPPORTED_FIELD. */
+ * XDE_E_UNSUPPORTED_FIELD.  status: optional device word, zeroed by the entry point, set to
+ * XDE_ST_TC_RANGE when some stage input left the fp16 operand range (read it after synchronising). */
 int xde_rk_fixed_mlp_tc_f32(int32_t method, const xde_mlp_field_t *field, const float *y0, int64_t B,
-                            const float *t_span, int32_t T, int32_t out_stride_t, float *out, void *stream);
+                            const float *t_span, int32_t T, int32_t out_stride_t, float *out, int32_t *status,
+                            void *stream);
 int xde_sde_mlp_tc_f32(int32_t scheme, const xde_mlp_field_t *drift, const xde_mlp_field_t *diffusion,
                        const float *y0, int64_t B, const float *t_span, int32_t T, const float *dW,
-                       int32_t out_stride_t, float *out, void *stream);
+                       int32_t out_stride_t, float *out, int32_t *status, void *stream);
 
 /* Brownian increments without a table.  The reference draws them on the host from
  * BrownianInterval (utils/brownian/brownian_interval.py:178-240; xde/base_sde.py:35-37); on a fixed grid the
@@ -215,7 +220,7 @@ int xde_brownian_increments_f32(uint64_t seed, int64_t traj_offset, const float 
 int xde_sde_mlp_philox_f32(int32_t scheme, int32_t math, const xde_mlp_field_t *drift,
                            const xde_mlp_field_t *diffusion, const float *y0, int64_t B, const float *t_span,
                            int32_t T, uint64_t seed, int64_t traj_offset, int32_t out_stride_t, float *out,
-                           void *stream);
+                           int32_t *status, void *stream);
 
 /* HistoryIndex.forward                                xde/base_dde.py:84-118
  *   -> InterpolationBase.evaluate / derivative        interpolation/interpolate_base.py:49-114

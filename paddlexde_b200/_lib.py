@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libxde_b200.so")
 
 XDE_OK, XDE_E_BAD_ARG, XDE_E_UNSUPPORTED_FIELD, XDE_E_CUDA = 0, -1, -2, -3
-ST_OK, ST_DT_UNDERFLOW, ST_NONFINITE_STATE, ST_MAX_STEPS, ST_INTERP_RANGE = 0, 1, 2, 3, 5
+ST_OK, ST_DT_UNDERFLOW, ST_NONFINITE_STATE, ST_MAX_STEPS, ST_INTERP_RANGE, ST_TC_RANGE = 0, 1, 2, 3, 5, 6
 
 PRE = {"id": 0, "identity": 0, None: 0, "square": 1, "cube": 2}
 CTRL = {"trajectory": 0, "batch": 1}
@@ -75,14 +75,15 @@ _EXPORTS = {
     "xde_sde_mlp_f32": (C.c_int, [C.c_int32, C.POINTER(MlpFieldC), C.POINTER(MlpFieldC), C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "xde_rk_fixed_mlp_tc_f32": (C.c_int, [C.c_int32, C.POINTER(MlpFieldC), C.c_void_p, C.c_int64, C.c_void_p,
-                                          C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+                                          C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xde_sde_mlp_tc_f32": (C.c_int, [C.c_int32, C.POINTER(MlpFieldC), C.POINTER(MlpFieldC), C.c_void_p, C.c_int64,
-                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
     "xde_brownian_increments_f32": (C.c_int, [C.c_uint64, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
                                               C.c_void_p, C.c_void_p]),
     "xde_sde_mlp_philox_f32": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(MlpFieldC), C.POINTER(MlpFieldC), C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int32, C.c_uint64, C.c_int64, C.c_int32,
-                                         C.c_void_p, C.c_void_p]),
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "xde_history_gather_f32": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xde_history_gather_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

@@ -90,6 +90,7 @@ struct TcParams {
   float *out;
   long long B;
   int T, stride, n_out;
+  int *status;  // device word or nullptr: XDE_ST_TC_RANGE when a stage input left the fp16 range
 };
 
 // ---- optional phase trace (debug builds only: -DXDE_TC_TRACE, tools/tc_trace.py) ------------------------
@@ -501,6 +502,7 @@ __global__ void __launch_bounds__(cta_threads(NJ), NJ == 4 ? 1 : 2) fixed_tc_ker
     const int pref = p.f.pre, preg = p.g.pre;
     const float one_third = (float)(1.0 / 3.0);
     uint32_t par = 0;
+    bool in_range = true;  // every stage input representable in fp16 (|pre(y)| < 65504, finite)
     [[maybe_unused]] int trace_n = (tid == 0) ? 0 : (1 << 30);
 
     // one evaluation of the field(s) at yi: kf (and kg) <- f(yi) (, g(yi)); state columns travel as packed pairs
@@ -515,8 +517,9 @@ __global__ void __launch_bounds__(cta_threads(NJ), NJ == 4 ? 1 : 2) fixed_tc_ker
 #pragma unroll
         for (int c = 0; c < NP; ++c) {
           float v0, v1;
-          upk(yi[c], v0, v1);
-          split2(pre_rt(pre, v0), pre_rt(pre, v1), uh[c], ul[c]);
+          upk(pre_rt2(pre, yi[c]), v0, v1);
+          in_range = in_range && (fabsf(v0) < 65504.0f) && (fabsf(v1) < 65504.0f);  // also false for NaN
+          split2(v0, v1, uh[c], ul[c]);
         }
         Tmem<NC / 2>::st(tl + G::U0 + net * D + j * (NC / 2), uh);
         Tmem<NC / 2>::st(tl + G::U0 + net * D + D / 2 + j * (NC / 2), ul);
@@ -705,6 +708,9 @@ __global__ void __launch_bounds__(cta_threads(NJ), NJ == 4 ? 1 : 2) fixed_tc_ker
         }
       }
     }
+    // a stage input outside the fp16 range (or non-finite) makes the MMA operands inf / NaN: report, the caller
+    // discards the result (the shim reruns on the FP32 kernels when math="auto")
+    if (p.status && !__all_sync(XDE_FULL_MASK, in_range) && lane == 0) atomicMax(p.status, XDE_ST_TC_RANGE);
   }
 
   // ---- teardown ----
@@ -878,6 +884,7 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
     const int pref = p.f.pre, preg = p.g.pre;
     const float one_third = (float)(1.0 / 3.0);
     uint32_t par = 0;
+    bool in_range = true;  // every stage input representable in fp16 (|pre(y)| < 65504, finite)
     [[maybe_unused]] int trace_n = (tid == 0) ? 0 : (1 << 30);
 
     auto phaseU_issue = [&](int s, const f32x2(&yi)[NP]) {  // stage input -> U of slot s (fp16 hi | lo)
@@ -890,6 +897,7 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
         for (int c = 0; c < NP; ++c) {
           float v0, v1;
           upk(pre_rt2(pre, yi[c]), v0, v1);
+          in_range = in_range && (fabsf(v0) < 65504.0f) && (fabsf(v1) < 65504.0f);  // also false for NaN
           split2(v0, v1, uh[c], ul[c]);
         }
         Tmem<NP>::st(ts + G::U0 + net * D + j * NP, uh);
@@ -1078,6 +1086,9 @@ __global__ void __launch_bounds__(cta_threads(4), 1) fixed_tc2_kernel(const TcPa
         }
       }
     }
+    // a stage input outside the fp16 range (or non-finite) makes the MMA operands inf / NaN: report, the caller
+    // discards the result (the shim reruns on the FP32 kernels when math="auto")
+    if (p.status && !__all_sync(XDE_FULL_MASK, in_range) && lane == 0) atomicMax(p.status, XDE_ST_TC_RANGE);
   }
 
   tc_fence_before();
@@ -1178,7 +1189,7 @@ extern "C" XDE_EXPORT int xde_tc_trace_set(long long *buf) {
 #endif
 
 int rk_fixed_tc(int method, const xde_mlp_field_t *f, const float *y0, long long B, const float *t_span, int T,
-                int stride, float *out, cudaStream_t s) {
+                int stride, float *out, int *status, cudaStream_t s) {
   tc::TcParams p{};
   p.f = *f;
   p.g = *f;
@@ -1189,13 +1200,15 @@ int rk_fixed_tc(int method, const xde_mlp_field_t *f, const float *y0, long long
   p.T = T;
   p.stride = stride;
   p.n_out = (T - 1 + stride - 1) / stride + 1;
+  p.status = status;
+  if (status) XDE_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), s));
   if (method == XDE_FIXED_EULER) return tc::tc_dispatch<0>(p, s);
   if (method == XDE_FIXED_MIDPOINT) return tc::tc_dispatch<3>(p, s);
   return tc::tc_dispatch<1>(p, s);
 }
 
 int sde_tc(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const float *y0, long long B,
-           const float *t_span, int T, const BmSource &bm, int stride, float *out, cudaStream_t s) {
+           const float *t_span, int T, const BmSource &bm, int stride, float *out, int *status, cudaStream_t s) {
   XDE_REQUIRE(scheme == XDE_SDE_EM, XDE_E_UNSUPPORTED_FIELD,
               "Milstein (an extension without a reference counterpart) is fused for small states (D <= 8) only");
   XDE_REQUIRE(f->h == g->h, XDE_E_UNSUPPORTED_FIELD, "tensor-core sde: drift and diffusion must share the hidden width");
@@ -1210,6 +1223,8 @@ int sde_tc(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const
   p.T = T;
   p.stride = stride;
   p.n_out = (T - 1 + stride - 1) / stride + 1;
+  p.status = status;
+  if (status) XDE_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), s));
   return bm.table ? tc::tc_dispatch<2>(p, s) : tc::tc_dispatch<4>(p, s);
 }
 

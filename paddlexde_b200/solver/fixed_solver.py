@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from .. import _tensor as T
-from .._lib import FIXED, SDE, XDE_E_UNSUPPORTED_FIELD, UnsupportedFieldError, check, lib
+from .._lib import FIXED, SDE, ST_TC_RANGE, XDE_E_UNSUPPORTED_FIELD, UnsupportedFieldError, check, lib
 from .adaptive_solver import host_tspan
 
 
@@ -17,7 +17,7 @@ class FixedSolver:
     method: str
 
     def __init__(self, xde, y0, step_size=None, grid_constructor=None, interp="linear", perturb=False,
-                 out_stride=1, math="auto", **kwargs):
+                 out_stride=1, math="auto", check_status=True, **kwargs):
         if step_size is not None and grid_constructor is not None:
             raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
         if step_size is not None or grid_constructor is not None:
@@ -41,16 +41,27 @@ class FixedSolver:
         if math not in ("auto", "fp32", "tensor"):
             raise ValueError(f"math must be 'auto', 'fp32' or 'tensor', got {math!r}")
         self.math = math
+        # the tensor-core kernels report stage inputs outside their fp16 operand range (|pre(y)| >= 65504 or
+        # non-finite) through a device status word; reading it synchronises (like the reference's asserts do).
+        # check_status=False stays asynchronous: the caller vouches for the range.
+        self.check_status = check_status
 
-    def _launch(self, tensor_entry, fp32_entry, args):
-        """Both entries are CUDA kernels of libxde_b200; "auto" asks the tensor-core one first and takes
-        the FP32 one when it reports that it has no kernel for the shape (XDE_E_UNSUPPORTED_FIELD)."""
+    def _launch(self, tensor_call, fp32_call, dev):
+        """Both are CUDA kernels of libxde_b200.  "auto" asks the tensor-core one first and takes the FP32 one
+        when it has no kernel for the shape (XDE_E_UNSUPPORTED_FIELD) or reports XDE_ST_TC_RANGE; "tensor"
+        raises in those cases (no silent change of arithmetic); "fp32" never touches the tensor cores."""
         if self.math == "fp32":
-            return check(fp32_entry(*args))
-        rc = tensor_entry(*args)
+            return check(fp32_call())
+        status = torch.zeros(1, dtype=torch.int32, device=dev) if self.check_status else None
+        rc = tensor_call(T.ptr(status))
         if rc == XDE_E_UNSUPPORTED_FIELD and self.math == "auto":
-            return check(fp32_entry(*args))
-        return check(rc)
+            return check(fp32_call())
+        check(rc)
+        if status is not None and int(status.item()) == ST_TC_RANGE:
+            if self.math == "auto":
+                return check(fp32_call())
+            raise OverflowError("a stage input left the fp16 operand range of the tensor-core kernels "
+                                "(|pre(y)| >= 65504 or non-finite): use math='fp32' (or 'auto')")
 
     def integrate(self, t_span):
         kind = getattr(self.xde, "kind", None)
@@ -64,29 +75,27 @@ class FixedSolver:
         out = torch.empty((B, n_out, D), device=y0.device, dtype=torch.float32)
         if kind == "ode":
             fs = self.xde.field.c_struct()
-            args = (FIXED[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), Tn, self.out_stride, T.ptr(out),
-                    T.stream())
-            self._launch(lib().xde_rk_fixed_mlp_tc_f32, lib().xde_rk_fixed_mlp_f32, args)
+            args = (FIXED[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), Tn, self.out_stride, T.ptr(out))
+            self._launch(lambda st: lib().xde_rk_fixed_mlp_tc_f32(*args, st, T.stream()),
+                         lambda: lib().xde_rk_fixed_mlp_f32(*args, T.stream()), y0.device)
         elif kind == "sde":
             if self.method != "euler" and self.xde.scheme == "em":
                 raise UnsupportedFieldError("sdeint is fused for solver=Euler (Euler-Maruyama) only")
             f, g = self.xde.drift.c_struct(), self.xde.diffusion.c_struct()
             if self.xde.bm_seed is not None:  # device-side Philox increments: no [T-1, B, D] table at all
-                def philox(math):
+                def philox(math, st=None):
                     return lib().xde_sde_mlp_philox_f32(SDE[self.xde.scheme], math, C.byref(f), C.byref(g), T.ptr(y0), B,
                                                         T.ptr(t_dev), Tn, int(self.xde.bm_seed) & (2 ** 64 - 1),
-                                                        self.xde.bm_offset, self.out_stride, T.ptr(out), T.stream())
-                rc = philox(0) if self.math == "fp32" else philox(1)
-                if rc == XDE_E_UNSUPPORTED_FIELD and self.math == "auto":
-                    rc = philox(0)
-                check(rc)
+                                                        self.xde.bm_offset, self.out_stride, T.ptr(out), st, T.stream())
+                self._launch(lambda st: philox(1, st), lambda: philox(0), y0.device)
             else:
                 dW = T.to_dev(self.xde.bm_increments)
                 if tuple(dW.shape) != (Tn - 1, B, D):
                     raise ValueError(f"bm_increments must be [T-1, B, D] = {(Tn - 1, B, D)}, got {tuple(dW.shape)}")
                 args = (SDE[self.xde.scheme], C.byref(f), C.byref(g), T.ptr(y0), B, T.ptr(t_dev), Tn, T.ptr(dW),
-                        self.out_stride, T.ptr(out), T.stream())
-                self._launch(lib().xde_sde_mlp_tc_f32, lib().xde_sde_mlp_f32, args)
+                        self.out_stride, T.ptr(out))
+                self._launch(lambda st: lib().xde_sde_mlp_tc_f32(*args, st, T.stream()),
+                             lambda: lib().xde_sde_mlp_f32(*args, T.stream()), y0.device)
         else:
             raise UnsupportedFieldError(f"fixed solvers integrate ODE/SDE problems on the device, not {kind!r}")
         # concat(axis=-2) of the per-time states (base_fixed_solver.py:143)

@@ -801,6 +801,27 @@ def test_tensor_many_tiles_per_cta(px, torch, oracle, kind, d, h):
     assert _close(sol[torch.from_numpy(idx).cuda()].cpu().numpy(), ref, rtol=1e-5)
 
 
+def test_tensor_path_reports_inputs_outside_its_fp16_range(px, torch, oracle):
+    """|pre(y)| >= 65504 (here y**3 with |y| ~ 50) cannot be split into fp16 operands: the kernels raise a
+    status word; math="auto" then reruns on the FP32 kernels (== oracle bit for bit), math="tensor" raises."""
+    d, h, B = 32, 64, 300
+    field, om = both(px, oracle, fanin_weights(d, h, seed=9), "cube")
+    y0 = np.random.default_rng(9).uniform(-1, 1, (B, d)).astype(f32)
+    y0[17, 3] = 50.0
+    t = np.linspace(0, 0.01, 3).astype(f32)
+    yd = torch.from_numpy(y0).cuda().reshape(B, 1, d)
+    ref = oracle.fixed_mlp("rk4", om, y0, t)
+    auto = px.odeint(field, yd, t, px.RK4)
+    assert np.array_equal(auto.cpu().numpy(), ref)
+    with pytest.raises(OverflowError):
+        px.odeint(field, yd, t, px.RK4, options={"math": "tensor"})
+    y0[17, 3] = 0.5                                    # back in range: the default is the tensor path again
+    yd = torch.from_numpy(y0).cuda().reshape(B, 1, d)
+    ok = px.odeint(field, yd, t, px.RK4)
+    ref = oracle.fixed_mlp("rk4", om, y0, t)
+    assert _close(ok.cpu().numpy(), ref, rtol=1e-5) and not np.array_equal(ok.cpu().numpy(), ref)
+
+
 def test_tensor_path_is_loud_about_unsupported_shapes(px, torch, oracle):
     t = np.linspace(0, 1, 5).astype(f32)
     small, _ = both(px, oracle, fanin_weights(2, 50), "cube")

@@ -13,7 +13,7 @@ if which == "cfg3":
     y0 = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, (B, 1, d)).astype(np.float32)).cuda()
     t = np.linspace(0, 1, 101).astype(np.float32)
     for _ in range(2):
-        px.odeint(field, y0, t, px.RK4, options={"math": math, "out_stride": 10})
+        px.odeint(field, y0, t, px.RK4, options={"math": math, "out_stride": 10, "check_status": False})
 else:
     d, h, B = 32, 64, 1 << 21
     f = px.MLPField(*fanin_weights(d, h, seed=2), pre="cube")
@@ -23,5 +23,5 @@ else:
     t = np.linspace(0, 1, 17).astype(np.float32)
     dW = torch.randn((16, B, d), device="cuda", generator=gen) * 0.25
     for _ in range(2):
-        px.sdeint(f, g, y0, t, px.Euler, options={"bm_increments": dW, "math": math, "out_stride": 16})
+        px.sdeint(f, g, y0, t, px.Euler, options={"bm_increments": dW, "math": math, "out_stride": 16, "check_status": False})
 torch.cuda.synchronize()
