@@ -206,6 +206,19 @@ int xde_sde_mlp_tc_f32(int32_t scheme, const xde_mlp_field_t *drift, const xde_m
                        const float *y0, int64_t B, const float *t_span, int32_t T, const float *dW,
                        int32_t out_stride_t, float *out, int32_t *status, void *stream);
 
+/* SdeintAdjointMethod.backward                        functional/sdeint_adjoint.py:57-230
+ * The reference's reverse solve is a placeholder (augmented_diffusion repeats the drift dynamics, :136-171; BaseSDE
+ * cannot be instantiated): there is no behaviour to reproduce.  Implemented: the exact adjoint of the
+ * Euler-Maruyama recursion the forward entry computes (discretise, then differentiate), small states (D <= 8,
+ * H <= 96).  y_all, grad_y [B,T,D] = the forward solution at EVERY grid point (out_stride_t = 1) and its
+ * cotangent; increments from dW [T-1,B,D], or dW = NULL and (seed, traj_offset) for the generator -- the same
+ * source as the forward pass; out_gdrift / out_gdiffusion = (gW1,gb1,gW2,gb2) summed over the B trajectories
+ * (all-reduce across GPUs is the caller's); out_adj_y0 [B,D] optional (dL/dy0). */
+int xde_sde_mlp_adjoint_f32(const xde_mlp_field_t *drift, const xde_mlp_field_t *diffusion, const float *t_span,
+                            int32_t T, const float *y_all, const float *grad_y, int64_t B, const float *dW,
+                            uint64_t seed, int64_t traj_offset, float *out_gdrift, float *out_gdiffusion,
+                            float *out_adj_y0, void *stream);
+
 /* Brownian increments without a table.  The reference draws them on the host from
  * BrownianInterval (utils/brownian/brownian_interval.py:178-240; xde/base_sde.py:35-37); on a fixed grid the
  * solver only ever asks for W(t[n+1]) - W(t[n]), so a counter-based generator addressed by

@@ -1076,6 +1076,75 @@ int orc_sde_mlp(int32_t scheme, const orc_mlp_t *drift, const orc_mlp_t *diffusi
   return ORC_OK;
 }
 
+/* sdeint_adjoint backward.  The reference's SdeintAdjointMethod.backward (functional/sdeint_adjoint.py:57-230)
+ * copies the ODE adjoint and its `augmented_diffusion` is a verbatim copy of the drift dynamics (:136-171), on
+ * top of the uninstantiable BaseSDE: there is no behaviour to restate.  What is defined
+ * here is what the code is reaching for on the solver's fixed grid: the EXACT adjoint of the Euler-Maruyama
+ * recursion y[n+1] = (y[n] + f(y[n]) dt_n) + g(y[n]) * dW_n  (discretise-then-differentiate):
+ *     lam[n] = lam[n+1] + J_f(y[n])^T (lam[n+1] dt_n) + J_g(y[n])^T (lam[n+1] * dW_n) + grad_y[n]
+ *     g_theta_f += (df/dtheta)(y[n])^T (lam[n+1] dt_n),  g_theta_g += (dg/dtheta)(y[n])^T (lam[n+1] * dW_n)
+ * with y[n] read from the stored forward solution.  PARITY UNPINNED; checked against fp64 autograd in tests.
+ * y_all, grad_y: [B,T,D] (the fixed solver's layout); dW [T-1,B,D]; out_gf / out_gg: parameter gradients of
+ * drift / diffusion (gW1,gb1,gW2,gb2), summed over trajectories in fp64; out_adj_y0 [B,D] optional. */
+int orc_sde_mlp_adjoint(const orc_mlp_t *drift, const orc_mlp_t *diffusion, const float *t_span, int32_t T,
+                        const float *y_all, const float *grad_y, int64_t B, const float *dW, float *out_gf,
+                        float *out_gg, float *out_adj_y0, int32_t nthreads) {
+  const int D = drift->d;
+  if (diffusion->d != D || D > ORC_MAX_D || drift->h > ORC_MAX_H || diffusion->h > ORC_MAX_H || T < 1)
+    return ORC_BAD_ARG;
+  const int64_t Pf = adj_nparams(drift), Pg = adj_nparams(diffusion);
+  double *accf = (double *)calloc((size_t)(Pf + Pg), sizeof(double));
+  if (!accf) return ORC_BAD_ARG;
+  double *accg = accf + Pf;
+#ifdef _OPENMP
+  if (nthreads < 1) nthreads = omp_get_max_threads();
+#pragma omp parallel num_threads(nthreads)
+#endif
+  {
+    float *gf = (float *)calloc((size_t)(Pf + Pg), sizeof(float));
+    float *gg = gf + Pf;
+    double *lf = (double *)calloc((size_t)(Pf + Pg), sizeof(double));
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+    for (int64_t b = 0; b < B; ++b) {
+      float lam[ORC_MAX_D], cf[ORC_MAX_D], cg[ORC_MAX_D], fo[ORC_MAX_D], dyf[ORC_MAX_D], dyg[ORC_MAX_D];
+      const float *yb = y_all + (size_t)b * T * D, *gb = grad_y + (size_t)b * T * D;
+      memset(gf, 0, sizeof(float) * (size_t)(Pf + Pg)); /* per-trajectory partials in fp32, batch sum in fp64 */
+      for (int e = 0; e < D; ++e) lam[e] = gb[(size_t)(T - 1) * D + e];
+      for (int n = T - 2; n >= 0; --n) {
+        const float dt = t_span[n + 1] - t_span[n];
+        const float *w = dW + ((size_t)n * B + b) * D;
+        const float *y = yb + (size_t)n * D;
+        for (int e = 0; e < D; ++e) {
+          cf[e] = lam[e] * dt;
+          cg[e] = lam[e] * w[e];
+        }
+        orc_mlp_vjp(drift, y, cf, fo, dyf, gf, gf + (size_t)D * drift->h, gf + (size_t)D * drift->h + drift->h,
+                    gf + (size_t)2 * D * drift->h + drift->h);
+        orc_mlp_vjp(diffusion, y, cg, fo, dyg, gg, gg + (size_t)D * diffusion->h,
+                    gg + (size_t)D * diffusion->h + diffusion->h, gg + (size_t)2 * D * diffusion->h + diffusion->h);
+        for (int e = 0; e < D; ++e) lam[e] = ((lam[e] + dyf[e]) + dyg[e]) + gb[(size_t)n * D + e];
+      }
+      if (out_adj_y0)
+        for (int e = 0; e < D; ++e) out_adj_y0[b * D + e] = lam[e];
+      for (int64_t q = 0; q < Pf + Pg; ++q) lf[q] += (double)gf[q];
+    }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+    {
+      for (int64_t q = 0; q < Pf + Pg; ++q) accf[q] += lf[q];
+    }
+    free(gf);
+    free(lf);
+  }
+  for (int64_t q = 0; q < Pf; ++q) out_gf[q] = (float)accf[q];
+  for (int64_t q = 0; q < Pg; ++q) out_gg[q] = (float)accg[q];
+  free(accf);
+  return ORC_OK;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* History gather                                                                               */
 /* ------------------------------------------------------------------------------------------ */

@@ -146,6 +146,13 @@ int orc_sde_mlp(int32_t scheme, const orc_mlp_t *drift, const orc_mlp_t *diffusi
                 int64_t B, const float *t_span, int32_t T, const float *dW, float *out,
                 int32_t nthreads);
 
+/* sdeint_adjoint backward on the fixed grid = the exact adjoint of the Euler-Maruyama recursion (the reference's
+ * functional/sdeint_adjoint.py:57-230 is a non-functional copy of the ODE adjoint; see the .c file).  PARITY
+ * UNPINNED.  y_all, grad_y [B,T,D]; dW [T-1,B,D]; out_gf / out_gg (gW1,gb1,gW2,gb2) of drift / diffusion. */
+int orc_sde_mlp_adjoint(const orc_mlp_t *drift, const orc_mlp_t *diffusion, const float *t_span, int32_t T,
+                        const float *y_all, const float *grad_y, int64_t B, const float *dW, float *out_gf,
+                        float *out_gg, float *out_adj_y0, int32_t nthreads);
+
 /* HistoryIndex.forward (xde/base_dde.py:84-118): interp.evaluate(lags) and interp.derivative(lags)
  * (interpolation/interpolate_base.py:49-114, interpolate.py:6-204).
  * his: [R, Th, D] with R = prod(leading dims); his_span: [Th]; lags: [L]; out_val, out_der: [R,L,D]. */

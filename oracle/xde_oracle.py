@@ -235,6 +235,21 @@ def sde_mlp(scheme: str, drift: MLP, diffusion: MLP, y0, t_span, dW, nthreads=0)
     return out
 
 
+def sde_mlp_adjoint(drift: MLP, diffusion: MLP, t_span, y_all, grad_y, dW, nthreads=0):
+    """Exact adjoint of the Euler-Maruyama recursion -> (g_drift flat, g_diffusion flat, adj_y0 [B,D]);
+    y_all, grad_y [B,T,D], dW [T-1,B,D]."""
+    t_span, y_all, grad_y, dW = _f32(t_span), _f32(y_all), _f32(grad_y), _f32(dW)
+    B, T, D = y_all.shape
+    assert dW.shape == (T - 1, B, D) and grad_y.shape == y_all.shape
+    gf, gg = np.zeros(drift.n_params, np.float32), np.zeros(diffusion.n_params, np.float32)
+    a0 = np.zeros((B, D), np.float32)
+    f, g = drift.c(), diffusion.c()
+    rc = lib().orc_sde_mlp_adjoint(C.byref(f), C.byref(g), _p(t_span), C.c_int32(T), _p(y_all), _p(grad_y),
+                                   C.c_int64(B), _p(dW), _p(gf), _p(gg), _p(a0), C.c_int32(nthreads))
+    assert rc == 0, STATUS.get(rc, rc)
+    return gf, gg, a0
+
+
 def history_gather(kind: str, his, his_span, lags):
     """his [..., Th, D] -> (values, derivs) [..., L, D]"""
     his, his_span, lags = _f32(his), _f32(his_span), _f32(np.atleast_1d(lags))

@@ -6,7 +6,7 @@ top level, solver classes under .solver, problem wrappers under .xde, interpolan
 include/xde_b200.h; there is no CPU fallback."""
 from ._lib import UnsupportedFieldError, XdeError, launch_count, library_path  # noqa: F401
 from .field import MLPField  # noqa: F401
-from .functional import ddeint, ddeint_adjoint, odeint, odeint_adjoint, sdeint  # noqa: F401
+from .functional import ddeint, ddeint_adjoint, odeint, odeint_adjoint, sdeint, sdeint_adjoint  # noqa: F401
 from .solver import RK4, AdaptiveHeun, Bosh3, Dopri5, Dopri8, Euler, Fehlberg2, Midpoint  # noqa: F401
 from . import interpolation, solver, utils, xde  # noqa: F401
 

@@ -84,6 +84,9 @@ _EXPORTS = {
     "xde_sde_mlp_philox_f32": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(MlpFieldC), C.POINTER(MlpFieldC), C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int32, C.c_uint64, C.c_int64, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xde_sde_mlp_adjoint_f32": (C.c_int, [C.POINTER(MlpFieldC), C.POINTER(MlpFieldC), C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "xde_history_gather_f32": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xde_history_gather_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

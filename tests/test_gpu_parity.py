@@ -631,6 +631,69 @@ def test_sdeint_with_generated_increments(px, torch, oracle, d, h, B, math, sche
 
 
 # ------------------------------------------------------------------------------------------------
+# sdeint_adjoint: the exact adjoint of the Euler-Maruyama recursion (parity unpinned:
+# the reference's own backward is a placeholder -- checked against the oracle and against fp64 autograd)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,h,B,T", [(2, 50, 333, 9), (4, 32, 65, 17), (1, 16, 31, 5), (8, 64, 100, 6), (4, 21, 40, 4),
+                                     (2, 96, 7, 3)])
+def test_sde_adjoint_matches_oracle(px, torch, oracle, d, h, B, T):
+    from paddlexde_b200.functional.sdeint_adjoint import sde_adjoint_backward
+    from paddlexde_b200.utils.brownian import brownian_increments
+
+    f, of = both(px, oracle, fanin_weights(d, h, seed=2), "cube")
+    g, og = both(px, oracle, fanin_weights(d, h, seed=3), "square")
+    rng = np.random.default_rng(d * 100 + h)
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, T).astype(f32)
+    table = brownian_increments(77, t, B, d)
+    dW = table.cpu().numpy()
+    sol = px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler, options={"bm_increments": table})
+    ref = oracle.sde_mlp("em", of, og, y0, t, dW)
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    gy = (rng.standard_normal(ref.shape) / ref.size).astype(f32)
+    gf_r, gg_r, a0_r = oracle.sde_mlp_adjoint(of, og, t, ref, gy, dW)
+    gyd = torch.from_numpy(gy).cuda()
+    gf, gg, a0 = sde_adjoint_backward(f, g, t, sol, gyd, bm_increments=table, return_adj_y0=True)
+    assert np.array_equal(a0.cpu().numpy(), a0_r)                     # adjoint state: bit for bit
+    for got, want in ((gf, gf_r), (gg, gg_r)):                          # parameter gradients: summation order
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-6 * np.abs(want).max())
+    # increments regenerated inside the backward kernel == the supplied table
+    gf2, gg2, a02 = sde_adjoint_backward(f, g, t, sol, gyd, bm_seed=77, return_adj_y0=True)
+    assert torch.equal(a02, a0)
+    np.testing.assert_allclose(gf2.cpu().numpy(), gf.cpu().numpy(), rtol=1e-6, atol=1e-7 * np.abs(gf_r).max())
+    np.testing.assert_allclose(gg2.cpu().numpy(), gg.cpu().numpy(), rtol=1e-6, atol=1e-7 * np.abs(gg_r).max())
+
+
+def test_sdeint_adjoint_autograd_surface_is_the_true_gradient(px, torch, oracle):
+    """sdeint_adjoint(...).backward() against fp64 autograd through the same Euler-Maruyama recursion."""
+    d, h, B, T = 2, 50, 257, 9
+    wf, wg = fanin_weights(d, h, seed=2), fanin_weights(d, h, seed=3)
+    rng = np.random.default_rng(5)
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, T).astype(f32)
+    dW = (np.sqrt(1 / (T - 1)) * rng.standard_normal((T - 1, B, d))).astype(f32)
+    tw = [torch.tensor(a, device="cuda", requires_grad=True) for a in (*wf, *wg)]
+    f, g = px.MLPField(*tw[:4], pre="cube"), px.MLPField(*tw[4:], pre="square")
+    sol = px.sdeint_adjoint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler,
+                            options={"bm_increments": torch.from_numpy(dW).cuda()})
+    assert tuple(sol.shape) == (B, T, d)
+    (sol[:, -1].abs().mean() + 0.1 * (sol[:, T // 2] ** 2).mean()).backward()
+    P = [torch.tensor(np.asarray(a, np.float64), requires_grad=True) for a in (*wf, *wg)]
+    F = lambda y, w1, b1, w2, b2, p: torch.tanh((y ** p) @ w1 + b1) @ w2 + b2
+    y = torch.tensor(y0.astype(np.float64))
+    ys = [y]
+    for n in range(T - 1):
+        y = y + F(y, *P[:4], 3) * (float(t[n + 1]) - float(t[n])) + F(y, *P[4:], 2) * torch.tensor(dW[n].astype(np.float64))
+        ys.append(y)
+    (ys[-1].abs().mean() + 0.1 * (ys[T // 2] ** 2).mean()).backward()
+    for a, b in zip(tw, P):
+        ref = b.grad.numpy()
+        np.testing.assert_allclose(a.grad.cpu().numpy(), ref, rtol=2e-4, atol=2e-5 * np.abs(ref).max())
+    with pytest.raises(ValueError):
+        px.sdeint_adjoint(f, g, torch.from_numpy(y0).cuda(), t, px.Euler, options={"bm_seed": 1})
+
+
+# ------------------------------------------------------------------------------------------------
 # large states: the register-tiled FFMA2 kernels (cfg3: 64-256-64 RK4, cfg4: 32-64-32 Euler-Maruyama)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("d,h,B", [(64, 256, 100), (64, 128, 33), (64, 64, 130), (32, 256, 31), (32, 128, 65),
