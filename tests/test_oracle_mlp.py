@@ -192,3 +192,33 @@ def test_philox_known_answers_and_increment_layout():
     assert not np.array_equal(brownian_increments(8, t, 64, 6), a)
     big = brownian_increments(3, np.array([0, 0.25], np.float32), 40000, 8)
     assert abs(big.mean()) < 3e-3 and abs(big.var() - 0.25) < 3e-3
+
+
+def test_sde_adjoint_oracle_is_the_gradient_of_the_em_recursion(oracle):
+    """orc_sde_mlp_adjoint (parity unpinned: the reference's sdeint_adjoint backward is a placeholder) against
+    fp64 autograd through the same Euler-Maruyama recursion."""
+    import torch
+    from tests.problems import fanin_weights
+
+    d, h, B, T = 4, 33, 29, 9
+    wf, wg = fanin_weights(d, h, seed=2), fanin_weights(d, h, seed=3)
+    of, og = oracle.MLP(*wf, pre="cube"), oracle.MLP(*wg, pre="square")
+    rng = np.random.default_rng(0)
+    y0 = rng.uniform(-1, 1, (B, d)).astype(np.float32)
+    t = np.linspace(0, 1, T).astype(np.float32)
+    dW = (np.sqrt(1 / (T - 1)) * rng.standard_normal((T - 1, B, d))).astype(np.float32)
+    sol = oracle.sde_mlp("em", of, og, y0, t, dW)
+    gy = (rng.standard_normal(sol.shape) / sol.size).astype(np.float32)
+    gf, gg, a0 = oracle.sde_mlp_adjoint(of, og, t, sol, gy, dW)
+    P = [torch.tensor(np.asarray(a, np.float64), requires_grad=True) for a in (*wf, *wg)]
+    F = lambda y, w1, b1, w2, b2, p: torch.tanh((y ** p) @ w1 + b1) @ w2 + b2
+    y = torch.tensor(y0.astype(np.float64), requires_grad=True)
+    ys = [y]
+    for n in range(T - 1):
+        y = y + F(y, *P[:4], 3) * (float(t[n + 1]) - float(t[n])) + F(y, *P[4:], 2) * torch.tensor(dW[n].astype(np.float64))
+        ys.append(y)
+    (torch.stack(ys, 1) * torch.tensor(gy.astype(np.float64))).sum().backward()
+    ref_f = np.concatenate([p.grad.numpy().ravel() for p in P[:4]])
+    ref_g = np.concatenate([p.grad.numpy().ravel() for p in P[4:]])
+    for got, want in ((gf, ref_f), (gg, ref_g), (a0, ys[0].grad.numpy())):
+        assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
