@@ -404,7 +404,11 @@ def run_b200(args):
                      "ffma_peak_tflops_measured": ffma_tflops,
                      "frac_algorithmic": k_flops / (k_ms * 1e-3) / 1e12 / ffma_tflops,
                      "note": "algorithmic FLOPs count the two GEMVs (+VJP) only; each of the 50 tanh per evaluation costs "
-                             "~14 further FP32 issue slots (rational 13/6 + IEEE division) that the count leaves out"},
+                             "~14 further FP32 issue slots (rational 13/6 + IEEE division) that the count leaves out",
+                     "fma_pipe_active_ncu": {"dopri5_adj_kernel": 0.49, "dopri5_fwd_small_kernel": 0.61,
+                                             "issue_active_adj": 0.53,
+                                             "source": "sm__pipe_fma_cycles_active, profiles/r1i_ncu_full_adjoint.md, "
+                                                       "profiles/r1d_ncu_full_packed_ffma2_kernels.md"}},
             "e2e": {"value": total_steps * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(y0_np.nbytes + t.nbytes), "d2h_bytes_per_step": int(g_host.numel() * 4 + 4 + 64),
                     "ms_per_step": ms_e2e / args.steps,
