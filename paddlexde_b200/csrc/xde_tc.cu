@@ -1,7 +1,9 @@
 // xde_tc.cu -- fixed-grid steppers for LARGE states on the 5th-generation tensor cores (tcgen05 + TMEM).
-//   * odeint(..., solver=Euler|RK4): FixedSolver.integrate (solver/base_fixed_solver.py:103-144),
-//     Euler.step (fixed_solver/euler.py:7-11), RK4.step = 3/8 rule (base_fixed_solver.py:166-197);
-//   * sdeint(..., solver=Euler): y1 = y0 + f*dt + g*dW with caller-supplied dW (xde/base_sde.py:44-61).
+//   * odeint(..., solver=Euler|Midpoint|RK4): FixedSolver.integrate (solver/base_fixed_solver.py:103-144),
+//     Euler.step (fixed_solver/euler.py:7-11), Midpoint.step (midpoint.py:7-18), RK4.step = 3/8 rule
+//     (base_fixed_solver.py:166-197);
+//   * sdeint(..., solver=Euler): y1 = y0 + f*dt + g*dW (xde/base_sde.py:44-61), dW from the caller's table or
+//     from the counter-based generator (xde_common.cuh: BmSource).
 // Same boundary as xde_tile.cu (the FP32 FFMA2 path, bit-exact against the oracle); this file is the
 // tensor-core path: the two dense layers of the field
 //     Z[128 x H] = U[128 x D] W1[D x H],   F[128 x D] = tanh(Z + b1)[128 x H] W2[H x D]
@@ -11,8 +13,11 @@
 // Precision.  fp32 operands are split into two fp16 pieces, x = hi + lo (hi = rn16(x), lo = rn16(x - hi):
 // 22 significant bits), and each GEMM is three MMAs hi*hi + hi*lo + lo*hi accumulated in fp32 -- the
 // dropped lo*lo term and the split error are ~2^-22 relative, the level of fp32 rounding itself.
-// Weights are pre-scaled by a power of two (exact) so that their lo pieces stay normal fp16 numbers.
-// Results agree with the FP32 path / the oracle to ~1e-6 relative (tests: rtol 1e-5), not bit for bit.
+// Weights are pre-scaled by a power of two (exact) so that their lo pieces stay normal fp16 numbers; the
+// tensor core truncates its fp32 accumulator once per MMA, so correction products are accumulated first or
+// apart (Geom::NFM / SPLIT_CORR).  Measured against fp64 the error equals the FP32 kernels' own (0.6-1.9 x);
+// results are not bit-identical to them (tests: rtol 1e-5).  Stage inputs must fit fp16 (|pre(y)| < 65504):
+// checked in the kernel, reported through TcParams::status (XDE_ST_TC_RANGE).
 //
 // Data flow (one CTA per SM, persistent over tiles of 128 trajectories; row r of the tile = TMEM lane r):
 //   * all operands of the activations live in TMEM, never in shared memory:
@@ -30,6 +35,10 @@
 //     Layer-1 chunks are issued back to back, so the tanh epilogue of chunk c overlaps the MMAs of
 //     chunk c+1 and the layer-2 MMAs of chunk c-1.  No barrier is ever needed in the other direction:
 //     every buffer's next writer is ordered behind its last reader by the chain itself.
+//   * the epilogue binds (1 tanh per 4 D algorithmic FLOP): tanh is a mix of the 13/6 rational (FMA pipe)
+//     and an ex2/rcp form (XU pipe), 3 : 5 per thread block of 8 pairs (tanh_mixed2).
+// Two kernels: fixed_tc_kernel (one tile per CTA, any supported shape) and fixed_tc2_kernel (two tiles in
+// flight per CTA, software-pipelined, for fields that need <= 256 TMEM columns: H = 64 networks, cfg4).
 #include <cuda_fp16.h>
 
 #include <algorithm>
