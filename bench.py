@@ -422,7 +422,7 @@ def run_b200(args):
             # because the fused kernel keeps (y, a) in registers across the attempts of a segment.
             out["roofline"]["traffic"] = 175887616
             out["roofline"]["traffic_source"] = "ncu --set full, profiles/r1i_ncu_full_adjoint.md"
-        if not args.no_cpu and world >= 1:
+        if not args.no_cpu and world == 1:  # the CPU leg is timed at N = 1 only (rank 0)
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         if world == 1 and not args.no_secondary:
             out["secondary"] = secondary_configs()

@@ -32,11 +32,20 @@
 //     once select_initial_step has produced dt.
 // Supported norm: the adjoint seminorm (functional/odeint_adjoint.py:301-309) -- with one
 // controller per trajectory g_theta is a per-trajectory partial integral.
+#include <type_traits>
+
 #include "xde_common.cuh"
+
+#ifndef XDE_ADJ_U
+#define XDE_ADJ_U 2  // hidden-unit pairs evaluated together (independent tanh chains in flight per lane)
+#endif
+#ifndef XDE_ADJ_CTAS
+#define XDE_ADJ_CTAS 4  // resident CTAs per SM the register budget is sized for (4: 160 registers, no spills with U = 2)
+#endif
 
 namespace xde {
 
-constexpr int kAdjThreads = 96;  // 3 warps: 5 CTAs (15 warps) per SM fit the per-warp tiles for H = 50
+constexpr int kAdjThreads = 96;  // 3 warps; the per-warp tiles for H = 50 allow 5 CTAs per SM, the registers 4 (XDE_ADJ_CTAS)
 constexpr int kAdjWarps = kAdjThreads / 32;
 constexpr int kTileStride = 33;  // float4 elements per hidden-unit-pair row (32 lanes + 1 pad)
 
@@ -81,7 +90,7 @@ struct AdjSmem {
 };
 
 template <int D, int HPL, int PRE>
-__global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? 5 : 1) dopri5_adj_kernel(const AdjParams p) {
+__global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? XDE_ADJ_CTAS : 1) dopri5_adj_kernel(const AdjParams p) {
   constexpr int C = 2 * D;                 // state components per trajectory: y then a
   constexpr int NTP = (2 * D + 1) * HPL;   // lane-private theta accumulator PAIRS (HPL unit pairs per lane)
   constexpr int NTH = 2 * NTP;
@@ -318,30 +327,52 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? 5 : 1) dop
         accf[k] = pk1(0.0f);
         pdu[k] = pk1(0.0f);
       }
-#pragma unroll 2
-      for (int jp = 0; jp < NP; ++jp) {
-        f32x2 w1p[D], b1p, w2p[D];
-        read_pair_rec<D>(sw, jp, w1p, b1p, w2p);
-        f32x2 z = first_layer_seed<D>(u[0], w1p[0]);
+      // U hidden-unit pairs per iteration: all weight records are read before and all tile columns are
+      // written after the arithmetic, so no shared-memory store sits between two pairs' chains (ptxas
+      // cannot prove that the tile and the weight records do not alias and would serialise the pairs);
+      // the U rational-tanh chains are independent and interleave.  The second-layer / VJP chains are
+      // advanced in pair order: per value the arithmetic is unchanged.
+      auto eval_pairs = [&](int jp0, auto ucount) {
+        constexpr int U = decltype(ucount)::value;
+        f32x2 w1p[U][D], b1p[U], w2p[U][D], h[U], dz[U];
 #pragma unroll
-        for (int k = 1; k < D; ++k) z = fma2(pk1(u[k]), w1p[k], z);
-        const f32x2 h = tanh_rat2(add2(z, b1p));
-        f32x2 dh = mul2(pk1(yin[D]), w2p[0]);
+        for (int i = 0; i < U; ++i) read_pair_rec<D>(sw, jp0 + i, w1p[i], b1p[i], w2p[i]);
 #pragma unroll
-        for (int d = 1; d < D; ++d) dh = fma2(pk1(yin[D + d]), w2p[d], dh);
-        const f32x2 sg = one_minus_sq2(h);
-        const f32x2 dz = mul2(dh, sg);
+        for (int i = 0; i < U; ++i) {
+          f32x2 z = first_layer_seed<D>(u[0], w1p[i][0]);
 #pragma unroll
-        for (int d = 0; d < D; ++d) accf[d] = fma2(h, w2p[d], accf[d]);
-#pragma unroll
-        for (int k = 0; k < D; ++k) pdu[k] = fma2(dz, w1p[k], pdu[k]);
-        if (wr) {
-          float h0, h1, z0, z1;
-          upk(h, h0, h1);
-          upk(dz, z0, z1);
-          tile[jp * kTileStride + lane] = make_float4(h0, h1, z0, z1);
+          for (int k = 1; k < D; ++k) z = fma2(pk1(u[k]), w1p[i][k], z);
+          h[i] = tanh_rat2(add2(z, b1p[i]));
         }
-      }
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          f32x2 dh = mul2(pk1(yin[D]), w2p[i][0]);
+#pragma unroll
+          for (int d = 1; d < D; ++d) dh = fma2(pk1(yin[D + d]), w2p[i][d], dh);
+          dz[i] = mul2(dh, one_minus_sq2(h[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) accf[d] = fma2(h[i], w2p[i][d], accf[d]);
+#pragma unroll
+          for (int k = 0; k < D; ++k) pdu[k] = fma2(dz[i], w1p[i][k], pdu[k]);
+        }
+        if (wr) {
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            float h0, h1, z0, z1;
+            upk(h[i], h0, h1);
+            upk(dz[i], z0, z1);
+            tile[(jp0 + i) * kTileStride + lane] = make_float4(h0, h1, z0, z1);
+          }
+        }
+      };
+      int jp = 0;
+#pragma unroll 1
+      for (; jp + XDE_ADJ_U <= NP; jp += XDE_ADJ_U) eval_pairs(jp, std::integral_constant<int, XDE_ADJ_U>());
+#pragma unroll 1
+      for (; jp < NP; ++jp) eval_pairs(jp, std::integral_constant<int, 1>());
       // solver-time dynamics: dy/ds = tsign * f ; da/ds = -tsign * vjp_y(a)
 #pragma unroll
       for (int d = 0; d < D; ++d) {
