@@ -111,6 +111,9 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? XDE_ADJ_CT
   float4 *tile = reinterpret_cast<float4 *>(wbase);                    // [H/2][33] of (h_j, h_j+1, dz_j, dz_j+1)
   const int NP = SmallRec<D>::pairs(H);
   float *coef = wbase + AdjSmem<D, HPL>::tile_floats(H);               // [32][CST]
+  const float4 *trow[HPL];  // fold phase: the tile row(s) of this lane's hidden-unit pair(s), clamped to the last row
+#pragma unroll
+  for (int q = 0; q < HPL; ++q) trow[q] = tile + min(lane + 32 * q, NP - 1) * kTileStride;
 
   load_small_field<D>(sw, p.field);
   // direction of the backward sweep: t_span increasing (usual) -> integrate s = -t
@@ -211,14 +214,14 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? XDE_ADJ_CT
       sy += (double)(v[e] * v[e]);
       sa += (double)(v[D + e] * v[D + e]);
     }
-    // mean over D: for a power of two the reciprocal multiply is the exact quotient (no fp64 division)
+    // max(rms(y), rms(a)) = rms of the larger sum: x -> (float)sqrt(x / D) is monotone, so it commutes with
+    // the max and ONE fp64 square root serves both parts (a NaN sum fails both comparisons exactly as a NaN
+    // rms failed `>` before).  Mean over D: for a power of two the reciprocal multiply is the exact quotient.
     constexpr bool kPow2 = (D & (D - 1)) == 0;
-    const float ny = kPow2 ? (float)sqrt(sy * (1.0 / D)) : rms_from_sumsq(sy, (double)D);
-    const float na = kPow2 ? (float)sqrt(sa * (1.0 / D)) : rms_from_sumsq(sa, (double)D);
-    float best = 0.0f;
-    if (ny > best) best = ny;
-    if (na > best) best = na;
-    return best;
+    double m = 0.0;
+    if (sy > m) m = sy;
+    if (sa > m) m = sa;
+    return kPow2 ? (float)sqrt(m * (1.0 / D)) : rms_from_sumsq(m, (double)D);
   };
   auto plan_attempt = [&]() {  // (t0, dt, te) -> does the attempt reach the segment end, and where
     const float t1n = t0 + dt;
@@ -597,17 +600,18 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? XDE_ADJ_CT
           }
 #pragma unroll
           for (int q = 0; q < HPL; ++q) {
-            const int jp = lane + 32 * q;
-            if (jp < NP) {
-              const float4 hv = tile[jp * kTileStride + b];
-              const f32x2 hp = pk(hv.x, hv.y), dzp = pk(hv.z, hv.w);
+            // no `pair < NP` test: a lane without a hidden-unit pair folds a copy of the last row into
+            // accumulators the epilogue never reads, so the 32 columns are ONE basic block and ptxas can
+            // keep the loads of several columns in flight (with the branch every column exposed a full
+            // shared-memory round trip)
+            const float4 hv = trow[q][b];
+            const f32x2 hp = pk(hv.x, hv.y), dzp = pk(hv.z, hv.w);
 #pragma unroll
-              for (int k = 0; k < D; ++k) Tt[q * (2 * D + 1) + k] = fma2(pk1(cb[k]), dzp, Tt[q * (2 * D + 1) + k]);
-              Tt[q * (2 * D + 1) + D] = fma2(pk1(cb[D]), dzp, Tt[q * (2 * D + 1) + D]);
+            for (int k = 0; k < D; ++k) Tt[q * (2 * D + 1) + k] = fma2(pk1(cb[k]), dzp, Tt[q * (2 * D + 1) + k]);
+            Tt[q * (2 * D + 1) + D] = fma2(pk1(cb[D]), dzp, Tt[q * (2 * D + 1) + D]);
 #pragma unroll
-              for (int d = 0; d < D; ++d)
-                Tt[q * (2 * D + 1) + D + 1 + d] = fma2(pk1(cb[D + 1 + d]), hp, Tt[q * (2 * D + 1) + D + 1 + d]);
-            }
+            for (int d = 0; d < D; ++d)
+              Tt[q * (2 * D + 1) + D + 1 + d] = fma2(pk1(cb[D + 1 + d]), hp, Tt[q * (2 * D + 1) + D + 1 + d]);
           }
         };
         // Fast path: every column is finite, so columns with zero weight contribute exactly +0 and all 32
