@@ -230,8 +230,9 @@ def secondary_configs():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_configs as bc
         res = []
-        for fn, kw in ((bc.cfg3, {"math": "tensor"}), (bc.cfg3, {"math": "fp32"}), (bc.cfg4, {"math": "tensor"}),
-                       (bc.cfg4, {"math": "fp32"}), (bc.cfg4, {"math": "tensor", "generated": True})):
+        for fn, kw in ((bc.cfg2_batch, {"norm": "mixed"}), (bc.cfg3, {"math": "tensor"}), (bc.cfg3, {"math": "fp32"}),
+                       (bc.cfg4, {"math": "tensor"}), (bc.cfg4, {"math": "fp32"}),
+                       (bc.cfg4, {"math": "tensor", "generated": True})):
             res.append(fn(**kw))
             torch.cuda.empty_cache()
         return res
@@ -405,10 +406,13 @@ def run_b200(args):
                      "frac_algorithmic": k_flops / (k_ms * 1e-3) / 1e12 / ffma_tflops,
                      "note": "algorithmic FLOPs count the two GEMVs (+VJP) only; each of the 50 tanh per evaluation costs "
                              "~14 further FP32 issue slots (rational 13/6 + IEEE division) that the count leaves out",
-                     "fma_pipe_active_ncu": {"dopri5_adj_kernel": 0.49, "dopri5_fwd_small_kernel": 0.61,
-                                             "issue_active_adj": 0.53,
-                                             "source": "sm__pipe_fma_cycles_active, profiles/r1i_ncu_full_adjoint.md, "
-                                                       "profiles/r1d_ncu_full_packed_ffma2_kernels.md"}},
+                     "fma_pipe_active_ncu": {"dopri5_adj_kernel": 0.54, "dopri5_fwd_small_kernel": 0.61,
+                                             "issue_active_adj": 0.57,
+                                             "source": "sm__pipe_fma_cycles_active, profiles/r1n_ncu_full_adjoint.md, "
+                                                       "profiles/r1d_ncu_full_packed_ffma2_kernels.md",
+                                             "note": "a packed FFMA2 holds the FMA pipe for 2 cycles while ALU/XU "
+                                                     "instructions co-issue (profiles/r1n_probe_issue.txt): the FMA "
+                                                     "pipe, not the issue slot, is the ceiling of these kernels"}},
             "e2e": {"value": total_steps * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(y0_np.nbytes + t.nbytes), "d2h_bytes_per_step": int(g_host.numel() * 4 + 4 + 64),
                     "ms_per_step": ms_e2e / args.steps,
@@ -418,10 +422,10 @@ def run_b200(args):
         }
         if args.batch == 1 << 20:
             # dram__bytes_read.sum + dram__bytes_write.sum of dopri5_adj_kernel, one launch at this batch:
-            # profiles/r1i_ncu_full_adjoint.md (170.96 MB + 4.92 MB).  Below the algorithmic 64 B/attempt
+            # profiles/r1n_ncu_full_adjoint.md (169.54 MB + 4.55 MB).  Below the algorithmic 64 B/attempt
             # because the fused kernel keeps (y, a) in registers across the attempts of a segment.
-            out["roofline"]["traffic"] = 175887616
-            out["roofline"]["traffic_source"] = "ncu --set full, profiles/r1i_ncu_full_adjoint.md"
+            out["roofline"]["traffic"] = 174085888
+            out["roofline"]["traffic_source"] = "ncu --set full, profiles/r1n_ncu_full_adjoint.md"
         if not args.no_cpu and world == 1:  # the CPU leg is timed at N = 1 only (rank 0)
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         if world == 1 and not args.no_secondary:

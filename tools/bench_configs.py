@@ -88,6 +88,39 @@ def cfg5(Bh=1024, kind="cubic"):
             "note": "his is 1.06 GB at B=1024 but only 12 of 288 time rows are touched: 20 B/element algorithmic"}
 
 
+def cfg2_batch(B=1 << 20, norm="mixed"):
+    """cfg2 with the REFERENCE-FAITHFUL controller: one global RMS norm and dt for the whole batch
+    (utils/ode_utils.py:8-9), adjoint with the reference's default mixed norm or the seminorm."""
+    from tests.problems import cfg2_tspan, cfg2_y0, spiral_weights
+    tw = [torch.tensor(a, device="cuda", requires_grad=True) for a in spiral_weights()]
+    field = px.MLPField(*tw, pre="cube")
+    y0 = torch.from_numpy(cfg2_y0(B)).cuda()
+    t = torch.from_numpy(cfg2_tspan(10))
+    opts = {"controller": "batch"}
+    aopts = {"controller": "batch"} if norm == "mixed" else {"controller": "batch", "norm": "seminorm"}
+    st = {}
+
+    def fwd():
+        st["sol"] = px.odeint_adjoint(field, y0, t, solver=px.Dopri5, options=opts, adjoint_options=aopts)
+
+    def bwd():
+        for p in tw:
+            p.grad = None
+        fwd()
+        st["sol"][-1].abs().mean().backward()
+
+    ms_f = timeit(fwd)
+    ms = timeit(bwd)
+    h = px.odeint_adjoint.last
+    att_f = int(h["fwd_solver"].read_stats().n_attempts)
+    att_b = int(h["bwd_stats"].read().n_attempts)
+    return {"config": f"cfg2 dopri5 fwd+adjoint, controller=batch (reference-faithful global dt), adjoint norm {norm}",
+            "B": B, "ms_fwd": ms_f, "ms_fwd_plus_adjoint": ms, "trajectory_steps": att_f + att_b,
+            "traj_steps_per_s": (att_f + att_b) / ms * 1e3,
+            "note": "one cooperative launch per solve, ~2 grid.sync per attempt; parity kernels (bit-exact dt / ratio / "
+                    "accept sequence vs the oracle's batch run), not the throughput path"}
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg3", "cfg4", "cfg5"]
     for w in which:
@@ -97,5 +130,8 @@ if __name__ == "__main__":
             if w == "cfg4":
                 print(json.dumps(cfg4(math="tensor", generated=True)), flush=True)
                 print(json.dumps(cfg4(B=1 << 22, math="tensor", generated=True)), flush=True)
+        elif w == "cfg2_batch":
+            for norm in ("mixed", "seminorm"):
+                print(json.dumps(cfg2_batch(norm=norm)), flush=True)
         else:
             print(json.dumps(globals()[w]()), flush=True)
