@@ -382,6 +382,9 @@ static int dispatch_pre(const FwdParams &p, cudaStream_t s) {
 int dopri5_fwd_batch(const xde_mlp_field_t *field, const float *y0, long long B, const float *t_span, int T,
                      const xde_ctrl_opts_t *opts, float *out, xde_stats_t *stats, const xde_attempt_log_t *log,
                      cudaStream_t s);  // xde_dopri5_batch.cu
+int dopri5_fwd_tile(const xde_mlp_field_t *field, const float *y0, long long B, const float *t_span, int T,
+                    const xde_ctrl_opts_t *opts, float *out, xde_stats_t *stats, const xde_attempt_log_t *log,
+                    cudaStream_t s);  // xde_tile_adaptive.cu (D >= 16)
 
 }  // namespace xde
 
@@ -421,7 +424,8 @@ extern "C" XDE_EXPORT int xde_dopri5_mlp_f32(const xde_mlp_field_t *field, const
     case 4: return dispatch_pre<4>(p, s);
     case 8: return dispatch_pre<8>(p, s);
     default:
-      set_last_error("dopri5 forward: state dim D=%d has no fused kernel (supported: 1,2,3,4,8)", field->d);
+      if (field->d >= 16) return dopri5_fwd_tile(field, y0, B, t_span, T, opts, out, stats, log, s);
+      set_last_error("dopri5 forward: state dim D=%d has no fused kernel (supported: 1,2,3,4,8 and 16,32,64)", field->d);
       return XDE_E_UNSUPPORTED_FIELD;
   }
 }

@@ -136,6 +136,69 @@ def test_dopri5_status_words(px, torch, oracle):
         solve_fwd(px, torch, f5, np.zeros((4, 5), f32), cfg2_tspan(4))
 
 
+# ------------------------------------------------------------------------------------------------
+# dopri5 forward, large states (xde_tile_adaptive.cu): register-tiled field, one controller per trajectory
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,h,pre,B", [(64, 256, "id", 100), (64, 128, "cube", 77), (32, 256, "id", 65),
+                                        (32, 128, "square", 130), (32, 64, "id", 64), (16, 64, "cube", 257)])
+def test_dopri5_large_state_bit_exact_and_step_sequence(px, torch, oracle, d, h, pre, B):
+    """Every tile geometry, ragged tiles (B not a multiple of TM), outputs by dense interpolation, identical
+    accept / reject sequences (dt, ratio) per trajectory."""
+    w = [1.5 * a for a in fanin_weights(d, h, seed=d + h)]
+    field, om = both(px, oracle, w, pre)
+    y0 = np.random.default_rng(d).uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1.5, 6).astype(f32)
+    kw = dict(rtol=1e-6, atol=1e-8)
+    sol, s = solve_fwd(px, torch, field, y0, t, log_attempts=512, **kw)
+    ref, st, _, rc = oracle.dopri5_mlp(om, y0, t, **kw)
+    assert rc == 0
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    assert s.stats.n_attempts == int(st.n_attempts.sum())
+    assert s.stats.n_accepted == int(st.n_accepted.sum())
+    assert s.stats.nfe == int(st.nfe.sum())
+    rec, cnt = s.attempt_log.read()
+    for b in (0, 1, B // 2, B - 1):
+        _, _, lg, _ = oracle.dopri5_mlp(om, y0, t, log_traj=b, **kw)
+        assert cnt[b] == len(lg)
+        r = rec[b, :cnt[b]]
+        assert np.array_equal(r.accepted, lg.accepted)
+        assert np.array_equal(r.dt, lg.dt) and np.array_equal(r.t0, lg.t0)
+        assert np.array_equal(r.ratio, lg.ratio)
+
+
+def test_dopri5_large_state_rejections_reverse_options_status(px, torch, oracle):
+    d, h = 32, 64
+    w = [4.0 * a for a in fanin_weights(d, h, seed=9)]
+    field, om = both(px, oracle, w, "id")
+    y0 = np.random.default_rng(3).uniform(-1, 1, (97, d)).astype(f32)
+    t = np.linspace(0, 2, 5).astype(f32)
+    kw = dict(rtol=1e-5, atol=1e-7)
+    sol, s = solve_fwd(px, torch, field, y0, t, **kw)
+    ref, st, _, _ = oracle.dopri5_mlp(om, y0, t, **kw)
+    assert (st.n_attempts > st.n_accepted).any(), "the case must exercise rejections"
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    assert s.stats.n_attempts == int(st.n_attempts.sum()) and s.stats.n_accepted == int(st.n_accepted.sum())
+    tr = t[::-1].copy()  # decreasing t_span (repair R5)
+    sol, _ = solve_fwd(px, torch, field, y0, tr, **kw)
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0, tr, **kw)
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    kw = dict(rtol=1e-5, atol=1e-7, first_step=0.01, max_step=0.2, safety=0.8, ifactor=5.0, dfactor=0.3)
+    sol, _ = solve_fwd(px, torch, field, y0, t, **kw)
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0, t, **kw)
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    # status words: max_num_steps, a non-finite trajectory leaves its tile mates untouched
+    with pytest.raises(AssertionError, match="max_num_steps"):
+        solve_fwd(px, torch, field, y0, t, max_num_steps=2, rtol=1e-7, atol=1e-9)
+    bad = y0.copy()
+    bad[5, 3] = np.inf
+    sol, s = solve_fwd(px, torch, field, bad, t, check_status=False, rtol=1e-5, atol=1e-7)
+    ref, _, _, rc = oracle.dopri5_mlp(om, bad, t, rtol=1e-5, atol=1e-7)
+    assert rc != 0 and s.read_stats().status == rc
+    keep = np.arange(97) != 5
+    assert np.array_equal(sol.cpu().numpy()[:, keep], ref[:, keep])
+    assert np.isnan(sol.cpu().numpy()[1:, 5]).all()
+
+
 @pytest.mark.parametrize("B", [1, 20, 1000, 40000])
 def test_dopri5_batch_controller_reference_faithful(px, torch, oracle, B):
     """controller="batch": the reference's single global RMS norm and dt (utils/ode_utils.py:8-9).  The
