@@ -11,7 +11,8 @@ the attempt counts are read from the device-side counters of the kernels.
   value  inputs resident in HBM, kernels only (+ the loss-gradient fill and, for N > 1, the NCCL
          all-reduce of the 252 parameter gradients); CUDA events, max over ranks.
   e2e    through the public API (paddlexde_b200.odeint_adjoint + .backward()) from pinned HOST
-         buffers: H2D of y0, forward, loss, backward, D2H of loss + parameter gradients, every step.
+         buffers: H2D of y0 (double-buffered on a copy stream: the copy for the next step overlaps this
+         step's solve), forward, loss, backward, D2H of loss + parameter gradients, every step.
   roofline       dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json), with the
                  FP32-pipe figures that actually bound this field (D=2, H=50) beside it.
   cpu_baseline   the CPU oracle (port of the reference algorithm; Paddle is not installable) on all
@@ -329,27 +330,42 @@ def run_b200(args):
     tw = [torch.tensor(a, device=dev, requires_grad=True) for a in w]
     field_e = px.MLPField(*tw, pre="cube")
     y0_pin = torch.from_numpy(y0_np).pin_memory()
-    y0_buf = torch.empty_like(y0)
     t_host = torch.from_numpy(t)
+    # input pipeline: every step's y0 is copied host -> device inside the timed region, on a copy stream, into the
+    # buffer the previous step is not using, so the copy of step n+1 overlaps the solve of step n
+    copy_stream = torch.cuda.Stream(device=dev)
+    y0_bufs = [torch.empty_like(y0), torch.empty_like(y0)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
+    def h2d(i):
+        with torch.cuda.stream(copy_stream):
+            y0_bufs[i % 2].copy_(y0_pin, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_step(i, last):
         flush.zero_()
         for p in tw:
             p.grad = None
-        y0_buf.copy_(y0_pin, non_blocking=True)
-        sol = px.odeint_adjoint(field_e, y0_buf, t_host, solver=px.Dopri5)
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        if not last:
+            h2d(i + 1)  # the other buffer: its last reader (step i-1) finished before that step's loss.item()
+        sol = px.odeint_adjoint(field_e, y0_bufs[i % 2], t_host, solver=px.Dopri5)
         loss = sol[-1].abs().mean()
         loss.backward()
         flat = reduce_grads(torch.cat([p.grad.reshape(-1) for p in tw]))
         return float(loss.item()), flat.cpu()
 
-    for _ in range(5):  # the first backward passes through autograd grow the allocator pools
-        e2e_step()
+    def e2e_run(n):
+        h2d(0)
+        for i in range(n):
+            out = e2e_step(i, i == n - 1)
+        return out
+
+    e2e_run(5)  # the first backward passes through autograd grow the allocator pools
     barrier()
     e0, e1 = ev(), ev()
     e0.record()
-    for _ in range(args.steps):
-        loss_v, g_host = e2e_step()
+    loss_v, g_host = e2e_run(args.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -416,7 +432,9 @@ def run_b200(args):
             "e2e": {"value": total_steps * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(y0_np.nbytes + t.nbytes), "d2h_bytes_per_step": int(g_host.numel() * 4 + 4 + 64),
                     "ms_per_step": ms_e2e / args.steps,
-                    "api": "paddlexde_b200.odeint_adjoint(field, y0, t, solver=Dopri5); loss.backward()"},
+                    "api": "paddlexde_b200.odeint_adjoint(field, y0, t, solver=Dopri5); loss.backward()",
+                    "input_pipeline": "one H2D copy of y0 per step from pinned memory on a copy stream, double-buffered: "
+                                      "the copy for step n+1 overlaps the solve of step n (all inside the timed region)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
