@@ -21,8 +21,14 @@
 //     (5 packed FFMA2 per pair and trajectory).  No shuffles, no atomics in the loop; tile rows are
 //     padded to 33 so both phases are bank-conflict free.
 //   * The field + VJP is evaluated two hidden units at a time with Blackwell's packed fp32
-//     instructions (FFMA2/FMUL2/FADD2, xde_common.cuh): the kernel is issue-bound, and a packed
-//     instruction does two IEEE operations per issue slot.
+//     instructions (FFMA2/FMUL2/FADD2, xde_common.cuh), and XDE_ADJ_U such pairs per loop trip: the
+//     weight records of the trip are read first and the tile columns stored last, so that no
+//     shared-memory store (a possible alias of the next record, as far as ptxas can tell) separates
+//     the independent rational-tanh chains.  A packed instruction holds the FMA pipe for 2 cycles
+//     while ALU / XU instructions co-issue (tools/probe_issue.cu): the FMA pipe is the ceiling.
+//   * The fold is branch-free: lanes without a hidden-unit pair (H/2 < 32) fold a copy of the last
+//     tile row into accumulators nobody reads, so the 32 columns form one basic block and the
+//     loads of several columns are in flight at once.
 //   * A rejected attempt has already been folded in.  The owning lane then spends one extra block
 //     of six evaluations (REPLAY) re-evaluating stages 1..5 of the failed attempt with weights -W_i
 //     and the start point with (W_0' - W_0) for the shrunk step; the other lanes keep working.
