@@ -422,6 +422,19 @@ def run_b200(args):
                      "frac_algorithmic": k_flops / (k_ms * 1e-3) / 1e12 / ffma_tflops,
                      "note": "algorithmic FLOPs count the two GEMVs (+VJP) only; each of the 50 tanh per evaluation costs "
                              "~14 further FP32 issue slots (rational 13/6 + IEEE division) that the count leaves out",
+                     # FMA-pipe model of the adjoint kernel, evaluated live: per field+VJP evaluation of one
+                     # trajectory 25 hidden-unit pairs x 27 packed instructions (2 x 3 first layer, 16 rational
+                     # tanh, 8 VJP / second layer) + 5 packed fold instructions per pair, each holding one
+                     # scheduler's FMA pipe for 2 cycles per warp of 32 trajectories (tools/probe_issue.cu)
+                     "fma_pipe_model": (lambda cyc, sms, mhz: {
+                         "packed_warp_instructions_per_evaluation": cyc / 2.0,
+                         "bound_ms": adj_stats.nfe * cyc / (sms * 4 * mhz * 1e3),
+                         "frac_of_bound": adj_stats.nfe * cyc / (sms * 4 * mhz * 1e3) / ms_adj,
+                         "note": "time the adjoint launch would take if its packed FP32 instructions alone kept every "
+                                 "scheduler's FMA pipe busy at the sampled SM clock; the controller's scalar work is "
+                                 "not counted"})(
+                         2.0 * (25 * 27 + 32 * 5) / 32.0, torch.cuda.get_device_properties(dev).multi_processor_count,
+                         (clocks or {}).get("sm_mhz") or 1965.0),
                      "fma_pipe_active_ncu": {"dopri5_adj_kernel": 0.54, "dopri5_fwd_small_kernel": 0.61,
                                              "issue_active_adj": 0.58,
                                              "source": "sm__pipe_fma_cycles_active, profiles/r1o_ncu_full_adjoint.md, "

@@ -813,7 +813,8 @@ extern "C" XDE_EXPORT int xde_dopri5_mlp_adjoint_f32(const xde_mlp_field_t *fiel
     case 2: rc = adj_hpl<2>(p, s); break;
     case 3: rc = adj_hpl<3>(p, s); break;
     case 4: rc = adj_hpl<4>(p, s); break;
-    default: set_last_error("adjoint: state dim D=%d has no fused kernel (D in {1,2,3,4})", D);
+    case 8: rc = adj_hpl<8>(p, s); break;
+    default: set_last_error("adjoint: state dim D=%d has no fused kernel (D in {1,2,3,4,8})", D);
   }
   if (rc == XDE_OK) {
     adj_cast_kernel<<<(P + 255) / 256, 256, 0, s>>>(p.gacc, out_gparams, P);

@@ -267,7 +267,8 @@ def loss_grad(sol_np):
     return gy
 
 
-@pytest.mark.parametrize("d,h,pre,B", [(2, 50, "cube", 300), (2, 20, "id", 64), (1, 40, "square", 100), (4, 64, "id", 50)])
+@pytest.mark.parametrize("d,h,pre,B", [(2, 50, "cube", 300), (2, 20, "id", 64), (1, 40, "square", 100), (4, 64, "id", 50),
+                                        (8, 32, "id", 70), (8, 64, "cube", 33), (3, 17, "id", 40)])
 def test_adjoint_parity(px, torch, oracle, d, h, pre, B):
     from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
 
