@@ -553,9 +553,12 @@ extern "C" XDE_EXPORT int xde_adaptive_rk_mlp_grid_f32(int32_t method, const xde
     case 2: return rk_dispatch_pre<2>(p, s);
     case 3: return rk_dispatch_pre<3>(p, s);
     case 4: return rk_dispatch_pre<4>(p, s);
+    case 5: return rk_dispatch_pre<5>(p, s);
+    case 6: return rk_dispatch_pre<6>(p, s);
+    case 7: return rk_dispatch_pre<7>(p, s);
     case 8: return rk_dispatch_pre<8>(p, s);
     default:
-      set_last_error("adaptive RK: state dim D=%d has no fused kernel (supported: 1,2,3,4,8)", field->d);
+      set_last_error("adaptive RK: state dim D=%d has no fused kernel (supported: 1..8)", field->d);
       return XDE_E_UNSUPPORTED_FIELD;
   }
 }

@@ -422,10 +422,13 @@ extern "C" XDE_EXPORT int xde_dopri5_mlp_f32(const xde_mlp_field_t *field, const
     case 2: return dispatch_pre<2>(p, s);
     case 3: return dispatch_pre<3>(p, s);
     case 4: return dispatch_pre<4>(p, s);
+    case 5: return dispatch_pre<5>(p, s);
+    case 6: return dispatch_pre<6>(p, s);
+    case 7: return dispatch_pre<7>(p, s);
     case 8: return dispatch_pre<8>(p, s);
     default:
       if (field->d >= 16) return dopri5_fwd_tile(field, y0, B, t_span, T, opts, out, stats, log, s);
-      set_last_error("dopri5 forward: state dim D=%d has no fused kernel (supported: 1,2,3,4,8 and 16,32,64)", field->d);
+      set_last_error("dopri5 forward: state dim D=%d has no fused kernel (supported: 1..8 and 16,32,64)", field->d);
       return XDE_E_UNSUPPORTED_FIELD;
   }
 }

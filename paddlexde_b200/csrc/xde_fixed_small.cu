@@ -260,6 +260,9 @@ int rk_fixed_small(int method, const xde_mlp_field_t *f, const float *y0, long l
     case 2: return fixed_pre<2>(p, s);
     case 3: return fixed_pre<3>(p, s);
     case 4: return fixed_pre<4>(p, s);
+    case 5: return fixed_pre<5>(p, s);
+    case 6: return fixed_pre<6>(p, s);
+    case 7: return fixed_pre<7>(p, s);
     case 8: return fixed_pre<8>(p, s);
   }
   set_last_error("fixed solver: state dim D=%d has no fused kernel", f->d);

@@ -70,7 +70,8 @@ def test_dopri5_cfg1_bit_exact_and_step_sequence(px, torch, oracle):
         assert np.array_equal(r.ratio, lg.ratio)
 
 
-@pytest.mark.parametrize("d,h,pre", [(1, 16, "id"), (2, 50, "cube"), (3, 20, "square"), (4, 33, "id"), (8, 64, "id")])
+@pytest.mark.parametrize("d,h,pre", [(1, 16, "id"), (2, 50, "cube"), (3, 20, "square"), (4, 33, "id"), (8, 64, "id"),
+                                     (5, 24, "id"), (6, 31, "cube"), (7, 40, "square")])
 def test_dopri5_shapes(px, torch, oracle, d, h, pre):
     field, om = both(px, oracle, fanin_weights(d, h, seed=d), pre)
     y0 = np.random.default_rng(d).uniform(-1, 1, (333, d)).astype(f32)
@@ -131,9 +132,9 @@ def test_dopri5_status_words(px, torch, oracle):
     assert rc != 0 and s.read_stats().status == rc
     keep = np.arange(64) != 7  # the other trajectories are unaffected (one controller per trajectory)
     assert np.array_equal(sol.cpu().numpy()[:, keep], ref[:, keep])
-    with pytest.raises(px.UnsupportedFieldError):  # no fused kernel for D=5: loud, no fallback
-        f5, _ = both(px, oracle, fanin_weights(5, 8), "id")
-        solve_fwd(px, torch, f5, np.zeros((4, 5), f32), cfg2_tspan(4))
+    with pytest.raises(px.UnsupportedFieldError):  # no fused kernel for D=9: loud, no fallback
+        f9, _ = both(px, oracle, fanin_weights(9, 8), "id")
+        solve_fwd(px, torch, f9, np.zeros((4, 9), f32), cfg2_tspan(4))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -483,7 +484,7 @@ def test_odeint_adjoint_autograd_surface(px, torch, oracle):
 # fixed-grid solvers, SDE
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("solver", ["Euler", "RK4"])
-@pytest.mark.parametrize("d,h,pre", [(2, 50, "cube"), (4, 32, "id"), (8, 48, "square")])
+@pytest.mark.parametrize("d,h,pre", [(2, 50, "cube"), (4, 32, "id"), (8, 48, "square"), (5, 20, "id"), (7, 33, "cube")])
 def test_fixed_solvers_bit_exact(px, torch, oracle, solver, d, h, pre):
     w = spiral_weights() if d == 2 else fanin_weights(d, h)
     field, om = both(px, oracle, w, pre)
@@ -544,7 +545,7 @@ def test_table_driven_kernel_equals_tuned_dopri5(px, torch, oracle):
 
 @pytest.mark.parametrize("name,rtol", [("Bosh3", 1e-6), ("Fehlberg2", 1e-4), ("AdaptiveHeun", 1e-4), ("Dopri8", 1e-7),
                                        ("Dopri8", 1e-5)])
-@pytest.mark.parametrize("d,h,pre,B", [(2, 50, "cube", 333), (4, 32, "id", 65), (1, 16, "square", 31)])
+@pytest.mark.parametrize("d,h,pre,B", [(2, 50, "cube", 333), (4, 32, "id", 65), (1, 16, "square", 31), (6, 24, "id", 40)])
 def test_other_tableaux_bit_exact_and_step_sequence(px, torch, oracle, name, rtol, d, h, pre, B):
     w = spiral_weights() if d == 2 else fanin_weights(d, h, seed=d)
     field, om = both(px, oracle, w, pre)
