@@ -285,7 +285,11 @@ int sde_small(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, co
   switch (f->d) {
     case 1: return sde_pref<1>(p, scheme, s);
     case 2: return sde_pref<2>(p, scheme, s);
+    case 3: return sde_pref<3>(p, scheme, s);
     case 4: return sde_pref<4>(p, scheme, s);
+    case 5: return sde_pref<5>(p, scheme, s);
+    case 6: return sde_pref<6>(p, scheme, s);
+    case 7: return sde_pref<7>(p, scheme, s);
     case 8: return sde_pref<8>(p, scheme, s);
   }
   set_last_error("sde: state dim D=%d has no fused kernel", f->d);

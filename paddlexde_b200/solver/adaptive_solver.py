@@ -150,7 +150,7 @@ class AdaptiveRKSolver:
             v = np.sort(v[v >= t_host[0]])
         if v.size == 0:
             return None
-        return torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+        return torch.from_numpy(v.copy()).to(dev)  # copy(): a reversed length-1 view keeps its negative stride
 
     def read_stats(self) -> SolveStats:
         self.stats = self._stats_buf.read()

@@ -502,8 +502,9 @@ def test_fixed_solvers_bit_exact(px, torch, oracle, solver, d, h, pre):
 
 
 @pytest.mark.parametrize("scheme", ["em", "milstein"])
-def test_sde_supplied_increments_bit_exact(px, torch, oracle, scheme):
-    d, h, B = 4, 32, 700
+@pytest.mark.parametrize("d", [4, 3, 7])
+def test_sde_supplied_increments_bit_exact(px, torch, oracle, scheme, d):
+    h, B = 32, 700
     wf, wg = fanin_weights(d, h, seed=2), fanin_weights(d, h, seed=3)
     f, of = both(px, oracle, wf, "cube")
     g, og = both(px, oracle, wg, "square")

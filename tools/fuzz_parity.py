@@ -149,7 +149,7 @@ def case_fixed():
 
 def case_sde():
     scheme = ["em", "milstein"][rng.integers(2)]
-    d = [1, 2, 4, 8][rng.integers(4)]; h = int(rng.integers(2, 50)); B = int(rng.integers(1, 300))
+    d = int(rng.integers(1, 9)); h = int(rng.integers(2, 50)); B = int(rng.integers(1, 300))
     wf, wg = weights(d, h, 1.0), weights(d, h, 0.7)
     pf, pg = PRES[rng.integers(3)], PRES[rng.integers(3)]
     y0 = rng.uniform(-1, 1, (B, d)).astype(f32); t = tspan(int(rng.integers(2, 10)), 1.0, False)
@@ -161,7 +161,92 @@ def case_sde():
     return desc, np.array_equal(sol, ref, equal_nan=True)
 
 
-CASES = [case_dopri5_small, case_dopri5_tile, case_other_tableaux, case_adjoint, case_fixed, case_sde]
+def case_gather():
+    from paddlexde_b200.xde.base_dde import history_gather, history_gather_bwd
+    kind = ["linear", "cubic", "bez"][rng.integers(3)]
+    Th = int(rng.integers(4, 40)); D = int(rng.integers(1, 9)); L = int(rng.integers(1, 30))
+    lead = (int(rng.integers(1, 40)), int(rng.integers(1, 12)))
+    span = np.cumsum(rng.uniform(0.2, 2.0, Th)).astype(f32) if rng.random() < 0.5 else np.arange(Th, dtype=f32)
+    lags = rng.uniform(span[0] - 1.0, span[-1] + 1.0, L).astype(f32)
+    if rng.random() < 0.5:  # queries exactly on grid points (right-open bucketize, interpolate_base.py:49-62)
+        lags[: L // 2] = span[rng.integers(0, Th, L // 2)]
+    his = rng.uniform(-2, 2, lead + (Th, D)).astype(f32)
+    if rng.random() < 0.2:
+        his[..., 1:] = np.round(his[..., 1:] * 5)  # integer-valued channels like the dataset
+    desc = f"gather {kind} lead={lead} Th={Th} D={D} L={L}"
+    v, dv = history_gather(torch.from_numpy(lags).cuda(), torch.from_numpy(his).cuda(), torch.from_numpy(span).cuda(), kind)
+    v_ref, d_ref = xo.history_gather(kind, his, span, lags)
+    ok = np.array_equal(v.cpu().numpy(), v_ref, equal_nan=True) and np.array_equal(dv.cpu().numpy(), d_ref, equal_nan=True)
+    if ok:
+        gy = rng.standard_normal(v_ref.shape).astype(f32)
+        gl = history_gather_bwd(torch.from_numpy(gy).cuda(), dv).cpu().numpy()
+        gl_ref = xo.history_gather_bwd(gy, d_ref)
+        ok = np.allclose(gl, gl_ref, rtol=1e-5, atol=1e-5 * max(np.abs(gl_ref).max(), 1e-30))
+        desc += " (bwd)"
+    return desc, ok
+
+
+def case_batch_controller():
+    d = [1, 2, 3, 4, 8][rng.integers(5)]; h = int(rng.integers(2, 60)); pre = PRES[rng.integers(3)]
+    B = int(rng.integers(1, 3000)); w = weights(d, h, rng.uniform(0.5, 2.5)); o = ctrl_opts()
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32); t = tspan(int(rng.integers(2, 7)), rng.uniform(0.2, 2), rng.random() < 0.3)
+    desc = f"dopri5 controller=batch d={d} h={h} pre={pre} B={B} T={t.size} {o}"
+    xde = px.xde.BaseODE(px.MLPField(*w, pre=pre), torch.from_numpy(y0).cuda(), t)
+    s = px.Dopri5(xde=xde, y0=xde.y0, check_status=False, controller="batch", **o)
+    sol = s.integrate(t).cpu().numpy()
+    ref, st, lg, rc = xo.dopri5_mlp(xo.MLP(*w, pre=pre), y0, t, controller="batch", **o)
+    stt = s.read_stats()
+    return desc, np.array_equal(sol, ref, equal_nan=True) and stt.status == rc
+
+
+def case_grid_points():
+    name = ["Dopri5", "Bosh3", "Fehlberg2", "AdaptiveHeun", "Dopri8"][rng.integers(5)]
+    d = int(rng.integers(1, 9)); h = int(rng.integers(2, 40)); pre = PRES[rng.integers(3)]
+    B = int(rng.integers(1, 150)); w = weights(d, h, rng.uniform(0.5, 2.0))
+    o = dict(rtol=float(10.0 ** rng.uniform(-6, -3))); o["atol"] = o["rtol"] * 1e-2
+    rev = rng.random() < 0.3
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32); t = tspan(int(rng.integers(2, 6)), 1.5, rev)
+    step_t = [float(x) for x in rng.uniform(-0.2, 1.7, int(rng.integers(0, 5)))]
+    jump_t = [float(x) for x in rng.uniform(-0.2, 1.7, int(rng.integers(0, 4)))]
+    if not step_t and not jump_t:
+        step_t = [0.5]
+    desc = f"{name} step_t={np.round(step_t, 3)} jump_t={np.round(jump_t, 3)} d={d} h={h} pre={pre} B={B} T={t.size} rev={rev} {o}"
+    xde = px.xde.BaseODE(px.MLPField(*w, pre=pre), torch.from_numpy(y0).cuda(), t)
+    s = getattr(px, name)(xde=xde, y0=xde.y0, check_status=False, step_t=step_t or None, jump_t=jump_t or None, **o)
+    sol = s.integrate(t).cpu().numpy()
+    key = {"Dopri5": "dopri5", "Bosh3": "bosh3", "Fehlberg2": "fehlberg2", "AdaptiveHeun": "adaptive_heun", "Dopri8": "dopri8"}[name]
+    ref, st, _, rc = xo.adaptive_rk_mlp(key, xo.MLP(*w, pre=pre), y0, t, step_t=step_t or None, jump_t=jump_t or None, **o)
+    stt = s.read_stats()
+    return desc, np.array_equal(sol, ref, equal_nan=True) and stt.n_attempts == int(st.n_attempts.sum()) and \
+        stt.nfe == int(st.nfe.sum()) and stt.status == rc
+
+
+def case_sde_adjoint():
+    from paddlexde_b200.functional.sdeint_adjoint import sde_adjoint_backward
+    d = [1, 2, 3, 4, 8][rng.integers(5)]; h = int(rng.integers(2, 90)); B = int(rng.integers(1, 300))
+    wf, wg = weights(d, h, 1.0), weights(d, h, 0.7)
+    pf, pg = PRES[rng.integers(3)], PRES[rng.integers(3)]
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32); t = tspan(int(rng.integers(2, 10)), 1.0, False)
+    dW = (0.2 * rng.standard_normal((t.size - 1, B, d))).astype(f32)
+    desc = f"sde adjoint d={d} h={h} pre={pf}/{pg} B={B} T={t.size}"
+    f, g = px.MLPField(*wf, pre=pf), px.MLPField(*wg, pre=pg)
+    of, og = xo.MLP(*wf, pre=pf), xo.MLP(*wg, pre=pg)
+    table = torch.from_numpy(dW).cuda()
+    sol = px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler, options={"bm_increments": table})
+    ref = xo.sde_mlp("em", of, og, y0, t, dW)
+    if not np.array_equal(sol.cpu().numpy(), ref, equal_nan=True):
+        return desc + " (forward)", False
+    gy = (np.abs(rng.standard_normal(ref.shape)) / ref.size).astype(f32)
+    gf_r, gg_r, a0_r = xo.sde_mlp_adjoint(of, og, t, ref, gy, dW)
+    gf, gg, a0 = sde_adjoint_backward(f, g, t, sol, torch.from_numpy(gy).cuda(), bm_increments=table, return_adj_y0=True)
+    ok = np.array_equal(a0.cpu().numpy(), a0_r, equal_nan=True)
+    for got, want in ((gf, gf_r), (gg, gg_r)):
+        ok = ok and np.allclose(got.cpu().numpy(), want, rtol=1e-5, atol=3e-5 * max(np.abs(want).max(), 1e-30))
+    return desc, ok
+
+
+CASES = [case_dopri5_small, case_dopri5_tile, case_other_tableaux, case_adjoint, case_fixed, case_sde, case_gather,
+         case_batch_controller, case_grid_points, case_sde_adjoint]
 counts = {c.__name__: [0, 0] for c in CASES}
 t_end = time.time() + budget
 i = int(sys.argv[3]) if ONE else 0
