@@ -245,8 +245,44 @@ def case_sde_adjoint():
     return desc, ok
 
 
+def case_tensor():
+    """tcgen05 path vs the FP32 kernels (themselves bit-exact vs the oracle): ragged batches, many tiles per CTA,
+    strides, supplied and generated increments; 1e-5 of the largest state."""
+    shapes = TILE + [(64, 64)]
+    kind = ["Euler", "RK4", "Midpoint", "sde", "sde_gen"][rng.integers(5)]
+    d, h = shapes[rng.integers(len(shapes))]
+    if kind.startswith("sde") and (d == 64 and h > 64 or h > 128):
+        d, h = 32, 64  # TMEM limits of the SDE variant (two networks)
+    B = int(rng.integers(1, 70000)) if rng.random() < 0.3 else int(rng.integers(1, 700))
+    T = int(rng.integers(2, 8)); stride = int(rng.integers(1, 4))
+    t = np.linspace(0, rng.uniform(0.2, 1.0), T).astype(f32)
+    y0 = torch.from_numpy(rng.uniform(-1, 1, (B, 1, d)).astype(f32)).cuda()
+    desc = f"tensor {kind} d={d} h={h} B={B} T={T} stride={stride}"
+    if not kind.startswith("sde"):
+        pre = PRES[rng.integers(3)]
+        field = px.MLPField(*weights(d, h, rng.uniform(0.5, 1.5)), pre=pre)
+        desc += f" pre={pre}"
+        run = lambda math: px.odeint(field, y0, t, getattr(px, kind), options={"math": math, "out_stride": stride})
+    else:
+        f = px.MLPField(*weights(d, h, 1.0), pre=PRES[rng.integers(3)])
+        g = px.MLPField(*weights(d, h, 0.7), pre=PRES[rng.integers(3)])
+        if kind == "sde":
+            dW = torch.randn((T - 1, B, d), device="cuda", generator=torch.Generator(device="cuda").manual_seed(int(rng.integers(1 << 30)))) * 0.2
+            opt = {"bm_increments": dW}
+        else:
+            opt = {"bm_seed": int(rng.integers(1 << 30))}
+        run = lambda math: px.sdeint(f, g, y0, t, px.Euler, options={**opt, "math": math, "out_stride": stride})
+    a, b = run("tensor"), run("fp32")
+    scale = float(b.abs().max())
+    err = float((a - b).abs().max())
+    ok = a.shape == b.shape and err <= 1e-5 * scale
+    if not ok:
+        desc += f" max|d|={err:.3e} scale={scale:.3e}"
+    return desc, ok
+
+
 CASES = [case_dopri5_small, case_dopri5_tile, case_other_tableaux, case_adjoint, case_fixed, case_sde, case_gather,
-         case_batch_controller, case_grid_points, case_sde_adjoint]
+         case_batch_controller, case_grid_points, case_sde_adjoint, case_tensor]
 counts = {c.__name__: [0, 0] for c in CASES}
 t_end = time.time() + budget
 i = int(sys.argv[3]) if ONE else 0
