@@ -233,7 +233,7 @@ def secondary_configs():
         res = []
         for fn, kw in ((bc.cfg2_batch, {"norm": "mixed"}), (bc.cfg3, {"math": "tensor"}), (bc.cfg3, {"math": "fp32"}),
                        (bc.cfg4, {"math": "tensor"}), (bc.cfg4, {"math": "fp32"}),
-                       (bc.cfg4, {"math": "tensor", "generated": True})):
+                       (bc.cfg4, {"math": "tensor", "generated": True}), (bc.cfg5, {})):
             res.append(fn(**kw))
             torch.cuda.empty_cache()
         return res
