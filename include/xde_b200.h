@@ -151,7 +151,9 @@ int xde_dopri5_mlp_f32(const xde_mlp_field_t *field, const float *y0, int64_t B,
  * tableau as data (stage count, FSAL shortcut base_adaptive_solver_rk.py:172-176, controller order):
  *   adaptive_solver/bosh3.py:5-27, fehlberg2.py:5-22, adaptive_heun.py:5-27, dopri8.py:5-252.
  * method = XDE_RK_*; XDE_RK_DOPRI5 forwards to xde_dopri5_mlp_f32.  The other pairs run the per-trajectory
- * controller (controller = XDE_CTRL_BATCH returns XDE_E_UNSUPPORTED_FIELD).  Same layouts as above. */
+ * controller (controller = XDE_CTRL_BATCH returns XDE_E_UNSUPPORTED_FIELD).  Same layouts as above.
+ * Fused shapes: D in 1..8 (every pair); the large-state shapes of xde_dopri5_mlp_f32 for the pairs with at most
+ * 6 stages (Dopri5, Bosh3, Fehlberg2, AdaptiveHeun; Dopri8 returns XDE_E_UNSUPPORTED_FIELD there). */
 int xde_adaptive_rk_mlp_f32(int32_t method, const xde_mlp_field_t *field, const float *y0, int64_t B,
                             const float *t_span, int32_t T, const xde_ctrl_opts_t *opts, int32_t controller,
                             float *out, xde_stats_t *stats, const xde_attempt_log_t *log, void *stream);

@@ -13,20 +13,11 @@
 // the breadth kernel: it shares every arithmetic rule with the tuned Dopri5 kernel
 // -- run with the Dormand-Prince tableau (XDE_RK_DOPRI5_TABLE) it reproduces that kernel bit for bit --
 // but has no lane refill, so diverging step counts cost warp efficiency.
-#include "xde_common.cuh"
+#include "xde_rk_tab.cuh"
 
 namespace xde {
 
 constexpr int kRkThreads = 128;
-constexpr int kMaxStages = 13;  // len(alpha) of Dopri8; k has one more column
-
-struct RkTab {
-  int S, order, fsal, _pad;
-  float alpha[kMaxStages];
-  float beta[kMaxStages][kMaxStages];
-  float csol[kMaxStages + 1], cerr[kMaxStages + 1], cmid[kMaxStages + 1];
-};
-
 struct RkParams {
   xde_mlp_field_t field;
   const float *y0, *t_span;
@@ -154,7 +145,7 @@ static void fill_tab(RkTab &t, int S, int order, const double *alpha, const doub
     if (csol[j] != beta[(S - 1) * ldb + j]) t.fsal = 0;
 }
 
-static bool make_tab(int method, RkTab &t) {
+bool make_tab(int method, RkTab &t) {
   using namespace tabs;
   switch (method) {
     case XDE_RK_DOPRI5_TABLE: {
@@ -207,24 +198,6 @@ static bool make_tab(int method, RkTab &t) {
 }
 
 // ---- device -------------------------------------------------------------------------------------------
-// r ** (1/p), r finite and > 0: p = 2 sqrt (IEEE), p = 8 three sqrts, p = 3 integer seed + 4 Newton steps
-// x <- (2x + r/x^2)/3, p = 5 root5 -- the oracle's orc_rootpf, operation for operation.
-__device__ __forceinline__ float rootp(float r, int p) {
-  if (p == 5) return root5(r);
-  if (p == 2) return __fsqrt_rn(r);
-  if (p == 8) return __fsqrt_rn(__fsqrt_rn(__fsqrt_rn(r)));
-  if (p == 3) {
-    float x = __uint_as_float(__float_as_uint(r) / 3u + 0x2A555555u);
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const float q = __fdiv_rn(r, x * x);
-      x = fmaf(2.0f, x, q) * (float)(1.0 / 3.0);
-    }
-    return x;
-  }
-  return powf(r, __fdiv_rn(1.0f, (float)p));
-}
-
 template <int D>
 __device__ __forceinline__ float rms_vec(const float (&v)[D]) {
   double acc = 0.0;
@@ -511,6 +484,12 @@ static int rk_dispatch_pre(const RkParams &p, cudaStream_t s) {
 
 }  // namespace xde
 
+namespace xde {
+int adaptive_rk_tile(int method, const xde_mlp_field_t *field, const float *y0, long long B, const float *t_span, int T,
+                     const xde_ctrl_opts_t *opts, float *out, xde_stats_t *stats, const xde_attempt_log_t *log,
+                     cudaStream_t s);  // xde_tile_adaptive.cu (D >= 16)
+}
+
 extern "C" XDE_EXPORT int xde_adaptive_rk_mlp_grid_f32(int32_t method, const xde_mlp_field_t *field,
                                                        const float *y0, int64_t B, const float *t_span, int32_t T,
                                                        const xde_ctrl_opts_t *opts, int32_t controller,
@@ -524,6 +503,13 @@ extern "C" XDE_EXPORT int xde_adaptive_rk_mlp_grid_f32(int32_t method, const xde
   if (method == XDE_RK_DOPRI5) method = XDE_RK_DOPRI5_TABLE;  // same arithmetic, table-driven
   XDE_REQUIRE(field && y0 && t_span && opts && out, XDE_E_BAD_ARG, "null argument");
   XDE_REQUIRE(B >= 1 && T >= 2, XDE_E_BAD_ARG, "need B >= 1 and T >= 2 (B=%lld T=%d)", (long long)B, T);
+  if (field->d >= 16) {  // large states: the register-tiled kernels (xde_tile_adaptive.cuh)
+    XDE_REQUIRE(!grid_pts, XDE_E_UNSUPPORTED_FIELD, "step_t / jump_t are fused for small states (D <= 8) only");
+    XDE_REQUIRE(controller == XDE_CTRL_TRAJECTORY, XDE_E_UNSUPPORTED_FIELD,
+                "large states (D >= 16) have the per-trajectory controller only");
+    if (stats) XDE_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(xde_stats_t), (cudaStream_t)stream));
+    return adaptive_rk_tile(method, field, y0, B, t_span, T, opts, out, stats, log, (cudaStream_t)stream);
+  }
   XDE_REQUIRE(n_step >= 0 && n_jump >= 0 && (n_step == 0 || step_t) && (n_jump == 0 || jump_t), XDE_E_BAD_ARG,
               "step_t / jump_t: negative count or null pointer");
   RkParams p{};

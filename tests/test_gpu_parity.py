@@ -200,6 +200,39 @@ def test_dopri5_large_state_rejections_reverse_options_status(px, torch, oracle)
     assert np.isnan(sol.cpu().numpy()[1:, 5]).all()
 
 
+@pytest.mark.parametrize("name,rtol", [("Bosh3", 1e-5), ("Fehlberg2", 1e-4), ("AdaptiveHeun", 1e-4)])
+@pytest.mark.parametrize("d,h,pre,B", [(64, 256, "id", 70), (32, 64, "cube", 130), (16, 64, "square", 33), (64, 128, "id", 5)])
+def test_other_tableaux_large_state(px, torch, oracle, name, rtol, d, h, pre, B):
+    """The tiled kernel with the tableau as data (stage count 3 / 2 / 1, FSAL or not, controller order 3 / 2):
+    bit-exact incl. counters and a trajectory's attempt log; Dopri8 (13 stages) is loud about not fitting."""
+    w = fanin_weights(d, h, seed=d + h)
+    field, om = both(px, oracle, w, pre)
+    y0 = np.random.default_rng(h).uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 0.8, 4).astype(f32)
+    method = {"Bosh3": "bosh3", "Fehlberg2": "fehlberg2", "AdaptiveHeun": "adaptive_heun"}[name]
+    xde = px.xde.BaseODE(field, torch.from_numpy(y0).cuda(), t)
+    s = getattr(px, name)(xde=xde, y0=xde.y0, rtol=rtol, atol=rtol * 1e-2, log_attempts=1024)
+    sol = s.integrate(t)
+    ref, st, _, rc = oracle.adaptive_rk_mlp(method, om, y0, t, rtol=rtol, atol=rtol * 1e-2)
+    assert rc == 0 and np.array_equal(sol.cpu().numpy(), ref)
+    assert s.stats.n_attempts == int(st.n_attempts.sum()) and s.stats.n_accepted == int(st.n_accepted.sum())
+    assert s.stats.nfe == int(st.nfe.sum())
+    rec, cnt = s.attempt_log.read()
+    b = B // 2
+    _, _, lg, _ = oracle.adaptive_rk_mlp(method, om, y0, t, rtol=rtol, atol=rtol * 1e-2, log_traj=b)
+    assert cnt[b] == len(lg) and rec[b, :cnt[b]].tobytes() == lg.tobytes()
+    tr = t[::-1].copy()
+    sol = getattr(px, name)(xde=px.xde.BaseODE(field, torch.from_numpy(y0).cuda(), tr), y0=xde.y0, rtol=rtol,
+                            atol=rtol * 1e-2).integrate(tr)
+    ref, _, _, _ = oracle.adaptive_rk_mlp(method, om, y0, tr, rtol=rtol, atol=rtol * 1e-2)
+    assert np.array_equal(sol.cpu().numpy(), ref)
+    if name == "Bosh3" and d == 16:
+        with pytest.raises(px.UnsupportedFieldError, match="stages"):
+            px.Dopri8(xde=xde, y0=xde.y0, rtol=1e-6, atol=1e-8).integrate(t)
+        with pytest.raises(px.UnsupportedFieldError, match="step_t"):
+            px.Bosh3(xde=xde, y0=xde.y0, rtol=1e-6, atol=1e-8, step_t=[0.3]).integrate(t)
+
+
 @pytest.mark.parametrize("B", [1, 20, 1000, 40000])
 def test_dopri5_batch_controller_reference_faithful(px, torch, oracle, B):
     """controller="batch": the reference's single global RMS norm and dt (utils/ode_utils.py:8-9).  The

@@ -87,6 +87,8 @@ def case_dopri5_tile():
 def case_other_tableaux():
     name = ["Bosh3", "Fehlberg2", "AdaptiveHeun", "Dopri8"][rng.integers(4)]
     d = int(rng.integers(1, 9)); h = int(rng.integers(2, 50)); pre = PRES[rng.integers(3)]
+    if name != "Dopri8" and rng.random() < 0.4:  # the tiled kernels (large states)
+        d, h = TILE[rng.integers(len(TILE))]
     B = int(rng.integers(1, 200)); w = weights(d, h, rng.uniform(0.5, 2.0)); o = ctrl_opts()
     o["rtol"] = max(o["rtol"], 1e-6); o["atol"] = o["rtol"] * 1e-2
     y0 = rng.uniform(-1, 1, (B, d)).astype(f32); t = tspan(int(rng.integers(2, 6)), rng.uniform(0.2, 1.5), rng.random() < 0.3)
