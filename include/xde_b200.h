@@ -163,7 +163,7 @@ int xde_adaptive_rk_mlp_f32(int32_t method, const xde_mlp_field_t *field, const 
  * re-evaluation of f after a jump).  step_t / jump_t: device arrays in t_span's time, sorted in integration
  * order and filtered to lie at or after t_span[0] (sort_tvals, utils/ode_utils.py:22-25, is the caller's);
  * null / 0 = none.  Any method, per-trajectory controller; Dopri5 with forced points runs on the
- * table-driven kernel (bit-identical arithmetic). */
+ * table-driven kernel (bit-identical arithmetic).  Same fused shapes as xde_adaptive_rk_mlp_f32. */
 int xde_adaptive_rk_mlp_grid_f32(int32_t method, const xde_mlp_field_t *field, const float *y0, int64_t B,
                                  const float *t_span, int32_t T, const xde_ctrl_opts_t *opts, int32_t controller,
                                  const float *step_t, int32_t n_step, const float *jump_t, int32_t n_jump,

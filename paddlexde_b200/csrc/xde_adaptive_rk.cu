@@ -486,8 +486,8 @@ static int rk_dispatch_pre(const RkParams &p, cudaStream_t s) {
 
 namespace xde {
 int adaptive_rk_tile(int method, const xde_mlp_field_t *field, const float *y0, long long B, const float *t_span, int T,
-                     const xde_ctrl_opts_t *opts, float *out, xde_stats_t *stats, const xde_attempt_log_t *log,
-                     cudaStream_t s);  // xde_tile_adaptive.cu (D >= 16)
+                     const xde_ctrl_opts_t *opts, const float *step_t, int n_step, const float *jump_t, int n_jump,
+                     float *out, xde_stats_t *stats, const xde_attempt_log_t *log, cudaStream_t s);  // xde_tile_adaptive.cu
 }
 
 extern "C" XDE_EXPORT int xde_adaptive_rk_mlp_grid_f32(int32_t method, const xde_mlp_field_t *field,
@@ -503,15 +503,15 @@ extern "C" XDE_EXPORT int xde_adaptive_rk_mlp_grid_f32(int32_t method, const xde
   if (method == XDE_RK_DOPRI5) method = XDE_RK_DOPRI5_TABLE;  // same arithmetic, table-driven
   XDE_REQUIRE(field && y0 && t_span && opts && out, XDE_E_BAD_ARG, "null argument");
   XDE_REQUIRE(B >= 1 && T >= 2, XDE_E_BAD_ARG, "need B >= 1 and T >= 2 (B=%lld T=%d)", (long long)B, T);
+  XDE_REQUIRE(n_step >= 0 && n_jump >= 0 && (n_step == 0 || step_t) && (n_jump == 0 || jump_t), XDE_E_BAD_ARG,
+              "step_t / jump_t: negative count or null pointer");
   if (field->d >= 16) {  // large states: the register-tiled kernels (xde_tile_adaptive.cuh)
-    XDE_REQUIRE(!grid_pts, XDE_E_UNSUPPORTED_FIELD, "step_t / jump_t are fused for small states (D <= 8) only");
     XDE_REQUIRE(controller == XDE_CTRL_TRAJECTORY, XDE_E_UNSUPPORTED_FIELD,
                 "large states (D >= 16) have the per-trajectory controller only");
     if (stats) XDE_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(xde_stats_t), (cudaStream_t)stream));
-    return adaptive_rk_tile(method, field, y0, B, t_span, T, opts, out, stats, log, (cudaStream_t)stream);
+    return adaptive_rk_tile(method, field, y0, B, t_span, T, opts, step_t, n_step, jump_t, n_jump, out, stats, log,
+                            (cudaStream_t)stream);
   }
-  XDE_REQUIRE(n_step >= 0 && n_jump >= 0 && (n_step == 0 || step_t) && (n_jump == 0 || jump_t), XDE_E_BAD_ARG,
-              "step_t / jump_t: negative count or null pointer");
   RkParams p{};
   XDE_REQUIRE(make_tab(method, p.tab), XDE_E_BAD_ARG, "unknown Runge-Kutta method %d", method);
   XDE_REQUIRE(controller == XDE_CTRL_TRAJECTORY, XDE_E_UNSUPPORTED_FIELD,

@@ -12,8 +12,8 @@ static int ad_tile_s6(const AdTileParams &p, cudaStream_t s) { return ad_tile_di
 
 // forward solve with one controller per trajectory for D >= 16; method = XDE_RK_* (Dopri8's 13 stages do not fit)
 int adaptive_rk_tile(int method, const xde_mlp_field_t *field, const float *y0, long long B, const float *t_span, int T,
-                     const xde_ctrl_opts_t *opts, float *out, xde_stats_t *stats, const xde_attempt_log_t *log,
-                     cudaStream_t s) {
+                     const xde_ctrl_opts_t *opts, const float *step_t, int n_step, const float *jump_t, int n_jump,
+                     float *out, xde_stats_t *stats, const xde_attempt_log_t *log, cudaStream_t s) {
   AdTileParams p{};
   XDE_REQUIRE(make_tab(method == XDE_RK_DOPRI5 ? XDE_RK_DOPRI5_TABLE : method, p.tab), XDE_E_BAD_ARG,
               "unknown Runge-Kutta method %d", method);
@@ -28,6 +28,10 @@ int adaptive_rk_tile(int method, const xde_mlp_field_t *field, const float *y0, 
   p.log_records = log ? log->records : nullptr;
   p.log_counts = log ? log->counts : nullptr;
   p.log_cap = log ? log->cap : 0;
+  p.step_t = step_t;
+  p.n_step = n_step;
+  p.jump_t = jump_t;
+  p.n_jump = n_jump;
   switch (p.tab.S) {
     case 1: return ad_tile_s1(p, s);
     case 2: return ad_tile_s2(p, s);
@@ -42,7 +46,7 @@ int adaptive_rk_tile(int method, const xde_mlp_field_t *field, const float *y0, 
 int dopri5_fwd_tile(const xde_mlp_field_t *field, const float *y0, long long B, const float *t_span, int T,
                     const xde_ctrl_opts_t *opts, float *out, xde_stats_t *stats, const xde_attempt_log_t *log,
                     cudaStream_t s) {
-  return adaptive_rk_tile(XDE_RK_DOPRI5, field, y0, B, t_span, T, opts, out, stats, log, s);
+  return adaptive_rk_tile(XDE_RK_DOPRI5, field, y0, B, t_span, T, opts, nullptr, 0, nullptr, 0, out, stats, log, s);
 }
 
 }  // namespace xde

@@ -36,6 +36,10 @@ struct AdTileParams {
   xde_attempt_t *log_records;
   int *log_counts;
   int log_cap;
+  // step_t / jump_t (base_adaptive_solver_rk.py:94-114): sorted in integration order, filtered to lie at or after
+  // t_span[0] (sort_tvals is the shim's), in t_span's own time; may be null / 0
+  const float *step_t, *jump_t;
+  int n_step, n_jump;
   RkTab tab;  // the embedded pair (S stages = the kernel's template argument)
 };
 
@@ -187,6 +191,18 @@ __global__ void __launch_bounds__(kTileThreads, 1) adaptive_tile_kernel(const Ad
       }
     }
 
+    // next_*_index = min(bisect.bisect(list, t_span[0]), len - 1) (:109-114); values in solver time
+    const float gsign = rev ? -1.0f : 1.0f;
+    int step_idx[R2], jump_idx[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      step_idx[r] = jump_idx[r] = 0;
+      while (step_idx[r] < p.n_step && !(t0[r] < gsign * p.step_t[step_idx[r]])) step_idx[r]++;
+      if (step_idx[r] > p.n_step - 1) step_idx[r] = p.n_step - 1;
+      while (jump_idx[r] < p.n_jump && !(t0[r] < gsign * p.jump_t[jump_idx[r]])) jump_idx[r]++;
+      if (jump_idx[r] > p.n_jump - 1) jump_idx[r] = p.n_jump - 1;
+    }
+
     // ================= adaptive steps until every row of the tile has produced its last output =================
     while (true) {
       // assertions of _adaptive_step (base_adaptive_solver_rk.py:200-203) + max_num_steps (:120-122)
@@ -236,9 +252,33 @@ __global__ void __launch_bounds__(kTileThreads, 1) adaptive_tile_kernel(const Ad
 #pragma unroll
       for (int r = 0; r < R2; ++r) all_done = all_done && done[r];
       if (__syncthreads_and(all_done)) break;
+      // "Make step, respecting prescribed grid points" (:209-224): step_t first, then jump_t
+      float t1v[R2];
+      bool on_step[R2], on_jump[R2];
 #pragma unroll
-      for (int r = 0; r < R2; ++r)
+      for (int r = 0; r < R2; ++r) {
         if (done[r]) dt[r] = 0.0f;  // idle rows re-evaluate their final state (finite, harmless)
+        t1v[r] = t0[r] + dt[r];
+        on_step[r] = on_jump[r] = false;
+        if (done[r]) continue;
+        if (p.n_step > 0) {
+          const float nt = gsign * p.step_t[step_idx[r]];
+          on_step[r] = (t0[r] < nt) && (nt < t0[r] + dt[r]);
+          if (on_step[r]) {
+            t1v[r] = nt;
+            dt[r] = t1v[r] - t0[r];
+          }
+        }
+        if (p.n_jump > 0) {
+          const float nj = gsign * p.jump_t[jump_idx[r]];
+          on_jump[r] = (t0[r] < nj) && (nj < t0[r] + dt[r]);
+          if (on_jump[r]) {
+            on_step[r] = false;
+            t1v[r] = nj;
+            dt[r] = t1v[r] - t0[r];
+          }
+        }
+      }
 
       // ---- the S stages (base_adaptive_solver_rk.py:129-181): y0 + sum_j k_j (beta_ij dt), products first ----
 #pragma unroll
@@ -288,10 +328,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) adaptive_tile_kernel(const Ad
           }
         row_rms(v, ratio);
       }
+      bool jumped[R2];
+#pragma unroll
+      for (int r = 0; r < R2; ++r) jumped[r] = false;
 #pragma unroll
       for (int r = 0; r < R2; ++r) {
         if (done[r]) continue;
-        const float t1 = t0[r] + dt[r];
+        const float t1 = t1v[r];
         const float rt = fabsf(ratio[r]);
         bool accept = (rt <= 1.0f);
         if (dt[r] > o.max_step) accept = false;
@@ -375,12 +418,34 @@ __global__ void __launch_bounds__(kTileThreads, 1) adaptive_tile_kernel(const Ad
             k[0][r][c] = k[S][r][c];
           }
           t0[r] = t1;
+          if (on_step[r] && step_idx[r] != p.n_step - 1) step_idx[r]++;
+          if (on_jump[r]) {  // past a discontinuity: f1 = self.func(t_next, y_next) (:263-273), below
+            if (jump_idx[r] != p.n_jump - 1) jump_idx[r]++;
+            jumped[r] = true;
+            if (speak) n_fe += 1;
+          }
           if (i_out[r] >= p.T) {
             if (speak && p.log_counts) p.log_counts[b0 + r] = n_logged[r];
             done[r] = true;
           }
         }
         dt[r] = dt_next;
+      }
+      if (p.n_jump > 0) {
+        bool any_t = false;
+#pragma unroll
+        for (int r = 0; r < R2; ++r) any_t = any_t || jumped[r];
+        if (__syncthreads_or(any_t)) {  // one more evaluation of the tile; rows that did not jump ignore it
+          float F[R2][C2];
+          put_u(y);
+          __syncthreads();
+          tile_eval<D, H, TM, R1, C1, R2, C2>(net, sU, sH, F);
+#pragma unroll
+          for (int r = 0; r < R2; ++r)
+#pragma unroll
+            for (int c = 0; c < C2; ++c)
+              if (jumped[r]) k[0][r][c] = F[r][c] * fsign;
+        }
       }
     }
   }

@@ -229,8 +229,17 @@ def test_other_tableaux_large_state(px, torch, oracle, name, rtol, d, h, pre, B)
     if name == "Bosh3" and d == 16:
         with pytest.raises(px.UnsupportedFieldError, match="stages"):
             px.Dopri8(xde=xde, y0=xde.y0, rtol=1e-6, atol=1e-8).integrate(t)
-        with pytest.raises(px.UnsupportedFieldError, match="step_t"):
-            px.Bosh3(xde=xde, y0=xde.y0, rtol=1e-6, atol=1e-8, step_t=[0.3]).integrate(t)
+    # forced grid points on the tiled kernel (per-row indices; a jump re-evaluates f for the whole tile)
+    step_t, jump_t = [0.21, 0.55, -1.0, 7.0], [0.4, 0.05]
+    kw = dict(rtol=rtol, atol=rtol * 1e-2, step_t=step_t, jump_t=jump_t)
+    s2 = getattr(px, name)(xde=xde, y0=xde.y0, log_attempts=1024, **kw)
+    sol = s2.integrate(t)
+    ref, st, _, rc = oracle.adaptive_rk_mlp(method, om, y0, t, **kw)
+    assert rc == 0 and np.array_equal(sol.cpu().numpy(), ref)
+    assert s2.stats.n_attempts == int(st.n_attempts.sum()) and s2.stats.nfe == int(st.nfe.sum())
+    rec, cnt = s2.attempt_log.read()
+    _, _, lg, _ = oracle.adaptive_rk_mlp(method, om, y0, t, log_traj=b, **kw)
+    assert cnt[b] == len(lg) and rec[b, :cnt[b]].tobytes() == lg.tobytes()
 
 
 @pytest.mark.parametrize("B", [1, 20, 1000, 40000])
