@@ -92,9 +92,36 @@ def oracle_vectors():
     return g
 
 
+def large_inputs():
+    """Seeded inputs of oracle_vectors_large.npz (shared with tests/test_golden.py)."""
+    w3 = fanin_weights(64, 256, seed=1)
+    y3 = np.random.default_rng(7).uniform(-1, 1, (40, 64)).astype(f32)
+    w4 = fanin_weights(32, 64, seed=2)
+    y4 = np.random.default_rng(8).uniform(-1, 1, (50, 32)).astype(f32)
+    return w3, y3, np.linspace(0, 1, 6).astype(f32), w4, y4, np.linspace(0, 1.2, 5).astype(f32)
+
+
+def oracle_vectors_large():
+    """Adaptive solvers on large states (added with csrc/xde_tile_adaptive.cuh): cfg3's field under Dopri5, the cfg4
+    drift under Bosh3 with forced grid points."""
+    w3, y3, t3, w4, y4, t4 = large_inputs()
+    g = {}
+    s, st, _, rc = xo.dopri5_mlp(xo.MLP(*w3, pre="id"), y3, t3, rtol=1e-5, atol=1e-7)
+    assert rc == 0
+    g.update(dopri5_cfg3_sol=s, dopri5_cfg3_attempts=st.n_attempts.astype(np.int64), dopri5_cfg3_nfe=st.nfe.astype(np.int64))
+    s, st, _, rc = xo.adaptive_rk_mlp("bosh3", xo.MLP(*w4, pre="cube"), y4, t4, rtol=1e-5, atol=1e-7, step_t=[0.25, 0.7],
+                                      jump_t=[0.5])
+    assert rc == 0
+    g.update(bosh3_cfg4_grid_sol=s, bosh3_cfg4_grid_attempts=st.n_attempts.astype(np.int64),
+             bosh3_cfg4_grid_nfe=st.nfe.astype(np.int64))
+    return g
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT, "reference_fixtures.npz"), **reference_fixtures())
-    np.savez_compressed(os.path.join(OUT, "oracle_vectors.npz"), **oracle_vectors())
+    if "--large-only" not in sys.argv:  # the first two files are frozen since r1h; re-create them only on purpose
+        np.savez_compressed(os.path.join(OUT, "reference_fixtures.npz"), **reference_fixtures())
+        np.savez_compressed(os.path.join(OUT, "oracle_vectors.npz"), **oracle_vectors())
+    np.savez_compressed(os.path.join(OUT, "oracle_vectors_large.npz"), **oracle_vectors_large())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
