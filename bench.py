@@ -349,7 +349,7 @@ def run_b200(args):
         torch.cuda.current_stream().wait_event(ready[i % 2])
         if not last:
             h2d(i + 1)  # the other buffer: its last reader (step i-1) finished before that step's loss.item()
-        sol = px.odeint_adjoint(field_e, y0_bufs[i % 2], t_host, solver=px.Dopri5)
+        sol = px.odeint_adjoint(field_e, y0_bufs[i % 2], t_host, solver=px.Dopri5, options={"check_status": "deferred"})
         loss = sol[-1].abs().mean()
         loss.backward()
         flat = reduce_grads(torch.cat([p.grad.reshape(-1) for p in tw]))
@@ -445,7 +445,9 @@ def run_b200(args):
             "e2e": {"value": total_steps * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(y0_np.nbytes + t.nbytes), "d2h_bytes_per_step": int(g_host.numel() * 4 + 4 + 64),
                     "ms_per_step": ms_e2e / args.steps,
-                    "api": "paddlexde_b200.odeint_adjoint(field, y0, t, solver=Dopri5); loss.backward()",
+                    "api": "paddlexde_b200.odeint_adjoint(field, y0, t, solver=Dopri5, options={'check_status': 'deferred'}); "
+                           "loss.backward()  [deferred: the forward solve's assertions are raised by backward(), so the "
+                           "host does not wait between the two solves; default (synchronous) costs +0.3 ms]",
                     "input_pipeline": "one H2D copy of y0 per step from pinned memory on a copy stream, double-buffered: "
                                       "the copy for step n+1 overlaps the solve of step n (all inside the timed region)"},
             "gpu_launches": int(launches),

@@ -69,10 +69,14 @@ class OdeintAdjointMethod(torch.autograd.Function):
         (ans,) = ctx.saved_tensors
         if h["adjoint_solver"] is not Dopri5:
             raise NotImplementedError("the fused adjoint backward integrates with Dopri5")
+        defer = h.get("defer_fwd_status", False)
         g, _, stats, _ = adjoint_backward(h["field"], ctx.t_span, ans, grad_y.contiguous(), rtol=h["adjoint_rtol"],
                                           atol=h["adjoint_atol"], controller=h["controller"],
-                                          adj_norm=h["adj_norm"], **h["adjoint_ctrl"])
+                                          adj_norm=h["adj_norm"], check_status=not defer, **h["adjoint_ctrl"])
         h["bwd_stats"] = stats
+        if defer:  # both solves are queued: the forward assertion first (it is the cause), then the adjoint's
+            raise_for_status(h["fwd_solver"].read_stats().status)
+            raise_for_status(stats.read().status)
         if h["allreduce"] is not None:
             h["allreduce"](g)  # 8(e): the only collective on the path (adjoint parameter gradients)
         grads = []
@@ -122,7 +126,13 @@ def odeint_adjoint(func, y0, t_span, *, rtol=1e-7, atol=1e-9, solver=None, optio
         raise UnsupportedFieldError("custom adjoint norm callables cannot be fused; use 'seminorm' or the default")
     adjoint_ctrl = {k: adjoint_options[k] for k in ("min_step", "max_step", "first_step", "safety", "ifactor",
                                                     "dfactor", "max_num_steps") if k in adjoint_options}
-    holder = dict(field=field, solver=solver, rtol=rtol, atol=atol, options=options or {},
+    # options={"check_status": "deferred"}: the forward solve does not synchronise; its assertions (dt underflow,
+    # non-finite state, max_num_steps: base_adaptive_solver_rk.py:120-122, 200-203) are raised by backward(), after
+    # the adjoint solve has been queued -- no host round trip between the two solves.  Default: raised by the call.
+    defer = isinstance(options, dict) and options.get("check_status") == "deferred"
+    if defer:
+        options = {**options, "check_status": False}
+    holder = dict(field=field, solver=solver, rtol=rtol, atol=atol, options=options or {}, defer_fwd_status=defer,
                   adjoint_rtol=adjoint_rtol, adjoint_atol=adjoint_atol, adjoint_solver=adjoint_solver,
                   adjoint_ctrl=adjoint_ctrl, controller=controller, adj_norm=adj_norm, params=params,
                   allreduce=(options or {}).get("grad_allreduce"))

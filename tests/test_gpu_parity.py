@@ -522,6 +522,32 @@ def test_odeint_adjoint_autograd_surface(px, torch, oracle):
     np.testing.assert_allclose(got, g_ref, rtol=1e-5, atol=1e-6 * np.abs(g_ref).max())
 
 
+def test_odeint_adjoint_deferred_status_check(px, torch, oracle):
+    """options={"check_status": "deferred"}: no host round trip between the two solves; same numbers, and the
+    forward assertion (here max_num_steps) surfaces in backward() instead of in the call."""
+    w = spiral_weights()
+    y0, t = torch.from_numpy(cfg2_y0(500)).cuda(), cfg2_tspan(6)
+
+    def grads(**kw):
+        tw = [torch.tensor(a, device="cuda", requires_grad=True) for a in w]
+        sol = px.odeint_adjoint(px.MLPField(*tw, pre="cube"), y0, t, solver=px.Dopri5, **kw)
+        sol[-1].abs().mean().backward()
+        return sol.detach(), torch.cat([p.grad.reshape(-1) for p in tw])
+
+    sol_a, g_a = grads()
+    sol_b, g_b = grads(options={"check_status": "deferred"})
+    assert torch.equal(sol_a, sol_b)
+    np.testing.assert_allclose(g_b.cpu().numpy(), g_a.cpu().numpy(), rtol=1e-6, atol=1e-7 * float(g_a.abs().max()))
+    tw = [torch.tensor(a, device="cuda", requires_grad=True) for a in w]
+    field = px.MLPField(*tw, pre="cube")
+    with pytest.raises(AssertionError, match="max_num_steps"):
+        px.odeint_adjoint(field, y0, np.array([0.0, 5.0], f32), solver=px.Dopri5, options={"max_num_steps": 3})
+    sol = px.odeint_adjoint(field, y0, np.array([0.0, 5.0], f32), solver=px.Dopri5,
+                            options={"max_num_steps": 3, "check_status": "deferred"})  # does not raise here ...
+    with pytest.raises(AssertionError, match="max_num_steps"):
+        sol[-1].nan_to_num().sum().backward()                                        # ... but here
+
+
 # ------------------------------------------------------------------------------------------------
 # fixed-grid solvers, SDE
 # ------------------------------------------------------------------------------------------------
