@@ -396,9 +396,12 @@ int dopri5_fwd_batch(const xde_mlp_field_t *field, const float *y0, long long B,
     case 2: return batch_pre<2>(p, s);
     case 3: return batch_pre<3>(p, s);
     case 4: return batch_pre<4>(p, s);
+    case 5: return batch_pre<5>(p, s);
+    case 6: return batch_pre<6>(p, s);
+    case 7: return batch_pre<7>(p, s);
     case 8: return batch_pre<8>(p, s);
   }
-  set_last_error("dopri5 (batch controller): state dim D=%d has no fused kernel (supported: 1,2,3,4,8)", field->d);
+  set_last_error("dopri5 (batch controller): state dim D=%d has no fused kernel (supported: 1..8)", field->d);
   return XDE_E_UNSUPPORTED_FIELD;
 }
 
