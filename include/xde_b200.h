@@ -140,7 +140,7 @@ int xde_probe_ffma2_f32(int32_t iters, float *sink, int64_t *n_flops_host, void 
  * One launch integrates every trajectory over the whole t_span (device-resident controller).
  * y0 [B,D]; t_span [T] strictly increasing or strictly decreasing; out [T,B,D] time-major
  * (base_adaptive_solver.py:25).  stats / log may be NULL.
- * Fused shapes: D in 1..8 with any H that fits shared memory (XDE_CTRL_BATCH: D in {1,2,3,4,8}); D = 64 with H in
+ * Fused shapes: D in 1..8 with any H that fits shared memory (both controllers); D = 64 with H in
  * {128,256}, D = 32 with H in {64,128,256}, D = 16 with H = 64 (XDE_CTRL_TRAJECTORY); anything else returns
  * XDE_E_UNSUPPORTED_FIELD. */
 int xde_dopri5_mlp_f32(const xde_mlp_field_t *field, const float *y0, int64_t B, const float *t_span,

@@ -189,7 +189,7 @@ def case_gather():
 
 
 def case_batch_controller():
-    d = [1, 2, 3, 4, 8][rng.integers(5)]; h = int(rng.integers(2, 60)); pre = PRES[rng.integers(3)]
+    d = int(rng.integers(1, 9)); h = int(rng.integers(2, 60)); pre = PRES[rng.integers(3)]
     B = int(rng.integers(1, 3000)); w = weights(d, h, rng.uniform(0.5, 2.5)); o = ctrl_opts()
     y0 = rng.uniform(-1, 1, (B, d)).astype(f32); t = tspan(int(rng.integers(2, 7)), rng.uniform(0.2, 2), rng.random() < 0.3)
     desc = f"dopri5 controller=batch d={d} h={h} pre={pre} B={B} T={t.size} {o}"
