@@ -43,11 +43,13 @@
 #include "xde_common.cuh"
 
 #ifndef XDE_ADJ_U
-#define XDE_ADJ_U 2  // hidden-unit pairs evaluated together (independent tanh chains in flight per lane)
+#define XDE_ADJ_U 5  // hidden-unit pairs evaluated together for D <= 2 (independent tanh chains in flight per lane)
 #endif
 #ifndef XDE_ADJ_CTAS
-#define XDE_ADJ_CTAS 4  // resident CTAs per SM the register budget is sized for (4: 160 registers, no spills with U = 2)
+#define XDE_ADJ_CTAS 3  // __launch_bounds__ minimum; ptxas settles at 166 registers, i.e. 4 resident CTAs per SM
 #endif
+// U x CTAS swept on B200 after the fold became branch-free (cfg2 forward + adjoint, ms): 2x4 15.8, 3x4 15.6, 4x4 15.1,
+// 5x4 15.8, 2x3 15.6, 4x3 15.3, 5x3 15.0 (H = 50: 25 pairs = 5 trips, no tail), 6x3 15.4, 8x3 16.3, 5x2 19.3.
 
 namespace xde {
 
@@ -377,9 +379,10 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? XDE_ADJ_CT
           }
         }
       };
+      constexpr int UT = (D <= 2) ? XDE_ADJ_U : 2;  // wider states: two pairs per trip (register budget)
       int jp = 0;
 #pragma unroll 1
-      for (; jp + XDE_ADJ_U <= NP; jp += XDE_ADJ_U) eval_pairs(jp, std::integral_constant<int, XDE_ADJ_U>());
+      for (; jp + UT <= NP; jp += UT) eval_pairs(jp, std::integral_constant<int, UT>());
 #pragma unroll 1
       for (; jp < NP; ++jp) eval_pairs(jp, std::integral_constant<int, 1>());
       // solver-time dynamics: dy/ds = tsign * f ; da/ds = -tsign * vjp_y(a)
