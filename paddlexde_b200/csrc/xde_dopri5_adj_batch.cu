@@ -23,6 +23,8 @@
 // combines stages per partial sum and reduces in fp64 -- algebraically equal, compared at rtol 1e-5.
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "xde_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -127,27 +129,48 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
       accf[k] = pk1(0.0f);
       pdu[k] = pk1(0.0f);
     }
-#pragma unroll 2
-    for (int jp = 0; jp < NP; ++jp) {
-      f32x2 w1p[D], b1p, w2p[D];
-      read_pair_rec<D>(sw, jp, w1p, b1p, w2p);
-      f32x2 z = first_layer_seed<D>(u[0], w1p[0]);
+    // U hidden-unit pairs per trip, weight records read first and tile columns stored last (see xde_dopri5_adj.cu:
+    // ptxas cannot prove that the tile and the records do not alias and would serialise the pairs)
+    auto eval_pairs = [&](int jp0, auto ucount) {
+      constexpr int U = decltype(ucount)::value;
+      f32x2 w1p[U][D], b1p[U], w2p[U][D], h[U], dz[U];
 #pragma unroll
-      for (int k = 1; k < D; ++k) z = fma2(pk1(u[k]), w1p[k], z);
-      const f32x2 h = tanh_rat2(add2(z, b1p));
-      f32x2 dh = mul2(pk1(yin[D]), w2p[0]);
+      for (int i = 0; i < U; ++i) read_pair_rec<D>(sw, jp0 + i, w1p[i], b1p[i], w2p[i]);
 #pragma unroll
-      for (int d = 1; d < D; ++d) dh = fma2(pk1(yin[D + d]), w2p[d], dh);
-      const f32x2 dz = mul2(dh, one_minus_sq2(h));
+      for (int i = 0; i < U; ++i) {
+        f32x2 z = first_layer_seed<D>(u[0], w1p[i][0]);
 #pragma unroll
-      for (int d = 0; d < D; ++d) accf[d] = fma2(h, w2p[d], accf[d]);
+        for (int k = 1; k < D; ++k) z = fma2(pk1(u[k]), w1p[i][k], z);
+        h[i] = tanh_rat2(add2(z, b1p[i]));
+      }
 #pragma unroll
-      for (int k = 0; k < D; ++k) pdu[k] = fma2(dz, w1p[k], pdu[k]);
-      float h0, h1, z0, z1;
-      upk(h, h0, h1);
-      upk(dz, z0, z1);
-      tile[jp * kABTileStride + lane] = make_float4(h0, h1, z0, z1);
-    }
+      for (int i = 0; i < U; ++i) {
+        f32x2 dh = mul2(pk1(yin[D]), w2p[i][0]);
+#pragma unroll
+        for (int d = 1; d < D; ++d) dh = fma2(pk1(yin[D + d]), w2p[i][d], dh);
+        dz[i] = mul2(dh, one_minus_sq2(h[i]));
+      }
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) accf[d] = fma2(h[i], w2p[i][d], accf[d]);
+#pragma unroll
+        for (int k = 0; k < D; ++k) pdu[k] = fma2(dz[i], w1p[i][k], pdu[k]);
+      }
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        float h0, h1, z0, z1;
+        upk(h[i], h0, h1);
+        upk(dz[i], z0, z1);
+        tile[(jp0 + i) * kABTileStride + lane] = make_float4(h0, h1, z0, z1);
+      }
+    };
+    constexpr int UT = (D <= 2) ? 5 : 2;
+    int jp = 0;
+#pragma unroll 1
+    for (; jp + UT <= NP; jp += UT) eval_pairs(jp, std::integral_constant<int, UT>());
+#pragma unroll 1
+    for (; jp < NP; ++jp) eval_pairs(jp, std::integral_constant<int, 1>());
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       float fe, fod, ue, uo;
@@ -184,18 +207,24 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
       }
 #pragma unroll
       for (int q = 0; q < HPL; ++q) {
+        // branch-free (one basic block for the 32 columns): a lane without a pair folds a copy of the last row
+        // and its sums are cleared below
         const int jp = lane + 32 * q;
-        if (jp < NP) {
-          const float4 hv = tile[jp * kABTileStride + b];
-          const f32x2 hp = pk(hv.x, hv.y), dzp = pk(hv.z, hv.w);
+        const float4 hv = tile[(jp < NP ? jp : NP - 1) * kABTileStride + b];
+        const f32x2 hp = pk(hv.x, hv.y), dzp = pk(hv.z, hv.w);
 #pragma unroll
-          for (int k = 0; k < D; ++k) X[q * NV + k] = fma2(pk1(cb[k]), dzp, X[q * NV + k]);
-          X[q * NV + D] = fma2(pk1(cb[D]), dzp, X[q * NV + D]);
+        for (int k = 0; k < D; ++k) X[q * NV + k] = fma2(pk1(cb[k]), dzp, X[q * NV + k]);
+        X[q * NV + D] = fma2(pk1(cb[D]), dzp, X[q * NV + D]);
 #pragma unroll
-          for (int d = 0; d < D; ++d) X[q * NV + D + 1 + d] = fma2(pk1(cb[D + 1 + d]), hp, X[q * NV + D + 1 + d]);
-        }
+        for (int d = 0; d < D; ++d) X[q * NV + D + 1 + d] = fma2(pk1(cb[D + 1 + d]), hp, X[q * NV + D + 1 + d]);
       }
     }
+#pragma unroll
+    for (int q = 0; q < HPL; ++q)
+      if (lane + 32 * q >= NP) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) X[q * NV + i] = pk1(0.0f);
+      }
     __syncwarp();
   };
 
