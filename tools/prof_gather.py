@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from paddlexde_b200.xde.base_dde import history_gather, history_gather_bwd
 rng = np.random.default_rng(5)
-his = torch.from_numpy(rng.uniform(-1, 1, (1024, 307, 288, 3)).astype(np.float32)).cuda()
+his = torch.from_numpy(rng.uniform(-1, 1, (4096, 307, 288, 3)).astype(np.float32)).cuda()
 span = torch.arange(288, dtype=torch.float32, device="cuda")
 lags = torch.from_numpy((np.arange(12) + rng.uniform(0, 1, 12)).astype(np.float32)).cuda()
 for _ in range(3):
