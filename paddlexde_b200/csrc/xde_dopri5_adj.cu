@@ -61,6 +61,7 @@ struct AdjParams {
   xde_mlp_field_t field;
   const float *t_span, *y_ans, *grad_y;
   double *gacc;       // [P] fp64 accumulator (zeroed)
+  unsigned long long *queue;  // next unclaimed trajectory, shared by the whole grid (zeroed)
   float *adj_y0;      // [B,D] or null
   long long B;
   int T;
@@ -69,7 +70,6 @@ struct AdjParams {
   xde_attempt_t *log_records;
   int *log_counts;
   int log_cap;
-  long long chunk;
 };
 
 struct AdjTables {   // shared-memory coefficient tables (dynamic stage lookup)
@@ -107,7 +107,6 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? XDE_ADJ_CT
 
   extern __shared__ __align__(16) float smem[];
   __shared__ AdjTables tb;
-  __shared__ unsigned long long s_next;
   __shared__ unsigned long long s_cnt[3];
   __shared__ int s_status;
 
@@ -157,10 +156,7 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? XDE_ADJ_CT
     if (j < 6) b = bt[i][j];
     tb.beta[i][j] = b;
   }
-  const long long c0 = (long long)blockIdx.x * p.chunk;
-  const long long c1 = (c0 + p.chunk < p.B) ? c0 + p.chunk : p.B;
   if (threadIdx.x == 0) {
-    s_next = (unsigned long long)c0;
     s_cnt[0] = s_cnt[1] = s_cnt[2] = 0ull;
     s_status = 0;
   }
@@ -238,18 +234,19 @@ __global__ void __launch_bounds__(kAdjThreads, (D <= 2 && HPL <= 1) ? XDE_ADJ_CT
   };
 
   while (true) {
-    // ================= refill idle lanes from the CTA queue (warp-aggregated) =================
+    // ================= refill idle lanes from the grid-wide queue (warp-aggregated atomic) =================
+    // One queue for the whole grid: with one contiguous chunk per CTA the CTAs finished up to 8 % apart (r1s).
     {
       const bool need = (mode == AM_IDLE);
       const unsigned m = __ballot_sync(XDE_FULL_MASK, need);
       if (m) {
         unsigned long long base = 0;
         const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(&s_next, (unsigned long long)__popc(m));
+        if (lane == leader) base = atomicAdd(p.queue, (unsigned long long)__popc(m));
         base = __shfl_sync(XDE_FULL_MASK, base, leader);
         if (need) {
           const long long cand = (long long)base + __popc(m & ((1u << lane) - 1u));
-          if (cand < c1) {
+          if (cand < p.B) {
             traj = cand;
             seg = p.T - 1;
             // aug_state = [y_ans[-1], grad_y[-1]] (functional/odeint_adjoint.py:75-82)
@@ -727,15 +724,12 @@ static int launch_adj(const AdjParams &p, cudaStream_t stream) {
   int per_sm = 0;
   XDE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kAdjThreads, smem));
   if (per_sm < 1) per_sm = 1;
-  // persistent grid: a whole number of CTAs per SM; each CTA owns a contiguous chunk of trajectories
+  // persistent grid: a whole number of CTAs per SM, all fed from one trajectory queue
   long long want = (p.B + kAdjThreads - 1) / kAdjThreads;
   long long grid = (long long)sm_count() * per_sm;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  AdjParams q = p;
-  q.chunk = (p.B + grid - 1) / grid;
-  grid = (p.B + q.chunk - 1) / q.chunk;
-  kern<<<(unsigned)grid, kAdjThreads, smem, stream>>>(q);
+  kern<<<(unsigned)grid, kAdjThreads, smem, stream>>>(p);
   count_launch();
   XDE_CUDA_CHECK(cudaGetLastError());
   return XDE_OK;
@@ -807,8 +801,9 @@ extern "C" XDE_EXPORT int xde_dopri5_mlp_adjoint_f32(const xde_mlp_field_t *fiel
   p.log_records = log ? log->records : nullptr;
   p.log_counts = log ? log->counts : nullptr;
   p.log_cap = log ? log->cap : 0;
-  XDE_CUDA_CHECK(scratch_alloc((void **)&p.gacc, sizeof(double) * P, s));
-  XDE_CUDA_CHECK(cudaMemsetAsync(p.gacc, 0, sizeof(double) * P, s));
+  XDE_CUDA_CHECK(scratch_alloc((void **)&p.gacc, sizeof(double) * (P + 1), s));  // + the trajectory queue
+  XDE_CUDA_CHECK(cudaMemsetAsync(p.gacc, 0, sizeof(double) * (P + 1), s));
+  p.queue = reinterpret_cast<unsigned long long *>(p.gacc + P);
   if (stats) XDE_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(xde_stats_t), s));
   int rc = XDE_E_UNSUPPORTED_FIELD;
   switch (D) {

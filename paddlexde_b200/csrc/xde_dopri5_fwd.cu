@@ -9,7 +9,7 @@
 //   * the MLP weights sit in shared memory as one 16-byte-aligned record per hidden unit
 //     (broadcast LDS.128), the field is evaluated with explicit fmaf chains + a rational tanh;
 //   * the warp advances in lock-step "blocks" of 6 field evaluations (one attempt); a lane that
-//     finished its trajectory fetches the next one from a per-CTA queue and spends its block on
+//     finished its trajectory fetches the next one from a grid-wide queue and spends its block on
 //     select_initial_step (2 evaluations) -- when every lane of the warp is initialising the block
 //     is cut to 2 evaluations, so uniform workloads pay nothing for the refill;
 //   * per-trajectory HBM traffic: y0 in, T output rows out (+ optional attempt log).
@@ -31,7 +31,7 @@ struct FwdParams {
   xde_attempt_t *log_records;
   int *log_counts;
   int log_cap;
-  long long chunk;  // trajectories per CTA
+  unsigned long long *queue;  // next unclaimed trajectory, shared by the whole grid (zeroed)
 };
 
 enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_ATTEMPT = 2, MODE_DONE = 3 };
@@ -47,7 +47,6 @@ __device__ __forceinline__ float rms_small(const float (&v)[D]) {
 template <int D, int PRE>
 __global__ void __launch_bounds__(kFwdThreads) dopri5_fwd_small_kernel(const FwdParams p) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ unsigned long long s_next;
   __shared__ unsigned long long s_cnt[3];
   __shared__ int s_status;
 
@@ -59,10 +58,7 @@ __global__ void __launch_bounds__(kFwdThreads) dopri5_fwd_small_kernel(const Fwd
   const bool rev = p.t_span[1] < p.t_span[0];
   for (int i = threadIdx.x; i < p.T; i += blockDim.x) st[i] = rev ? -p.t_span[i] : p.t_span[i];
 
-  const long long c0 = (long long)blockIdx.x * p.chunk;
-  const long long c1 = (c0 + p.chunk < p.B) ? c0 + p.chunk : p.B;
   if (threadIdx.x == 0) {
-    s_next = (unsigned long long)c0;
     s_cnt[0] = s_cnt[1] = s_cnt[2] = 0ull;
     s_status = 0;
   }
@@ -87,18 +83,19 @@ __global__ void __launch_bounds__(kFwdThreads) dopri5_fwd_small_kernel(const Fwd
   int status = 0;
 
   while (true) {
-    // ---- refill idle lanes from the CTA queue (warp-aggregated) ----
+    // ---- refill idle lanes from the grid-wide queue (warp-aggregated atomic; one queue for the whole grid:
+    // with a contiguous chunk per CTA the CTAs of the adjoint finished up to 8 % apart) ----
     {
       const bool need = (mode == MODE_IDLE);
       const unsigned m = __ballot_sync(XDE_FULL_MASK, need);
       if (m) {
         unsigned long long base = 0;
         const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(&s_next, (unsigned long long)__popc(m));
+        if (lane == leader) base = atomicAdd(p.queue, (unsigned long long)__popc(m));
         base = __shfl_sync(XDE_FULL_MASK, base, leader);
         if (need) {
           const long long cand = (long long)base + __popc(m & ((1u << lane) - 1u));
-          if (cand < c1) {
+          if (cand < p.B) {
             traj = cand;
 #pragma unroll
             for (int e = 0; e < D; ++e) {
@@ -354,17 +351,19 @@ static int launch_fwd_small(const FwdParams &p, cudaStream_t stream) {
   int per_sm = 0;
   XDE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFwdThreads, smem));
   if (per_sm < 1) per_sm = 1;
-  // persistent grid: a whole number of CTAs per SM; each CTA owns a contiguous chunk of trajectories
+  // persistent grid: a whole number of CTAs per SM, all fed from one trajectory queue
   long long want = (p.B + kFwdThreads - 1) / kFwdThreads;
   long long grid = (long long)sm_count() * per_sm;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   FwdParams q = p;
-  q.chunk = (p.B + grid - 1) / grid;
-  grid = (p.B + q.chunk - 1) / q.chunk;
+  XDE_CUDA_CHECK(scratch_alloc((void **)&q.queue, sizeof(unsigned long long), stream));
+  XDE_CUDA_CHECK(cudaMemsetAsync(q.queue, 0, sizeof(unsigned long long), stream));
   kern<<<(unsigned)grid, kFwdThreads, smem, stream>>>(q);
   count_launch();
-  XDE_CUDA_CHECK(cudaGetLastError());
+  cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(q.queue, stream);
+  XDE_CUDA_CHECK(le);
   return XDE_OK;
 }
 
