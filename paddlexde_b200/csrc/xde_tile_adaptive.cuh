@@ -40,6 +40,7 @@ struct AdTileParams {
   // t_span[0] (sort_tvals is the shim's), in t_span's own time; may be null / 0
   const float *step_t, *jump_t;
   int n_step, n_jump;
+  unsigned long long *queue;  // next unclaimed tile, shared by the whole grid (zeroed)
   RkTab tab;  // the embedded pair (S stages = the kernel's template argument)
 };
 
@@ -103,7 +104,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) adaptive_tile_kernel(const Ad
     }
   };
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // tiles are handed out by one grid-wide counter: their durations differ (the slowest row of a tile decides)
+  __shared__ long long s_tile;
+  while (true) {
+    __syncthreads();  // the previous tile's readers of s_tile (and of sU / sH) are done
+    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(p.queue, 1ull);
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile >= n_tiles) break;
     const long long b0 = tile * TM + rg2 * R2;  // first of this thread's R2 trajectories
     float y[R2][C2], k[S + 1][R2][C2], yin[R2][C2];
     float t0[R2], dt[R2];
@@ -480,9 +488,14 @@ static int launch_ad_tile(const AdTileParams &p, cudaStream_t s) {
   long long n_tiles = (p.B + TM - 1) / TM;
   long long grid = (long long)sm_count() * per_sm;  // persistent: a whole number of CTAs per SM
   if (grid > n_tiles) grid = n_tiles;
-  kern<<<(unsigned)grid, kTileThreads, smem, s>>>(p);
+  AdTileParams q = p;
+  XDE_CUDA_CHECK(scratch_alloc((void **)&q.queue, sizeof(unsigned long long), s));
+  XDE_CUDA_CHECK(cudaMemsetAsync(q.queue, 0, sizeof(unsigned long long), s));
+  kern<<<(unsigned)grid, kTileThreads, smem, s>>>(q);
   count_launch();
-  XDE_CUDA_CHECK(cudaGetLastError());
+  cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(q.queue, s);
+  XDE_CUDA_CHECK(le);
   return XDE_OK;
 }
 
