@@ -441,9 +441,9 @@ def run_b200(args):
                                  "not counted"})(
                          2.0 * (25 * 27 + 32 * 5) / 32.0, torch.cuda.get_device_properties(dev).multi_processor_count,
                          (clocks or {}).get("sm_mhz") or 1965.0),
-                     "fma_pipe_active_ncu": {"dopri5_adj_kernel": 0.565, "dopri5_fwd_small_kernel": 0.61,
-                                             "issue_active_adj": 0.56,
-                                             "source": "sm__pipe_fma_cycles_active, profiles/r1r_ncu_full_adjoint.md, "
+                     "fma_pipe_active_ncu": {"dopri5_adj_kernel": 0.60, "dopri5_fwd_small_kernel": 0.61,
+                                             "issue_active_adj": 0.59,
+                                             "source": "sm__pipe_fma_cycles_active, profiles/r1t_ncu_full_adjoint.md, "
                                                        "profiles/r1d_ncu_full_packed_ffma2_kernels.md",
                                              "note": "a packed FFMA2 holds the FMA pipe for 2 cycles while ALU/XU "
                                                      "instructions co-issue (profiles/r1n_probe_issue.txt): the FMA "
@@ -463,10 +463,10 @@ def run_b200(args):
         }
         if args.batch == 1 << 20:
             # dram__bytes_read.sum + dram__bytes_write.sum of dopri5_adj_kernel, one launch at this batch:
-            # profiles/r1r_ncu_full_adjoint.md (169.39 MB + 5.38 MB).  Below the algorithmic 64 B/attempt
+            # profiles/r1t_ncu_full_adjoint.md (168.31 MB + 3.92 MB).  Below the algorithmic 64 B/attempt
             # because the fused kernel keeps (y, a) in registers across the attempts of a segment.
-            out["roofline"]["traffic"] = 174765568
-            out["roofline"]["traffic_source"] = "ncu --set full, profiles/r1r_ncu_full_adjoint.md"
+            out["roofline"]["traffic"] = 172224256
+            out["roofline"]["traffic_source"] = "ncu --set full, profiles/r1t_ncu_full_adjoint.md"
         if not args.no_cpu and world == 1:  # the CPU leg is timed at N = 1 only (rank 0)
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         if world == 1 and not args.no_secondary:
