@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define XDE_ABI_VERSION 2 /* 2: + tensor-core, table-driven adaptive RK, forced grid points, Philox, Bezier */
+#define XDE_ABI_VERSION 3 /* 2: + tensor-core, table-driven adaptive RK, forced grid points, Philox, Bezier
+                             3: + out_grad_t of the adjoint entry */
 
 /* return codes */
 enum {
@@ -173,11 +174,15 @@ int xde_adaptive_rk_mlp_grid_f32(int32_t method, const xde_mlp_field_t *field, c
  * (augmented_dynamics :89-124 integrated backwards segment by segment :134-159).
  * y_ans, grad_y [T,B,D]; out_gparams [d*h + h + h*d + d] = (gW1, gb1, gW2, gb2) summed over the
  * B trajectories handed to this call (all-reduce across GPUs is the caller's, 8(e));
- * out_adj_y0 [B,D] optional (dL/dy0: computed and discarded by the reference, :167). */
+ * out_adj_y0 [B,D] optional (dL/dy0: computed and discarded by the reference, :167);
+ * out_grad_t [T] optional (NULL = t_span does not require a gradient): grad_t_span of :129-141,161-162,
+ * i.e. out_grad_t[i] = sum_b func(t_i, y_i) . grad_y[i] for i >= 1 and out_grad_t[0] = the final aug_state[0]
+ * (XDE_CTRL_TRAJECTORY only; the g_t slot then takes part in the controller norm as the reference's does).
+ * Fused shapes: D in 1..8 with H <= 64 (H <= 128 for D <= 2). */
 int xde_dopri5_mlp_adjoint_f32(const xde_mlp_field_t *field, const float *t_span, int32_t T,
                                const float *y_ans, const float *grad_y, int64_t B,
                                const xde_ctrl_opts_t *opts, int32_t controller, int32_t adj_norm,
-                               float *out_gparams, float *out_adj_y0, xde_stats_t *stats,
+                               float *out_gparams, float *out_adj_y0, float *out_grad_t, xde_stats_t *stats,
                                const xde_attempt_log_t *log, void *stream);
 
 /* odeint(func, y0, t_span, solver=Euler|RK4|Midpoint) functional/odeint.py:28-35

@@ -913,8 +913,8 @@ static float adj_norm(void *ctx, const float *V) {
 
 static int adj_solve(const orc_mlp_t *m, const float *t_span, int T, const float *y_ans,
                      const float *grad_y, int64_t B, int64_t b0, int64_t Bm, const orc_opts_t *opts,
-                     int adj_norm_kind, double *gsum, float *gout, float *adj_y0, orc_stats_t *st,
-                     orc_attempt_t *log, int64_t log_cap, int64_t *log_len) {
+                     int adj_norm_kind, double *gsum, float *gout, float *adj_y0, double *gt_sum,
+                     orc_stats_t *st, orc_attempt_t *log, int64_t log_cap, int64_t *log_len) {
   const int D = m->d;
   const int64_t P = adj_nparams(m);
   const int64_t n = 1 + 2 * Bm * D + P;
@@ -931,6 +931,21 @@ static int adj_solve(const orc_mlp_t *m, const float *t_span, int T, const float
       aug[1 + (Bm + b) * D + e] = grad_y[((size_t)(T - 1) * B + b0 + b) * D + e];
     }
   for (int i = T - 1; i >= 1; --i) {
+    if (gt_sum) {
+      /* t_requires_grad (:135-141): dLd_cur_t = func(t_i, y_i) . grad_y[i]; aug_state[0] -= dLd_cur_t;
+       * grad_t_span[i] = dLd_cur_t.  Dot product: products rounded, summed left to right over (b, e). */
+      float dl = 0.0f;
+      for (int64_t b = 0; b < Bm; ++b) {
+        float fe[ORC_MAX_D];
+        orc_mlp_eval(m, aug + 1 + b * D, fe, NULL);
+        for (int e = 0; e < D; ++e) {
+          const float pr = fe[e] * grad_y[((size_t)i * B + b0 + b) * D + e];
+          dl = (b == 0 && e == 0) ? pr : dl + pr;
+        }
+      }
+      aug[0] = aug[0] - dl;
+      gt_sum[i] += (double)dl;
+    }
     float seg[2] = {t_span[i], t_span[i - 1]}; /* t_span[i-1:i+1].flip(0) (:147) */
     d.rhs = adj_rhs;
     d.norm = adj_norm;
@@ -958,6 +973,7 @@ static int adj_solve(const orc_mlp_t *m, const float *t_span, int T, const float
     if (adj_y0)
       for (int64_t b = 0; b < Bm; ++b)
         memcpy(adj_y0 + (b0 + b) * D, aug + 1 + (Bm + b) * D, sizeof(float) * D);
+    if (gt_sum) gt_sum[0] += (double)aug[0]; /* grad_t_span[0] = aug_state[0] (:161-162) */
   }
   free(aug);
   drv_free(&d);
@@ -967,7 +983,7 @@ static int adj_solve(const orc_mlp_t *m, const float *t_span, int T, const float
 int orc_dopri5_mlp_adjoint(const orc_mlp_t *m, const float *t_span, int32_t T, const float *y_ans,
                            const float *grad_y, int64_t B, const orc_opts_t *opts,
                            int32_t controller, int32_t adj_norm_kind, float *out_gparams,
-                           float *out_adj_y0, orc_stats_t *stats, orc_attempt_t *log,
+                           float *out_adj_y0, float *out_grad_t, orc_stats_t *stats, orc_attempt_t *log,
                            int64_t log_cap, int64_t log_traj, int64_t *log_len, int32_t nthreads) {
   const int64_t P = adj_nparams(m);
   if (m->d > ORC_MAX_D || m->h > ORC_MAX_H || T < 2 || B < 1) return ORC_BAD_ARG;
@@ -975,8 +991,13 @@ int orc_dopri5_mlp_adjoint(const orc_mlp_t *m, const float *t_span, int32_t T, c
   if (controller == ORC_CTRL_BATCH) {
     orc_stats_t st;
     stats_reset(&st);
+    double *gtb = out_grad_t ? (double *)calloc((size_t)T, sizeof(double)) : NULL;
     int rc = adj_solve(m, t_span, T, y_ans, grad_y, B, 0, B, opts, adj_norm_kind, NULL, out_gparams,
-                       out_adj_y0, &st, log, log_cap, log_len);
+                       out_adj_y0, gtb, &st, log, log_cap, log_len);
+    if (gtb) {
+      for (int i = 0; i < T; ++i) out_grad_t[i] = (float)gtb[i];
+      free(gtb);
+    }
     st.status = rc;
     if (stats) stats[0] = st;
     return rc;
@@ -985,6 +1006,7 @@ int orc_dopri5_mlp_adjoint(const orc_mlp_t *m, const float *t_span, int32_t T, c
    * integrals are summed at the end (valid: g_theta never feeds back). The sum is
    * taken in fp64 so it does not depend on the trajectory order. */
   double *gtot = (double *)calloc((size_t)P, sizeof(double));
+  double *gttot = out_grad_t ? (double *)calloc((size_t)T, sizeof(double)) : NULL;
   int worst = ORC_OK;
 #ifdef _OPENMP
   if (nthreads < 1) nthreads = omp_get_max_threads();
@@ -992,6 +1014,7 @@ int orc_dopri5_mlp_adjoint(const orc_mlp_t *m, const float *t_span, int32_t T, c
 #endif
   {
     double *gloc = (double *)calloc((size_t)P, sizeof(double));
+    double *gtloc = out_grad_t ? (double *)calloc((size_t)T, sizeof(double)) : NULL;
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 16)
 #endif
@@ -1000,7 +1023,7 @@ int orc_dopri5_mlp_adjoint(const orc_mlp_t *m, const float *t_span, int32_t T, c
       stats_reset(&st);
       int want_log = (log && b == log_traj);
       int rc = adj_solve(m, t_span, T, y_ans, grad_y, B, b, 1, opts, adj_norm_kind, gloc, NULL,
-                         out_adj_y0, &st, want_log ? log : NULL, log_cap, want_log ? log_len : NULL);
+                         out_adj_y0, gtloc, &st, want_log ? log : NULL, log_cap, want_log ? log_len : NULL);
       st.status = rc;
       if (stats) stats[b] = st;
       if (rc) {
@@ -1015,11 +1038,18 @@ int orc_dopri5_mlp_adjoint(const orc_mlp_t *m, const float *t_span, int32_t T, c
 #endif
     {
       for (int64_t p = 0; p < P; ++p) gtot[p] += gloc[p];
+      if (gttot)
+        for (int i = 0; i < T; ++i) gttot[i] += gtloc[i];
     }
     free(gloc);
+    free(gtloc);
   }
   for (int64_t p = 0; p < P; ++p) out_gparams[p] = (float)gtot[p];
   free(gtot);
+  if (gttot) {
+    for (int i = 0; i < T; ++i) out_grad_t[i] = (float)gttot[i];
+    free(gttot);
+  }
   return worst;
 }
 

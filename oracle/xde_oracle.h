@@ -133,11 +133,13 @@ int orc_fixed_mlp(int32_t method, const orc_mlp_t *m, const float *y0, int64_t B
 /* OdeintAdjointMethod.backward (functional/odeint_adjoint.py:47-167) with repairs R4-R6.
  * y_ans, grad_y: [T,B,D] time-major.  out_gparams: [d*h + h + h*d + d] = (gW1,gb1,gW2,gb2).
  * out_adj_y0: optional [B,D] (dL/dy0; the reference computes and then discards it, :167).
+ * out_grad_t: optional [T] = grad_t_span of the t_requires_grad branch (:129-141,161-162); NULL = t_span
+ *   does not require a gradient (aug_state[0] stays 0).  TRAJECTORY: the per-trajectory values summed in fp64.
  * stats: per trajectory (TRAJECTORY) or single (BATCH). */
 int orc_dopri5_mlp_adjoint(const orc_mlp_t *m, const float *t_span, int32_t T, const float *y_ans,
                            const float *grad_y, int64_t B, const orc_opts_t *opts,
                            int32_t controller, int32_t adj_norm, float *out_gparams,
-                           float *out_adj_y0, orc_stats_t *stats, orc_attempt_t *log,
+                           float *out_adj_y0, float *out_grad_t, orc_stats_t *stats, orc_attempt_t *log,
                            int64_t log_cap, int64_t log_traj, int64_t *log_len, int32_t nthreads);
 
 /* sdeint with Euler(-Maruyama) / Milstein and caller-supplied increments (repairs R2,R3;

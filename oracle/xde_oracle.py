@@ -201,8 +201,9 @@ def fixed_mlp(method: str, mlp: MLP, y0, t_span, nthreads=0):
 
 
 def dopri5_mlp_adjoint(mlp: MLP, t_span, y_ans, grad_y, *, controller="trajectory", adj_norm="seminorm",
-                       log_traj: Optional[int] = None, log_cap=100000, nthreads=0, **opt_kw):
-    """-> (gparams flat [P], adj_y0 [B,D], stats, log|None, status)"""
+                       log_traj: Optional[int] = None, log_cap=100000, nthreads=0, grad_t=None, **opt_kw):
+    """-> (gparams flat [P], adj_y0 [B,D], stats, log|None, status); grad_t: optional float32 [T] array that
+    receives grad_t_span (the reference's t_requires_grad branch)"""
     t_span, y_ans, grad_y = _f32(t_span), _f32(y_ans), _f32(grad_y)
     T, B, D = y_ans.shape
     g = np.zeros(mlp.n_params, np.float32)
@@ -215,7 +216,7 @@ def dopri5_mlp_adjoint(mlp: MLP, t_span, y_ans, grad_y, *, controller="trajector
     m, o = mlp.c(), make_opts(**opt_kw)
     rc = lib().orc_dopri5_mlp_adjoint(C.byref(m), _p(t_span), C.c_int32(T), _p(y_ans), _p(grad_y),
                                       C.c_int64(B), C.byref(o), C.c_int32(CTRL[controller]),
-                                      C.c_int32(ADJ_NORM[adj_norm]), _p(g), _p(a0), _p(stats),
+                                      C.c_int32(ADJ_NORM[adj_norm]), _p(g), _p(a0), _p(grad_t), _p(stats),
                                       _p(log) if want_log else None, C.c_int64(log_cap),
                                       C.c_int64(log_traj or 0), C.byref(log_len), C.c_int32(nthreads))
     return g, a0, stats.view(np.recarray), (log[:log_len.value].view(np.recarray) if want_log else None), rc

@@ -69,7 +69,8 @@ _EXPORTS = {
                                                C.POINTER(AttemptLogC), C.c_void_p]),
     "xde_dopri5_mlp_adjoint_f32": (C.c_int, [C.POINTER(MlpFieldC), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                              C.c_int64, C.POINTER(CtrlOptsC), C.c_int32, C.c_int32, C.c_void_p,
-                                             C.c_void_p, C.c_void_p, C.POINTER(AttemptLogC), C.c_void_p]),
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AttemptLogC),
+                                             C.c_void_p]),
     "xde_rk_fixed_mlp_f32": (C.c_int, [C.c_int32, C.POINTER(MlpFieldC), C.c_void_p, C.c_int64, C.c_void_p,
                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "xde_sde_mlp_f32": (C.c_int, [C.c_int32, C.POINTER(MlpFieldC), C.POINTER(MlpFieldC), C.c_void_p, C.c_int64,
@@ -114,7 +115,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the ABI is incomplete
             fn.restype = res
             fn.argtypes = args
-        if handle.xde_abi_version() != 2:
+        if handle.xde_abi_version() != 3:
             raise ImportError("libxde_b200.so ABI version mismatch")
         _lib = handle
     return _lib

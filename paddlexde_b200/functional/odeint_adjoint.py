@@ -22,11 +22,13 @@ from .odeint import odeint
 
 def adjoint_backward(field, t_span, y_ans, grad_y, *, rtol=1e-7, atol=1e-9, controller="trajectory",
                      adj_norm="seminorm", log_attempts=0, check_status=True, return_adj_y0=False,
-                     **ctrl_kw):
+                     out_grad_t=None, **ctrl_kw):
     """OdeintAdjointMethod.backward as a plain function on device buffers.
 
     y_ans, grad_y: [T, B, D] (time-major, as `odeint(..., Dopri5)` returns).  Returns
-    (gparams_flat [P], adj_y0 [B, D] | None, stats_reader, attempt_log | None)."""
+    (gparams_flat [P], adj_y0 [B, D] | None, stats_reader, attempt_log | None).
+    out_grad_t: optional fp32 device tensor [T] that receives grad_t_span (functional/odeint_adjoint.py:129-141,
+    161-162; the reference computes it only when t_span requires a gradient)."""
     y_ans_d, grad_d = T.to_dev(y_ans), T.to_dev(grad_y)
     t_host = host_tspan(t_span)
     Tn = t_host.size
@@ -44,7 +46,7 @@ def adjoint_backward(field, t_span, y_ans, grad_y, *, rtol=1e-7, atol=1e-9, cont
     t_dev = T.to_dev(t_host)
     check(lib().xde_dopri5_mlp_adjoint_f32(C.byref(fs), T.ptr(t_dev), Tn, T.ptr(y_ans_d), T.ptr(grad_d), B,
                                            C.byref(opts), CTRL[controller], ADJ_NORM[adj_norm], T.ptr(g),
-                                           T.ptr(a0), T.ptr(stats.buf),
+                                           T.ptr(a0), T.ptr(out_grad_t), T.ptr(stats.buf),
                                            C.byref(log.c_struct()) if log else None, T.stream()))
     if check_status:
         raise_for_status(stats.read().status)

@@ -37,7 +37,7 @@ def test_header_symbols_are_exported(so):
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/xde_b200.h but not exported"
     assert sorted(so.exported_symbols()) == names, "ctypes binding table and header disagree"
-    assert so.lib().xde_abi_version() == 2
+    assert so.lib().xde_abi_version() == 3
 
 
 def test_struct_layouts(so):
