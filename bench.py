@@ -20,7 +20,9 @@ the attempt counts are read from the device-side counters of the kernels.
 
 `--impl reference` times that CPU oracle as the reference arm (the reference is pure Python on
 Paddle, which cannot be installed offline here; DESIGN.md "Reference arm").
-Multi-GPU: launched by torchrun, one rank per GPU, trajectories sharded by batch (weak scaling).
+Multi-GPU: launched by torchrun, one rank per GPU, trajectories sharded by batch.  `--scaling weak` (default:
+2^20 trajectories PER GPU) or `--scaling strong` (the 1M-trajectory batch split N ways).
+`--config cfg3|cfg4|cfg5` measures the other BASELINE.json configs with the same line schema (tools/bench_lines.py).
 """
 from __future__ import annotations
 
@@ -54,6 +56,45 @@ def workload(B, seed=0, n_t=10):
     y0 = (np.array([2.0, 0.0]) + 0.5 * np.random.default_rng(seed).standard_normal((B, 2))).astype(np.float32)
     t = np.linspace(0.0, 25.0, 1000).astype(np.float32)[:n_t]
     return w, y0, t
+
+
+def latest_profile(kernel_substr, ms_measured, tol=0.02):
+    """ncu evidence for the dominant kernel WITHOUT pasted constants: the newest profiles/r*_ncu_full_*.md whose
+    section for `kernel_substr` was captured on a launch as long as the one this run timed (CUDA events vs
+    gpu__time_duration within `tol`).  -> dict(traffic bytes, fma_pipe_active, duration_ms, source) or None."""
+    import glob
+    import re
+
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_*.md"))):
+        sec = None
+        for block in open(path).read().split("### ")[1:]:
+            if kernel_substr in block.splitlines()[0]:
+                sec = block
+                break
+        if sec is None:
+            continue
+        vals = {}
+        for m in re.finditer(r"\| ([a-z_0-9.]+) \| ([-0-9.e+]+) \| ([^|]*) \|", sec):
+            vals[m.group(1)] = (float(m.group(2)), m.group(3).strip())
+        if "gpu__time_duration.sum" not in vals:
+            continue
+        dur, unit = vals["gpu__time_duration.sum"]
+        dur_ms = dur * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(unit, 1.0)
+
+        def nbytes(k):
+            v, u = vals.get(k, (0.0, "byte"))
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+
+        rec = {"duration_ms_ncu": dur_ms, "traffic": int(nbytes("dram__bytes_read.sum") + nbytes("dram__bytes_write.sum")),
+               "fma_pipe_active": vals.get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", (None,))[0],
+               "issue_ipc": vals.get("sm__inst_issued.avg.per_cycle_active", (None,))[0],
+               "source": "ncu --set full, " + os.path.relpath(path, ROOT),
+               "matches_this_run": abs(dur_ms - ms_measured) <= tol * ms_measured}
+        if rec["matches_this_run"] or best is None or not best["matches_this_run"]:
+            if rec["matches_this_run"] or best is None:
+                best = rec
+    return best
 
 
 def peaks():
@@ -126,10 +167,12 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
-def config_dict(B, n, where):
+def config_dict(B, n, where, args=None):
+    strong = args is not None and args.scaling == "strong"
     return {"workload": "cfg2: odeint_adjoint dopri5 rtol=1e-7 atol=1e-9, MLP 2-50-2 (y**3), "
                         "t=linspace(0,25,1000)[:10], loss=mean|y_T|",
-            "batch_per_gpu": B, "global_batch": B * n, "state_dim": 2, "hidden": 50, "n_out_times": 10,
+            "batch_per_gpu": B, "global_batch": (args.batch if strong else B * n), "state_dim": 2, "hidden": 50,
+            "n_out_times": 10,
             "controller": "trajectory", "adjoint_norm": "seminorm", "parallelism": f"batch-sharded x{n}",
             "l2": "256 MiB buffer written between steps (inside the timed region); working set 168 MiB > 126 MB L2"
                   if where == "device" else "n/a"}
@@ -232,8 +275,9 @@ def secondary_configs():
         import bench_configs as bc
         res = []
         for fn, kw in ((bc.cfg2_batch, {"norm": "mixed"}), (bc.cfg3, {"math": "tensor"}), (bc.cfg3, {"math": "fp32"}),
-                       (bc.cfg4, {"math": "tensor"}), (bc.cfg4, {"math": "fp32"}),
-                       (bc.cfg4, {"math": "tensor", "generated": True}), (bc.cfg5, {})):
+                       (bc.cfg4, {"math": "tensor", "B": 1 << 22}), (bc.cfg4, {"math": "fp32"}),
+                       (bc.cfg4, {"math": "tensor", "generated": True, "B": 1 << 22}), (bc.cfg5, {}),
+                       (bc.cfg5_real_size, {})):
             res.append(fn(**kw))
             torch.cuda.empty_cache()
         return res
@@ -260,20 +304,26 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     reduce_grads = pxd.grad_allreduce()
     lib = _lib.lib()
-    B = args.batch
-    w, y0_np, t = workload(B, seed=rank)
+    if args.scaling == "strong":  # the 1M-trajectory batch of the north star, split across the ranks
+        lo, hi = pxd.shard_rows(args.batch, rank, world)
+        w, y0_all, t = workload(args.batch, seed=0)
+        y0_np = np.ascontiguousarray(y0_all[lo:hi])
+        B = hi - lo
+    else:
+        B = args.batch
+        w, y0_np, t = workload(B, seed=rank)
     field = px.MLPField(*w, pre="cube")
     y0 = torch.from_numpy(y0_np).to(dev)
     xde = px.xde.BaseODE(field, y0, t)
     gy = torch.zeros((t.size, B, 2), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    inv_n = 1.0 / (B * 2)
+    inv_n = 1.0 / ((args.batch if args.scaling == "strong" else B) * 2)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     k_ev = {"fwd": [], "adj": []}
 
     def step(timed):
         flush.zero_()
-        s = px.Dopri5(xde=xde, y0=y0, rtol=1e-7, atol=1e-9, check_status=False)
+        s = px.Dopri5(xde=xde, y0=y0, rtol=1e-7, atol=1e-9, controller="trajectory", check_status=False)
         e = [ev() for _ in range(4)] if timed else None
         if timed:
             e[0].record()
@@ -349,8 +399,9 @@ def run_b200(args):
         torch.cuda.current_stream().wait_event(ready[i % 2])
         if not last:
             h2d(i + 1)  # the other buffer: its last reader (step i-1) finished before that step's loss.item()
-        sol = px.odeint_adjoint(field_e, y0_bufs[i % 2], t_host, solver=px.Dopri5, **opts)
-        loss = sol[-1].abs().mean()
+        sol = px.odeint_adjoint(field_e, y0_bufs[i % 2], t_host, solver=px.Dopri5,
+                                options={"controller": "trajectory", **opts.get("options", {})})
+        loss = sol[-1].abs().sum() * inv_n   # mean|y_T| over the GLOBAL batch
         loss.backward()
         flat = reduce_grads(torch.cat([p.grad.reshape(-1) for p in tw]))
         return float(loss.item()), flat.cpu()
@@ -372,9 +423,9 @@ def run_b200(args):
         return e0.elapsed_time(e1), out
 
     ms_e2e, (loss_v, g_host) = e2e_time({})  # the default call: the headline e2e
-    # the same with the forward solve's assertions raised by backward() instead of by the call (no host round trip
-    # between the two solves); reported next to the headline, not instead of it
-    ms_e2e_def, _ = e2e_time({"options": {"check_status": "deferred"}})
+    # the same with the forward solve's assertions raised by the call itself, as the reference does (the host waits
+    # between the two solves); reported next to the headline
+    ms_e2e_sync, _ = e2e_time({"options": {"check_status": True}})
 
     # ---- FP32 pipe ceiling (measured) ----
     sink = torch.zeros(1, device=dev)
@@ -390,9 +441,9 @@ def run_b200(args):
     ffma_tflops = nfl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
     if world > 1:
-        tt = torch.tensor([ms, ms_e2e, ms_fwd, ms_adj, ms_e2e_def], device=dev, dtype=torch.float64)
+        tt = torch.tensor([ms, ms_e2e, ms_fwd, ms_adj, ms_e2e_sync], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_fwd, ms_adj, ms_e2e_def = tt.tolist()
+        ms, ms_e2e, ms_fwd, ms_adj, ms_e2e_sync = tt.tolist()
         cnt = torch.tensor([n_traj_steps, fwd_stats.n_attempts, adj_stats.n_attempts], device=dev, dtype=torch.int64)
         cnt_local = cnt.clone()
         dist.all_reduce(cnt)
@@ -403,70 +454,73 @@ def run_b200(args):
         hbm, which = peaks()
         value = total_steps * args.steps / (ms * 1e-3)
         dom = "adj" if ms_adj >= ms_fwd else "fwd"
+        k_name = "dopri5_adj_kernel" if dom == "adj" else "dopri5_fwd_small_kernel"
         k_attempts = adj_stats.n_attempts if dom == "adj" else fwd_stats.n_attempts
+        k_nfe = adj_stats.nfe if dom == "adj" else fwd_stats.nfe
         k_ms = ms_adj if dom == "adj" else ms_fwd
         k_bytes = (BYTES_ADJ if dom == "adj" else BYTES_FWD) * k_attempts
         k_flops = (FLOPS_ADJ if dom == "adj" else FLOPS_FWD) * k_attempts
-        achieved = k_bytes / (k_ms * 1e-3) / 1e9
+        achieved_gbs = k_bytes / (k_ms * 1e-3) / 1e9
+        achieved_tf = k_flops / (k_ms * 1e-3) / 1e12
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        # FMA-pipe model of the adjoint kernel, evaluated on THIS run's counters: per field+VJP evaluation of one
+        # trajectory 25 hidden-unit pairs x 27 packed instructions (2 x 3 first layer, 16 rational tanh, 8 VJP / second
+        # layer) + 5 packed fold instructions per pair and column, each holding one scheduler's FMA pipe for 2 cycles
+        # per warp of 32 trajectories (tools/probe_issue.cu).  Evaluations really executed: 2 per segment start
+        # (f0 + probe; the reference counts 3) + 6 per attempt.
+        n_seg = (t.size - 1) * B
+        evals = 6 * adj_stats.n_attempts + 2 * n_seg
+        cyc = 2.0 * (25 * 27 + 32 * 5) / 32.0
+        bound_ms = evals * cyc / (sms * 4 * mhz * 1e3)
+        prof = latest_profile(k_name, k_ms)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(B, world, "device"),
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(B, world, "device", args),
             "trajectory_steps_per_step": {"forward": fwd_stats.n_attempts, "adjoint": adj_stats.n_attempts,
                                           "accepted_forward": fwd_stats.n_accepted, "accepted_adjoint": adj_stats.n_accepted,
                                           "nfe_forward": fwd_stats.nfe, "nfe_adjoint": adj_stats.nfe, "per": "rank 0"},
             "kernel_ms": {"dopri5_fwd_small_kernel": ms_fwd, "dopri5_adj_kernel(+cast)": ms_adj},
-            "roofline": {"bound": "hbm", "kernel": "dopri5_adj_kernel" if dom == "adj" else "dopri5_fwd_small_kernel",
-                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                         "peak_source": which,
-                         "algorithmic_bytes_per_launch": k_bytes,
-                         "note": "D=2, H=50: 75-112 FLOP/B of scalar FP32 + 50 tanh per field evaluation, K=2/N=2 "
-                                 "degenerate for MMA -> the FP32 pipe binds, not HBM (SURVEY 8(d)); see fp32"},
-            "fp32": {"achieved_tflops_algorithmic": k_flops / (k_ms * 1e-3) / 1e12,
-                     "ffma_peak_tflops_measured": ffma_tflops,
-                     "frac_algorithmic": k_flops / (k_ms * 1e-3) / 1e12 / ffma_tflops,
-                     "note": "algorithmic FLOPs count the two GEMVs (+VJP) only; each of the 50 tanh per evaluation costs "
-                             "~14 further FP32 issue slots (rational 13/6 + IEEE division) that the count leaves out",
-                     # FMA-pipe model of the adjoint kernel, evaluated live: per field+VJP evaluation of one
-                     # trajectory 25 hidden-unit pairs x 27 packed instructions (2 x 3 first layer, 16 rational
-                     # tanh, 8 VJP / second layer) + 5 packed fold instructions per pair, each holding one
-                     # scheduler's FMA pipe for 2 cycles per warp of 32 trajectories (tools/probe_issue.cu)
-                     "fma_pipe_model": (lambda cyc, sms, mhz: {
-                         "packed_warp_instructions_per_evaluation": cyc / 2.0,
-                         "bound_ms": adj_stats.nfe * cyc / (sms * 4 * mhz * 1e3),
-                         "frac_of_bound": adj_stats.nfe * cyc / (sms * 4 * mhz * 1e3) / ms_adj,
-                         "note": "time the adjoint launch would take if its packed FP32 instructions alone kept every "
-                                 "scheduler's FMA pipe busy at the sampled SM clock; the controller's scalar work is "
-                                 "not counted"})(
-                         2.0 * (25 * 27 + 32 * 5) / 32.0, torch.cuda.get_device_properties(dev).multi_processor_count,
-                         (clocks or {}).get("sm_mhz") or 1965.0),
-                     "fma_pipe_active_ncu": {"dopri5_adj_kernel": 0.60, "dopri5_fwd_small_kernel": 0.61,
-                                             "issue_active_adj": 0.59,
-                                             "source": "sm__pipe_fma_cycles_active, profiles/r1t_ncu_full_adjoint.md, "
-                                                       "profiles/r1d_ncu_full_packed_ffma2_kernels.md",
-                                             "note": "a packed FFMA2 holds the FMA pipe for 2 cycles while ALU/XU "
-                                                     "instructions co-issue (profiles/r1n_probe_issue.txt): the FMA "
-                                                     "pipe, not the issue slot, is the ceiling of these kernels"}},
+            # D = 2, H = 50: 75-112 FLOP/B of scalar FP32 + 50 tanh per evaluation, K = 2 / N = 2 GEMVs (degenerate for
+            # an MMA): the FP32 FMA pipe binds, not HBM.  peak = the FFMA probe of THIS run.
+            "roofline": {"bound": "fp32", "kernel": k_name, "achieved": achieved_tf, "peak": ffma_tflops,
+                         "unit": "TFLOP/s", "frac": achieved_tf / ffma_tflops,
+                         "peak_source": "xde_probe_ffma_f32 timed in this run (8 independent FFMA chains per thread, "
+                                        "every SM); not in MEASURED_PEAKS.json, which holds HBM and bf16 only",
+                         "algorithmic_flops_per_launch": k_flops,
+                         "traffic": prof["traffic"] if prof and prof["matches_this_run"] else None,
+                         "traffic_source": (prof or {}).get("source") if prof and prof["matches_this_run"] else
+                         "no committed ncu capture matches this run's kernel time within 2 %",
+                         "note": "algorithmic FLOPs = SURVEY 8(d)'s 72*D*H (adjoint) / 24*D*H (forward) per trajectory-step: "
+                                 "the two GEMVs and their VJPs only.  The arithmetic specification (rational 13/6 tanh + IEEE "
+                                 "division, bit-exact against the oracle) adds 16 of the 27 packed FMA-pipe instructions per "
+                                 "hidden-unit pair that this count leaves out: see fma_pipe_model"},
+            "roofline_hbm": {"bound": "hbm", "kernel": k_name, "achieved": achieved_gbs, "peak": hbm, "unit": "GB/s",
+                             "frac": achieved_gbs / hbm, "peak_source": which, "algorithmic_bytes_per_launch": k_bytes,
+                             "note": "reported because the contract asks for it; the kernel keeps (y, a) in registers across "
+                                     "the attempts of a segment, so even the algorithmic bytes are not moved"},
+            "fma_pipe_model": {"evaluations": evals, "fma_pipe_cycles_per_evaluation_and_warp": cyc * 32.0,
+                               "bound_ms": bound_ms, "frac_of_bound": bound_ms / ms_adj, "sm_mhz": mhz,
+                               "note": "time the adjoint launch would take if the packed FP32 instructions the arithmetic "
+                                       "specification requires (field + VJP + parameter-gradient fold) kept every scheduler's "
+                                       "FMA pipe busy at the sampled SM clock; controller arithmetic not counted"},
+            "ncu": prof,
             "e2e": {"value": total_steps * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(y0_np.nbytes + t.nbytes), "d2h_bytes_per_step": int(g_host.numel() * 4 + 4 + 64),
                     "ms_per_step": ms_e2e / args.steps,
-                    "api": "paddlexde_b200.odeint_adjoint(field, y0, t, solver=Dopri5); loss.backward()",
-                    "with_deferred_status_check": {
-                        "value": total_steps * args.steps / (ms_e2e_def * 1e-3), "ms_per_step": ms_e2e_def / args.steps,
-                        "api": "odeint_adjoint(..., options={'check_status': 'deferred'}): the forward solve's assertions "
-                               "are raised by backward(), the host does not wait between the two solves"},
+                    "api": "paddlexde_b200.odeint_adjoint(field, y0, t, solver=Dopri5); loss.backward()  (a training step: the "
+                           "forward solve's assertions are raised by backward(), one D2H for both status words)",
+                    "with_synchronous_status_check": {
+                        "value": total_steps * args.steps / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync / args.steps,
+                        "api": "odeint_adjoint(..., options={'check_status': True}): the call itself raises, as the reference "
+                               "does (the host waits between the two solves)"},
                     "input_pipeline": "one H2D copy of y0 per step from pinned memory on a copy stream, double-buffered: "
                                       "the copy for step n+1 overlaps the solve of step n (all inside the timed region)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if args.batch == 1 << 20:
-            # dram__bytes_read.sum + dram__bytes_write.sum of dopri5_adj_kernel, one launch at this batch:
-            # profiles/r1t_ncu_full_adjoint.md (168.31 MB + 3.92 MB).  Below the algorithmic 64 B/attempt
-            # because the fused kernel keeps (y, a) in registers across the attempts of a segment.
-            out["roofline"]["traffic"] = 172224256
-            out["roofline"]["traffic_source"] = "ncu --set full, profiles/r1t_ncu_full_adjoint.md"
         if not args.no_cpu and world == 1:  # the CPU leg is timed at N = 1 only (rank 0)
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         if world == 1 and not args.no_secondary:
@@ -488,7 +542,16 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the cfg3/cfg4 kernel timings")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch trajectories per GPU; strong: --batch trajectories in total, split across the GPUs")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json config to measure (cfg2 = the headline; the others print the same line schema)")
     args = ap.parse_args()
+    if args.config != "cfg2":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_lines
+
+        return bench_lines.main(args, ClockSampler, peaks)
     if args.impl == "reference":
         run_reference(args)
     else:

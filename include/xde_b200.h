@@ -261,6 +261,10 @@ int xde_history_gather_bwd_f32(const float *grad_y, const float *deriv, int64_t 
 /* BaseDDE.fuse (damped Euler update)                  xde/base_dde.py:55-58
  * y1 = (dy - 0.001*(dy*dt + y0))*dt + y0, elementwise over n values. */
 int xde_dde_fuse_f32(const float *dy, float dt, const float *y0, int64_t n, float *y1, void *stream);
+/* its cotangents (the solution of ddeint is differentiated through by the D3STN trainer,
+ * example/D3STN/train_dde.py:424-454): grad_dy = grad_y1 * dt*(1 - 0.001*dt), grad_y0 = grad_y1 * (1 - 0.001*dt);
+ * either output may be NULL. */
+int xde_dde_fuse_bwd_f32(const float *grad_y1, float dt, int64_t n, float *grad_dy, float *grad_y0, void *stream);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,7 @@ _EXPORTS = {
     "xde_history_gather_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                              C.c_void_p, C.c_void_p]),
     "xde_dde_fuse_f32": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "xde_dde_fuse_bwd_f32": (C.c_int, [C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

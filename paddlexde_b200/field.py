@@ -19,14 +19,20 @@ from ._lib import PRE, MlpFieldC, UnsupportedFieldError
 
 
 class MLPField:
-    def __init__(self, w1, b1, w2, b2, pre: str = "cube", act: str = "tanh"):
+    def __init__(self, w1, b1, w2, b2, pre: str = "cube", act: str = "tanh", weight_layout: str = "in_out"):
+        """weight_layout: "in_out" = Paddle nn.Linear ([in, out]: w1 [D, H], w2 [H, D]); "out_in" = torch nn.Linear
+        ([out, in]: w1 [H, D], w2 [D, H]).  The caller's tensors are kept as they are (they stay the leaves that
+        autograd / the optimizer see); the kernels read [in, out] device copies made here and by refresh()."""
+        if weight_layout not in ("in_out", "out_in"):
+            raise ValueError("weight_layout must be 'in_out' (Paddle) or 'out_in' (torch)")
+        self.weight_layout = weight_layout
         if act != "tanh":
             raise UnsupportedFieldError(f"activation {act!r} has no fused kernel (tanh only)")
         if pre not in PRE:
             raise UnsupportedFieldError(f"pre-activation {pre!r} has no fused kernel (id|square|cube)")
         self.pre = pre
         self._src = (w1, b1, w2, b2)  # kept so autograd can route gradients to the caller's tensors
-        self.w1, self.b1, self.w2, self.b2 = (T.to_dev(a) for a in (w1, b1, w2, b2))
+        self._load()
         if self.w1.dim() != 2:
             raise ValueError("w1 must be [D, H] (Paddle nn.Linear layout [in, out])")
         self.d, self.h = self.w1.shape
@@ -39,10 +45,24 @@ class MLPField:
         """Like nn.Layer.parameters() (functional/odeint_adjoint.py:276)."""
         return list(self._src)
 
+    def _load(self):
+        w1, b1, w2, b2 = (T.to_dev(a) for a in self._src)
+        if self.weight_layout == "out_in":
+            w1, w2 = w1.t().contiguous(), w2.t().contiguous()
+        self.w1, self.b1, self.w2, self.b2 = w1, b1, w2, b2
+
     def refresh(self):
-        """Re-read the caller's parameter tensors (after an optimizer step on host/other tensors)."""
-        self.w1, self.b1, self.w2, self.b2 = (T.to_dev(a) for a in self._src)
+        """Re-read the caller's parameter tensors (after an optimizer step; device tensors in the [in, out]
+        layout are shared, everything else is copied)."""
+        self._load()
         return self
+
+    def grads_like_params(self, flat: torch.Tensor):
+        """The flat (gW1, gb1, gW2, gb2) of the adjoint entries, shaped like `parameters()`."""
+        gw1, gb1, gw2, gb2 = self.split_flat(flat)
+        if self.weight_layout == "out_in":
+            gw1, gw2 = gw1.t(), gw2.t()
+        return [gw1, gb1, gw2, gb2]
 
     @property
     def n_params(self) -> int:
@@ -70,9 +90,9 @@ class MLPField:
         w1, w2 = l1.weight, l2.weight
         if weight_layout == "auto":
             weight_layout = "out_in" if isinstance(w1, torch.Tensor) else "in_out"
-        if weight_layout == "out_in":  # torch nn.Linear stores [out, in]
-            w1, w2 = w1.detach().t().contiguous(), w2.detach().t().contiguous()
-        return cls(w1, l1.bias, w2, l2.bias, pre=pre)
+        # the module's own Parameters stay the leaves: gradients are routed (and transposed back) to them, and
+        # refresh() re-reads them after an optimizer step
+        return cls(w1, l1.bias, w2, l2.bias, pre=pre, weight_layout=weight_layout)
 
 
 def as_field(func) -> MLPField:

@@ -14,15 +14,15 @@ import torch
 from .. import _tensor as T
 from .._lib import ADJ_NORM, CTRL, UnsupportedFieldError, check, lib, raise_for_status
 from ..field import as_field
-from ..solver.adaptive_solver import (AttemptLog, Dopri5, StatsBuffer, check_norm, host_tspan,
-                                      make_ctrl_opts)
+from ..solver.adaptive_solver import (AttemptLog, Dopri5, StatsBuffer, StatsPair, check_norm, default_controller,
+                                      device_tspan, host_tspan, make_ctrl_opts)
 from ..utils.ode_utils import _rms_norm
 from .odeint import odeint
 
 
 def adjoint_backward(field, t_span, y_ans, grad_y, *, rtol=1e-7, atol=1e-9, controller="trajectory",
                      adj_norm="seminorm", log_attempts=0, check_status=True, return_adj_y0=False,
-                     out_grad_t=None, **ctrl_kw):
+                     out_grad_t=None, stats_buffer=None, **ctrl_kw):
     """OdeintAdjointMethod.backward as a plain function on device buffers.
 
     y_ans, grad_y: [T, B, D] (time-major, as `odeint(..., Dopri5)` returns).  Returns
@@ -39,11 +39,11 @@ def adjoint_backward(field, t_span, y_ans, grad_y, *, rtol=1e-7, atol=1e-9, cont
     dev = y_ans_d.device
     g = torch.zeros(field.n_params, device=dev, dtype=torch.float32)
     a0 = torch.empty((B, D), device=dev, dtype=torch.float32) if return_adj_y0 else None
-    stats = StatsBuffer(dev)
+    stats = StatsBuffer(dev) if stats_buffer is None else stats_buffer
     log = AttemptLog(B, log_attempts, dev) if log_attempts > 0 else None
     opts = make_ctrl_opts(rtol, atol, **ctrl_kw)
     fs = field.c_struct()
-    t_dev = T.to_dev(t_host)
+    t_dev = device_tspan(t_host, dev)
     check(lib().xde_dopri5_mlp_adjoint_f32(C.byref(fs), T.ptr(t_dev), Tn, T.ptr(y_ans_d), T.ptr(grad_d), B,
                                            C.byref(opts), CTRL[controller], ADJ_NORM[adj_norm], T.ptr(g),
                                            T.ptr(a0), T.ptr(out_grad_t), T.ptr(stats.buf),
@@ -72,22 +72,32 @@ class OdeintAdjointMethod(torch.autograd.Function):
         if h["adjoint_solver"] is not Dopri5:
             raise NotImplementedError("the fused adjoint backward integrates with Dopri5")
         defer = h.get("defer_fwd_status", False)
+        # grad_t_span only when t_span requires a gradient (t_requires_grad, functional/odeint_adjoint.py:27,130-141)
+        t_req = isinstance(ctx.t_span, torch.Tensor) and ctx.needs_input_grad[2]
+        grad_t = torch.empty(ctx.t_span.numel(), device=ans.device, dtype=torch.float32) if t_req else None
         g, _, stats, _ = adjoint_backward(h["field"], ctx.t_span, ans, grad_y.contiguous(), rtol=h["adjoint_rtol"],
                                           atol=h["adjoint_atol"], controller=h["controller"],
-                                          adj_norm=h["adj_norm"], check_status=not defer, **h["adjoint_ctrl"])
+                                          adj_norm=h["adj_norm"], check_status=False, out_grad_t=grad_t,
+                                          stats_buffer=h["stats_pair"].adj, **h["adjoint_ctrl"])
         h["bwd_stats"] = stats
-        if defer:  # both solves are queued: the forward assertion first (it is the cause), then the adjoint's
-            raise_for_status(h["fwd_solver"].read_stats().status)
-            raise_for_status(stats.read().status)
+        # both solves are queued; ONE device-to-host copy brings both status words.  The forward assertion first
+        # (it is the cause) when its check was deferred to here, then the adjoint's.
+        st_fwd, st_adj = h["stats_pair"].read()
+        if defer:
+            h["fwd_solver"].stats = st_fwd
+            raise_for_status(st_fwd.status)
+        raise_for_status(st_adj.status)
         if h["allreduce"] is not None:
             h["allreduce"](g)  # 8(e): the only collective on the path (adjoint parameter gradients)
         grads = []
-        for p, gp in zip(h["params"], h["field"].split_flat(g)):
+        for p, gp in zip(h["params"], h["field"].grads_like_params(g)):
             if isinstance(p, torch.Tensor) and p.requires_grad:
                 grads.append(gp.to(p.device).reshape(p.shape).to(p.dtype))
             else:
                 grads.append(None)
-        return (None, None, None, *grads)  # y0 gets no gradient (functional/odeint_adjoint.py:167)
+        if grad_t is not None:
+            grad_t = grad_t.to(ctx.t_span.device).reshape(ctx.t_span.shape).to(ctx.t_span.dtype)
+        return (None, None, grad_t, *grads)  # y0 gets no gradient (functional/odeint_adjoint.py:167)
 
 
 def odeint_adjoint(func, y0, t_span, *, rtol=1e-7, atol=1e-9, solver=None, options={"norm": _rms_norm},
@@ -115,7 +125,16 @@ def odeint_adjoint(func, y0, t_span, *, rtol=1e-7, atol=1e-9, solver=None, optio
         check_norm(options.get("norm"))
 
     # adjoint norm (handle_adjoint_norm_, :280-327): default mixed norm | "seminorm"
-    controller = adjoint_options.pop("controller", (options or {}).get("controller", "trajectory"))
+    controller = adjoint_options.pop("controller", (options or {}).get("controller"))
+    if controller is None:  # announced once: the reference's default is the batch controller + mixed norm
+        shp = getattr(y0, "shape", None)
+        rows = None
+        if shp is not None and len(shp) >= 1:
+            rows = 1
+            for v in shp[:-1]:
+                rows *= int(v)
+        controller = default_controller(rows)
+        options = {**(options or {}), "controller": controller}
     norm = adjoint_options.pop("norm", None)
     if norm is None:
         # With one controller per trajectory the parameter-gradient state is a per-trajectory partial
@@ -128,12 +147,20 @@ def odeint_adjoint(func, y0, t_span, *, rtol=1e-7, atol=1e-9, solver=None, optio
         raise UnsupportedFieldError("custom adjoint norm callables cannot be fused; use 'seminorm' or the default")
     adjoint_ctrl = {k: adjoint_options[k] for k in ("min_step", "max_step", "first_step", "safety", "ifactor",
                                                     "dfactor", "max_num_steps") if k in adjoint_options}
-    # options={"check_status": "deferred"}: the forward solve does not synchronise; its assertions (dt underflow,
-    # non-finite state, max_num_steps: base_adaptive_solver_rk.py:120-122, 200-203) are raised by backward(), after
-    # the adjoint solve has been queued -- no host round trip between the two solves.  Default: raised by the call.
-    defer = isinstance(options, dict) and options.get("check_status") == "deferred"
-    if defer:
-        options = {**options, "check_status": False}
+    # When the forward solve's assertions (dt underflow, non-finite state, max_num_steps: base_adaptive_solver_rk.py:
+    # 120-122, 200-203) are raised:
+    #   options={"check_status": True}        by the call itself, like the reference (one host round trip per solve);
+    #   options={"check_status": "deferred"}  by backward(), after the adjoint solve has been queued -- the GPU does
+    #                                         not idle while the host walks from one solve to the other;
+    #   options={"check_status": False}       never (the caller reads `odeint_adjoint.last["fwd_solver"].read_stats()`).
+    # Default: "deferred" when some adjoint parameter requires a gradient (a training step: backward() follows),
+    # True otherwise.
+    cs = (options or {}).get("check_status", None)
+    if cs is None:
+        training = any(isinstance(p, torch.Tensor) and p.requires_grad for p in params)
+        cs = "deferred" if training else True
+    defer = (cs == "deferred")
+    options = {**(options or {}), "check_status": False if defer else cs}
     holder = dict(field=field, solver=solver, rtol=rtol, atol=atol, options=options or {}, defer_fwd_status=defer,
                   adjoint_rtol=adjoint_rtol, adjoint_atol=adjoint_atol, adjoint_solver=adjoint_solver,
                   adjoint_ctrl=adjoint_ctrl, controller=controller, adj_norm=adj_norm, params=params,
@@ -141,6 +168,8 @@ def odeint_adjoint(func, y0, t_span, *, rtol=1e-7, atol=1e-9, solver=None, optio
     if "grad_allreduce" in holder["options"]:
         holder["options"] = {k: v for k, v in holder["options"].items() if k != "grad_allreduce"}
     y0_t = y0 if isinstance(y0, torch.Tensor) else T.to_dev(y0)
+    holder["stats_pair"] = StatsPair(y0_t.device if y0_t.is_cuda else T.device())
+    holder["options"]["stats_buffer"] = holder["stats_pair"].fwd
     tensor_params = [p if isinstance(p, torch.Tensor) else torch.as_tensor(p) for p in params]
     sol = OdeintAdjointMethod.apply(holder, y0_t, t_span, *tensor_params)
     odeint_adjoint.last = holder

@@ -71,7 +71,7 @@ class SdeintAdjointMethod(torch.autograd.Function):
         if h["allreduce"] is not None:  # 8(e): batch shards sum their parameter gradients
             h["allreduce"](gf)
             h["allreduce"](gg)
-        flat = list(h["drift"].split_flat(gf)) + list(h["diffusion"].split_flat(gg))
+        flat = list(h["drift"].grads_like_params(gf)) + list(h["diffusion"].grads_like_params(gg))
         grads = []
         for p, gp in zip(h["params"], flat):
             if isinstance(p, torch.Tensor) and p.requires_grad:

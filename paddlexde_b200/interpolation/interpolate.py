@@ -15,8 +15,10 @@ class _Interp:
     def __init__(self, series, t=None):
         self._series = T.to_dev(series)
         n = self._series.shape[-2]
-        if t is None:  # interpolate_base.py:21-27
-            t = torch.linspace(0, n, n + 1)
+        if t is None:
+            # interpolate_base.py:21-27 builds linspace(0, n, n + 1) but only ever reads its first n entries (one
+            # per sample of the series): the grid is 0, 1, ..., n-1
+            t = torch.arange(n, dtype=torch.float32)
         self._t = T.to_dev(t)
 
     @property

@@ -10,6 +10,8 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
+import warnings
 from dataclasses import dataclass
 
 import numpy as np
@@ -18,6 +20,39 @@ import torch
 from .. import _tensor as T
 from .._lib import (CTRL, RK, AttemptLogC, CtrlOptsC, StatsC, UnsupportedFieldError, check, lib,
                     raise_for_status)
+
+
+class ControllerDefaultWarning(UserWarning):
+    """Raised once per process when the controller granularity was not chosen by the caller (see default_controller)."""
+
+
+_warned_default = False
+
+
+def default_controller(batch_rows: int | None = None) -> str:
+    """Controller granularity when the caller does not pass `controller=`.
+
+    The reference applies `_rms_norm` to the whole [B, D] state: ONE dt and one accept/reject for the batch, and its
+    adjoint default is the mixed norm over (y, a, g_theta) (utils/ode_utils.py:8-9, functional/odeint_adjoint.py:
+    284-291) -- that is controller="batch".  This package defaults to one controller per trajectory
+    ("trajectory": each trajectory is stepped as the reference would step it alone, B = 1; the adjoint then uses the
+    seminorm), which is what BASELINE.json's north star asks for and what the throughput kernels implement.  For
+    B > 1 the two give different step sequences (both within tolerance), so the choice is announced once per process.
+    Set PADDLEXDE_B200_CONTROLLER=batch|trajectory to choose the default globally (no warning then)."""
+    global _warned_default
+    env = os.environ.get("PADDLEXDE_B200_CONTROLLER")
+    if env:
+        if env not in CTRL:
+            raise ValueError("PADDLEXDE_B200_CONTROLLER must be 'trajectory' or 'batch'")
+        return env
+    if not _warned_default and (batch_rows is None or batch_rows > 1):
+        _warned_default = True
+        warnings.warn("paddlexde_b200 steps every trajectory with its own error controller (controller='trajectory', "
+                      "adjoint seminorm); the reference uses one global RMS norm / dt for the whole batch and the mixed "
+                      "adjoint norm.  Pass options={'controller': 'batch'} (or set PADDLEXDE_B200_CONTROLLER=batch) for "
+                      "the reference's step sequence; pass controller='trajectory' to silence this notice.",
+                      ControllerDefaultWarning, stacklevel=3)
+    return "trajectory"
 
 
 @dataclass
@@ -56,16 +91,52 @@ def host_tspan(t_span) -> np.ndarray:
     return t
 
 
-class StatsBuffer:
-    """Device-resident xde_stats_t read back lazily (one tiny D2H copy when asked)."""
+_STATS_WORDS = C.sizeof(StatsC) // 8
 
-    def __init__(self, dev):
-        self.buf = torch.zeros(C.sizeof(StatsC) // 8, dtype=torch.int64, device=dev)
+
+def _decode_stats(words) -> SolveStats:
+    s = StatsC.from_buffer_copy(words.tobytes())
+    return SolveStats(int(s.n_attempts), int(s.n_accepted), int(s.nfe), int(s.status))
+
+
+class StatsBuffer:
+    """Device-resident xde_stats_t read back lazily (one tiny D2H copy when asked).  The entry points zero it."""
+
+    def __init__(self, dev, buf=None):
+        self.buf = torch.empty(_STATS_WORDS, dtype=torch.int64, device=dev) if buf is None else buf
 
     def read(self) -> SolveStats:
-        raw = self.buf.cpu().numpy().tobytes()
-        s = StatsC.from_buffer_copy(raw)
-        return SolveStats(int(s.n_attempts), int(s.n_accepted), int(s.nfe), int(s.status))
+        return _decode_stats(self.buf.cpu().numpy())
+
+
+class StatsPair:
+    """The forward solve's and the adjoint solve's xde_stats_t side by side, so that odeint_adjoint's backward reads
+    both status words with ONE device-to-host copy."""
+
+    def __init__(self, dev):
+        self.both = torch.zeros(2 * _STATS_WORDS, dtype=torch.int64, device=dev)
+        self.fwd = StatsBuffer(dev, self.both[:_STATS_WORDS])
+        self.adj = StatsBuffer(dev, self.both[_STATS_WORDS:])
+
+    def read(self):
+        w = self.both.cpu().numpy()
+        return _decode_stats(w[:_STATS_WORDS]), _decode_stats(w[_STATS_WORDS:])
+
+
+_tspan_cache: dict = {}
+
+
+def device_tspan(t_host: np.ndarray, dev) -> torch.Tensor:
+    """fp32 device copy of t_span; the handful of grids a training loop uses are cached (forward and backward ask for
+    the same one every step, and a pageable H2D copy costs more than the rest of the launch path)."""
+    key = (t_host.tobytes(), str(dev))
+    t = _tspan_cache.get(key)
+    if t is None:
+        if len(_tspan_cache) >= 64:
+            _tspan_cache.clear()
+        t = torch.from_numpy(t_host).to(dev)
+        _tspan_cache[key] = t
+    return t
 
 
 class AttemptLog:
@@ -93,11 +164,19 @@ class AdaptiveRKSolver:
 
     def __init__(self, xde, y0, rtol, atol, min_step=0, max_step=float("inf"), first_step=None, step_t=None,
                  jump_t=None, safety=0.9, ifactor=10.0, dfactor=0.2, max_num_steps=2 ** 31 - 1, dtype=None,
-                 norm=None, controller="trajectory", log_attempts=0, check_status=True, **unused_kwargs):
+                 norm=None, controller=None, log_attempts=0, check_status=True, stats_buffer=None, **unused_kwargs):
         self.step_t, self.jump_t = step_t, jump_t
         if getattr(xde, "kind", None) != "ode":
             raise UnsupportedFieldError(f"{type(self).__name__} integrates BaseODE problems")
         check_norm(norm)
+        if controller is None:
+            shp = getattr(y0, "shape", None)
+            rows = None
+            if shp is not None and len(shp) >= 1:
+                rows = 1
+                for v in shp[:-1]:
+                    rows *= int(v)
+            controller = default_controller(rows)
         if controller not in CTRL:
             raise ValueError("controller must be 'trajectory' or 'batch'")
         self.xde, self.y0 = xde, y0
@@ -107,6 +186,7 @@ class AdaptiveRKSolver:
         self.controller = controller
         self.log_attempts = int(log_attempts)
         self.check_status = check_status
+        self._stats_buf = stats_buffer  # optional caller-owned StatsBuffer (odeint_adjoint shares one with its backward)
         self.stats = None
         self.attempt_log = None
 
@@ -118,9 +198,10 @@ class AdaptiveRKSolver:
             raise ValueError(f"y0 last dim {y0.shape[-1]} != field state dim {field.d}")
         B = y0.numel() // field.d
         t_host = host_tspan(t_span)
-        t_dev = T.to_dev(t_host)
+        t_dev = device_tspan(t_host, y0.device)
         out = torch.empty((t_host.size,) + tuple(y0.shape), device=y0.device, dtype=torch.float32)
-        self._stats_buf = StatsBuffer(y0.device)
+        if self._stats_buf is None:
+            self._stats_buf = StatsBuffer(y0.device)
         log_c = None
         if self.log_attempts > 0:
             self.attempt_log = AttemptLog(B, self.log_attempts, y0.device)

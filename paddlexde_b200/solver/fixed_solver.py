@@ -73,6 +73,13 @@ class FixedSolver:
         B = y0.numel() // D
         n_out = (Tn - 1 + self.out_stride - 1) // self.out_stride + 1
         out = torch.empty((B, n_out, D), device=y0.device, dtype=torch.float32)
+        # the kernels are specialised on the field's state dim and index y0 / out / dW with it: a mismatch would read
+        # and write out of bounds on the device (the C ABI sees only pointers), so it is refused here
+        fields = {"ode": ("field",), "sde": ("drift", "diffusion")}.get(kind, ())
+        for name in fields:
+            fd = getattr(self.xde, name).d
+            if D != fd:
+                raise ValueError(f"y0 last dim {D} != state dim {fd} of the {name} field")
         if kind == "ode":
             fs = self.xde.field.c_struct()
             args = (FIXED[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), Tn, self.out_stride, T.ptr(out))

@@ -56,6 +56,49 @@ class HistoryIndex(torch.autograd.Function):
         return history_gather_bwd(grad_y.contiguous(), deriv), None, None, None
 
 
+class DdeFuse(torch.autograd.Function):
+    """BaseDDE.fuse (xde/base_dde.py:55-58) with its cotangents: the D3STN trainer backpropagates through the
+    solution of ddeint into `func`'s parameters (example/D3STN/train_dde.py:424-454), so the update must stay on
+    the autograd graph.  y1 = (dy - 0.001*(dy*dt + y0))*dt + y0."""
+
+    @staticmethod
+    def forward(ctx, dy, dt, y0):
+        dy_d, y0_d = T.to_dev(dy), T.to_dev(y0)
+        if dy_d.shape != y0_d.shape:
+            dy_d, y0_d = (a.contiguous() for a in torch.broadcast_tensors(dy_d, y0_d))
+        out = torch.empty_like(y0_d)
+        check(lib().xde_dde_fuse_f32(T.ptr(dy_d), float(dt), T.ptr(y0_d), y0_d.numel(), T.ptr(out), T.stream()))
+        ctx.dt = float(dt)
+        ctx.shapes = (tuple(dy.shape), tuple(y0.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        need_dy, need_y0 = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
+        g_dy = torch.empty_like(g) if need_dy else None
+        g_y0 = torch.empty_like(g) if need_y0 else None
+        if need_dy or need_y0:
+            check(lib().xde_dde_fuse_bwd_f32(T.ptr(g), ctx.dt, g.numel(), T.ptr(g_dy), T.ptr(g_y0), T.stream()))
+        if g_dy is not None and g_dy.shape != ctx.shapes[0]:
+            g_dy = g_dy.sum_to_size(ctx.shapes[0])
+        if g_y0 is not None and g_y0.shape != ctx.shapes[1]:
+            g_y0 = g_y0.sum_to_size(ctx.shapes[1])
+        return g_dy, None, g_y0
+
+
+def _as_graph_tensor(x):
+    """fp32 CUDA tensor that KEEPS its autograd history (T.to_dev detaches: right for kernel inputs, wrong for
+    values the caller differentiates through)."""
+    if not isinstance(x, torch.Tensor):
+        return T.to_dev(x)
+    if x.dtype != torch.float32:
+        x = x.to(torch.float32)
+    if not x.is_cuda:
+        x = x.to(T.device())
+    return x
+
+
 class BaseDDE(BaseXDE):
     """xde/base_dde.py:14-79: one-shot history resampling, then a fixed-step solve with
     move = func(y_lags, y0) and the damped fuse (lambda = 0.001, :55-58)."""
@@ -79,7 +122,4 @@ class BaseDDE(BaseXDE):
         return self.func(self.y_lags, y0)
 
     def fuse(self, dy, dt, y0):
-        dy_d, y0_d = T.to_dev(dy), T.to_dev(y0)
-        out = torch.empty_like(y0_d)
-        check(lib().xde_dde_fuse_f32(T.ptr(dy_d), float(dt), T.ptr(y0_d), y0_d.numel(), T.ptr(out), T.stream()))
-        return out
+        return DdeFuse.apply(_as_graph_tensor(dy), float(dt), _as_graph_tensor(y0))

@@ -534,14 +534,20 @@ def test_odeint_adjoint_deferred_status_check(px, torch, oracle):
         sol[-1].abs().mean().backward()
         return sol.detach(), torch.cat([p.grad.reshape(-1) for p in tw])
 
-    sol_a, g_a = grads()
+    sol_a, g_a = grads(options={"check_status": True})
     sol_b, g_b = grads(options={"check_status": "deferred"})
+    sol_c, g_c = grads()  # the default of a training step (parameters require grad) is the deferred check
+    assert torch.equal(sol_a, sol_c) and torch.equal(g_b, g_c)
     assert torch.equal(sol_a, sol_b)
     np.testing.assert_allclose(g_b.cpu().numpy(), g_a.cpu().numpy(), rtol=1e-6, atol=1e-7 * float(g_a.abs().max()))
     tw = [torch.tensor(a, device="cuda", requires_grad=True) for a in w]
     field = px.MLPField(*tw, pre="cube")
     with pytest.raises(AssertionError, match="max_num_steps"):
-        px.odeint_adjoint(field, y0, np.array([0.0, 5.0], f32), solver=px.Dopri5, options={"max_num_steps": 3})
+        px.odeint_adjoint(field, y0, np.array([0.0, 5.0], f32), solver=px.Dopri5,
+                          options={"max_num_steps": 3, "check_status": True})
+    with pytest.raises(AssertionError, match="max_num_steps"):  # nothing requires grad: checked by the call
+        px.odeint_adjoint(px.MLPField(*w, pre="cube"), y0, np.array([0.0, 5.0], f32), solver=px.Dopri5,
+                          options={"max_num_steps": 3})
     sol = px.odeint_adjoint(field, y0, np.array([0.0, 5.0], f32), solver=px.Dopri5,
                             options={"max_num_steps": 3, "check_status": "deferred"})  # does not raise here ...
     with pytest.raises(AssertionError, match="max_num_steps"):
@@ -1105,7 +1111,7 @@ def test_ddeint_one_damped_euler_step(px, torch, oracle):
     dy = func(torch.from_numpy(yl_ref).cuda(), torch.from_numpy(y0).cuda()).cpu().numpy()
     y1_ref = oracle.dde_fuse(dy, 1.0, y0)
     assert tuple(sol.shape) == (8, 307, 24, 3)  # concat(axis=-2) of y0 and y1
-    assert np.array_equal(sol[..., 12:, :].cpu().numpy(), y1_ref)
+    assert np.array_equal(sol[..., 12:, :].detach().cpu().numpy(), y1_ref)
     gy = rng.standard_normal(yl_ref.shape).astype(f32)
     y_lags.backward(torch.from_numpy(gy).cuda())
     gl_ref = oracle.history_gather_bwd(gy, d_ref)

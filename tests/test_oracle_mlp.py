@@ -222,3 +222,42 @@ def test_sde_adjoint_oracle_is_the_gradient_of_the_em_recursion(oracle):
     ref_g = np.concatenate([p.grad.numpy().ravel() for p in P[4:]])
     for got, want in ((gf, ref_f), (gg, ref_g), (a0, ys[0].grad.numpy())):
         assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
+def test_oracle_grad_t_span_is_the_true_time_gradient(oracle):
+    """t_requires_grad branch of the adjoint (functional/odeint_adjoint.py:129-141,161-162) in the C oracle, against
+    fp64 autograd through a fine RK4 integration whose step sizes are differentiable functions of t_span."""
+    import torch
+
+    rng = np.random.default_rng(8)
+    d, h, B = 3, 12, 5
+    w = [rng.standard_normal((d, h)) / np.sqrt(d), 0.1 * rng.standard_normal(h),
+         rng.standard_normal((h, d)) / np.sqrt(h), 0.1 * rng.standard_normal(d)]
+    om = oracle.MLP(*[a.astype(np.float32) for a in w], pre="id")
+    y0 = rng.uniform(-1, 1, (B, d)).astype(np.float32)
+    t = np.array([0.0, 0.3, 0.7, 1.2], np.float32)
+    ref, _, _, rc = oracle.dopri5_mlp(om, y0, t)
+    assert rc == 0
+    gy = rng.standard_normal(ref.shape).astype(np.float32)
+    gt = np.zeros(t.size, np.float32)
+    g, a0, _, _, rc = oracle.dopri5_mlp_adjoint(om, t, ref, gy, grad_t=gt)
+    assert rc == 0
+    g_plain, a_plain, _, _, _ = oracle.dopri5_mlp_adjoint(om, t, ref, gy)
+    np.testing.assert_allclose(a0, a_plain, rtol=1e-5, atol=1e-6)  # the g_t slot only perturbs the step sequence
+
+    W = [torch.tensor(np.asarray(a, np.float32), dtype=torch.float64) for a in w]
+    f = lambda y: torch.tanh(y @ W[0] + W[1]) @ W[2] + W[3]
+    tt = torch.tensor(t, dtype=torch.float64, requires_grad=True)
+    y = torch.tensor(y0, dtype=torch.float64)
+    sols = [y]
+    for i in range(1, t.size):
+        n = 64
+        hh = (tt[i] - tt[i - 1]) / n
+        for _ in range(n):
+            k1 = f(y); k2 = f(y + 0.5 * hh * k1); k3 = f(y + 0.5 * hh * k2); k4 = f(y + hh * k3)
+            y = y + hh / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        sols.append(y)
+    L = (torch.stack(sols) * torch.tensor(gy, dtype=torch.float64)).sum()
+    L.backward()
+    want = tt.grad.numpy()
+    np.testing.assert_allclose(gt, want, rtol=2e-4, atol=2e-5 * np.abs(want).max())

@@ -63,13 +63,18 @@ def cfg4(B=1 << 21, math="tensor", generated=False):
     steps = B * 16
     flops = steps * (4 * d * h * 2)
     byts = steps * 12 * d  # read y, read dW, write y per trajectory-step
-    moved = steps * 4 * d + B * 2 * d * 4 + B * d * 4  # what the fused kernel really moves: dW + y0 in + 2 rows out
-    return {"config": "cfg4 sde-EM 2x(32-64-32)" + (" increments generated in-kernel (Philox)" if generated else ""),
+    # what a FUSED solve has to move: the increments (0 when generated in the kernel) + y0 in + the 2 emitted rows out
+    moved = (0 if generated else steps * 4 * d) + B * d * 4 + B * 2 * d * 4
+    return {"config": "cfg4 sde-EM 2x(32-64-32)" + (" increments generated in-kernel (Philox)" if generated else
+                                                     " supplied increments"),
             "math": math, "B": B, "ms": ms,
             "traj_steps_per_s": steps / ms * 1e3, "tflops_algorithmic": flops / ms / 1e9,
-            "hbm_gbs_algorithmic": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / HBM,
-            "hbm_gbs_moved": moved / ms / 1e6,
-            "note": "B=2^21 (half of cfg4's 2^22: the full dW table is 8 GiB; fits, but halves the run time)"}
+            "hbm_gbs_required": moved / ms / 1e6, "frac_hbm": moved / ms / 1e6 / HBM,
+            "hbm_gbs_survey_formula": byts / ms / 1e6, "frac_hbm_survey_formula": byts / ms / 1e6 / HBM,
+            "note": "frac_hbm counts the bytes a fused solve must move (dW table + y0 + emitted rows); the SURVEY 8(d) "
+                    "formula (12*D B per trajectory-step) also charges a y read+write per step that the fused kernel "
+                    "never performs (r1 quoted that figure: inflated 2.6x).  B=2^22 is BASELINE's 4M (dW table 8 GiB)"
+                    if B == 1 << 22 else "reduced batch (BASELINE's cfg4 is B=2^22)"}
 
 
 def cfg5(Bh=4096, kind="cubic"):
@@ -92,6 +97,28 @@ def cfg5(Bh=4096, kind="cubic"):
             "hbm_gbs_algorithmic_bwd": n * 8 / ms_b / 1e6, "frac_hbm_bwd": n * 8 / ms_b / 1e6 / HBM,
             "note": "his is 4.2 GB at B=4096 (the kernel must outlast the ~75 us host side of a call to be timed from the "
                     "host) but only 13 of 288 time rows are touched: 20 B/element algorithmic"}
+
+
+def cfg5_real_size(kind="cubic"):
+    """cfg5 at the size D3STN really calls it with (example/D3STN/train_dde.py: batch 8, 307 graph nodes, 288 history
+    steps, 3 channels, 12 lags): 88 K output elements -- launch-bound.  Latency of one call through the shim (host
+    side included) and of the kernel alone (20 queued launches between the events)."""
+    rng = np.random.default_rng(5)
+    his = torch.from_numpy(rng.uniform(-1, 1, (8, 307, 288, 3)).astype(np.float32)).cuda()
+    span = torch.arange(288, dtype=torch.float32, device="cuda")
+    lags = torch.from_numpy((np.arange(12) + rng.uniform(0, 1, 12)).astype(np.float32)).cuda()
+    NB = 20
+    ms = timeit(lambda: [history_gather(lags, his, span, kind) for _ in range(NB)]) / NB
+    t0 = time.perf_counter()
+    for _ in range(200):
+        history_gather(lags, his, span, kind)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / 200
+    n = 8 * 307 * 12 * 3
+    return {"config": f"cfg5 history gather {kind}, D3STN call size (8 x 307 rows, 288 steps, 12 lags, 3 channels)",
+            "elements": n, "us_per_call_gpu_queued": ms * 1e3, "us_per_call_host_wall": wall * 1e6,
+            "note": "88 K elements = 1.8 MB algorithmic: a few microseconds of kernel; the call is bound by launch + host "
+                    "overhead (two allocations + one ctypes call), not by HBM"}
 
 
 def cfg2_batch(B=1 << 20, norm="mixed"):

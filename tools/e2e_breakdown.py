@@ -5,7 +5,7 @@ import numpy as np, torch
 import paddlexde_b200 as px
 from bench import workload
 
-B = 1 << 20
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 w, y0_np, t = workload(B)
 dev = torch.device("cuda", 0)
 tw = [torch.tensor(a, device=dev, requires_grad=True) for a in w]
@@ -27,7 +27,7 @@ for it in range(4):
     for p in tw: p.grad = None
     y0_buf.copy_(y0_pin, non_blocking=True)
     t0 = tick("h2d", t0)
-    sol = px.odeint_adjoint(field, y0_buf, th, solver=px.Dopri5)
+    sol = px.odeint_adjoint(field, y0_buf, th, solver=px.Dopri5, options={"controller": "trajectory"})
     t0 = tick("odeint_adjoint fwd", t0)
     loss = sol[-1].abs().mean()
     t0 = tick("loss", t0)
