@@ -82,11 +82,14 @@ class OdeintAdjointMethod(torch.autograd.Function):
         h["bwd_stats"] = stats
         # both solves are queued; ONE device-to-host copy brings both status words.  The forward assertion first
         # (it is the cause) when its check was deferred to here, then the adjoint's.
-        st_fwd, st_adj = h["stats_pair"].read()
-        if defer:
-            h["fwd_solver"].stats = st_fwd
-            raise_for_status(st_fwd.status)
-        raise_for_status(st_adj.status)
+        if h.get("check_status", True) is not False:
+            st_fwd, st_adj = h["stats_pair"].read()
+            if defer:
+                h["fwd_solver"].stats = st_fwd
+                raise_for_status(st_fwd.status)
+            raise_for_status(st_adj.status)
+        # check_status=False: nothing is read back (the call sequence stays capturable in a CUDA graph); the caller
+        # reads `odeint_adjoint.last["stats_pair"]` when it wants the status words
         if h["allreduce"] is not None:
             h["allreduce"](g)  # 8(e): the only collective on the path (adjoint parameter gradients)
         grads = []
@@ -162,6 +165,7 @@ def odeint_adjoint(func, y0, t_span, *, rtol=1e-7, atol=1e-9, solver=None, optio
     defer = (cs == "deferred")
     options = {**(options or {}), "check_status": False if defer else cs}
     holder = dict(field=field, solver=solver, rtol=rtol, atol=atol, options=options or {}, defer_fwd_status=defer,
+                  check_status=cs,
                   adjoint_rtol=adjoint_rtol, adjoint_atol=adjoint_atol, adjoint_solver=adjoint_solver,
                   adjoint_ctrl=adjoint_ctrl, controller=controller, adj_norm=adj_norm, params=params,
                   allreduce=(options or {}).get("grad_allreduce"))

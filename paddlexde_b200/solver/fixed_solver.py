@@ -9,7 +9,7 @@ import torch
 
 from .. import _tensor as T
 from .._lib import FIXED, SDE, ST_TC_RANGE, XDE_E_UNSUPPORTED_FIELD, UnsupportedFieldError, check, lib
-from .adaptive_solver import host_tspan
+from .adaptive_solver import device_tspan, host_tspan
 
 
 class FixedSolver:
@@ -67,7 +67,7 @@ class FixedSolver:
         kind = getattr(self.xde, "kind", None)
         y0 = T.to_dev(self.y0)
         t_host = host_tspan(t_span)
-        t_dev = T.to_dev(t_host)
+        t_dev = device_tspan(t_host, y0.device)
         Tn = t_host.size
         D = y0.shape[-1]
         B = y0.numel() // D

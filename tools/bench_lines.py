@@ -188,6 +188,7 @@ def main(args, ClockSampler, peaks):
         evs = []
         barrier()
         e0, e1 = ev(), ev()
+        w0 = time.perf_counter()
         e0.record()
         for _ in range(n):
             if flush_l2:
@@ -198,7 +199,9 @@ def main(args, ClockSampler, peaks):
             b.record()
             evs.append((a, b))
         e1.record()
+        host_ms = 1e3 * (time.perf_counter() - w0) / n  # host time to ENQUEUE a step (diagnostic)
         barrier()
+        extra.setdefault("host_enqueue_ms_per_step", []).append(round(host_ms, 3))
         return e0.elapsed_time(e1), float(np.mean([a.elapsed_time(b) for a, b in evs]))
 
     W = max(args.warmup, 3)
