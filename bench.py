@@ -182,9 +182,11 @@ def config_dict(B, n, where, args=None):
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock / power / throttle reasons sampled DURING the timed region.  NVML from a thread every ~4 ms
+    """SM clock / power / throttle reasons sampled DURING the timed region.  NVML from a thread every ~20 ms
     (the timed region of the default run is ~0.1 s: `nvidia-smi -lms` takes longer than that to print its
-    first row); `nvidia-smi` is the fallback when NVML cannot be loaded."""
+    first row; every 4 ms the NVML queries made the host side of a launch several times slower -- they
+    contend with the CUDA driver -- which showed as 2-5 ms bubbles between short kernels, r2c);
+    `nvidia-smi` is the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -209,7 +211,7 @@ class ClockSampler:
                                           [k for k, b in bits.items() if r & b]))
                     except Exception:
                         pass
-                    time.sleep(0.004)
+                    time.sleep(0.02)
 
             import threading
             self.thr = threading.Thread(target=loop, daemon=True)

@@ -863,6 +863,72 @@ static int64_t adj_nparams(const orc_mlp_t *m) {
   return (int64_t)m->d * m->h + m->h + (int64_t)m->h * m->d + m->d;
 }
 
+/* ---- order-independent batch sums of the parameter-gradient dynamics (round 2) ----------------------------
+ * The reference sums the per-trajectory outer products over the batch inside paddle.autograd.grad, in whatever order
+ * the backend's reduction takes.  At the reference's default tolerances the error estimate of the g_theta part is of
+ * the size of the rounding noise of that sum, so the accept/reject sequence of the mixed norm depends on the
+ * summation ORDER.  To make it reproducible on any machine (CPU oracle, any GPU grid) the sum is specified as:
+ *   1. blocks of 32 consecutive trajectories (b = 32m .. 32m+31, the last block short): a sequential fp32 fma chain
+ *      from 0 in trajectory order, X = fma(c_b, v_b, X)
+ *        gW1[k][j]: c = u_k, v = dz_j;   gb1[j]: c = 1, v = dz_j;   gW2[j][d]: c = cot_d, v = h_j;
+ *      gb2[d]: no chain, the addends are the values cot_d themselves;
+ *   2. the block values are added EXACTLY in a 128-bit two's-complement fixed-point accumulator with LSB 2^-90
+ *      (an addend is truncated toward zero to that grid: < 1 fp32 ulp of anything above 2^-66; an addend that is
+ *      not finite or >= 2^36 in magnitude makes the result NaN) -- integer addition is associative, so every
+ *      summation tree gives the same bits;
+ *   3. the total is rounded ONCE to fp32 (round to nearest even).
+ * With one trajectory (the per-trajectory controller) this is the plain product, as before. */
+typedef struct {
+  unsigned __int128 v; /* two's complement */
+  int bad;
+} fx128_t;
+
+static void fx_add_float(fx128_t *a, float x) {
+  uint32_t bits;
+  memcpy(&bits, &x, 4);
+  const int E = (int)((bits >> 23) & 0xffu);
+  const uint32_t M = bits & 0x7fffffu;
+  if (E == 255) {
+    a->bad = 1;
+    return;
+  }
+  const uint32_t mant = E ? (M | 0x800000u) : M;
+  const int shift = (E ? E - 150 : -149) + 90;
+  unsigned __int128 mag;
+  if (shift >= 0) {
+    if (shift > 102) { /* |x| >= 2^36 */
+      a->bad = 1;
+      return;
+    }
+    mag = (unsigned __int128)mant << shift;
+  } else {
+    mag = (-shift >= 32) ? 0 : (unsigned __int128)(mant >> (-shift));
+  }
+  a->v += (bits >> 31) ? (unsigned __int128)0 - mag : mag;
+}
+
+static float fx_to_float(const fx128_t *a) {
+  if (a->bad) return NAN;
+  unsigned __int128 v = a->v;
+  const int neg = (int)(v >> 127);
+  unsigned __int128 mag = neg ? (unsigned __int128)0 - v : v;
+  if (mag == 0) return 0.0f;
+  int p = 127;
+  while (!((mag >> p) & 1)) --p;
+  float r;
+  if (p <= 23) {
+    r = ldexpf((float)(uint32_t)mag, -90);
+  } else {
+    const int sh = p - 23;
+    uint32_t top = (uint32_t)(mag >> sh);
+    const unsigned __int128 rem = mag & ((((unsigned __int128)1) << sh) - 1);
+    const unsigned __int128 half = ((unsigned __int128)1) << (sh - 1);
+    if (rem > half || (rem == half && (top & 1u))) top++;
+    r = ldexpf((float)top, sh - 90);
+  }
+  return neg ? -r : r;
+}
+
 /* augmented_dynamics (functional/odeint_adjoint.py:89-124) */
 static void adj_rhs(void *ctx, float t, const float *Y, float *dY) {
   (void)t;
@@ -870,6 +936,7 @@ static void adj_rhs(void *ctx, float t, const float *Y, float *dY) {
   const orc_mlp_t *m = c->m;
   const int D = m->d, H = m->h;
   const int64_t Bm = c->Bm;
+  const int64_t P = adj_nparams(m);
   const float *y = Y + 1, *a = Y + 1 + Bm * D;
   float *fy = dY + 1, *fa = dY + 1 + Bm * D;
   float *gw1 = dY + 1 + 2 * Bm * D;
@@ -877,12 +944,46 @@ static void adj_rhs(void *ctx, float t, const float *Y, float *dY) {
   float *gw2 = gb1 + H;
   float *gb2 = gw2 + (size_t)H * D;
   dY[0] = 0.0f; /* vjp_t: the field ignores t -> allow_unused zero (:116-118) */
-  memset(gw1, 0, sizeof(float) * adj_nparams(m));
+  memset(gw1, 0, sizeof(float) * P);
   float cot[ORC_MAX_D];
-  for (int64_t b = 0; b < Bm; ++b) {
-    for (int e = 0; e < D; ++e) cot[e] = -a[b * D + e]; /* grad_outputs=-adj_y */
-    orc_mlp_vjp(m, y + b * D, cot, fy + b * D, fa + b * D, gw1, gb1, gw2, gb2);
+  if (Bm == 1) { /* one trajectory: every sum has one term */
+    for (int e = 0; e < D; ++e) cot[e] = -a[e]; /* grad_outputs=-adj_y */
+    orc_mlp_vjp(m, y, cot, fy, fa, gw1, gb1, gw2, gb2);
+    return;
   }
+  fx128_t *tot = (fx128_t *)calloc((size_t)P, sizeof(fx128_t));
+  float *X = (float *)malloc(sizeof(float) * (size_t)P);
+  float u[ORC_MAX_D], h[ORC_MAX_H], dz[ORC_MAX_H];
+  for (int64_t b0 = 0; b0 < Bm; b0 += 32) {
+    const int64_t b1 = (b0 + 32 < Bm) ? b0 + 32 : Bm;
+    float *xw1 = X, *xb1 = X + (size_t)D * H, *xw2 = xb1 + H;
+    for (int64_t i = 0; i < P; ++i) X[i] = 0.0f;
+    for (int64_t b = b0; b < b1; ++b) {
+      const float *yb = y + b * D;
+      for (int e = 0; e < D; ++e) cot[e] = -a[b * D + e];
+      /* f, dy exactly as orc_mlp_vjp; the parameter terms enter the block chains */
+      for (int k = 0; k < D; ++k) u[k] = pre_act(m->pre, yb[k]);
+      orc_mlp_eval(m, yb, fy + b * D, h);
+      for (int j = 0; j < H; ++j) {
+        float acc = cot[0] * m->w2[(size_t)j * D];
+        for (int d = 1; d < D; ++d) acc = fmaf(cot[d], m->w2[(size_t)j * D + d], acc);
+        float sd = fmaf(-h[j], h[j], 1.0f);
+        dz[j] = acc * sd;
+      }
+      for (int k = 0; k < D; ++k)
+        fa[b * D + k] = chain2_dot(dz, m->w1 + (size_t)k * H, 1, H) * pre_act_grad(m->pre, yb[k]);
+      for (int k = 0; k < D; ++k)
+        for (int j = 0; j < H; ++j) xw1[(size_t)k * H + j] = fmaf(u[k], dz[j], xw1[(size_t)k * H + j]);
+      for (int j = 0; j < H; ++j) xb1[j] = fmaf(1.0f, dz[j], xb1[j]);
+      for (int j = 0; j < H; ++j)
+        for (int d = 0; d < D; ++d) xw2[(size_t)j * D + d] = fmaf(cot[d], h[j], xw2[(size_t)j * D + d]);
+      for (int d = 0; d < D; ++d) fx_add_float(&tot[(size_t)D * H + H + (size_t)H * D + d], cot[d]);
+    }
+    for (int64_t i = 0; i < (int64_t)D * H + H + (int64_t)H * D; ++i) fx_add_float(&tot[i], X[i]);
+  }
+  for (int64_t i = 0; i < P; ++i) gw1[i] = fx_to_float(&tot[i]);
+  free(X);
+  free(tot);
 }
 
 /* default_adjoint_norm / adjoint_seminorm (functional/odeint_adjoint.py:284-309) with
