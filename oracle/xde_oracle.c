@@ -872,9 +872,9 @@ static int64_t adj_nparams(const orc_mlp_t *m) {
  *      from 0 in trajectory order, X = fma(c_b, v_b, X)
  *        gW1[k][j]: c = u_k, v = dz_j;   gb1[j]: c = 1, v = dz_j;   gW2[j][d]: c = cot_d, v = h_j;
  *      gb2[d]: no chain, the addends are the values cot_d themselves;
- *   2. the block values are added EXACTLY in a 128-bit two's-complement fixed-point accumulator with LSB 2^-90
- *      (an addend is truncated toward zero to that grid: < 1 fp32 ulp of anything above 2^-66; an addend that is
- *      not finite or >= 2^36 in magnitude makes the result NaN) -- integer addition is associative, so every
+ *   2. the block values are added EXACTLY in a 128-bit two's-complement fixed-point accumulator with LSB 2^-59
+ *      (an addend is truncated toward zero to that grid: exact for anything above 2^-35, at most 1.7e-18 absolute
+ *      below; an addend that is not finite or >= 2^40 in magnitude makes the result NaN; 2^28 addends fit) -- integer addition is associative, so every
  *      summation tree gives the same bits;
  *   3. the total is rounded ONCE to fp32 (round to nearest even).
  * With one trajectory (the per-trajectory controller) this is the plain product, as before. */
@@ -893,10 +893,10 @@ static void fx_add_float(fx128_t *a, float x) {
     return;
   }
   const uint32_t mant = E ? (M | 0x800000u) : M;
-  const int shift = (E ? E - 150 : -149) + 90;
+  const int shift = (E ? E - 150 : -149) + 59;
   unsigned __int128 mag;
   if (shift >= 0) {
-    if (shift > 102) { /* |x| >= 2^36 */
+    if (shift > 75) { /* |x| >= 2^40 */
       a->bad = 1;
       return;
     }
@@ -917,16 +917,23 @@ static float fx_to_float(const fx128_t *a) {
   while (!((mag >> p) & 1)) --p;
   float r;
   if (p <= 23) {
-    r = ldexpf((float)(uint32_t)mag, -90);
+    r = ldexpf((float)(uint32_t)mag, -59);
   } else {
     const int sh = p - 23;
     uint32_t top = (uint32_t)(mag >> sh);
     const unsigned __int128 rem = mag & ((((unsigned __int128)1) << sh) - 1);
     const unsigned __int128 half = ((unsigned __int128)1) << (sh - 1);
     if (rem > half || (rem == half && (top & 1u))) top++;
-    r = ldexpf((float)top, sh - 90);
+    r = ldexpf((float)top, sh - 59);
   }
   return neg ? -r : r;
+}
+
+/* test hook: the exact sum of n fp32 addends, rounded once */
+float orc_fx_sum(const float *x, int64_t n) {
+  fx128_t a = {0, 0};
+  for (int64_t i = 0; i < n; ++i) fx_add_float(&a, x[i]);
+  return fx_to_float(&a);
 }
 
 /* augmented_dynamics (functional/odeint_adjoint.py:89-124) */

@@ -142,6 +142,11 @@ int orc_dopri5_mlp_adjoint(const orc_mlp_t *m, const float *t_span, int32_t T, c
                            float *out_adj_y0, float *out_grad_t, orc_stats_t *stats, orc_attempt_t *log,
                            int64_t log_cap, int64_t log_traj, int64_t *log_len, int32_t nthreads);
 
+/* Order-independent batch sum of the arithmetic specification (see adj_rhs in the .c file): the n fp32 addends are
+ * truncated toward zero to a grid of 2^-59, added exactly in 128-bit fixed point, and the total is rounded once to
+ * fp32 (RN-even).  NaN if an addend is not finite or >= 2^40 in magnitude. */
+float orc_fx_sum(const float *x, int64_t n);
+
 /* sdeint with Euler(-Maruyama) / Milstein and caller-supplied increments (repairs R2,R3;
  * xde/base_sde.py:44-61, fixed_solver/euler.py:7-11).  dW: [T-1,B,D].  out: [B,T,D]. */
 int orc_sde_mlp(int32_t scheme, const orc_mlp_t *drift, const orc_mlp_t *diffusion, const float *y0,

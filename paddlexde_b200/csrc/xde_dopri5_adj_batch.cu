@@ -8,24 +8,24 @@
 // (as in xde_dopri5_batch.cu).  Every thread owns a fixed grid-stride set of trajectories; their
 // (y, a) and FSAL derivatives live in L2-resident double buffers that are flipped on accept.
 //
-// Parameter gradients.  With a global dt the stage weights are global too, so g_theta never has to be
-// integrated per trajectory: per stage the warp folds its 32 (h, dz) tile columns (the transposed-role
-// machinery of xde_dopri5_adj.cu) into lane-private partial sums X of k_i^theta, and adds
-// w_sol,i * X, w_err,i * X (and the dense-output weights w_fin,i * X when the attempt ends the segment)
-// to three running vectors.  The FSAL property carries over: the partial k_6^theta of an accepted
-// attempt is the k_0^theta of the next one.  SEMI: the vectors are committed lane-privately in fp64 on
-// accept and reduced once at the end.  MIXED: S_sol, S_err (and S_fin, k_0^theta, k_probe^theta in
-// select_initial_step) are reduced over the grid every attempt -- deterministically, no atomics --
-// because the error norm needs them, and g_theta itself is kept replicated in shared memory.
-//
-// The (y, a) path follows the oracle's arithmetic order exactly.  The g_theta path cannot: the
-// oracle sums k_i^theta over the batch sequentially in fp32 and then combines stages, this kernel
-// combines stages per partial sum and reduces in fp64 -- algebraically equal, compared at rtol 1e-5.
+// Parameter gradients (round 2: sequence-exact).  g_theta is a state of the solve like y and a, replicated in the
+// shared memory of every CTA, and advanced with the oracle's flat-state arithmetic from the seven stage derivatives
+// k_0..k_6 of the parameter-gradient dynamics.  Each k_i^theta is a sum over the batch, and at the reference's
+// default tolerances the error estimate of the g_theta part is the rounding noise of that sum -- the accept/reject
+// sequence of the mixed norm depends on HOW it is summed.  The sum is therefore specified so that it has one value on
+// every machine (xde_fixed128.cuh, oracle/xde_oracle.c adj_rhs): per 32 consecutive trajectories a sequential fp32
+// fma chain (this is what a warp's fold of its 32 tile columns computes), the chain values added exactly in a
+// 128-bit fixed-point accumulator (shared-memory atomics per CTA, then global atomics: integer addition commutes),
+// the total rounded once to fp32.  Per attempt the six new stage sums travel through one grid-wide reduction
+// (the same two grid.sync() that the error norm of (y, a) needs); the FSAL property carries over: k_6^theta of an
+// accepted attempt is k_0^theta of the next one.  Both norms run this path; with it the whole (dt, ratio, accept)
+// sequence of the reference's DEFAULT configuration (mixed norm, rtol 1e-7) equals the oracle's bit for bit.
 #include <cooperative_groups.h>
 
 #include <type_traits>
 
 #include "xde_common.cuh"
+#include "xde_fixed128.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -39,8 +39,9 @@ constexpr int kABScalars = 8;  // scalar slots in front of the vectors in a redu
 struct AdjBatchParams {
   xde_mlp_field_t field;
   const float *t_span, *y_ans, *grad_y;
-  float *out_g;    // [P] fp32 (MIXED: written directly; SEMI: via gacc + cast)
-  double *gacc;    // [P] fp64 accumulator (SEMI)
+  float *out_g;    // [P] fp32
+  unsigned long long *gfx;  // [3][6][P][2] grid-wide 128-bit accumulators, triple buffered (zeroed)
+  int *gbad;                // [3] "an addend was not representable" flags (zeroed)
   float *adj_y0;   // [B,D] or null
   long long B;
   int T;
@@ -53,7 +54,7 @@ struct AdjBatchParams {
   float *ws;        // [4][B*2D]: S[2], F[2]
   double *partial;  // [gridDim.x][row]
   double *reduced;  // [row]
-  int row;          // kABScalars + 3*P
+  int row;          // kABScalars
 };
 
 template <int D, int HPL, int PRE>
@@ -67,16 +68,19 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
 
   extern __shared__ __align__(16) float smem[];
   __shared__ double s_warp[kABWarps];
+  __shared__ int s_bad;
 
   const int H = p.field.h, NP = SmallRec<D>::pairs(H);
   const int P = 2 * D * H + H + D;
+  const int P4 = ((P + 3) / 4) * 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // shared-memory carve-up
   float *sw = smem;
   float *st = sw + SmallRec<D>::floats(H);
-  float *g0 = st + ((p.T + 3) / 4) * 4;            // [P]  g_theta (MIXED: the state; replicated)
-  float *k0t = g0 + ((P + 3) / 4) * 4;             // [P]  reduced k_0^theta (select_initial_step, MIXED)
-  double *sred = reinterpret_cast<double *>(k0t + ((P + 3) / 4) * 4);  // [row] CTA partial / reduced row
+  float *g0 = st + ((p.T + 3) / 4) * 4;            // [P]     g_theta: a state of the solve, replicated in every CTA
+  float *kth = g0 + P4;                            // [8][P4] k_0..k_6 of the g_theta dynamics, [7] = the Euler probe
+  unsigned long long *fxacc = reinterpret_cast<unsigned long long *>(kth + 8 * P4);  // [6][P][2] CTA partial sums
+  double *sred = reinterpret_cast<double *>(fxacc + (size_t)6 * P * 2);              // [kABScalars]
   float *wbase = reinterpret_cast<float *>(sred + p.row) + (size_t)warp * (4 * NP * kABTileStride + 32 * CST);
   float4 *tile = reinterpret_cast<float4 *>(wbase);
   float *coef = wbase + 4 * NP * kABTileStride;
@@ -84,40 +88,25 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
   load_small_field<D>(sw, p.field);
   const float tsign = (p.t_span[1] > p.t_span[0]) ? -1.0f : 1.0f;  // backward sweep as s = tsign * t
   for (int i = threadIdx.x; i < p.T; i += blockDim.x) st[i] = tsign * p.t_span[i];
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    g0[i] = 0.0f;
-    k0t[i] = 0.0f;
-  }
+  for (int i = threadIdx.x; i < P; i += blockDim.x) g0[i] = 0.0f;
+  for (int i = threadIdx.x; i < 8 * P4; i += blockDim.x) kth[i] = 0.0f;
+  for (int i = threadIdx.x; i < 6 * P * 2; i += blockDim.x) fxacc[i] = 0ull;
   for (int i = lane; i < NP * kABTileStride; i += 32) tile[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = lane; i < 32 * CST; i += 32) coef[i] = 0.0f;
+  if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
 
   const xde_ctrl_opts_t o = p.o;
   const bool mixed = p.mixed != 0;
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long gstride = (long long)gridDim.x * blockDim.x;
-  const long long wbeg = gtid - lane;  // first trajectory of this warp in iteration 0
+  const long long wbeg = gtid - lane;  // first trajectory of this warp in iteration 0 (a multiple of 32)
   const long long nel = p.B * C;
   float *Sb[2] = {p.ws, p.ws + nel};
   float *Fb[2] = {p.ws + 2 * nel, p.ws + 3 * nel};
   const double n_half = (double)(p.B * D);  // elements of the y part (= of the a part)
   const bool leader = (gtid == 0);
   const float ths = -tsign;  // d g_theta / ds = -tsign * vjp_theta(a)
-
-  // ---------------- lane-private theta partials (fold role: hidden-unit pairs lane + 32 q) ----------------
-  f32x2 K0[NTP], K6[NTP], Tsol[NTP], Terr[NTP], Tfin[NTP];
-  double acc[2 * NTP];
-#pragma unroll
-  for (int i = 0; i < NTP; ++i) K0[i] = K6[i] = Tsol[i] = Terr[i] = Tfin[i] = pk1(0.0f);
-#pragma unroll
-  for (int i = 0; i < 2 * NTP; ++i) acc[i] = 0.0;
-  double gb2acc[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) gb2acc[d] = 0.0;
-  // gb2 = sum_b a_d: per-thread partial of k^theta for the b2 slots, same roles as K0/K6/T*
-  float kb0[D], kb6[D], tbs[D], tbe[D], tbf[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) kb0[d] = kb6[d] = tbs[d] = tbe[d] = tbf[d] = 0.0f;
 
   // field + VJP of this lane's trajectory (xde_dopri5_adj.cu, Appendix B); writes the tile column
   auto eval = [&](const float (&yin)[C], float (&fo)[C]) {
@@ -228,49 +217,49 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
     __syncwarp();
   };
 
-  // ---------------- grid reduction: scalars + up to three P-vectors, deterministic ----------------
-  // layout of a row: [kABScalars scalars][vec0 P][vec1 P][vec2 P]
-  auto lane_vec_to_row = [&](const f32x2 (&V)[NTP], const float (&vb)[D], int slot) {
-    // lane-private pairs -> the CTA row in shared memory, warps in fixed order (no atomics)
-    double *dst = sred + kABScalars + (size_t)slot * P;
-    for (int w = 0; w < kABWarps; ++w) {
-      if (warp == w) {
+  // ---------------- exact batch sums of a stage's parameter-gradient terms (xde_fixed128.cuh) ----------------
+  // X: the fp32 chain values of this warp's 32 trajectories (lane = hidden-unit pair); xb: a_d of this lane's
+  // trajectory (0 for a lane past the batch).  Added into the CTA's accumulators of stage vector `v`.
+  auto accumulate = [&](const f32x2 (&X)[NTP], const float (&xb)[D], int v) {
+    unsigned long long *dst = fxacc + (size_t)v * P * 2;
+    bool ok = true;
 #pragma unroll
-        for (int q = 0; q < HPL; ++q)
+    for (int q = 0; q < HPL; ++q)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int j = 2 * (lane + 32 * q) + e;
-            if (j < H) {
+      for (int e = 0; e < 2; ++e) {
+        const int j = 2 * (lane + 32 * q) + e;
+        if (j < H) {
 #pragma unroll
-              for (int i = 0; i < NV; ++i) {
-                float lo, hi;
-                upk(V[q * NV + i], lo, hi);
-                const double v = (double)(e ? hi : lo);
-                const int idx = (i < D) ? i * H + j : (i == D ? D * H + j : D * H + H + j * D + (i - D - 1));
-                dst[idx] += v;
-              }
-            }
+          for (int i = 0; i < NV; ++i) {
+            float lo, hi;
+            upk(X[q * NV + i], lo, hi);
+            const int idx = (i < D) ? i * H + j : (i == D ? D * H + j : D * H + H + j * D + (i - D - 1));
+            Fx128 f;
+            if (fx_from_float(e ? hi : lo, f)) fx_atomic_add(dst + 2 * idx, f); else ok = false;
           }
+        }
       }
-      __syncthreads();
-    }
-    // gb2 slots: per-thread values, fixed order: lane xor-tree, then warps in order
+    // gb2 slots: one addend per trajectory; summed over the warp in integer arithmetic first (one atomic per warp)
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      double v = (double)vb[d];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(XDE_FULL_MASK, v, off);
-      if (lane == 0) s_warp[warp] = v;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kABWarps; ++w) s += s_warp[w];
-        dst[D * H + H + H * D + d] += s;
+      Fx128 f;
+      if (!fx_from_float(xb[d], f)) {
+        ok = false;
+        f.lo = f.hi = 0ull;
       }
-      __syncthreads();
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        Fx128 g;
+        g.lo = __shfl_xor_sync(XDE_FULL_MASK, f.lo, off);
+        g.hi = __shfl_xor_sync(XDE_FULL_MASK, f.hi, off);
+        f = fx_add(f, g);
+      }
+      if (lane == 0) fx_atomic_add(dst + 2 * (D * H + H + H * D + d), f);
     }
+    if (!ok) s_bad = 1;
   };
+
+  // ---------------- grid reduction of the scalars: deterministic (thread -> warp -> CTA -> fixed-order re-sum) ----------------
   auto scalar_to_row = [&](double v, int slot) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(XDE_FULL_MASK, v, off);
@@ -311,6 +300,42 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
     grid.sync();
     for (int i = threadIdx.x; i < ncols; i += blockDim.x) sred[i] = p.reduced[i];
     __syncthreads();
+  };
+  // One reduction phase: the scalars already sit in sred[0..kABScalars); the CTA's 128-bit partial sums of `nv` stage
+  // vectors go to the grid-wide accumulators of this phase's buffer, and after the two grid.sync() of the scalar
+  // reduction every CTA converts the totals to fp32 into kth[slot0 + v].  Buffers rotate over three phases: the one
+  // the NEXT phase will use was last read two phases ago, i.e. before the previous phase's grid.sync().
+  int phase = 0;
+  auto reduce_phase = [&](int nv, int slot0) {
+    __syncthreads();  // every warp has added its last chain values
+    unsigned long long *gb = p.gfx + (size_t)(phase % 3) * 6 * P * 2;
+    for (int i = threadIdx.x; i < nv * P; i += blockDim.x) {
+      Fx128 f;
+      f.lo = fxacc[2 * i];
+      f.hi = fxacc[2 * i + 1];
+      fx_atomic_add(gb + 2 * i, f);
+      fxacc[2 * i] = 0ull;
+      fxacc[2 * i + 1] = 0ull;
+    }
+    if (threadIdx.x == 0 && s_bad) atomicOr(p.gbad + phase % 3, 1);
+    if (blockIdx.x == 0) {
+      unsigned long long *gn = p.gfx + (size_t)((phase + 1) % 3) * 6 * P * 2;
+      for (int i = threadIdx.x; i < 6 * P * 2; i += blockDim.x) gn[i] = 0ull;
+      if (threadIdx.x == 0) p.gbad[(phase + 1) % 3] = 0;
+    }
+    __threadfence();
+    grid_reduce(kABScalars);
+    const bool bad = __ldcg(p.gbad + phase % 3) != 0;
+    for (int i = threadIdx.x; i < nv * P; i += blockDim.x) {
+      Fx128 f;
+      f.lo = __ldcg(gb + 2 * i);
+      f.hi = __ldcg(gb + 2 * i + 1);
+      const int v = i / P, q = i - v * P;
+      kth[(slot0 + v) * P4 + q] = bad ? NAN : ths * fx_to_float(f);
+    }
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    phase++;
   };
   // max_p rms over the four parameter tensors of a P-vector given element-wise by fn(idx) (computed by all
   // threads of the CTA redundantly per tensor; fixed order)
@@ -354,10 +379,6 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
     // ======== segment start: y <- y_ans[seg], a <- a + grad_y[seg] (functional/odeint_adjoint.py:75-82,153-159) ========
     // ======== INIT 0: f0 = rhs(start), k_0^theta, d0, d1 (base_adaptive_solver.py:44-57) ========
     double sy0 = 0.0, sa0 = 0.0, sy1 = 0.0, sa1 = 0.0;
-#pragma unroll
-    for (int i = 0; i < NTP; ++i) K0[i] = pk1(0.0f);
-#pragma unroll
-    for (int d = 0; d < D; ++d) kb0[d] = 0.0f;
     for (long long base = wbeg; base < p.B; base += gstride) {
       const long long b = base + lane;
       const bool ok = b < p.B;
@@ -373,10 +394,7 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
       f32x2 X[NTP];
       float xb[D];
       fold(s0, ok ? 1.0f : 0.0f, X, xb);
-#pragma unroll
-      for (int i = 0; i < NTP; ++i) K0[i] = add2(K0[i], X[i]);
-#pragma unroll
-      for (int d = 0; d < D; ++d) kb0[d] += xb[d];
+      accumulate(X, xb, 0);
       if (ok) {
 #pragma unroll
         for (int e = 0; e < C; ++e) {
@@ -394,34 +412,21 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
         }
       }
     }
+    clear_row(kABScalars);
+    scalar_to_row(sy0, 0);
+    scalar_to_row(sa0, 1);
+    scalar_to_row(sy1, 2);
+    scalar_to_row(sa1, 3);
+    reduce_phase(1, 0);  // -> kth[0] = k_0^theta
     float t0 = t_start, dt;
     if (has_first) {
       dt = o.first_step;
       n_fe += 1;
     } else {
-      const int ncols0 = kABScalars + (mixed ? P : 0);
-      clear_row(ncols0);
-      scalar_to_row(sy0, 0);
-      scalar_to_row(sa0, 1);
-      scalar_to_row(sy1, 2);
-      scalar_to_row(sa1, 3);
-      if (mixed) {
-        // k_0^theta = ths * sum_b X_0(b)
-        f32x2 V[NTP];
-        float vb[D];
-#pragma unroll
-        for (int i = 0; i < NTP; ++i) V[i] = mul2(pk1(ths), K0[i]);
-#pragma unroll
-        for (int d = 0; d < D; ++d) vb[d] = ths * kb0[d];
-        lane_vec_to_row(V, vb, 0);
-      }
-      grid_reduce(ncols0);
       float pn0 = 0.f, pn1 = 0.f;
       if (mixed) {
-        for (int i = threadIdx.x; i < P; i += blockDim.x) k0t[i] = (float)sred[kABScalars + i];
-        __syncthreads();
         pn0 = param_norm([&](int i) { return __fdiv_rn(g0[i], o.atol + fabsf(g0[i]) * o.rtol); });
-        pn1 = param_norm([&](int i) { return __fdiv_rn(k0t[i], o.atol + fabsf(g0[i]) * o.rtol); });
+        pn1 = param_norm([&](int i) { return __fdiv_rn(kth[i], o.atol + fabsf(g0[i]) * o.rtol); });
       }
       const float d0 = fabsf(mixed_of(sred[0], sred[1], pn0));
       const float d1 = fabsf(mixed_of(sred[2], sred[3], pn1));
@@ -431,12 +436,6 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
       h0 = fabsf(h0);
       // ======== INIT 1: Euler probe rhs(start + h0 f0) (base_adaptive_solver.py:60-64) ========
       double sy2 = 0.0, sa2 = 0.0;
-      f32x2 Kp[NTP];
-      float kbp[D];
-#pragma unroll
-      for (int i = 0; i < NTP; ++i) Kp[i] = pk1(0.0f);
-#pragma unroll
-      for (int d = 0; d < D; ++d) kbp[d] = 0.0f;
       for (long long base = wbeg; base < p.B; base += gstride) {
         const long long b = base + lane;
         const bool ok = b < p.B;
@@ -452,10 +451,7 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
           f32x2 X[NTP];
           float xb[D];
           fold(yi, ok ? 1.0f : 0.0f, X, xb);
-#pragma unroll
-          for (int i = 0; i < NTP; ++i) Kp[i] = add2(Kp[i], X[i]);
-#pragma unroll
-          for (int d = 0; d < D; ++d) kbp[d] += xb[d];
+          accumulate(X, xb, 0);
         } else {
           __syncwarp();  // the tile column is rewritten by the next evaluation
         }
@@ -468,23 +464,14 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
           }
         }
       }
-      clear_row(ncols0);
+      clear_row(kABScalars);
       scalar_to_row(sy2, 0);
       scalar_to_row(sa2, 1);
-      if (mixed) {
-        f32x2 V[NTP];
-        float vb[D];
-#pragma unroll
-        for (int i = 0; i < NTP; ++i) V[i] = mul2(pk1(ths), Kp[i]);
-#pragma unroll
-        for (int d = 0; d < D; ++d) vb[d] = ths * kbp[d];
-        lane_vec_to_row(V, vb, 0);
-      }
-      grid_reduce(ncols0);
+      reduce_phase(mixed ? 1 : 0, 7);  // -> kth[7] = the probe's k^theta
       float pn2 = 0.f;
       if (mixed)
         pn2 = param_norm([&](int i) {
-          return __fdiv_rn((float)sred[kABScalars + i] - k0t[i], o.atol + fabsf(g0[i]) * o.rtol);
+          return __fdiv_rn(kth[7 * P4 + i] - kth[i], o.atol + fabsf(g0[i]) * o.rtol);
         });
       const float d2 = fabsf(__fdiv_rn(mixed_of(sred[0], sred[1], pn2), h0));
       __syncthreads();
@@ -516,36 +503,6 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
       const float t1 = t0 + dt;
       const bool fin = !(te > t1);
       const float x = fin ? __fdiv_rn(te - t0, t1 - t0) : 0.f;
-      // theta weights of the seven stage points: solution (c_sol), error (c_err), dense output at x
-      float wsol[7], werr[7], wfin[7];
-      {
-        const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-          const float cs = DP::csol(i), cm = DP::cmid(i);
-          const float d0f = (i == 0) ? 1.f : 0.f, d6f = (i == 6) ? 1.f : 0.f;
-          const float wa = fmaf(16.0f, cm, fmaf(-5.0f, cs, d6f - 4.0f * d0f));
-          const float wb = fmaf(-32.0f, cm, fmaf(14.0f, cs, 5.0f * d0f - 3.0f * d6f));
-          const float wc = fmaf(16.0f, cm, fmaf(-8.0f, cs, 2.0f * d6f - 2.0f * d0f));
-          wsol[i] = ths * (dt * cs);
-          werr[i] = ths * (dt * DP::cerr(i));
-          wfin[i] = ths * (dt * ((((i == 0) ? x : 0.0f) + x2 * wa) + x3 * wb + x4 * wc));
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < NTP; ++i) {
-        Tsol[i] = mul2(pk1(wsol[0]), K0[i]);
-        Terr[i] = mul2(pk1(werr[0]), K0[i]);
-        Tfin[i] = mul2(pk1(wfin[0]), K0[i]);
-        K6[i] = pk1(0.0f);
-      }
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        tbs[d] = wsol[0] * kb0[d];
-        tbe[d] = werr[0] * kb0[d];
-        tbf[d] = wfin[0] * kb0[d];
-        kb6[d] = 0.0f;
-      }
       double sqy = 0.0, sqa = 0.0, bad = 0.0;
       for (long long base = wbeg; base < p.B; base += gstride) {
         const long long b = base + lane;
@@ -574,20 +531,7 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
           f32x2 X[NTP];
           float xb[D];
           fold(yin, ok ? 1.0f : 0.0f, X, xb);
-#pragma unroll
-          for (int q = 0; q < NTP; ++q) {
-            Tsol[q] = fma2(pk1(wsol[i + 1]), X[q], Tsol[q]);
-            Terr[q] = fma2(pk1(werr[i + 1]), X[q], Terr[q]);
-            if (fin) Tfin[q] = fma2(pk1(wfin[i + 1]), X[q], Tfin[q]);
-            if (i == 5) K6[q] = add2(K6[q], X[q]);
-          }
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            tbs[d] = fmaf(wsol[i + 1], xb[d], tbs[d]);
-            tbe[d] = fmaf(werr[i + 1], xb[d], tbe[d]);
-            if (fin) tbf[d] = fmaf(wfin[i + 1], xb[d], tbf[d]);
-            if (i == 5) kb6[d] += xb[d];
-          }
+          accumulate(X, xb, i);
         }
         if (ok) {
           const float two_dt = 2.0f * dt;
@@ -624,28 +568,33 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
           }
         }
       }
-      // ---- reduce: error sums (+ S_sol, S_err, S_fin for the mixed norm) ----
-      const int ncols = kABScalars + (mixed ? 3 * P : 0);
-      clear_row(ncols);
+      // ---- reduce: the error sums of (y, a) and the six new stage sums k_1..k_6 of the g_theta dynamics ----
+      clear_row(kABScalars);
       scalar_to_row(sqy, 0);
       scalar_to_row(sqa, 1);
       scalar_to_row(bad, 2);
-      if (mixed) {
-        lane_vec_to_row(Tsol, tbs, 0);
-        lane_vec_to_row(Terr, tbe, 1);
-        if (fin) lane_vec_to_row(Tfin, tbf, 2);
-      }
-      grid_reduce(ncols);
+      reduce_phase(6, 1);
       if (sred[2] > 0.0) {
         status = XDE_ST_NONFINITE_STATE;
         break;
       }
+      // the g_theta part of the step in the oracle's flat-state arithmetic (xde_oracle.c drv_adaptive_step):
+      // y1 = g + sum_j k_j (beta_5j dt) [FSAL: the stage-6 input], err = sum_j k_j (dt c_err,j)
+      auto g_y1 = [&](int i) -> float {
+        float s = kth[i] * (DP::beta(5, 0) * dt);
+#pragma unroll
+        for (int j = 1; j < 6; ++j) s = s + kth[j * P4 + i] * (DP::beta(5, j) * dt);
+        return g0[i] + s;
+      };
       float pn = 0.f;
       if (mixed)
         pn = param_norm([&](int i) {
-          const float g1 = g0[i] + (float)sred[kABScalars + i];
+          const float g1 = g_y1(i);
+          float er = kth[i] * (dt * DP::cerr(0));
+#pragma unroll
+          for (int j = 1; j < 7; ++j) er = er + kth[j * P4 + i] * (dt * DP::cerr(j));
           const float tol = o.atol + o.rtol * fmaxf(fabsf(g0[i]), fabsf(g1));
-          return __fdiv_rn((float)sred[kABScalars + P + i], tol);
+          return __fdiv_rn(er, tol);
         });
       const float ratio = fabsf(mixed_of(sred[0], sred[1], pn));
       bool accept = (ratio <= 1.0f);
@@ -664,34 +613,39 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
         p.log_records[n_logged] = r;
       }
       n_logged++;
+      __syncthreads();
       if (accept) {
         n_acc++;
-        if (mixed) {
-          const int voff = kABScalars + (fin ? 2 * P : 0);
-          for (int i = threadIdx.x; i < P; i += blockDim.x) g0[i] = g0[i] + (float)sred[voff + i];
-        } else {
+        const float two_dt = 2.0f * dt;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+          const float Y0 = g0[i], Y1 = g_y1(i), F0 = kth[i], F1 = kth[6 * P4 + i];
+          float gnew = Y1;
+          if (fin) {
+            float sm = kth[i] * (dt * DP::cmid(0));
 #pragma unroll
-          for (int i = 0; i < NTP; ++i) {
-            float lo, hi;
-            upk(fin ? Tfin[i] : Tsol[i], lo, hi);
-            acc[2 * i] += (double)lo;
-            acc[2 * i + 1] += (double)hi;
+            for (int j = 1; j < 7; ++j) sm = sm + kth[j * P4 + i] * (dt * DP::cmid(j));
+            const float ym = Y0 + sm;
+            const float ca = (two_dt * (F1 - F0) - 8.0f * (Y1 + Y0)) + 16.0f * ym;
+            const float cb = ((dt * (5.0f * F0 - 3.0f * F1) + 18.0f * Y0) + 14.0f * Y1) - 32.0f * ym;
+            const float cc = ((dt * (F1 - 4.0f * F0) - 11.0f * Y0) - 5.0f * Y1) + 16.0f * ym;
+            const float cd = dt * F0;
+            float total = Y0 + x * cd;
+            float xp = x * x;
+            total = total + xp * cc;
+            xp = xp * x;
+            total = total + xp * cb;
+            xp = xp * x;
+            total = total + xp * ca;
+            gnew = total;
           }
-#pragma unroll
-          for (int d = 0; d < D; ++d) gb2acc[d] += (double)(fin ? tbf[d] : tbs[d]);
+          g0[i] = gnew;
+          kth[i] = F1;  // FSAL for the parameter-gradient dynamics (unused after a segment end)
         }
         cur ^= 1;
         t0 = t1;
-        if (fin) {
-          seg_done = true;
-        } else {
-#pragma unroll
-          for (int i = 0; i < NTP; ++i) K0[i] = K6[i];  // FSAL for the parameter-gradient dynamics
-#pragma unroll
-          for (int d = 0; d < D; ++d) kb0[d] = kb6[d];
-        }
+        if (fin) seg_done = true;
       }
-      __syncthreads();  // g0 / sred are read above and rewritten by the next reduction
+      __syncthreads();  // g0 / kth are rewritten above and read by the next phase
       dt = dt_next;
     }
   }
@@ -708,40 +662,8 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
 #pragma unroll
       for (int d = 0; d < D; ++d) p.adj_y0[b * D + d] = NAN;
   }
-  if (mixed) {
-    if (blockIdx.x == 0)
-      for (int i = threadIdx.x; i < P; i += blockDim.x) p.out_g[i] = g0[i];
-  } else {
-    clear_row(kABScalars + P);
-    double *dst = sred + kABScalars;
-    for (int w = 0; w < kABWarps; ++w) {
-      if (warp == w) {
-#pragma unroll
-        for (int q = 0; q < HPL; ++q)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int j = 2 * (lane + 32 * q) + e;
-            if (j < H) {
-#pragma unroll
-              for (int i = 0; i < NV; ++i) {
-                const int idx = (i < D) ? i * H + j : (i == D ? D * H + j : D * H + H + j * D + (i - D - 1));
-                dst[idx] += acc[2 * (q * NV + i) + e];
-              }
-            }
-          }
-      }
-      __syncthreads();
-    }
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      double v = gb2acc[d];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(XDE_FULL_MASK, v, off);
-      if (lane == 0) atomicAdd(&dst[D * H + H + H * D + d], v);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < P; i += blockDim.x) atomicAdd(&p.gacc[i], dst[i]);
-  }
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < P; i += blockDim.x) p.out_g[i] = g0[i];
   if (leader) {
     if (p.stats) {
       p.stats->n_attempts = n_att * (unsigned long long)p.B;
@@ -753,19 +675,16 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
   }
 }
 
-__global__ void adj_batch_cast_kernel(const double *__restrict__ a, float *__restrict__ o, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) o[i] = (float)a[i];
-}
-
 template <int D, int HPL, int PRE>
 static int launch_adj_batch(AdjBatchParams &p, cudaStream_t stream) {
   const int H = p.field.h, NP = SmallRec<D>::pairs(H);
   const int P = 2 * D * H + H + D;
+  const int P4 = ((P + 3) / 4) * 4;
   constexpr int CST = ((2 * D + 1 + 3) / 4) * 4;
-  p.row = (kABScalars + 3 * P + 1) & ~1;  // even: keeps the per-warp tiles behind it 16-byte aligned
-  const size_t smem = sizeof(float) * (SmallRec<D>::floats(H) + ((p.T + 3) / 4) * 4 + 2 * (((size_t)P + 3) / 4) * 4) +
-                      sizeof(double) * p.row + sizeof(float) * kABWarps * (4 * (size_t)NP * kABTileStride + 32 * CST);
+  p.row = kABScalars;
+  const size_t smem = sizeof(float) * (SmallRec<D>::floats(H) + ((p.T + 3) / 4) * 4 + (size_t)9 * P4) +
+                      sizeof(unsigned long long) * (size_t)6 * P * 2 + sizeof(double) * p.row +
+                      sizeof(float) * kABWarps * (4 * (size_t)NP * kABTileStride + 32 * CST);
   XDE_REQUIRE(smem <= 200 * 1024, XDE_E_UNSUPPORTED_FIELD, "adjoint (batch controller): field + t_span exceed shared memory");
   auto kern = dopri5_adj_batch_kernel<D, HPL, PRE>;
   XDE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -778,28 +697,26 @@ static int launch_adj_batch(AdjBatchParams &p, cudaStream_t stream) {
   if (grid < 1) grid = 1;
   const long long nel = p.B * 2 * D;
   float *ws = nullptr;
-  double *partial = nullptr, *reduced = nullptr, *gacc = nullptr;
+  double *partial = nullptr, *reduced = nullptr;
+  unsigned long long *gfx = nullptr;
+  const size_t gfx_bytes = sizeof(unsigned long long) * (size_t)3 * 6 * P * 2 + 4 * sizeof(int);
   XDE_CUDA_CHECK(scratch_alloc((void **)&ws, sizeof(float) * 4 * nel, stream));
   XDE_CUDA_CHECK(scratch_alloc((void **)&partial, sizeof(double) * (size_t)grid * p.row, stream));
   XDE_CUDA_CHECK(scratch_alloc((void **)&reduced, sizeof(double) * p.row, stream));
-  XDE_CUDA_CHECK(scratch_alloc((void **)&gacc, sizeof(double) * P, stream));
-  XDE_CUDA_CHECK(cudaMemsetAsync(gacc, 0, sizeof(double) * P, stream));
+  XDE_CUDA_CHECK(scratch_alloc((void **)&gfx, gfx_bytes, stream));
+  XDE_CUDA_CHECK(cudaMemsetAsync(gfx, 0, gfx_bytes, stream));
   p.ws = ws;
   p.partial = partial;
   p.reduced = reduced;
-  p.gacc = gacc;
+  p.gfx = gfx;
+  p.gbad = reinterpret_cast<int *>(gfx + (size_t)3 * 6 * P * 2);
   void *args[] = {(void *)&p};
   cudaError_t e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)grid), dim3(kABThreads), args, smem, stream);
   count_launch();
-  if (e == cudaSuccess && !p.mixed) {
-    adj_batch_cast_kernel<<<(P + 255) / 256, 256, 0, stream>>>(gacc, p.out_g, P);
-    count_launch();
-    e = cudaGetLastError();
-  }
   cudaFreeAsync(ws, stream);
   cudaFreeAsync(partial, stream);
   cudaFreeAsync(reduced, stream);
-  cudaFreeAsync(gacc, stream);
+  cudaFreeAsync(gfx, stream);
   if (e != cudaSuccess) {
     set_last_error("cooperative launch of dopri5_adj_batch_kernel failed: %s", cudaGetErrorString(e));
     return XDE_E_CUDA;

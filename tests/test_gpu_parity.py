@@ -372,12 +372,11 @@ def test_adjoint_with_rejections_and_replay(px, torch, oracle):
 def test_adjoint_batch_controller_reference_default(px, torch, oracle, norm, B, d, h, pre):
     """controller="batch": one dt / one error norm for the whole augmented state -- with norm="mixed" this is
     the reference's DEFAULT odeint_adjoint configuration (functional/odeint_adjoint.py:284-291).
-    seminorm: the controller sees only (y, a), whose arithmetic is specified exactly -> bit-exact dt / ratio
-    sequence and dL/dy0.  mixed: at rtol 1e-7 (below fp32 epsilon) the parameter-gradient error estimate is
-    pure rounding noise of the batch sum (ratio ~1e-2) and this kernel sums in another order
-    (fp64 tree vs the oracle's sequential fp32 loop): step sizes inside a segment (and with them the attempt
-    count) are not comparable there -- only each segment's initial step, the results and the gradients are;
-    the looser-tolerance test below compares the whole sequence where truncation error dominates."""
+    At rtol 1e-7 (below fp32 epsilon) the parameter-gradient error estimate of the mixed norm is the rounding noise
+    of the batch sum (ratio ~1e-2), so the accept/reject sequence depends on how that sum is taken.
+    Round 2 specifies it order-independently (32-trajectory fp32 fma chains added exactly in 128-bit fixed point,
+    one rounding: oracle adj_rhs, csrc/xde_fixed128.cuh): the WHOLE (dt, ratio, accept) sequence, dL/dy0 and the
+    parameter gradients are now bit-identical to the oracle's for both norms."""
     from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
 
     w = spiral_weights() if (d, h) == (2, 50) else fanin_weights(d, h, seed=h)
@@ -395,26 +394,16 @@ def test_adjoint_batch_controller_reference_default(px, torch, oracle, norm, B, 
     assert s.status == 0
     rec, cnt = log.read()
     r = rec[0, :cnt[0]]
-    scale = np.abs(g_ref).max()
-    if norm == "seminorm":
-        assert cnt[0] == len(lg) and np.array_equal(r.accepted, lg.accepted)
-        assert s.n_attempts == int(st_ref.n_attempts[0]) * B and s.nfe == int(st_ref.nfe[0]) * B
-        assert np.array_equal(r.dt, lg.dt) and np.array_equal(r.ratio, lg.ratio)
-        assert np.array_equal(a0.cpu().numpy(), a_ref)
-    else:
-        # every segment's select_initial_step (its norms include k_0^theta and the probe's k^theta) must agree
-        first = np.flatnonzero(np.isin(r.t0, t))
-        first_ref = np.flatnonzero(np.isin(lg.t0, t))
-        np.testing.assert_allclose(r.dt[first], lg.dt[first_ref], rtol=1e-4)
-        assert r.accepted.all() and lg.accepted.all()
-        np.testing.assert_allclose(a0.cpu().numpy(), a_ref, rtol=1e-5, atol=2e-6 * np.abs(a_ref).max())
-    np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-5, atol=2e-6 * scale)
+    assert cnt[0] == len(lg) and np.array_equal(r.accepted, lg.accepted)
+    assert s.n_attempts == int(st_ref.n_attempts[0]) * B and s.nfe == int(st_ref.nfe[0]) * B
+    assert np.array_equal(r.dt, lg.dt) and np.array_equal(r.ratio, lg.ratio)
+    assert np.array_equal(a0.cpu().numpy(), a_ref)
+    assert np.array_equal(g.cpu().numpy(), g_ref), "g_theta is a state of this solve: bit-exact like y and a"
 
 
-def test_adjoint_batch_mixed_norm_step_sizes_where_truncation_dominates(px, torch, oracle):
-    """Same configuration at rtol 1e-4 / atol 1e-6 on a stiffer field: the error estimate is now truncation
-    error, not rounding noise, so the mixed-norm controller must reproduce the oracle's dt and ratio sequence
-    (to the accuracy the different batch-summation order allows) including its rejections."""
+def test_adjoint_batch_mixed_norm_with_rejections(px, torch, oracle):
+    """The reference's default configuration at rtol 1e-4 / atol 1e-6 on a stiffer field, so that the mixed-norm
+    controller REJECTS steps: the whole sequence including the rejections, and every result, bit for bit."""
     from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
 
     w = [3.0 * a for a in fanin_weights(2, 50, seed=5)]
@@ -431,11 +420,30 @@ def test_adjoint_batch_mixed_norm_step_sizes_where_truncation_dominates(px, torc
     assert rc == 0 and stats.read().status == 0
     rec, cnt = log.read()
     r = rec[0, :cnt[0]]
+    assert (lg.accepted == 0).any(), "the case must exercise rejections"
     assert cnt[0] == len(lg) and np.array_equal(r.accepted, lg.accepted)
-    np.testing.assert_allclose(r.dt, lg.dt, rtol=2e-2)
-    np.testing.assert_allclose(r.ratio, lg.ratio, rtol=1e-1, atol=1e-3)
-    np.testing.assert_allclose(a0.cpu().numpy(), a_ref, rtol=1e-3, atol=1e-4 * np.abs(a_ref).max())
-    np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-3, atol=1e-4 * np.abs(g_ref).max())
+    assert np.array_equal(r.dt, lg.dt) and np.array_equal(r.ratio, lg.ratio)
+    assert np.array_equal(a0.cpu().numpy(), a_ref) and np.array_equal(g.cpu().numpy(), g_ref)
+
+
+def test_adjoint_batch_mixed_norm_at_baseline_size_subset(px, torch, oracle):
+    """B = 2^16 rows of the cfg2 batch under the reference-default controller: 2048 chain blocks, every CTA of the
+    cooperative grid contributes to the 128-bit sums -- still the oracle's sequence and gradients bit for bit."""
+    from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
+
+    field, om = both(px, oracle, spiral_weights(), "cube")
+    B = 1 << 16
+    y0, t = cfg2_y0(B), cfg2_tspan(4)
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0, t, controller="batch")
+    gy = loss_grad(ref)
+    g, a0, stats, log = adjoint_backward(field, t, ref, gy, return_adj_y0=True, log_attempts=256, controller="batch",
+                                         adj_norm="mixed")
+    g_ref, a_ref, st_ref, lg, rc = oracle.dopri5_mlp_adjoint(om, t, ref, gy, controller="batch", adj_norm="mixed")
+    assert rc == 0 and stats.read().status == 0
+    rec, cnt = log.read()
+    r = rec[0, :cnt[0]]
+    assert cnt[0] == len(lg) and np.array_equal(r.dt, lg.dt) and np.array_equal(r.ratio, lg.ratio)
+    assert np.array_equal(a0.cpu().numpy(), a_ref) and np.array_equal(g.cpu().numpy(), g_ref)
 
 
 def test_odeint_adjoint_reference_defaults_via_options(px, torch, oracle):

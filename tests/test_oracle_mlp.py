@@ -261,3 +261,42 @@ def test_oracle_grad_t_span_is_the_true_time_gradient(oracle):
     L.backward()
     want = tt.grad.numpy()
     np.testing.assert_allclose(gt, want, rtol=2e-4, atol=2e-5 * np.abs(want).max())
+
+
+def test_oracle_exact_batch_sum_is_order_independent_and_correctly_rounded(oracle):
+    """fx_add_float / fx_to_float (the order-independent batch sum of the arithmetic specification): any permutation
+    gives the same bits, and the result is the correctly rounded exact sum (addends above 2^-35 are not truncated)."""
+    import ctypes as C
+    from fractions import Fraction
+
+    lib = oracle.lib()
+    lib.orc_fx_sum.restype = C.c_float
+    lib.orc_fx_sum.argtypes = [C.c_void_p, C.c_int64]
+
+    def fx(x):
+        x = np.ascontiguousarray(x, np.float32)
+        return np.float32(lib.orc_fx_sum(x.ctypes.data_as(C.c_void_p), x.size))
+
+    def rn32(fr):  # exact rational -> fp32, round to nearest even
+        c = np.float32(float(fr))
+        cands = sorted({np.nextafter(c, np.float32(-np.inf)), c, np.nextafter(c, np.float32(np.inf))}, key=float)
+        best = min(cands, key=lambda v: (abs(Fraction(float(v)) - fr), int(np.float32(v).view(np.uint32)) & 1))
+        return np.float32(best)
+
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        n = int(rng.integers(1, 4000))
+        x = (rng.standard_normal(n) * 10.0 ** rng.uniform(-6, 6, n)).astype(np.float32)
+        if trial % 3 == 0:  # heavy cancellation
+            x = np.concatenate([x, -x[: n // 2], (1e-3 * rng.standard_normal(5)).astype(np.float32)])
+        want = rn32(sum((Fraction(float(v)) for v in x), Fraction(0)))
+        got = fx(x)
+        assert got == want, (trial, got, want)
+        for _ in range(3):
+            assert fx(rng.permutation(x)) == got
+    # ties round to even; tiny addends are truncated toward zero to the 2^-59 grid; unrepresentable addends -> NaN
+    assert fx([np.float32(2 ** 24), np.float32(1.0)]) == np.float32(2 ** 24)
+    assert fx([np.float32(2 ** 24), np.float32(3.0)]) == np.float32(2 ** 24 + 4)
+    assert fx([np.float32(2.0 ** -60), np.float32(-2.0 ** -60)]) == 0.0 and fx([np.float32(2.0 ** -61)] * 8) == 0.0
+    assert fx([np.float32(3 * 2.0 ** -60)]) == np.float32(2.0 ** -59)
+    assert np.isnan(fx([np.float32(2.0 ** 40)])) and np.isnan(fx([np.float32(np.inf), 1.0])) and fx([np.float32(2.0 ** 39)]) == 2.0 ** 39
