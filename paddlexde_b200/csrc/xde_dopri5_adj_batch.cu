@@ -15,7 +15,7 @@
 // sequence of the mixed norm depends on HOW it is summed.  The sum is therefore specified so that it has one value on
 // every machine (xde_fixed128.cuh, oracle/xde_oracle.c adj_rhs): per 32 consecutive trajectories a sequential fp32
 // fma chain (this is what a warp's fold of its 32 tile columns computes), the chain values added exactly in a
-// 128-bit fixed-point accumulator (shared-memory atomics per CTA, then global atomics: integer addition commutes),
+// 128-bit fixed-point accumulator (carry-free integer limbs: shared-memory REDs per CTA, then global REDs),
 // the total rounded once to fp32.  Per attempt the six new stage sums travel through one grid-wide reduction
 // (the same two grid.sync() that the error norm of (y, a) needs); the FSAL property carries over: k_6^theta of an
 // accepted attempt is k_0^theta of the next one.  Both norms run this path; with it the whole (dt, ratio, accept)
@@ -40,7 +40,7 @@ struct AdjBatchParams {
   xde_mlp_field_t field;
   const float *t_span, *y_ans, *grad_y;
   float *out_g;    // [P] fp32
-  unsigned long long *gfx;  // [3][6][P][2] grid-wide 128-bit accumulators, triple buffered (zeroed)
+  unsigned long long *gfx;  // [3][6][P][kFxGLimbs] grid-wide fixed-point accumulators, triple buffered (zeroed)
   int *gbad;                // [3] "an addend was not representable" flags (zeroed)
   float *adj_y0;   // [B,D] or null
   long long B;
@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
   float *st = sw + SmallRec<D>::floats(H);
   float *g0 = st + ((p.T + 3) / 4) * 4;            // [P]     g_theta: a state of the solve, replicated in every CTA
   float *kth = g0 + P4;                            // [8][P4] k_0..k_6 of the g_theta dynamics, [7] = the Euler probe
-  unsigned long long *fxacc = reinterpret_cast<unsigned long long *>(kth + 8 * P4);  // [6][P][2] CTA partial sums
-  double *sred = reinterpret_cast<double *>(fxacc + (size_t)6 * P * 2);              // [kABScalars]
+  int *fxacc = reinterpret_cast<int *>(kth + 8 * P4);  // [6][P][kFxSLimbs] CTA partial sums (carry-free limbs)
+  double *sred = reinterpret_cast<double *>(fxacc + (((size_t)6 * P * kFxSLimbs + 3) / 4) * 4);  // [kABScalars]
   float *wbase = reinterpret_cast<float *>(sred + p.row) + (size_t)warp * (4 * NP * kABTileStride + 32 * CST);
   float4 *tile = reinterpret_cast<float4 *>(wbase);
   float *coef = wbase + 4 * NP * kABTileStride;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
   for (int i = threadIdx.x; i < p.T; i += blockDim.x) st[i] = tsign * p.t_span[i];
   for (int i = threadIdx.x; i < P; i += blockDim.x) g0[i] = 0.0f;
   for (int i = threadIdx.x; i < 8 * P4; i += blockDim.x) kth[i] = 0.0f;
-  for (int i = threadIdx.x; i < 6 * P * 2; i += blockDim.x) fxacc[i] = 0ull;
+  for (int i = threadIdx.x; i < 6 * P * kFxSLimbs; i += blockDim.x) fxacc[i] = 0;
   for (int i = lane; i < NP * kABTileStride; i += 32) tile[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = lane; i < 32 * CST; i += 32) coef[i] = 0.0f;
   if (threadIdx.x == 0) s_bad = 0;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
   // X: the fp32 chain values of this warp's 32 trajectories (lane = hidden-unit pair); xb: a_d of this lane's
   // trajectory (0 for a lane past the batch).  Added into the CTA's accumulators of stage vector `v`.
   auto accumulate = [&](const f32x2 (&X)[NTP], const float (&xb)[D], int v) {
-    unsigned long long *dst = fxacc + (size_t)v * P * 2;
+    int *dst = fxacc + (size_t)v * P * kFxSLimbs;
     bool ok = true;
 #pragma unroll
     for (int q = 0; q < HPL; ++q)
@@ -234,8 +234,7 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
             float lo, hi;
             upk(X[q * NV + i], lo, hi);
             const int idx = (i < D) ? i * H + j : (i == D ? D * H + j : D * H + H + j * D + (i - D - 1));
-            Fx128 f;
-            if (fx_from_float(e ? hi : lo, f)) fx_atomic_add(dst + 2 * idx, f); else ok = false;
+            ok = fx_limbs_add_float(dst + kFxSLimbs * idx, e ? hi : lo) && ok;
           }
         }
       }
@@ -254,7 +253,22 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
         g.hi = __shfl_xor_sync(XDE_FULL_MASK, f.hi, off);
         f = fx_add(f, g);
       }
-      if (lane == 0) fx_atomic_add(dst + 2 * (D * H + H + H * D + d), f);
+      if (lane == 0) {  // the warp's exact integer sum, split over the limbs (carry-free: signed limbs with headroom)
+        const bool neg = (f.hi >> 63) != 0ull;
+        unsigned long long lo = f.lo, hi = f.hi;
+        if (neg) {
+          lo = ~lo + 1ull;
+          hi = ~hi + (lo == 0ull ? 1ull : 0ull);
+        }
+        int *a = dst + kFxSLimbs * (D * H + H + H * D + d);
+#pragma unroll
+        for (int k = 0; k < kFxSLimbs; ++k) {
+          const int sh = kFxSBits * k;
+          const unsigned long long w = (sh < 64) ? ((lo >> sh) | (sh ? (hi << (64 - sh)) : 0ull)) : (hi >> (sh - 64));
+          const int limb = (int)(w & ((1u << kFxSBits) - 1u));
+          if (limb) atomicAdd(a + k, neg ? -limb : limb);
+        }
+      }
     }
     if (!ok) s_bad = 1;
   };
@@ -308,30 +322,25 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
   int phase = 0;
   auto reduce_phase = [&](int nv, int slot0) {
     __syncthreads();  // every warp has added its last chain values
-    unsigned long long *gb = p.gfx + (size_t)(phase % 3) * 6 * P * 2;
+    unsigned long long *gb = p.gfx + (size_t)(phase % 3) * 6 * P * kFxGLimbs;
     for (int i = threadIdx.x; i < nv * P; i += blockDim.x) {
-      Fx128 f;
-      f.lo = fxacc[2 * i];
-      f.hi = fxacc[2 * i + 1];
-      fx_atomic_add(gb + 2 * i, f);
-      fxacc[2 * i] = 0ull;
-      fxacc[2 * i + 1] = 0ull;
+      int *a = fxacc + (size_t)i * kFxSLimbs;
+      fx_glimbs_add(gb + (size_t)i * kFxGLimbs, fx_limbs_total(a));
+#pragma unroll
+      for (int k = 0; k < kFxSLimbs; ++k) a[k] = 0;
     }
     if (threadIdx.x == 0 && s_bad) atomicOr(p.gbad + phase % 3, 1);
     if (blockIdx.x == 0) {
-      unsigned long long *gn = p.gfx + (size_t)((phase + 1) % 3) * 6 * P * 2;
-      for (int i = threadIdx.x; i < 6 * P * 2; i += blockDim.x) gn[i] = 0ull;
+      unsigned long long *gn = p.gfx + (size_t)((phase + 1) % 3) * 6 * P * kFxGLimbs;
+      for (int i = threadIdx.x; i < 6 * P * kFxGLimbs; i += blockDim.x) gn[i] = 0ull;
       if (threadIdx.x == 0) p.gbad[(phase + 1) % 3] = 0;
     }
     __threadfence();
     grid_reduce(kABScalars);
     const bool bad = __ldcg(p.gbad + phase % 3) != 0;
     for (int i = threadIdx.x; i < nv * P; i += blockDim.x) {
-      Fx128 f;
-      f.lo = __ldcg(gb + 2 * i);
-      f.hi = __ldcg(gb + 2 * i + 1);
       const int v = i / P, q = i - v * P;
-      kth[(slot0 + v) * P4 + q] = bad ? NAN : ths * fx_to_float(f);
+      kth[(slot0 + v) * P4 + q] = bad ? NAN : ths * fx_to_float(fx_glimbs_total(gb + (size_t)i * kFxGLimbs));
     }
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
@@ -683,7 +692,7 @@ static int launch_adj_batch(AdjBatchParams &p, cudaStream_t stream) {
   constexpr int CST = ((2 * D + 1 + 3) / 4) * 4;
   p.row = kABScalars;
   const size_t smem = sizeof(float) * (SmallRec<D>::floats(H) + ((p.T + 3) / 4) * 4 + (size_t)9 * P4) +
-                      sizeof(unsigned long long) * (size_t)6 * P * 2 + sizeof(double) * p.row +
+                      sizeof(int) * ((((size_t)6 * P * kFxSLimbs + 3) / 4) * 4) + sizeof(double) * p.row +
                       sizeof(float) * kABWarps * (4 * (size_t)NP * kABTileStride + 32 * CST);
   XDE_REQUIRE(smem <= 200 * 1024, XDE_E_UNSUPPORTED_FIELD, "adjoint (batch controller): field + t_span exceed shared memory");
   auto kern = dopri5_adj_batch_kernel<D, HPL, PRE>;
@@ -699,7 +708,10 @@ static int launch_adj_batch(AdjBatchParams &p, cudaStream_t stream) {
   float *ws = nullptr;
   double *partial = nullptr, *reduced = nullptr;
   unsigned long long *gfx = nullptr;
-  const size_t gfx_bytes = sizeof(unsigned long long) * (size_t)3 * 6 * P * 2 + 4 * sizeof(int);
+  const size_t gfx_bytes = sizeof(unsigned long long) * (size_t)3 * 6 * P * kFxGLimbs + 4 * sizeof(int);
+  // headroom of the shared-memory limbs: one addend per accumulator, warp and 32-trajectory block
+  XDE_REQUIRE((p.B + 31) / 32 / grid < 4000, XDE_E_UNSUPPORTED_FIELD,
+              "adjoint (batch controller): more than 4000 trajectory blocks per CTA (B = %lld on %lld CTAs)", p.B, grid);
   XDE_CUDA_CHECK(scratch_alloc((void **)&ws, sizeof(float) * 4 * nel, stream));
   XDE_CUDA_CHECK(scratch_alloc((void **)&partial, sizeof(double) * (size_t)grid * p.row, stream));
   XDE_CUDA_CHECK(scratch_alloc((void **)&reduced, sizeof(double) * p.row, stream));
@@ -709,7 +721,7 @@ static int launch_adj_batch(AdjBatchParams &p, cudaStream_t stream) {
   p.partial = partial;
   p.reduced = reduced;
   p.gfx = gfx;
-  p.gbad = reinterpret_cast<int *>(gfx + (size_t)3 * 6 * P * 2);
+  p.gbad = reinterpret_cast<int *>(gfx + (size_t)3 * 6 * P * kFxGLimbs);
   void *args[] = {(void *)&p};
   cudaError_t e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)grid), dim3(kABThreads), args, smem, stream);
   count_launch();

@@ -107,4 +107,89 @@ __device__ __forceinline__ float fx_to_float(Fx128 a) {
   return neg ? -r : r;
 }
 
+// ---- carry-free limb accumulators (same value, cheaper atomics) --------------------------------------------------
+// A 128-bit atomic add needs the low word's return value for the carry: ~150 cycles of shared-memory round trip per
+// addend, serialised at the occupancy of the cooperative kernel (r2d: 3x slower).  Integer limbs with HEADROOM need
+// no carries while accumulating: the value is sum_i limb_i * 2^(W i) with signed limbs, every add is a
+// fire-and-forget RED, and the carries are propagated once when the total is read.
+//   shared memory: 6 x int32 limbs of 19 bits (an addend touches <= 3 of them; 2^12 adds of headroom per limb)
+//   global memory: 3 x int64 limbs of 43 bits (2^20 adds of headroom)
+constexpr int kFxSLimbs = 6, kFxSBits = 19;
+constexpr int kFxGLimbs = 3, kFxGBits = 43;
+
+__device__ __forceinline__ Fx128 fx_shl_signed(long long v, int sh) {  // sign-extended v * 2^sh, 0 <= sh < 128
+  Fx128 r;
+  const unsigned long long u = (unsigned long long)v, ext = (v < 0) ? ~0ull : 0ull;
+  if (sh == 0) {
+    r.lo = u;
+    r.hi = ext;
+  } else if (sh < 64) {
+    r.lo = u << sh;
+    r.hi = (ext << sh) | (u >> (64 - sh));
+  } else {
+    r.lo = 0ull;
+    r.hi = u << (sh - 64);
+  }
+  return r;
+}
+
+// acc: kFxSLimbs int32 words in shared memory
+__device__ __forceinline__ bool fx_limbs_add_float(int *acc, float x) {
+  const unsigned bits = __float_as_uint(x);
+  const int E = (int)((bits >> 23) & 0xffu);
+  const unsigned M = bits & 0x7fffffu;
+  if (E == 255) return false;
+  const unsigned long long mant = E ? (unsigned long long)(M | 0x800000u) : (unsigned long long)M;
+  const int shift = (E ? E - 150 : -149) + 59;
+  if (shift > 75) return false;
+  int i0 = 0;
+  unsigned long long m;
+  if (shift >= 0) {
+    i0 = shift / kFxSBits;
+    m = mant << (shift - kFxSBits * i0);  // < 2^(24 + 18)
+  } else {
+    m = (-shift >= 32) ? 0ull : (mant >> (-shift));
+  }
+  const int neg = (int)(bits >> 31);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int limb = (int)((m >> (kFxSBits * k)) & ((1u << kFxSBits) - 1u));
+    if (limb) atomicAdd(acc + i0 + k, neg ? -limb : limb);
+  }
+  return true;
+}
+
+__device__ __forceinline__ Fx128 fx_limbs_total(const int *acc) {
+  Fx128 t;
+  t.lo = t.hi = 0ull;
+#pragma unroll
+  for (int i = 0; i < kFxSLimbs; ++i) t = fx_add(t, fx_shl_signed((long long)acc[i], kFxSBits * i));
+  return t;
+}
+
+// add a 128-bit value to kFxGLimbs int64 words in global memory (no return values needed)
+__device__ __forceinline__ void fx_glimbs_add(unsigned long long *acc, Fx128 v) {
+  const bool neg = (v.hi >> 63) != 0ull;
+  unsigned long long lo = v.lo, hi = v.hi;
+  if (neg) {
+    lo = ~lo + 1ull;
+    hi = ~hi + (lo == 0ull ? 1ull : 0ull);
+  }
+  const unsigned long long mask = (1ull << kFxGBits) - 1ull;
+  const unsigned long long l0 = lo & mask;
+  const unsigned long long l1 = ((lo >> kFxGBits) | (hi << (64 - kFxGBits))) & mask;
+  const unsigned long long l2 = hi >> (2 * kFxGBits - 64);
+  if (l0) atomicAdd(acc, neg ? (0ull - l0) : l0);
+  if (l1) atomicAdd(acc + 1, neg ? (0ull - l1) : l1);
+  if (l2) atomicAdd(acc + 2, neg ? (0ull - l2) : l2);
+}
+
+__device__ __forceinline__ Fx128 fx_glimbs_total(const unsigned long long *acc) {
+  Fx128 t;
+  t.lo = t.hi = 0ull;
+#pragma unroll
+  for (int i = 0; i < kFxGLimbs; ++i) t = fx_add(t, fx_shl_signed((long long)__ldcg(acc + i), kFxGBits * i));
+  return t;
+}
+
 }  // namespace xde
