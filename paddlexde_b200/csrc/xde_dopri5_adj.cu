@@ -834,6 +834,10 @@ static int adj_hpl(const AdjParams &p, cudaStream_t s) {
   return XDE_E_UNSUPPORTED_FIELD;
 }
 
+int dopri5_adj_tile(const xde_mlp_field_t *field, const float *t_span, int T, const float *y_ans, const float *grad_y,
+                    long long B, const xde_ctrl_opts_t *opts, double *gacc, unsigned long long *queue, float *out_adj_y0,
+                    xde_stats_t *stats, const xde_attempt_log_t *log, cudaStream_t s);  // xde_adj_tile.cu
+
 int dopri5_adj_batch(const xde_mlp_field_t *field, const float *t_span, int T, const float *y_ans,
                      const float *grad_y, long long B, const xde_ctrl_opts_t *opts, int adj_norm,
                      float *out_gparams, float *out_adj_y0, xde_stats_t *stats, const xde_attempt_log_t *log,
@@ -897,7 +901,13 @@ extern "C" XDE_EXPORT int xde_dopri5_mlp_adjoint_f32(const xde_mlp_field_t *fiel
     case 6: rc = adj_hpl<6>(p, s); break;
     case 7: rc = adj_hpl<7>(p, s); break;
     case 8: rc = adj_hpl<8>(p, s); break;
-    default: set_last_error("adjoint: state dim D=%d has no fused kernel (D in 1..8)", D);
+    default:  // large states: tiles of trajectories per CTA (xde_adj_tile.cu)
+      if (out_grad_t) {
+        set_last_error("adjoint: grad_t_span is computed by the small-state kernels only (D <= 8)");
+        rc = XDE_E_UNSUPPORTED_FIELD;
+      } else {
+        rc = dopri5_adj_tile(field, t_span, T, y_ans, grad_y, B, opts, p.gacc, p.queue, out_adj_y0, stats, log, s);
+      }
   }
   if (rc == XDE_OK) {
     const int ncast = P > T ? P : T;

@@ -73,14 +73,19 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
   const int H = p.field.h, NP = SmallRec<D>::pairs(H);
   const int P = 2 * D * H + H + D;
   const int P4 = ((P + 3) / 4) * 4;
+  // accumulator slots of one stage vector: kind i (gW1 rows, gb1, gW2 columns) x parity e x hidden-unit pair, then the
+  // D slots of gb2.  Consecutive lanes (pairs) hit consecutive 32-bit words: the shared-memory REDs are conflict free
+  // (the parameter order [i*H + j] made them 4-way conflicts).  PS = slots per vector; limb k of slot s at [k*PS + s].
+  const int HP2 = 32 * HPL;  // pairs per parity row, padded to the lanes
+  const int PS = NV * 2 * HP2 + D;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // shared-memory carve-up
   float *sw = smem;
   float *st = sw + SmallRec<D>::floats(H);
   float *g0 = st + ((p.T + 3) / 4) * 4;            // [P]     g_theta: a state of the solve, replicated in every CTA
   float *kth = g0 + P4;                            // [8][P4] k_0..k_6 of the g_theta dynamics, [7] = the Euler probe
-  int *fxacc = reinterpret_cast<int *>(kth + 8 * P4);  // [6][P][kFxSLimbs] CTA partial sums (carry-free limbs)
-  double *sred = reinterpret_cast<double *>(fxacc + (((size_t)6 * P * kFxSLimbs + 3) / 4) * 4);  // [kABScalars]
+  int *fxacc = reinterpret_cast<int *>(kth + 8 * P4);  // [6][kFxSLimbs][PS] CTA partial sums (carry-free limbs)
+  double *sred = reinterpret_cast<double *>(fxacc + (((size_t)6 * PS * kFxSLimbs + 3) / 4) * 4);  // [kABScalars]
   float *wbase = reinterpret_cast<float *>(sred + p.row) + (size_t)warp * (4 * NP * kABTileStride + 32 * CST);
   float4 *tile = reinterpret_cast<float4 *>(wbase);
   float *coef = wbase + 4 * NP * kABTileStride;
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
   for (int i = threadIdx.x; i < p.T; i += blockDim.x) st[i] = tsign * p.t_span[i];
   for (int i = threadIdx.x; i < P; i += blockDim.x) g0[i] = 0.0f;
   for (int i = threadIdx.x; i < 8 * P4; i += blockDim.x) kth[i] = 0.0f;
-  for (int i = threadIdx.x; i < 6 * P * kFxSLimbs; i += blockDim.x) fxacc[i] = 0;
+  for (int i = threadIdx.x; i < 6 * PS * kFxSLimbs; i += blockDim.x) fxacc[i] = 0;
   for (int i = lane; i < NP * kABTileStride; i += 32) tile[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = lane; i < 32 * CST; i += 32) coef[i] = 0.0f;
   if (threadIdx.x == 0) s_bad = 0;
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
   // X: the fp32 chain values of this warp's 32 trajectories (lane = hidden-unit pair); xb: a_d of this lane's
   // trajectory (0 for a lane past the batch).  Added into the CTA's accumulators of stage vector `v`.
   auto accumulate = [&](const f32x2 (&X)[NTP], const float (&xb)[D], int v) {
-    int *dst = fxacc + (size_t)v * P * kFxSLimbs;
+    int *dst = fxacc + (size_t)v * PS * kFxSLimbs;
     bool ok = true;
 #pragma unroll
     for (int q = 0; q < HPL; ++q)
@@ -233,8 +238,7 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
           for (int i = 0; i < NV; ++i) {
             float lo, hi;
             upk(X[q * NV + i], lo, hi);
-            const int idx = (i < D) ? i * H + j : (i == D ? D * H + j : D * H + H + j * D + (i - D - 1));
-            ok = fx_limbs_add_float(dst + kFxSLimbs * idx, e ? hi : lo) && ok;
+            ok = fx_limbs_add_float(dst + (i * 2 + e) * HP2 + lane + 32 * q, PS, e ? hi : lo) && ok;
           }
         }
       }
@@ -260,13 +264,13 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
           lo = ~lo + 1ull;
           hi = ~hi + (lo == 0ull ? 1ull : 0ull);
         }
-        int *a = dst + kFxSLimbs * (D * H + H + H * D + d);
+        int *a = dst + NV * 2 * HP2 + d;
 #pragma unroll
         for (int k = 0; k < kFxSLimbs; ++k) {
           const int sh = kFxSBits * k;
           const unsigned long long w = (sh < 64) ? ((lo >> sh) | (sh ? (hi << (64 - sh)) : 0ull)) : (hi >> (sh - 64));
           const int limb = (int)(w & ((1u << kFxSBits) - 1u));
-          if (limb) atomicAdd(a + k, neg ? -limb : limb);
+          if (limb) atomicAdd(a + k * PS, neg ? -limb : limb);
         }
       }
     }
@@ -324,10 +328,24 @@ __global__ void __launch_bounds__(kABThreads, 1) dopri5_adj_batch_kernel(const A
     __syncthreads();  // every warp has added its last chain values
     unsigned long long *gb = p.gfx + (size_t)(phase % 3) * 6 * P * kFxGLimbs;
     for (int i = threadIdx.x; i < nv * P; i += blockDim.x) {
-      int *a = fxacc + (size_t)i * kFxSLimbs;
-      fx_glimbs_add(gb + (size_t)i * kFxGLimbs, fx_limbs_total(a));
+      const int v = i / P, q = i - v * P;  // parameter q of stage vector v -> its accumulator slot
+      int slot;
+      if (q < D * H) {
+        const int k = q / H, j = q - k * H;
+        slot = (k * 2 + (j & 1)) * HP2 + (j >> 1);
+      } else if (q < D * H + H) {
+        const int j = q - D * H;
+        slot = (D * 2 + (j & 1)) * HP2 + (j >> 1);
+      } else if (q < D * H + H + H * D) {
+        const int r = q - D * H - H, j = r / D, d = r - j * D;
+        slot = ((D + 1 + d) * 2 + (j & 1)) * HP2 + (j >> 1);
+      } else {
+        slot = NV * 2 * HP2 + (q - D * H - H - H * D);
+      }
+      int *a = fxacc + (size_t)v * PS * kFxSLimbs + slot;
+      fx_glimbs_add(gb + (size_t)i * kFxGLimbs, fx_limbs_total(a, PS));
 #pragma unroll
-      for (int k = 0; k < kFxSLimbs; ++k) a[k] = 0;
+      for (int k = 0; k < kFxSLimbs; ++k) a[k * PS] = 0;
     }
     if (threadIdx.x == 0 && s_bad) atomicOr(p.gbad + phase % 3, 1);
     if (blockIdx.x == 0) {
@@ -692,7 +710,8 @@ static int launch_adj_batch(AdjBatchParams &p, cudaStream_t stream) {
   constexpr int CST = ((2 * D + 1 + 3) / 4) * 4;
   p.row = kABScalars;
   const size_t smem = sizeof(float) * (SmallRec<D>::floats(H) + ((p.T + 3) / 4) * 4 + (size_t)9 * P4) +
-                      sizeof(int) * ((((size_t)6 * P * kFxSLimbs + 3) / 4) * 4) + sizeof(double) * p.row +
+                      sizeof(int) * ((((size_t)6 * ((2 * D + 1) * 2 * 32 * HPL + D) * kFxSLimbs + 3) / 4) * 4) +
+                      sizeof(double) * p.row +
                       sizeof(float) * kABWarps * (4 * (size_t)NP * kABTileStride + 32 * CST);
   XDE_REQUIRE(smem <= 200 * 1024, XDE_E_UNSUPPORTED_FIELD, "adjoint (batch controller): field + t_span exceed shared memory");
   auto kern = dopri5_adj_batch_kernel<D, HPL, PRE>;

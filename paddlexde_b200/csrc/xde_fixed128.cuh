@@ -133,8 +133,8 @@ __device__ __forceinline__ Fx128 fx_shl_signed(long long v, int sh) {  // sign-e
   return r;
 }
 
-// acc: kFxSLimbs int32 words in shared memory
-__device__ __forceinline__ bool fx_limbs_add_float(int *acc, float x) {
+// acc: kFxSLimbs int32 words in shared memory, `stride` words apart
+__device__ __forceinline__ bool fx_limbs_add_float(int *acc, int stride, float x) {
   const unsigned bits = __float_as_uint(x);
   const int E = (int)((bits >> 23) & 0xffu);
   const unsigned M = bits & 0x7fffffu;
@@ -154,16 +154,16 @@ __device__ __forceinline__ bool fx_limbs_add_float(int *acc, float x) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int limb = (int)((m >> (kFxSBits * k)) & ((1u << kFxSBits) - 1u));
-    if (limb) atomicAdd(acc + i0 + k, neg ? -limb : limb);
+    if (limb) atomicAdd(acc + (i0 + k) * stride, neg ? -limb : limb);
   }
   return true;
 }
 
-__device__ __forceinline__ Fx128 fx_limbs_total(const int *acc) {
+__device__ __forceinline__ Fx128 fx_limbs_total(const int *acc, int stride) {
   Fx128 t;
   t.lo = t.hi = 0ull;
 #pragma unroll
-  for (int i = 0; i < kFxSLimbs; ++i) t = fx_add(t, fx_shl_signed((long long)acc[i], kFxSBits * i));
+  for (int i = 0; i < kFxSLimbs; ++i) t = fx_add(t, fx_shl_signed((long long)acc[i * stride], kFxSBits * i));
   return t;
 }
 

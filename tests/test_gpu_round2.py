@@ -265,3 +265,101 @@ def test_interpolants_default_grid(px, torch, oracle, cls, kind):
     val, der = it.evaluate(q), it.derivative(q)
     v_ref, d_ref = oracle.history_gather(kind, series, np.arange(12, dtype=f32), q)
     assert np.array_equal(val.cpu().numpy(), v_ref) and np.array_equal(der.cpu().numpy(), d_ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# adjoint for large states (csrc/xde_adj_tile.cu): tiles of trajectories per CTA, gradients in tensor memory
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,h,pre,B", [(64, 256, "id", 70), (64, 128, "cube", 33), (32, 256, "id", 65), (32, 128, "square", 130),
+                                        (32, 64, "cube", 129), (16, 64, "id", 200)])
+def test_adjoint_large_state_parity(px, torch, oracle, d, h, pre, B):
+    """odeint_adjoint's backward for D = 16 / 32 / 64 (cfg3's 64-256-64 field): dL/dy0 bit-exact, the per-trajectory
+    (dt, ratio, accept) sequences identical, parameter gradients within rtol 1e-5 of the oracle."""
+    from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
+
+    w = fanin_weights(d, h, seed=h + d)
+    field, om = px.MLPField(*w, pre=pre), oracle.MLP(*w, pre=pre)
+    y0 = np.random.default_rng(3).uniform(-1, 1, (B, d)).astype(f32)
+    t = np.linspace(0, 1, 4).astype(f32)
+    kw = dict(rtol=1e-6, atol=1e-8)
+    ref, _, _, rc = oracle.dopri5_mlp(om, y0, t, **kw)
+    assert rc == 0
+    gy = loss_grad(ref)
+    gy[1] = (0.01 / ref[1].size) * np.random.default_rng(4).standard_normal(gy[1].shape).astype(f32)
+    g, a0, stats, log = adjoint_backward(field, t, ref, gy, return_adj_y0=True, log_attempts=256, **kw)
+    g_ref, a_ref, st_ref, _, rc = oracle.dopri5_mlp_adjoint(om, t, ref, gy, **kw)
+    assert rc == 0
+    s = stats.read()
+    assert s.status == 0
+    assert s.n_attempts == int(st_ref.n_attempts.sum()) and s.n_accepted == int(st_ref.n_accepted.sum())
+    assert s.nfe == int(st_ref.nfe.sum())
+    assert np.array_equal(a0.cpu().numpy(), a_ref), "adjoint state dL/dy0 must be bit-exact"
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-5, atol=1e-6 * np.abs(g_ref).max())
+    rec, cnt = log.read()
+    for b in (0, B // 2, B - 1):
+        _, _, _, lg, _ = oracle.dopri5_mlp_adjoint(om, t, ref, gy, log_traj=b, **kw)
+        assert cnt[b] == len(lg)
+        r = rec[b, :cnt[b]]
+        assert np.array_equal(r.accepted, lg.accepted) and np.array_equal(r.dt, lg.dt) and np.array_equal(r.ratio, lg.ratio)
+
+
+def test_adjoint_large_state_rejections_reverse_time_and_status(px, torch, oracle):
+    from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
+
+    d, h, B = 32, 64, 97
+    w = [2.5 * a for a in fanin_weights(d, h, seed=9)]
+    field, om = px.MLPField(*w, pre="id"), oracle.MLP(*w, pre="id")
+    y0 = np.random.default_rng(1).uniform(-1, 1, (B, d)).astype(f32)
+    kw = dict(rtol=1e-5, atol=1e-7)
+    for t in (np.linspace(0, 1.5, 4).astype(f32), np.linspace(1.5, 0, 4).astype(f32)):
+        ref, _, _, rc = oracle.dopri5_mlp(om, y0, t, **kw)
+        assert rc == 0
+        gy = (np.random.default_rng(5).standard_normal(ref.shape) / ref[0].size).astype(f32)
+        g, a0, stats, _ = adjoint_backward(field, t, ref, gy, return_adj_y0=True, **kw)
+        g_ref, a_ref, st_ref, _, rc = oracle.dopri5_mlp_adjoint(om, t, ref, gy, **kw)
+        assert rc == 0
+        if t[1] > t[0]:
+            assert (st_ref.n_attempts > st_ref.n_accepted).any(), "the case must exercise rejections (replay passes)"
+        s = stats.read()
+        assert s.status == 0 and s.n_attempts == int(st_ref.n_attempts.sum()) and s.n_accepted == int(st_ref.n_accepted.sum())
+        assert np.array_equal(a0.cpu().numpy(), a_ref)
+        np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-5, atol=2e-6 * np.abs(g_ref).max())
+    # max_num_steps -> status word, NaN rows
+    t = np.array([0.0, 3.0], f32)
+    ref, _, _, _ = oracle.dopri5_mlp(om, y0, t, **kw)
+    gy = np.ones_like(ref) / ref[0].size
+    with pytest.raises(AssertionError, match="max_num_steps"):
+        adjoint_backward(field, t, ref, gy, max_num_steps=2, **kw)
+
+
+def test_large_state_neural_ode_trains_through_the_public_api(px, torch, oracle):
+    """A 64-256-64 neural ODE through odeint_adjoint + backward(): gradients of every parameter against fp64 torch
+    autograd through a fine RK4 integration (the true gradient, rtol 2e-3 at these tolerances)."""
+    rng = np.random.default_rng(0)
+    d, h, B = 64, 256, 48
+    w = fanin_weights(d, h, seed=3)
+    tw = [torch.tensor(a, device="cuda", requires_grad=True) for a in w]
+    field = px.MLPField(*tw, pre="id")
+    y0 = torch.tensor(rng.uniform(-1, 1, (B, d)).astype(f32), device="cuda")
+    t = np.linspace(0, 0.5, 3).astype(f32)
+    target = torch.tensor(rng.uniform(-1, 1, (B, d)).astype(f32), device="cuda")
+    sol = px.odeint_adjoint(field, y0, t, solver=px.Dopri5, rtol=1e-6, atol=1e-8, options={"controller": "trajectory"})
+    loss = ((sol[-1] - target) ** 2).mean() + 0.1 * (sol[1] ** 2).mean()
+    loss.backward()
+    got = [p.grad.double().cpu() for p in tw]
+    W = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in w]
+    f = lambda y: torch.tanh(y @ W[0] + W[1]) @ W[2] + W[3]
+    y = y0.double().cpu()
+    outs = [y]
+    for i in range(1, t.size):
+        n = 40
+        hh = float(t[i] - t[i - 1]) / n
+        for _ in range(n):
+            k1 = f(y); k2 = f(y + 0.5 * hh * k1); k3 = f(y + 0.5 * hh * k2); k4 = f(y + hh * k3)
+            y = y + hh / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        outs.append(y)
+    ref_loss = ((outs[-1] - target.double().cpu()) ** 2).mean() + 0.1 * (outs[1] ** 2).mean()
+    ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
+    for gq, Wq in zip(got, W):
+        np.testing.assert_allclose(gq.numpy(), Wq.grad.numpy(), rtol=2e-3, atol=2e-4 * float(Wq.grad.abs().max()))

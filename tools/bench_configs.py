@@ -174,6 +174,37 @@ def cfg3_dopri5(B=1 << 15):
             "note": "tiles of 32 trajectories advance together until the slowest row is done (no refill inside a tile)"}
 
 
+def cfg3_adjoint(B=1 << 14):
+    """The cfg3 field (MLP 64-256-64) trained with odeint_adjoint: dopri5 forward + adjoint, rtol 1e-6, one controller per
+    trajectory (forward: xde_tile_adaptive.cu, backward: xde_adj_tile.cu -- FP32 tiles, gradients in tensor memory)."""
+    from paddlexde_b200.functional.odeint_adjoint import adjoint_backward
+    d, h = 64, 256
+    field = px.MLPField(*fanin_weights(d, h, seed=1), pre="id")
+    y0 = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, (B, d)).astype(np.float32)).cuda()
+    t = np.linspace(0, 1, 5).astype(np.float32)
+    xde = px.xde.BaseODE(field, y0, t)
+    s = px.Dopri5(xde=xde, y0=y0, rtol=1e-6, atol=1e-8, controller="trajectory", check_status=False)
+    sol = s.integrate(t)
+    gy = torch.zeros_like(sol)
+    gy[-1] = torch.sign(sol[-1]) / sol[-1].numel()
+    ms_f = timeit(lambda: s.integrate(t))
+    st = {}
+
+    def bwd():
+        st["r"] = adjoint_backward(field, t, sol, gy, rtol=1e-6, atol=1e-8, check_status=False)
+
+    ms_b = timeit(bwd)
+    a = st["r"][2].read()
+    f = s.read_stats()
+    evals = 6 * a.n_attempts + 3 * (t.size - 1) * B  # f0 + probe + the theta-only pass of f0 per segment
+    flops = evals * 12 * d * h  # 4 state GEMMs + 2 gradient GEMMs of 2*D*H each
+    return {"config": "cfg3 field 64-256-64, dopri5 rtol=1e-6 forward + adjoint (per-trajectory controller, seminorm)",
+            "math": "fp32", "B": B, "ms_fwd": ms_f, "ms_adjoint": ms_b, "trajectory_steps_fwd": int(f.n_attempts),
+            "trajectory_steps_adjoint": int(a.n_attempts), "status": [int(f.status), int(a.status)],
+            "traj_steps_per_s": (f.n_attempts + a.n_attempts) / (ms_f + ms_b) * 1e3,
+            "tflops_adjoint": flops / ms_b / 1e9, "frac_ffma_peak_adjoint": flops / ms_b / 1e9 / FFMA}
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg3", "cfg4", "cfg5"]
     for w in which:
@@ -185,6 +216,8 @@ if __name__ == "__main__":
                 print(json.dumps(cfg4(B=1 << 22, math="tensor", generated=True)), flush=True)
         elif w == "cfg3_dopri5":
             print(json.dumps(cfg3_dopri5()), flush=True)
+        elif w == "cfg3_adjoint":
+            print(json.dumps(cfg3_adjoint()), flush=True)
         elif w == "cfg2_batch":
             for norm in ("mixed", "seminorm"):
                 print(json.dumps(cfg2_batch(norm=norm)), flush=True)
