@@ -266,6 +266,33 @@ int xde_dde_fuse_f32(const float *dy, float dt, const float *y0, int64_t n, floa
  * either output may be NULL. */
 int xde_dde_fuse_bwd_f32(const float *grad_y1, float dt, int64_t n, float *grad_dy, float *grad_y0, void *stream);
 
+/* ---- torch-free host surface (csrc/xde_hostapi.cu) ---------------------------------------------------------
+ * The reference creates its tensors with Paddle eager ops (solver/base_adaptive_solver.py:25-31,
+ * base_fixed_solver.py:119-143).  A host layer that wants no tensor library binds these instead: device memory from
+ * the stream-ordered pool, copies, streams, and a DLPack producer through which Paddle / PyTorch / CuPy import the
+ * results without a copy (paddlexde_b200/_native.py is such a host layer: ctypes + numpy only). */
+int xde_device_count(int32_t *n);
+int xde_set_device(int32_t dev);
+int xde_get_device(int32_t *dev);
+int xde_malloc(void **ptr, uint64_t bytes, void *stream);
+int xde_free(void *ptr, void *stream);
+/* kind: 0 host->device, 1 device->host, 2 device->device */
+int xde_memcpy_async(void *dst, const void *src, uint64_t bytes, int32_t kind, void *stream);
+int xde_memset_async(void *dst, int32_t value, uint64_t bytes, void *stream);
+int xde_host_alloc(void **ptr, uint64_t bytes); /* pinned */
+int xde_host_free(void *ptr);
+int xde_stream_create(void **stream);
+int xde_stream_destroy(void *stream);
+int xde_stream_synchronize(void *stream);
+/* -> DLManagedTensor* (DLPack v0.8) for a contiguous device buffer; dtype_code 2 = float, 0 = int; owns != 0: the
+ * deleter frees the buffer.  Wrap it in a PyCapsule named "dltensor".  NULL on a bad argument. */
+void *xde_dlpack_wrap(void *dev_ptr, int32_t ndim, const int64_t *shape, int32_t dtype_code, int32_t bits,
+                      int32_t device_id, int32_t owns);
+void xde_dlpack_release(void *managed);
+/* in-place sum of the adjoint parameter gradients over the batch shards, the only collective of the
+ * path (example/D3STN/train_dde.py:201-202,454-456).  comm: the caller's ncclComm_t. */
+int xde_allreduce_grads(void *comm, float *buf, int64_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,22 @@ _EXPORTS = {
     "xde_history_gather_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                              C.c_void_p, C.c_void_p]),
     "xde_dde_fuse_f32": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "xde_device_count": (C.c_int, [C.POINTER(C.c_int32)]),
+    "xde_set_device": (C.c_int, [C.c_int32]),
+    "xde_get_device": (C.c_int, [C.POINTER(C.c_int32)]),
+    "xde_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64, C.c_void_p]),
+    "xde_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "xde_memcpy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]),
+    "xde_memset_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p]),
+    "xde_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
+    "xde_host_free": (C.c_int, [C.c_void_p]),
+    "xde_stream_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "xde_stream_destroy": (C.c_int, [C.c_void_p]),
+    "xde_stream_synchronize": (C.c_int, [C.c_void_p]),
+    "xde_dlpack_wrap": (C.c_void_p, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32]),
+    "xde_dlpack_release": (None, [C.c_void_p]),
+    "xde_allreduce_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "xde_dde_fuse_bwd_f32": (C.c_int, [C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

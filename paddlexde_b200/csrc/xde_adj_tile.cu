@@ -31,7 +31,10 @@
 
 namespace xde {
 
-constexpr int kAdjTileFlushEvery = 24;
+#ifndef XDE_ADJ_TILE_FLUSH
+#define XDE_ADJ_TILE_FLUSH 24
+#endif
+constexpr int kAdjTileFlushEvery = XDE_ADJ_TILE_FLUSH;
 
 struct AdjTileParams {
   xde_mlp_field_t f;

@@ -7,10 +7,11 @@ adjoint parameter-gradient vector per backward -- the counterpart of the DataPar
 all-reduce in the reference's example trainer (example/D3STN/train_dde.py:201-202,454-456)."""
 from __future__ import annotations
 
+import ctypes as C
 import os
 
-import torch
-import torch.distributed as dist
+from . import _tensor as T
+from ._lib import check, lib
 
 
 def shard_rows(n: int, rank: int, world: int):
@@ -35,6 +36,11 @@ def init_from_env(backend: str | None = None):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        return rank, world, local
+    import torch
+    import torch.distributed as dist
+
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
@@ -52,9 +58,25 @@ def grad_allreduce(group=None):
     """The hook for ``options={"grad_allreduce": ...}`` of odeint_adjoint: sums the flat parameter-gradient
     vector over the ranks in place (NCCL over NVLink on GPUs; a no-op for a single process)."""
 
-    def hook(g: torch.Tensor):
+    def hook(g):
+        if T.torch is None:
+            return g
+        import torch.distributed as dist
+
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+        return g
+
+    return hook
+
+
+def nccl_grad_allreduce(comm: int):
+    """The same hook WITHOUT torch.distributed: `comm` is the address of an ncclComm_t the caller created (Paddle's,
+    its own, ...); the sum runs through the library's xde_allreduce_grads on the stream of the gradient buffer
+    (include/xde_b200.h; SURVEY 8(b) proposed exactly this entry)."""
+
+    def hook(g):
+        check(lib().xde_allreduce_grads(C.c_void_p(int(comm)), T.ptr(g), g.numel(), T.stream(g)))
         return g
 
     return hook

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 from typing import Sequence
 
-import torch
+import numpy as np
 
 from . import _tensor as T
 from ._lib import PRE, MlpFieldC, UnsupportedFieldError
@@ -46,10 +46,16 @@ class MLPField:
         return list(self._src)
 
     def _load(self):
-        w1, b1, w2, b2 = (T.to_dev(a) for a in self._src)
-        if self.weight_layout == "out_in":
-            w1, w2 = w1.t().contiguous(), w2.t().contiguous()
-        self.w1, self.b1, self.w2, self.b2 = w1, b1, w2, b2
+        def dev(a, transpose):
+            if T.is_torch(a):
+                t = T.to_dev(a)
+                return t.t().contiguous() if transpose else t
+            h = np.asarray(T.to_host(a), dtype=np.float32)
+            return T.to_dev(np.ascontiguousarray(h.T) if transpose else h)
+
+        tr = self.weight_layout == "out_in"
+        w1, b1, w2, b2 = self._src
+        self.w1, self.b1, self.w2, self.b2 = dev(w1, tr), dev(b1, False), dev(w2, tr), dev(b2, False)
 
     def refresh(self):
         """Re-read the caller's parameter tensors (after an optimizer step; device tensors in the [in, out]
@@ -57,7 +63,7 @@ class MLPField:
         self._load()
         return self
 
-    def grads_like_params(self, flat: torch.Tensor):
+    def grads_like_params(self, flat):
         """The flat (gW1, gb1, gW2, gb2) of the adjoint entries, shaped like `parameters()`."""
         gw1, gb1, gw2, gb2 = self.split_flat(flat)
         if self.weight_layout == "out_in":
@@ -68,11 +74,16 @@ class MLPField:
     def n_params(self) -> int:
         return 2 * self.d * self.h + self.h + self.d
 
-    def split_flat(self, flat: torch.Tensor):
+    def split_flat(self, flat):
         d, h = self.d, self.h
-        sizes = [d * h, h, h * d, d]
-        shapes = [(d, h), (h,), (h, d), (d,)]
-        return [c.reshape(s) for c, s in zip(torch.split(flat, sizes), shapes)]
+        out, o = [], 0
+        for shp in ((d, h), (h,), (h, d), (d,)):
+            n = 1
+            for v in shp:
+                n *= v
+            out.append(flat[o:o + n].reshape(shp))
+            o += n
+        return out
 
     def c_struct(self) -> MlpFieldC:
         return MlpFieldC(self.d, self.h, PRE[self.pre], 0, self.w1.data_ptr(), self.b1.data_ptr(),
@@ -89,7 +100,7 @@ class MLPField:
         l1, _, l2 = layers
         w1, w2 = l1.weight, l2.weight
         if weight_layout == "auto":
-            weight_layout = "out_in" if isinstance(w1, torch.Tensor) else "in_out"
+            weight_layout = "out_in" if T.is_torch(w1) else "in_out"
         # the module's own Parameters stay the leaves: gradients are routed (and transposed back) to them, and
         # refresh() re-reads them after an optimizer step
         return cls(w1, l1.bias, w2, l2.bias, pre=pre, weight_layout=weight_layout)

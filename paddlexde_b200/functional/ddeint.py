@@ -1,8 +1,7 @@
 from __future__ import annotations
 
-import torch
-
 from .. import _tensor as T
+from .._tensor import torch
 from ..utils.ode_utils import _rms_norm
 from ..xde import BaseDDE
 
@@ -46,6 +45,10 @@ def ddeint(func, y0, t_span, lags, his, his_span, solver, his_processed=False, r
     output interpolants return the end of the step (interp_fn.py:4-20)."""
     from ..solver import FixedSolver
     from ..xde.base_dde import _as_graph_tensor
+
+    if torch is None:
+        raise ImportError("ddeint calls back into the caller's `func(y_lags, y)` on framework tensors: it needs PyTorch "
+                          "(the history gather and the fuse kernels are available without it: xde.base_dde)")
 
     xde = BaseDDE(func, y0=y0, t_span=t_span, lags=lags, his=his, his_span=his_span, his_processed=his_processed)
     if not (isinstance(solver, type) and issubclass(solver, FixedSolver)):

@@ -7,11 +7,9 @@ Gradient convention of the reference (:167): grads for `adjoint_params` only, `y
 from __future__ import annotations
 
 import ctypes as C
-import warnings
-
-import torch
 
 from .. import _tensor as T
+from .._tensor import torch  # None when PyTorch is not installed: adjoint_backward still works (numpy / DeviceArray)
 from .._lib import ADJ_NORM, CTRL, UnsupportedFieldError, check, lib, raise_for_status
 from ..field import as_field
 from ..solver.adaptive_solver import (AttemptLog, Dopri5, StatsBuffer, StatsPair, check_norm, default_controller,
@@ -29,31 +27,35 @@ def adjoint_backward(field, t_span, y_ans, grad_y, *, rtol=1e-7, atol=1e-9, cont
     (gparams_flat [P], adj_y0 [B, D] | None, stats_reader, attempt_log | None).
     out_grad_t: optional fp32 device tensor [T] that receives grad_t_span (functional/odeint_adjoint.py:129-141,
     161-162; the reference computes it only when t_span requires a gradient)."""
-    y_ans_d, grad_d = T.to_dev(y_ans), T.to_dev(grad_y)
+    y_ans_d = T.to_dev(y_ans, like=grad_y if T.is_torch(grad_y) else None)
+    grad_d = T.to_dev(grad_y, like=y_ans_d)
     t_host = host_tspan(t_span)
     Tn = t_host.size
     D = field.d
     if y_ans_d.shape[0] != Tn or y_ans_d.shape[-1] != D or y_ans_d.shape != grad_d.shape:
         raise ValueError("y_ans and grad_y must both be [T, ..., D]")
     B = y_ans_d.numel() // (Tn * D)
-    dev = y_ans_d.device
-    g = torch.zeros(field.n_params, device=dev, dtype=torch.float32)
-    a0 = torch.empty((B, D), device=dev, dtype=torch.float32) if return_adj_y0 else None
-    stats = StatsBuffer(dev) if stats_buffer is None else stats_buffer
-    log = AttemptLog(B, log_attempts, dev) if log_attempts > 0 else None
+    g = T.zeros((field.n_params,), y_ans_d)
+    a0 = T.empty((B, D), y_ans_d) if return_adj_y0 else None
+    stats = StatsBuffer(y_ans_d) if stats_buffer is None else stats_buffer
+    log = AttemptLog(B, log_attempts, y_ans_d) if log_attempts > 0 else None
     opts = make_ctrl_opts(rtol, atol, **ctrl_kw)
     fs = field.c_struct()
-    t_dev = device_tspan(t_host, dev)
+    t_dev = device_tspan(t_host, y_ans_d)
     check(lib().xde_dopri5_mlp_adjoint_f32(C.byref(fs), T.ptr(t_dev), Tn, T.ptr(y_ans_d), T.ptr(grad_d), B,
                                            C.byref(opts), CTRL[controller], ADJ_NORM[adj_norm], T.ptr(g),
                                            T.ptr(a0), T.ptr(out_grad_t), T.ptr(stats.buf),
-                                           C.byref(log.c_struct()) if log else None, T.stream()))
+                                           C.byref(log.c_struct()) if log else None, T.stream(y_ans_d)))
     if check_status:
         raise_for_status(stats.read().status)
     return g, a0, stats, log
 
 
-class OdeintAdjointMethod(torch.autograd.Function):
+class OdeintAdjointMethod(torch.autograd.Function if torch is not None else object):
+    """The autograd surface needs an autograd framework: this is the PyTorch adapter (INTEGRATION.md shows the Paddle
+    `PyLayer` twin).  Without PyTorch installed the class is inert and `odeint_adjoint` raises ImportError; the
+    numerical work is `adjoint_backward` above either way."""
+
     @staticmethod
     def forward(ctx, holder, y0, t_span, *params):
         with torch.no_grad():
@@ -106,6 +108,10 @@ class OdeintAdjointMethod(torch.autograd.Function):
 def odeint_adjoint(func, y0, t_span, *, rtol=1e-7, atol=1e-9, solver=None, options={"norm": _rms_norm},
                    event_fn=None, adjoint_rtol=None, adjoint_atol=None, adjoint_solver=None,
                    adjoint_options=None, adjoint_params=None):
+    if torch is None:
+        raise ImportError("odeint_adjoint returns a tensor with an autograd graph: it needs PyTorch (or the Paddle PyLayer "
+                          "of INTEGRATION.md). Without an autograd framework call odeint(...) and "
+                          "paddlexde_b200.functional.odeint_adjoint.adjoint_backward(...) directly.")
     field = as_field(func)  # nn.Layer check of the reference (:186-192) becomes: must be a fused field
     if event_fn is not None:
         raise NotImplementedError("event_fn is not supported (the reference ignores it as well)")
@@ -171,8 +177,10 @@ def odeint_adjoint(func, y0, t_span, *, rtol=1e-7, atol=1e-9, solver=None, optio
                   allreduce=(options or {}).get("grad_allreduce"))
     if "grad_allreduce" in holder["options"]:
         holder["options"] = {k: v for k, v in holder["options"].items() if k != "grad_allreduce"}
-    y0_t = y0 if isinstance(y0, torch.Tensor) else T.to_dev(y0)
-    holder["stats_pair"] = StatsPair(y0_t.device if y0_t.is_cuda else T.device())
+    y0_t = y0 if isinstance(y0, torch.Tensor) else T.to_dev(y0, like=torch.empty(0, device=T.device()))
+    if not y0_t.is_cuda:
+        y0_t = y0_t.to(T.device())
+    holder["stats_pair"] = StatsPair(y0_t)
     holder["options"]["stats_buffer"] = holder["stats_pair"].fwd
     tensor_params = [p if isinstance(p, torch.Tensor) else torch.as_tensor(p) for p in params]
     sol = OdeintAdjointMethod.apply(holder, y0_t, t_span, *tensor_params)

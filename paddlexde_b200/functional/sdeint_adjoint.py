@@ -10,12 +10,11 @@ from __future__ import annotations
 
 import ctypes as C
 
-import torch
-
 from .. import _tensor as T
 from .._lib import UnsupportedFieldError, check, lib
+from .._tensor import torch  # None when PyTorch is not installed: sde_adjoint_backward still works
 from ..field import as_field
-from ..solver.adaptive_solver import host_tspan
+from ..solver.adaptive_solver import device_tspan, host_tspan
 from ..utils.ode_utils import _rms_norm
 from .sdeint import sdeint
 
@@ -25,30 +24,30 @@ def sde_adjoint_backward(drift, diffusion, t_span, y_all, grad_y, *, bm_incremen
     """SdeintAdjointMethod.backward as a plain function on device buffers.
     y_all, grad_y: [B, T, D] (the fixed solver's layout, every grid point).  -> (g_drift [Pf], g_diffusion [Pg],
     adj_y0 [B, D] | None)."""
-    y_d, g_d = T.to_dev(y_all).contiguous(), T.to_dev(grad_y).contiguous()
+    y_d = T.to_dev(y_all, like=grad_y if T.is_torch(grad_y) else None).contiguous()
+    g_d = T.to_dev(grad_y, like=y_d).contiguous()
     t_host = host_tspan(t_span)
     Tn, D = t_host.size, drift.d
     if y_d.shape[-1] != D or y_d.shape[-2] != Tn or y_d.shape != g_d.shape:
         raise ValueError("y_all and grad_y must both be [B, T, D] with every grid point stored")
     B = y_d.numel() // (Tn * D)
-    dev = y_d.device
-    gf = torch.empty(drift.n_params, device=dev, dtype=torch.float32)
-    gg = torch.empty(diffusion.n_params, device=dev, dtype=torch.float32)
-    a0 = torch.empty((B, D), device=dev, dtype=torch.float32) if return_adj_y0 else None
+    gf = T.empty((drift.n_params,), y_d)
+    gg = T.empty((diffusion.n_params,), y_d)
+    a0 = T.empty((B, D), y_d) if return_adj_y0 else None
     dW = None
     if bm_seed is None:
-        dW = T.to_dev(bm_increments)
+        dW = T.to_dev(bm_increments, like=y_d)
         if tuple(dW.shape) != (Tn - 1, B, D):
             raise ValueError(f"bm_increments must be [T-1, B, D] = {(Tn - 1, B, D)}, got {tuple(dW.shape)}")
     f, g = drift.c_struct(), diffusion.c_struct()
-    t_dev = T.to_dev(t_host)
+    t_dev = device_tspan(t_host, y_d)
     check(lib().xde_sde_mlp_adjoint_f32(C.byref(f), C.byref(g), T.ptr(t_dev), Tn, T.ptr(y_d), T.ptr(g_d), B, T.ptr(dW),
                                         0 if bm_seed is None else int(bm_seed) & (2 ** 64 - 1), int(bm_offset),
-                                        T.ptr(gf), T.ptr(gg), T.ptr(a0), T.stream()))
+                                        T.ptr(gf), T.ptr(gg), T.ptr(a0), T.stream(y_d)))
     return gf, gg, a0
 
 
-class SdeintAdjointMethod(torch.autograd.Function):
+class SdeintAdjointMethod(torch.autograd.Function if torch is not None else object):
     @staticmethod
     def forward(ctx, holder, y0, t, *params):
         with torch.no_grad():
@@ -84,6 +83,9 @@ class SdeintAdjointMethod(torch.autograd.Function):
 def sdeint_adjoint(drift, diffusion, y0, t, solver, *, rtol=1e-7, atol=1e-9, options={"norm": _rms_norm},
                    event_fn=None, adjoint_rtol=None, adjoint_atol=None, adjoint_solver=None, adjoint_options=None,
                    adjoint_params=None):
+    if torch is None:
+        raise ImportError("sdeint_adjoint needs an autograd framework (PyTorch); without one call sdeint(...) and "
+                          "sde_adjoint_backward(...) directly")
     f, g = as_field(drift), as_field(diffusion)
     if event_fn is not None:
         raise NotImplementedError("event_fn is not supported (the reference ignores it as well)")
@@ -104,7 +106,7 @@ def sdeint_adjoint(drift, diffusion, y0, t, solver, *, rtol=1e-7, atol=1e-9, opt
     params = (tuple(f.parameters()) + tuple(g.parameters())) if adjoint_params is None else tuple(adjoint_params)
     holder = dict(drift=f, diffusion=g, solver=solver, rtol=rtol, atol=atol, options=options, params=params,
                   allreduce=allreduce)
-    y0_t = y0 if isinstance(y0, torch.Tensor) else T.to_dev(y0)
+    y0_t = y0 if isinstance(y0, torch.Tensor) else T.to_dev(y0, like=torch.empty(0, device=T.device()))
     if y0_t.dim() != 3 or y0_t.shape[-2] != 1:
         raise ValueError("sdeint_adjoint takes y0 of shape [B, 1, D] (the fixed solvers then return [B, T, D])")
     tensor_params = [p if isinstance(p, torch.Tensor) else torch.as_tensor(p) for p in params]

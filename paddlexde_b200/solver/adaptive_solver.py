@@ -15,7 +15,6 @@ import warnings
 from dataclasses import dataclass
 
 import numpy as np
-import torch
 
 from .. import _tensor as T
 from .._lib import (CTRL, RK, AttemptLogC, CtrlOptsC, StatsC, UnsupportedFieldError, check, lib,
@@ -80,10 +79,7 @@ def check_norm(norm):
 
 def host_tspan(t_span) -> np.ndarray:
     """fp32 host copy of t_span (solver/base_adaptive_solver.py:27 casts to the fp32 time dtype)."""
-    if isinstance(t_span, torch.Tensor):
-        t = t_span.detach().to("cpu", torch.float32).numpy()
-    else:
-        t = np.asarray(t_span, dtype=np.float32)
+    t = np.asarray(T.to_host(t_span), dtype=np.float32)
     t = np.ascontiguousarray(t.reshape(-1))
     d = np.diff(t)
     if t.size < 2 or not (np.all(d > 0) or np.all(d < 0)):
@@ -102,39 +98,41 @@ def _decode_stats(words) -> SolveStats:
 class StatsBuffer:
     """Device-resident xde_stats_t read back lazily (one tiny D2H copy when asked).  The entry points zero it."""
 
-    def __init__(self, dev, buf=None):
-        self.buf = torch.empty(_STATS_WORDS, dtype=torch.int64, device=dev) if buf is None else buf
+    def __init__(self, like, buf=None):
+        """like: any device buffer of the call (decides the provider: torch / native)."""
+        self.buf = T.empty((_STATS_WORDS,), like, "i64") if buf is None else buf
 
     def read(self) -> SolveStats:
-        return _decode_stats(self.buf.cpu().numpy())
+        return _decode_stats(T.to_host(self.buf))
 
 
 class StatsPair:
     """The forward solve's and the adjoint solve's xde_stats_t side by side, so that odeint_adjoint's backward reads
     both status words with ONE device-to-host copy."""
 
-    def __init__(self, dev):
-        self.both = torch.zeros(2 * _STATS_WORDS, dtype=torch.int64, device=dev)
-        self.fwd = StatsBuffer(dev, self.both[:_STATS_WORDS])
-        self.adj = StatsBuffer(dev, self.both[_STATS_WORDS:])
+    def __init__(self, like):
+        self.both = T.zeros((2 * _STATS_WORDS,), like, "i64")
+        self.fwd = StatsBuffer(like, self.both[:_STATS_WORDS])
+        self.adj = StatsBuffer(like, self.both[_STATS_WORDS:])
 
     def read(self):
-        w = self.both.cpu().numpy()
+        w = T.to_host(self.both)
         return _decode_stats(w[:_STATS_WORDS]), _decode_stats(w[_STATS_WORDS:])
 
 
 _tspan_cache: dict = {}
 
 
-def device_tspan(t_host: np.ndarray, dev) -> torch.Tensor:
-    """fp32 device copy of t_span; the handful of grids a training loop uses are cached (forward and backward ask for
-    the same one every step, and a pageable H2D copy costs more than the rest of the launch path)."""
-    key = (t_host.tobytes(), str(dev))
+def device_tspan(t_host: np.ndarray, like):
+    """fp32 device copy of t_span (same provider and device as `like`); the handful of grids a training loop uses are
+    cached (forward and backward ask for the same one every step, and a pageable H2D copy costs more than the rest of
+    the launch path)."""
+    key = (t_host.tobytes(), str(getattr(like, "device", None)), T.is_torch(like))
     t = _tspan_cache.get(key)
     if t is None:
         if len(_tspan_cache) >= 64:
             _tspan_cache.clear()
-        t = torch.from_numpy(t_host).to(dev)
+        t = T.from_host(t_host, like)
         _tspan_cache[key] = t
     return t
 
@@ -143,17 +141,17 @@ class AttemptLog:
     """Optional per-trajectory attempt log (tests / diagnostics): records [B, cap]."""
     dtype = np.dtype([("t0", np.float32), ("dt", np.float32), ("ratio", np.float32), ("accepted", np.int32)])
 
-    def __init__(self, B, cap, dev):
+    def __init__(self, B, cap, like):
         self.cap = cap
-        self.records = torch.zeros((B, cap, 4), dtype=torch.float32, device=dev)
-        self.counts = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.records = T.zeros((B, cap, 4), like, "f32")
+        self.counts = T.zeros((B,), like, "i32")
 
     def c_struct(self):
         return AttemptLogC(self.records.data_ptr(), self.counts.data_ptr(), self.cap, 0)
 
     def read(self):
-        rec = self.records.cpu().numpy().view(self.dtype).reshape(self.records.shape[0], self.cap)
-        return rec.view(np.recarray), self.counts.cpu().numpy()
+        rec = T.to_host(self.records).view(self.dtype).reshape(self.records.shape[0], self.cap)
+        return rec.view(np.recarray), T.to_host(self.counts)
 
 
 class AdaptiveRKSolver:
@@ -198,40 +196,40 @@ class AdaptiveRKSolver:
             raise ValueError(f"y0 last dim {y0.shape[-1]} != field state dim {field.d}")
         B = y0.numel() // field.d
         t_host = host_tspan(t_span)
-        t_dev = device_tspan(t_host, y0.device)
-        out = torch.empty((t_host.size,) + tuple(y0.shape), device=y0.device, dtype=torch.float32)
+        t_dev = device_tspan(t_host, y0)
+        out = T.empty((t_host.size,) + tuple(y0.shape), y0)
         if self._stats_buf is None:
-            self._stats_buf = StatsBuffer(y0.device)
+            self._stats_buf = StatsBuffer(y0)
         log_c = None
         if self.log_attempts > 0:
-            self.attempt_log = AttemptLog(B, self.log_attempts, y0.device)
+            self.attempt_log = AttemptLog(B, self.log_attempts, y0)
             log_c = C.byref(self.attempt_log.c_struct())
         fs = field.c_struct()
-        step_t, jump_t = (self._sort_tvals(v, t_host, y0.device) for v in (self.step_t, self.jump_t))
+        step_t, jump_t = (self._sort_tvals(v, t_host, y0) for v in (self.step_t, self.jump_t))
         check(lib().xde_adaptive_rk_mlp_grid_f32(
             RK[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), t_host.size, C.byref(self.opts),
             CTRL[self.controller], T.ptr(step_t) if step_t is not None else None, 0 if step_t is None else step_t.numel(),
             T.ptr(jump_t) if jump_t is not None else None, 0 if jump_t is None else jump_t.numel(), T.ptr(out),
-            T.ptr(self._stats_buf.buf), log_c, T.stream()))
+            T.ptr(self._stats_buf.buf), log_c, T.stream(y0)))
         if self.check_status:  # the reference asserts synchronously; opt out to stay asynchronous
             self.stats = self._stats_buf.read()
             raise_for_status(self.stats.status)
         return T.like_input(out, self.y0)
 
     @staticmethod
-    def _sort_tvals(tvals, t_host, dev):
+    def _sort_tvals(tvals, t_host, like):
         """sort_tvals (utils/ode_utils.py:22-25): drop the points before t_span[0], sort in integration
         order (ascending for an increasing t_span, descending for a decreasing one: repair R5)."""
         if tvals is None:
             return None
-        v = (tvals.detach().cpu().numpy() if isinstance(tvals, torch.Tensor) else np.asarray(tvals)).astype(np.float32).reshape(-1)
+        v = np.asarray(T.to_host(tvals)).astype(np.float32).reshape(-1)
         if t_host[1] < t_host[0]:
             v = np.sort(v[v <= t_host[0]])[::-1]
         else:
             v = np.sort(v[v >= t_host[0]])
         if v.size == 0:
             return None
-        return torch.from_numpy(v.copy()).to(dev)  # copy(): a reversed length-1 view keeps its negative stride
+        return T.from_host(v.copy(), like)  # copy(): a reversed length-1 view keeps its negative stride
 
     def read_stats(self) -> SolveStats:
         self.stats = self._stats_buf.read()

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-import torch
+import numpy as np
 
 from .. import _tensor as T
 from .._lib import FIXED, SDE, ST_TC_RANGE, XDE_E_UNSUPPORTED_FIELD, UnsupportedFieldError, check, lib
@@ -52,12 +52,12 @@ class FixedSolver:
         raises in those cases (no silent change of arithmetic); "fp32" never touches the tensor cores."""
         if self.math == "fp32":
             return check(fp32_call())
-        status = torch.zeros(1, dtype=torch.int32, device=dev) if self.check_status else None
+        status = T.zeros((1,), dev, "i32") if self.check_status else None
         rc = tensor_call(T.ptr(status))
         if rc == XDE_E_UNSUPPORTED_FIELD and self.math == "auto":
             return check(fp32_call())
         check(rc)
-        if status is not None and int(status.item()) == ST_TC_RANGE:
+        if status is not None and int(T.to_host(status)[0]) == ST_TC_RANGE:
             if self.math == "auto":
                 return check(fp32_call())
             raise OverflowError("a stage input left the fp16 operand range of the tensor-core kernels "
@@ -67,12 +67,13 @@ class FixedSolver:
         kind = getattr(self.xde, "kind", None)
         y0 = T.to_dev(self.y0)
         t_host = host_tspan(t_span)
-        t_dev = device_tspan(t_host, y0.device)
+        t_dev = device_tspan(t_host, y0)
         Tn = t_host.size
         D = y0.shape[-1]
         B = y0.numel() // D
         n_out = (Tn - 1 + self.out_stride - 1) // self.out_stride + 1
-        out = torch.empty((B, n_out, D), device=y0.device, dtype=torch.float32)
+        out = T.empty((B, n_out, D), y0)
+        stream = T.stream(y0)
         # the kernels are specialised on the field's state dim and index y0 / out / dW with it: a mismatch would read
         # and write out of bounds on the device (the C ABI sees only pointers), so it is refused here
         fields = {"ode": ("field",), "sde": ("drift", "diffusion")}.get(kind, ())
@@ -83,8 +84,8 @@ class FixedSolver:
         if kind == "ode":
             fs = self.xde.field.c_struct()
             args = (FIXED[self.method], C.byref(fs), T.ptr(y0), B, T.ptr(t_dev), Tn, self.out_stride, T.ptr(out))
-            self._launch(lambda st: lib().xde_rk_fixed_mlp_tc_f32(*args, st, T.stream()),
-                         lambda: lib().xde_rk_fixed_mlp_f32(*args, T.stream()), y0.device)
+            self._launch(lambda st: lib().xde_rk_fixed_mlp_tc_f32(*args, st, stream),
+                         lambda: lib().xde_rk_fixed_mlp_f32(*args, stream), y0)
         elif kind == "sde":
             if self.method != "euler" and self.xde.scheme == "em":
                 raise UnsupportedFieldError("sdeint is fused for solver=Euler (Euler-Maruyama) only")
@@ -93,31 +94,42 @@ class FixedSolver:
                 def philox(math, st=None):
                     return lib().xde_sde_mlp_philox_f32(SDE[self.xde.scheme], math, C.byref(f), C.byref(g), T.ptr(y0), B,
                                                         T.ptr(t_dev), Tn, int(self.xde.bm_seed) & (2 ** 64 - 1),
-                                                        self.xde.bm_offset, self.out_stride, T.ptr(out), st, T.stream())
-                self._launch(lambda st: philox(1, st), lambda: philox(0), y0.device)
+                                                        self.xde.bm_offset, self.out_stride, T.ptr(out), st, stream)
+                self._launch(lambda st: philox(1, st), lambda: philox(0), y0)
             else:
-                dW = T.to_dev(self.xde.bm_increments)
+                dW = T.to_dev(self.xde.bm_increments, like=y0)
                 if tuple(dW.shape) != (Tn - 1, B, D):
                     raise ValueError(f"bm_increments must be [T-1, B, D] = {(Tn - 1, B, D)}, got {tuple(dW.shape)}")
                 args = (SDE[self.xde.scheme], C.byref(f), C.byref(g), T.ptr(y0), B, T.ptr(t_dev), Tn, T.ptr(dW),
                         self.out_stride, T.ptr(out))
-                self._launch(lambda st: lib().xde_sde_mlp_tc_f32(*args, st, T.stream()),
-                             lambda: lib().xde_sde_mlp_f32(*args, T.stream()), y0.device)
+                self._launch(lambda st: lib().xde_sde_mlp_tc_f32(*args, st, stream),
+                             lambda: lib().xde_sde_mlp_f32(*args, stream), y0)
         else:
             raise UnsupportedFieldError(f"fixed solvers integrate ODE/SDE problems on the device, not {kind!r}")
         # concat(axis=-2) of the per-time states (base_fixed_solver.py:143)
         shp = tuple(y0.shape)
         if len(shp) >= 3 and shp[-2] == 1:          # y0 [..., 1, D] -> [..., T, D]
             res = out.reshape(shp[:-2] + (n_out, D))
-        elif len(shp) == 2:                          # y0 [B, D] -> [T*B, D] (time-major blocks)
-            res = out.permute(1, 0, 2).reshape(n_out * B, D)
         elif len(shp) == 1:
             res = out.reshape(n_out * D)
-        else:                                        # y0 [..., L, D] -> [..., T*L, D]
-            L = shp[-2]
-            lead = shp[:-2]
-            res = out.reshape(lead + (L, n_out, D)).transpose(-3, -2).reshape(lead + (n_out * L, D))
-        return T.like_input(res.contiguous(), self.y0)
+        elif T.is_torch(out):
+            if len(shp) == 2:                        # y0 [B, D] -> [T*B, D] (time-major blocks)
+                res = out.permute(1, 0, 2).reshape(n_out * B, D)
+            else:                                    # y0 [..., L, D] -> [..., T*L, D]
+                L = shp[-2]
+                lead = shp[:-2]
+                res = out.reshape(lead + (L, n_out, D)).transpose(-3, -2).reshape(lead + (n_out * L, D))
+            res = res.contiguous()
+        else:  # native buffers: the same two layouts on the host copy (numpy in -> numpy out anyway)
+            h = T.to_host(out)
+            if len(shp) == 2:
+                h = np.ascontiguousarray(h.transpose(1, 0, 2).reshape(n_out * B, D))
+            else:
+                L = shp[-2]
+                lead = shp[:-2]
+                h = np.ascontiguousarray(np.swapaxes(h.reshape(lead + (L, n_out, D)), -3, -2).reshape(lead + (n_out * L, D)))
+            res = h if isinstance(self.y0, (np.ndarray, list, tuple)) else T.from_host(h, out)
+        return T.like_input(res, self.y0)
 
 
 class Euler(FixedSolver):

@@ -6,8 +6,13 @@ device-side reduction.  Passing any other callable as options["norm"] raises Uns
 
 
 def _rms_norm(tensor):  # utils/ode_utils.py:8-9
-    import torch
-    return tensor.abs().pow(2).mean().sqrt() if isinstance(tensor, torch.Tensor) else None
+    from .. import _tensor as T
+
+    if T.is_torch(tensor):
+        return tensor.abs().pow(2).mean().sqrt()
+    import numpy as np
+
+    return float(np.sqrt(np.mean(np.square(np.abs(T.to_host(tensor)), dtype=np.float64))))
 
 
 def _mixed_norm(tensor_tuple):  # utils/ode_utils.py:16-19

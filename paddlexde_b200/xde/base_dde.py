@@ -1,9 +1,8 @@
 from __future__ import annotations
 
-import torch
-
 from .. import _tensor as T
 from .._lib import INTERP, check, lib
+from .._tensor import torch  # None when PyTorch is not installed: the gathers below still work
 from .base_xde import BaseXDE
 
 
@@ -12,7 +11,8 @@ def history_gather(lags, his, his_span, interp_method="cubic"):
     (interpolation/interpolate_base.py:49-114). his [..., Th, D] -> two [..., L, D] tensors."""
     if interp_method not in ("linear", "cubic", "bez"):
         raise NotImplementedError(interp_method)  # xde/base_dde.py:104-111
-    his_d, span_d, lags_d = T.to_dev(his), T.to_dev(his_span), T.to_dev(lags).reshape(-1)
+    his_d = T.to_dev(his, like=lags if T.is_torch(lags) else None)
+    span_d, lags_d = T.to_dev(his_span, like=his_d), T.to_dev(lags, like=his_d).reshape(-1)
     lead, Th, D = his_d.shape[:-2], his_d.shape[-2], his_d.shape[-1]
     if span_d.numel() != Th:
         raise ValueError("his_span must have his.shape[-2] entries")
@@ -20,24 +20,25 @@ def history_gather(lags, his, his_span, interp_method="cubic"):
     for s in lead:
         R *= s
     L = lags_d.numel()
-    val = torch.empty(tuple(lead) + (L, D), device=his_d.device, dtype=torch.float32)
-    der = torch.empty_like(val)
+    val = T.empty(tuple(lead) + (L, D), his_d)
+    der = T.empty(tuple(lead) + (L, D), his_d)
     check(lib().xde_history_gather_f32(INTERP[interp_method], T.ptr(his_d), R, Th, D, T.ptr(span_d),
-                                       T.ptr(lags_d), L, T.ptr(val), T.ptr(der), T.stream()))
+                                       T.ptr(lags_d), L, T.ptr(val), T.ptr(der), T.stream(his_d)))
     return val, der
 
 
 def history_gather_bwd(grad_y, deriv):
     """sum(grad_y * deriv, axis=[0,1,3]) generalised to all leading dims (xde/base_dde.py:121-127)."""
-    g, d = T.to_dev(grad_y), T.to_dev(deriv)
+    g = T.to_dev(grad_y, like=deriv if T.is_torch(deriv) else None)
+    d = T.to_dev(deriv, like=g)
     L, D = g.shape[-2], g.shape[-1]
     R = g.numel() // (L * D)
-    out = torch.empty(L, device=g.device, dtype=torch.float32)
-    check(lib().xde_history_gather_bwd_f32(T.ptr(g), T.ptr(d), R, L, D, T.ptr(out), T.stream()))
+    out = T.empty((L,), g)
+    check(lib().xde_history_gather_bwd_f32(T.ptr(g), T.ptr(d), R, L, D, T.ptr(out), T.stream(g)))
     return out
 
 
-class HistoryIndex(torch.autograd.Function):
+class HistoryIndex(torch.autograd.Function if torch is not None else object):
     """xde/base_dde.py:82-127: differentiable (wrt the real-valued lags) resampling of a fixed history."""
 
     @staticmethod
@@ -56,7 +57,7 @@ class HistoryIndex(torch.autograd.Function):
         return history_gather_bwd(grad_y.contiguous(), deriv), None, None, None
 
 
-class DdeFuse(torch.autograd.Function):
+class DdeFuse(torch.autograd.Function if torch is not None else object):
     """BaseDDE.fuse (xde/base_dde.py:55-58) with its cotangents: the D3STN trainer backpropagates through the
     solution of ddeint into `func`'s parameters (example/D3STN/train_dde.py:424-454), so the update must stay on
     the autograd graph.  y1 = (dy - 0.001*(dy*dt + y0))*dt + y0."""
@@ -91,7 +92,7 @@ def _as_graph_tensor(x):
     """fp32 CUDA tensor that KEEPS its autograd history (T.to_dev detaches: right for kernel inputs, wrong for
     values the caller differentiates through)."""
     if not isinstance(x, torch.Tensor):
-        return T.to_dev(x)
+        return T.to_dev(x, like=torch.empty(0, device=T.device()))
     if x.dtype != torch.float32:
         x = x.to(torch.float32)
     if not x.is_cuda:
@@ -109,7 +110,7 @@ class BaseDDE(BaseXDE):
         self.func = func
         self.lags = lags
         if not his_processed:
-            if isinstance(lags, torch.Tensor) and lags.requires_grad:
+            if T.is_torch(lags) and lags.requires_grad:
                 self.y_lags = HistoryIndex.apply(lags, his, his_span)
             else:
                 self.y_lags = history_gather(lags, his, his_span, "cubic")[0]
@@ -122,4 +123,10 @@ class BaseDDE(BaseXDE):
         return self.func(self.y_lags, y0)
 
     def fuse(self, dy, dt, y0):
-        return DdeFuse.apply(_as_graph_tensor(dy), float(dt), _as_graph_tensor(y0))
+        if torch is not None and (T.is_torch(dy) or T.is_torch(y0)):
+            return DdeFuse.apply(_as_graph_tensor(dy), float(dt), _as_graph_tensor(y0))
+        dy_d = T.to_dev(dy)
+        y0_d = T.to_dev(y0, like=dy_d)
+        out = T.empty(tuple(y0_d.shape), y0_d)
+        check(lib().xde_dde_fuse_f32(T.ptr(dy_d), float(dt), T.ptr(y0_d), y0_d.numel(), T.ptr(out), T.stream(y0_d)))
+        return out

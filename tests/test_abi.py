@@ -112,8 +112,11 @@ def test_sort_tvals_single_point_on_a_decreasing_span():
     """found by tools/fuzz_parity.py: a reversed length-1 NumPy view keeps a negative stride"""
     from paddlexde_b200.solver.adaptive_solver import AdaptiveRKSolver
 
+    import torch
+
     t = np.array([1.5, 1.0, 0.2], np.float32)
-    assert AdaptiveRKSolver._sort_tvals([0.5], t, "cpu").tolist() == [0.5]
-    assert AdaptiveRKSolver._sort_tvals([0.5, 0.75, 9.0], t, "cpu").tolist() == [0.75, 0.5]
-    assert AdaptiveRKSolver._sort_tvals([0.5, 0.25, -1.0], t[::-1].copy(), "cpu").tolist() == [0.25, 0.5]
-    assert AdaptiveRKSolver._sort_tvals([9.0], t, "cpu") is None
+    like = torch.empty(0)  # a host tensor: the sorted values land on its device (no GPU in this suite)
+    assert AdaptiveRKSolver._sort_tvals([0.5], t, like).tolist() == [0.5]
+    assert AdaptiveRKSolver._sort_tvals([0.5, 0.75, 9.0], t, like).tolist() == [0.75, 0.5]
+    assert AdaptiveRKSolver._sort_tvals([0.5, 0.25, -1.0], t[::-1].copy(), like).tolist() == [0.25, 0.5]
+    assert AdaptiveRKSolver._sort_tvals([9.0], t, like) is None
