@@ -23,6 +23,8 @@
 //     (columns [0,256) for warps 0-3, [256,512) for warps 4-7) and round-trips its 64 + 64 partial sums with
 //     tcgen05.ld / tcgen05.st around the fused multiply-adds; they are flushed to an fp64 accumulator in global
 //     memory every kFlushEvery folds (fp32 partial sums stay short, as in the small-state kernel).
+//   * the stage-6 evaluation is folded AFTER the controller (its operands are still in shared memory): with its own
+//     weight if the attempt is accepted, plus the stage-0 weight of the next attempt (FSAL);
 //   * a rejected attempt has already been folded in: its rows replay stages 0..5 with the negated weights in a
 //     theta-only pass (the two [TM x H] GEMMs + the two gradient GEMMs), the other rows carry weight 0.  The f0
 //     evaluation of a segment is folded by such a pass too, once select_initial_step has produced dt.
@@ -664,9 +666,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) adjoint_tile_kernel(const Adj
               yin[r][c] = s0[r][c] + s;
             }
           eval(yin, kk[i + 1], false);
+          if (i < 5) {  // stage 6 is folded after the controller: its weight exists only if the attempt is accepted
 #pragma unroll
-          for (int r = 0; r < R2; ++r) wrow[r] = seg_done[r] ? 0.0f : theta_w(i + 1, dt[r], fin[r], xfin[r]);
-          if (put_weights(wrow)) fold();
+            for (int r = 0; r < R2; ++r) wrow[r] = seg_done[r] ? 0.0f : theta_w(i + 1, dt[r], fin[r], xfin[r]);
+            if (put_weights(wrow)) fold();
+          }
         }
 
         // ---- error estimate, ratio (ode_utils.py:80-82), accept / reject, next step ----
@@ -714,6 +718,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) adjoint_tile_kernel(const Adj
           n_steps[r]++;
           if (accept) {
             if (speaker) n_acc++;
+            const float w_eval = theta_w(6, dt[r], fin[r], xfin[r]);  // weight of the stage-6 evaluation in this attempt
+            w_next[r] = w_eval;
             if (fin[r]) {
               // dense output at the segment end (interp_fit + interp_evaluate), then
               // y <- y_ans[i-1], a += grad_y[i-1] (functional/odeint_adjoint.py:153-159)
@@ -755,7 +761,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) adjoint_tile_kernel(const Adj
               dt[r] = dt_next;
               plan_attempt(r);
               // FSAL: the stage-6 evaluation (still in shared memory) is also stage 0 of the next attempt
-              w_next[r] = theta_w(0, dt[r], fin[r], xfin[r]);
+              w_next[r] = w_eval + theta_w(0, dt[r], fin[r], xfin[r]);
             }
           } else {
             // rejected: everything folded for this attempt is taken back by a replay pass below
