@@ -30,12 +30,16 @@ struct TileParams {
 };
 
 // KIND 0: ODE Euler, 1: ODE RK4 (3/8 rule), 2: SDE Euler-Maruyama (increments from the caller's table),
-// 3: ODE Midpoint (fixed_solver/midpoint.py:7-18), 4: SDE Euler-Maruyama, increments generated (BmSource)
+// 3: ODE Midpoint (fixed_solver/midpoint.py:7-18), 4: SDE Euler-Maruyama, increments generated (BmSource),
+// 5 / 6: SDE Milstein with table / generated increments (north_star (4); no reference counterpart: the analytic
+//        diagonal of the diffusion Jacobian, oracle mlp_eval_diag_jac)
 template <int D, int H, int TM, int R1, int C1, int R2, int C2, int KIND>
 __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileParams p) {
   using G = TileGeom<D, H, TM, R1, C1, R2, C2>;
   extern __shared__ __align__(16) float smem[];
-  constexpr bool SDE = (KIND == 2 || KIND == 4);
+  constexpr bool SDE = (KIND == 2 || KIND == 4 || KIND == 5 || KIND == 6);
+  constexpr bool MILSTEIN = (KIND == 5 || KIND == 6);
+  constexpr bool GEN = (KIND == 4 || KIND == 6);
   constexpr int NETS = SDE ? 2 : 1;
   float *netf = smem;
   float *netg = smem + G::net_floats;  // only when NETS == 2
@@ -147,6 +151,48 @@ __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileP
         float g[R2][C2];
         __syncthreads();  // sH is reused by the second network
         tile_eval<D, H, TM, R1, C1, R2, C2>(netg, sUg, sH, g);
+        float gp[R2][C2];
+        if (MILSTEIN) {
+          // d g_d / d y_d = pre'(y_d) * sum_j ((1 - h_j^2) W1[d][j]) W2[j][d]: the product with W1 is rounded first, then
+          // the two-chain reduction over the hidden axis (oracle mlp_eval_diag_jac); sH still holds h of the diffusion net
+          const float *gW1 = netg, *gW2 = netg + D * H;
+          f32x2 acc[R2][C2 / 2];
+#pragma unroll
+          for (int r = 0; r < R2; ++r)
+#pragma unroll
+            for (int c = 0; c < C2 / 2; ++c) acc[r][c] = pk1(0.0f);
+          const float2 *h2 = reinterpret_cast<const float2 *>(sH + rg2 * R2);
+          const float4 *w4 = reinterpret_cast<const float4 *>(gW2 + c0);
+#pragma unroll 2
+          for (int j = e; j < H; j += 2) {
+            const float2 hv = h2[j * (TM / 2)];
+            const float s0 = fmaf(-hv.x, hv.x, 1.0f), s1 = fmaf(-hv.y, hv.y, 1.0f);
+            f32x2 w2v[C2 / 2];
+#pragma unroll
+            for (int q = 0; q < C2 / 4; ++q) {
+              const float4 wv = w4[j * (D / 4) + q];
+              w2v[2 * q] = pk(wv.x, wv.y);
+              w2v[2 * q + 1] = pk(wv.z, wv.w);
+            }
+#pragma unroll
+            for (int c = 0; c < C2 / 2; ++c) {
+              const f32x2 w1v = pk(gW1[(c0 + 2 * c) * H + j], gW1[(c0 + 2 * c + 1) * H + j]);
+              acc[0][c] = fma2(mul2(pk1(s0), w1v), w2v[c], acc[0][c]);
+              acc[1][c] = fma2(mul2(pk1(s1), w1v), w2v[c], acc[1][c]);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < R2; ++r)
+#pragma unroll
+            for (int c = 0; c < C2 / 2; ++c) {
+              const f32x2 other = __shfl_xor_sync(XDE_FULL_MASK, acc[r][c], 16);
+              float j0, j1;
+              upk(add2(acc[r][c], other), j0, j1);
+              const float y0v = y[r][2 * c], y1v = y[r][2 * c + 1];
+              gp[r][2 * c] = j0 * (preg == XDE_PRE_CUBE ? 3.0f * (y0v * y0v) : (preg == XDE_PRE_SQUARE ? 2.0f * y0v : 1.0f));
+              gp[r][2 * c + 1] = j1 * (preg == XDE_PRE_CUBE ? 3.0f * (y1v * y1v) : (preg == XDE_PRE_SQUARE ? 2.0f * y1v : 1.0f));
+            }
+        }
 #pragma unroll
         for (int r = 0; r < R2; ++r) {
           const long long b = b0 + r;
@@ -154,12 +200,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileP
 #pragma unroll
           for (int q = 0; q < C2 / 4; ++q) {
             float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) wv = bm_increment4<KIND == 4>(p.bm, i - 1, b, p.B, D, c0 / 4 + q, dt);
+            if (ok) wv = bm_increment4<GEN>(p.bm, i - 1, b, p.B, D, c0 / 4 + q, dt);
             const float w[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
             for (int z = 0; z < 4; ++z) {
               const int c = 4 * q + z;
-              y[r][c] = (y[r][c] + k1[r][c] * dt) + g[r][c] * w[z];
+              float v = (y[r][c] + k1[r][c] * dt) + g[r][c] * w[z];
+              if (MILSTEIN) v = v + ((0.5f * g[r][c]) * gp[r][c]) * (w[z] * w[z] - dt);
+              y[r][c] = v;
             }
           }
         }
@@ -184,7 +232,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) fixed_tile_kernel(const TileP
 template <int D, int H, int TM, int R1, int C1, int R2, int C2, int KIND>
 static int launch_tile(const TileParams &p, cudaStream_t s) {
   using G = TileGeom<D, H, TM, R1, C1, R2, C2>;
-  const size_t smem = G::bytes((KIND == 2 || KIND == 4) ? 2 : 1, p.T);
+  const size_t smem = G::bytes((KIND == 2 || KIND >= 4) ? 2 : 1, p.T);
   XDE_REQUIRE(smem <= 227 * 1024, XDE_E_UNSUPPORTED_FIELD,
               "tiled solver: weights + tiles + grid need %zu bytes of shared memory (> 227 KB)", smem);
   auto kern = fixed_tile_kernel<D, H, TM, R1, C1, R2, C2, KIND>;
@@ -236,8 +284,7 @@ int rk_fixed_tile(int method, const xde_mlp_field_t *f, const float *y0, long lo
 
 int sde_tile(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const float *y0, long long B,
              const float *t_span, int T, const BmSource &bm, int stride, float *out, cudaStream_t s) {
-  XDE_REQUIRE(scheme == XDE_SDE_EM, XDE_E_UNSUPPORTED_FIELD,
-              "Milstein (an extension without a reference counterpart) is fused for small states (D <= 8) only");
+  XDE_REQUIRE(scheme == XDE_SDE_EM || scheme == XDE_SDE_MILSTEIN, XDE_E_BAD_ARG, "unknown SDE scheme %d", scheme);
   XDE_REQUIRE(f->h == g->h, XDE_E_UNSUPPORTED_FIELD, "tiled sde: drift and diffusion must share the hidden width");
   TileParams p{};
   p.f = *f;
@@ -250,6 +297,7 @@ int sde_tile(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, con
   p.T = T;
   p.stride = stride;
   p.n_out = (T - 1 + stride - 1) / stride + 1;
+  if (scheme == XDE_SDE_MILSTEIN) return bm.table ? tile_dispatch<5>(p, s) : tile_dispatch<6>(p, s);
   return bm.table ? tile_dispatch<2>(p, s) : tile_dispatch<4>(p, s);
 }
 

@@ -363,3 +363,30 @@ def test_large_state_neural_ode_trains_through_the_public_api(px, torch, oracle)
     assert abs(float(loss) - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
     for gq, Wq in zip(got, W):
         np.testing.assert_allclose(gq.numpy(), Wq.grad.numpy(), rtol=2e-3, atol=2e-4 * float(Wq.grad.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# Milstein for large states (north_star (4) at cfg4's shape): FP32 tiles, bit-exact against the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,h,B,pref,preg", [(32, 64, 130, "cube", "square"), (64, 128, 33, "id", "id"), (16, 64, 70, "id", "cube"),
+                                              (32, 128, 65, "square", "id")])
+def test_milstein_large_state_bit_exact(px, torch, oracle, d, h, B, pref, preg):
+    rng = np.random.default_rng(d + h)
+    wf, wg = fanin_weights(d, h, seed=2), fanin_weights(d, h, seed=3)
+    f, g = px.MLPField(*wf, pre=pref), px.MLPField(*wg, pre=preg)
+    y0 = rng.uniform(-1, 1, (B, 1, d)).astype(f32)
+    t = np.linspace(0, 1, 9).astype(f32)
+    dW = (0.3 * rng.standard_normal((8, B, d))).astype(f32)
+    ref = oracle.sde_mlp("milstein", oracle.MLP(*wf, pref), oracle.MLP(*wg, preg), y0[:, 0], t, dW)
+    got = px.sdeint(f, g, torch.from_numpy(y0).cuda(), t, px.Euler,
+                    options={"bm_increments": torch.from_numpy(dW).cuda(), "scheme": "milstein"})  # math="auto" -> FP32 tiles
+    assert np.array_equal(got.cpu().numpy(), ref)
+    assert not np.array_equal(ref, oracle.sde_mlp("em", oracle.MLP(*wf, pref), oracle.MLP(*wg, preg), y0[:, 0], t, dW))
+    # the device-side generator gives the same solution as its own table
+    tab = px.utils.brownian.brownian_increments(7, t, B, d)
+    a = px.sdeint(f, g, torch.from_numpy(y0).cuda(), t, px.Euler, options={"bm_seed": 7, "scheme": "milstein"})
+    b = px.sdeint(f, g, torch.from_numpy(y0).cuda(), t, px.Euler, options={"bm_increments": tab, "scheme": "milstein"})
+    assert torch.equal(a, b)
+    with pytest.raises(px.UnsupportedFieldError):  # the tcgen05 path has no Milstein: no silent change of arithmetic
+        px.sdeint(f, g, torch.from_numpy(y0).cuda(), t, px.Euler,
+                  options={"bm_increments": torch.from_numpy(dW).cuda(), "scheme": "milstein", "math": "tensor"})
