@@ -195,6 +195,14 @@ int xde_rk_fixed_mlp_f32(int32_t method, const xde_mlp_field_t *field, const flo
                          const float *t_span, int32_t T, int32_t out_stride_t, float *out,
                          void *stream);
 
+/* FixedSolver(step_size= | grid_constructor=)         solver/base_fixed_solver.py:49-89,119-139
+ * The reference's loop takes its first len(t_span) steps on the constructed grid and reports, for output i, the linear
+ * interpolant of step i evaluated at t_span[i] (interpolation/functional/interp_fn.py:4-10; an extrapolation whenever
+ * the grid is finer than t_span -- reproduced as is).  y_grid [B,T,D] = the solution on grid[0..T) from
+ * xde_rk_fixed_mlp_f32; out [B,T,D]. */
+int xde_fixed_interp_linear_f32(const float *y_grid, const float *grid, const float *t_out, int64_t B, int32_t T,
+                                int32_t D, float *out, void *stream);
+
 /* sdeint(drift, diffusion, y0, t, solver=Euler)       functional/sdeint.py:30-37
  *   -> BaseSDE.move/fuse xde/base_sde.py:44-61 (intended Euler-Maruyama, diagonal noise) with the
  *      Brownian increments supplied by the caller: dW [T-1,B,D].  out [B,T,D].

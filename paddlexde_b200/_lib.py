@@ -73,6 +73,8 @@ _EXPORTS = {
                                              C.c_void_p]),
     "xde_rk_fixed_mlp_f32": (C.c_int, [C.c_int32, C.POINTER(MlpFieldC), C.c_void_p, C.c_int64, C.c_void_p,
                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "xde_fixed_interp_linear_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                              C.c_void_p, C.c_void_p]),
     "xde_sde_mlp_f32": (C.c_int, [C.c_int32, C.POINTER(MlpFieldC), C.POINTER(MlpFieldC), C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "xde_rk_fixed_mlp_tc_f32": (C.c_int, [C.c_int32, C.POINTER(MlpFieldC), C.c_void_p, C.c_int64, C.c_void_p,

@@ -15,7 +15,44 @@ int rk_fixed_tc(int method, const xde_mlp_field_t *f, const float *y0, long long
                 int stride, float *out, int *status, cudaStream_t s);
 int sde_tc(int scheme, const xde_mlp_field_t *f, const xde_mlp_field_t *g, const float *y0, long long B,
            const float *t_span, int T, const BmSource &bm, int stride, float *out, int *status, cudaStream_t s);
+// linear_interp (interpolation/functional/interp_fn.py:4-10) of the solver's grid solution at the caller's output
+// times: out[b, i] = y[b, i-1] + ((t_out[i] - grid[i-1]) / (grid[i] - grid[i-1])) * (y[b, i] - y[b, i-1]), with the
+// two equality shortcuts of the reference; row 0 is copied.  One thread per value.
+__global__ void __launch_bounds__(256) fixed_interp_linear_kernel(const float *__restrict__ y, const float *__restrict__ grid,
+                                                                  const float *__restrict__ t_out, long long B, int T, int D,
+                                                                  float *__restrict__ out) {
+  const long long n = B * (long long)T * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int it = (int)((i / D) % T);
+    if (it == 0) {
+      out[i] = y[i];
+      continue;
+    }
+    const float t0 = grid[it - 1], t1 = grid[it], t = t_out[it];
+    const float y0 = y[i - D], y1 = y[i];
+    float v;
+    if (t == t0) v = y0;
+    else if (t == t1) v = y1;
+    else v = y0 + __fdiv_rn(t - t0, t1 - t0) * (y1 - y0);
+    out[i] = v;
+  }
+}
 }  // namespace xde
+
+extern "C" XDE_EXPORT int xde_fixed_interp_linear_f32(const float *y_grid, const float *grid, const float *t_out, int64_t B,
+                                                      int32_t T, int32_t D, float *out, void *stream) {
+  using namespace xde;
+  XDE_REQUIRE(y_grid && grid && t_out && out, XDE_E_BAD_ARG, "null argument");
+  XDE_REQUIRE(B >= 1 && T >= 1 && D >= 1, XDE_E_BAD_ARG, "need B>=1, T>=1, D>=1");
+  const long long n = B * (long long)T * D;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  fixed_interp_linear_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y_grid, grid, t_out, B, T, D, out);
+  count_launch();
+  XDE_CUDA_CHECK(cudaGetLastError());
+  return XDE_OK;
+}
 
 extern "C" XDE_EXPORT int xde_rk_fixed_mlp_f32(int32_t method, const xde_mlp_field_t *field, const float *y0,
                                                int64_t B, const float *t_span, int32_t T, int32_t out_stride_t,

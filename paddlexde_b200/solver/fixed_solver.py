@@ -20,9 +20,14 @@ class FixedSolver:
                  out_stride=1, math="auto", check_status=True, **kwargs):
         if step_size is not None and grid_constructor is not None:
             raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
-        if step_size is not None or grid_constructor is not None:
-            # the reference's own loop only ever visits len(t_span) grid points: grid == t_span
-            raise NotImplementedError("step_size / grid_constructor grids are not on the fused path (SURVEY 8(f) rank 2)")
+        # step_size / grid_constructor (base_fixed_solver.py:49-89).  The reference's loop (:119-139) takes its first
+        # len(t_span) steps on the constructed grid and reports, for output i, the LINEAR interpolant of step i evaluated
+        # at t_span[i] -- an extrapolation when the grid is finer than t_span.  Reproduced as it is: the fused kernel
+        # integrates over grid[:len(t_span)], a second kernel applies linear_interp (interp_fn.py:4-10).
+        self.step_size, self.grid_constructor = step_size, grid_constructor
+        if (step_size is not None or grid_constructor is not None) and interp == "cubic":
+            raise NotImplementedError("interp='cubic' on a step_size / grid_constructor grid needs f at the grid points "
+                                      "(cubic_hermite_interp, interp_fn.py:13-20); the fused path offers interp='linear'")
         # Output interpolation (base_fixed_solver.py:133-139).  The grid IS t_span, so every output time is the
         # end of its step: linear_interp returns y1 (interp_fn.py:7-8) and cubic_hermite_interp evaluates at
         # h = 1, i.e. h00 = h10 = h11 = 0, h01 = 1 -> y1 as well (interp_fn.py:13-20).  Both run the same kernel.
@@ -63,7 +68,50 @@ class FixedSolver:
             raise OverflowError("a stage input left the fp16 operand range of the tensor-core kernels "
                                 "(|pre(y)| >= 65504 or non-finite): use math='fp32' (or 'auto')")
 
+    def _time_grid(self, t_host):
+        """grid_constructor(y0, t) / _grid_constructor_from_step_size (base_fixed_solver.py:66-89) in fp32."""
+        if self.grid_constructor is not None:
+            g = np.asarray(T.to_host(self.grid_constructor(self.y0, t_host)), dtype=np.float32).reshape(-1)
+        else:
+            start, end = t_host[0], t_host[-1]
+            niters = int(np.ceil(np.float32((end - start) / np.float32(self.step_size)) + np.float32(1.0)))
+            g = np.arange(0, niters, dtype=np.float32) * np.float32(self.step_size) + start
+            g[-1] = end
+        if g.size < 1 or g[0] != t_host[0] or g[-1] != t_host[-1]:  # the reference's two asserts (:116-117)
+            raise AssertionError("the time grid must start at t_span[0] and end at t_span[-1]")
+        if g.size < t_host.size:
+            raise ValueError(f"the time grid has {g.size} points but the solver takes len(t_span) - 1 = {t_host.size - 1} steps "
+                             "on it (base_fixed_solver.py:119-121)")
+        return np.ascontiguousarray(g[:t_host.size])
+
     def integrate(self, t_span):
+        if self.step_size is not None or self.grid_constructor is not None:
+            return self._integrate_on_grid(t_span)
+        return self._integrate(t_span)
+
+    def _integrate_on_grid(self, t_span):
+        if self.out_stride != 1:
+            raise ValueError("out_stride needs grid == t_span")
+        t_host = host_tspan(t_span)
+        grid = self._time_grid(t_host)
+        host_tspan(grid)  # strictly monotone, like every grid the kernels integrate over
+        y0 = T.to_dev(self.y0)
+        D = y0.shape[-1]
+        B = y0.numel() // D
+        Tn = t_host.size
+        # the grid solution in the kernels' own [B, T, D] layout
+        saved = self.y0
+        try:
+            self.y0 = y0.reshape(B, 1, D)
+            y_grid = T.to_dev(self._integrate(grid), like=y0)
+        finally:
+            self.y0 = saved
+        out = T.empty((B, Tn, D), y0)
+        check(lib().xde_fixed_interp_linear_f32(T.ptr(y_grid), T.ptr(device_tspan(grid, y0)), T.ptr(device_tspan(t_host, y0)),
+                                                B, Tn, D, T.ptr(out), T.stream(y0)))
+        return self._layout(out, y0, B, Tn, D)
+
+    def _integrate(self, t_span):
         kind = getattr(self.xde, "kind", None)
         y0 = T.to_dev(self.y0)
         t_host = host_tspan(t_span)
@@ -106,6 +154,9 @@ class FixedSolver:
                              lambda: lib().xde_sde_mlp_f32(*args, stream), y0)
         else:
             raise UnsupportedFieldError(f"fixed solvers integrate ODE/SDE problems on the device, not {kind!r}")
+        return self._layout(out, y0, B, n_out, D)
+
+    def _layout(self, out, y0, B, n_out, D):
         # concat(axis=-2) of the per-time states (base_fixed_solver.py:143)
         shp = tuple(y0.shape)
         if len(shp) >= 3 and shp[-2] == 1:          # y0 [..., 1, D] -> [..., T, D]

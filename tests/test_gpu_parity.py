@@ -706,8 +706,8 @@ def test_fixed_interp_cubic_is_the_same_kernel(px, torch, oracle):
     yd = torch.from_numpy(y0).cuda().reshape(64, 1, 2)
     a = px.odeint(field, yd, t, px.RK4, options={"interp": "cubic"})
     assert np.array_equal(a.cpu().numpy(), oracle.fixed_mlp("rk4", om, y0, t))
-    with pytest.raises(NotImplementedError):  # the reference's own loop never visits a finer grid
-        px.odeint(field, yd, t, px.RK4, options={"step_size": 0.01})
+    with pytest.raises(NotImplementedError):  # cubic interpolation on a constructed grid needs f at the grid points
+        px.odeint(field, yd, t, px.RK4, options={"step_size": 0.01, "interp": "cubic"})
 
 
 @pytest.mark.parametrize("d,h,pre,B", [(2, 50, "cube", 100), (8, 48, "square", 33), (64, 256, "id", 70), (32, 64, "cube", 129)])

@@ -390,3 +390,55 @@ def test_milstein_large_state_bit_exact(px, torch, oracle, d, h, B, pref, preg):
     with pytest.raises(px.UnsupportedFieldError):  # the tcgen05 path has no Milstein: no silent change of arithmetic
         px.sdeint(f, g, torch.from_numpy(y0).cuda(), t, px.Euler,
                   options={"bm_increments": torch.from_numpy(dW).cuda(), "scheme": "milstein", "math": "tensor"})
+
+
+# ------------------------------------------------------------------------------------------------
+# FixedSolver(step_size= | grid_constructor=): the reference's loop as it is (base_fixed_solver.py:49-89,119-139)
+# ------------------------------------------------------------------------------------------------
+def _reference_grid_solution(oracle, method, om, y0, t, grid):
+    """The reference's FixedSolver.integrate restated: len(t) - 1 steps on grid[0..len(t)), output i = linear_interp of
+    step i evaluated at t[i] (interp_fn.py:4-10), fp32 throughout."""
+    g = np.ascontiguousarray(grid[:t.size])
+    y = oracle.fixed_mlp(method, om, y0, g)            # [B, T, D] on the grid
+    out = np.empty_like(y)
+    out[:, 0] = y[:, 0]
+    for i in range(1, t.size):
+        t0, t1, tq = g[i - 1], g[i], t[i]
+        if tq == t0:
+            out[:, i] = y[:, i - 1]
+        elif tq == t1:
+            out[:, i] = y[:, i]
+        else:
+            slope = np.float32(np.float32(tq - t0) / np.float32(t1 - t0))
+            out[:, i] = y[:, i - 1] + slope * (y[:, i] - y[:, i - 1])
+    return out
+
+
+@pytest.mark.parametrize("solver", ["Euler", "RK4", "Midpoint"])
+@pytest.mark.parametrize("d,h", [(2, 50), (32, 64)])
+def test_fixed_solver_step_size_and_grid_constructor(px, torch, oracle, solver, d, h):
+    w = spiral_weights() if d == 2 else fanin_weights(d, h, seed=4)
+    pre = "cube" if d == 2 else "id"
+    field, om = px.MLPField(*w, pre=pre), oracle.MLP(*w, pre=pre)
+    B = 77
+    y0 = np.random.default_rng(2).uniform(-1, 1, (B, 1, d)).astype(f32)
+    t = np.linspace(0, 1, 6).astype(f32)
+    step = 0.05
+    niters = int(np.ceil(np.float32((t[-1] - t[0]) / np.float32(step)) + np.float32(1.0)))
+    grid = np.arange(0, niters, dtype=f32) * np.float32(step) + t[0]
+    grid[-1] = t[-1]
+    ref = _reference_grid_solution(oracle, solver.lower(), om, y0[:, 0], t, grid)
+    got = px.odeint(field, torch.from_numpy(y0).cuda(), t, getattr(px, solver), options={"step_size": step, "math": "fp32"})
+    assert tuple(got.shape) == (B, t.size, d) and np.array_equal(got.cpu().numpy(), ref)
+    # the same grid through grid_constructor; the plain call (grid == t_span) differs
+    got2 = px.odeint(field, torch.from_numpy(y0).cuda(), t, getattr(px, solver),
+                     options={"grid_constructor": lambda y, tt: grid, "math": "fp32"})
+    assert torch.equal(got, got2)
+    plain = px.odeint(field, torch.from_numpy(y0).cuda(), t, getattr(px, solver), options={"math": "fp32"})
+    assert not torch.equal(plain, got)
+    with pytest.raises(ValueError):
+        px.odeint(field, torch.from_numpy(y0).cuda(), t, px.RK4, options={"step_size": 0.1, "grid_constructor": lambda y, tt: grid})
+    with pytest.raises(AssertionError):  # the reference asserts the grid's end points
+        px.odeint(field, torch.from_numpy(y0).cuda(), t, px.RK4, options={"grid_constructor": lambda y, tt: grid[:-1]})
+    with pytest.raises(NotImplementedError):
+        px.odeint(field, torch.from_numpy(y0).cuda(), t, px.RK4, options={"step_size": step, "interp": "cubic"})
