@@ -890,9 +890,10 @@ def test_tiled_sde_cfg4_shapes(px, torch, oracle):
     auto = px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler,
                      options={"bm_increments": torch.from_numpy(dW).cuda()})  # default: tensor cores
     assert _close(auto.cpu().numpy(), ref, rtol=1e-5) and not np.array_equal(auto.cpu().numpy(), ref)
-    with pytest.raises(px.UnsupportedFieldError):  # Milstein is an extension, fused for small states only
-        px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler,
-                  options={"bm_increments": torch.from_numpy(dW).cuda(), "scheme": "milstein"})
+    # Milstein at this shape (round 2): the FP32 tiles, bit-exact (tests/test_gpu_round2.py covers more shapes)
+    mil = px.sdeint(f, g, torch.from_numpy(y0).cuda().reshape(B, 1, d), t, px.Euler,
+                    options={"bm_increments": torch.from_numpy(dW).cuda(), "scheme": "milstein"})
+    assert np.array_equal(mil.cpu().numpy(), oracle.sde_mlp("milstein", of, og, y0, t, dW))
     with pytest.raises(px.UnsupportedFieldError):  # no kernel for this shape: loud, no fallback
         f48, _ = both(px, oracle, fanin_weights(48, 64), "id")
         px.odeint(f48, torch.zeros(4, 1, 48).cuda(), t, px.RK4)
