@@ -103,7 +103,7 @@ def case_other_tableaux():
 
 
 def case_adjoint():
-    d = [1, 2, 3, 4, 8][rng.integers(5)]; h = int(rng.integers(2, 65)); pre = PRES[rng.integers(3)]
+    d = int(rng.integers(1, 9)); h = int(rng.integers(2, 65)); pre = PRES[rng.integers(3)]
     B = int(rng.integers(1, 300)); w = weights(d, h, rng.uniform(0.5, 2.5))
     o = dict(rtol=float(10.0 ** rng.uniform(-7, -4))); o["atol"] = o["rtol"] * 1e-2
     y0 = rng.uniform(-1, 1, (B, d)).astype(f32); t = tspan(int(rng.integers(2, 7)), rng.uniform(0.2, 2), rng.random() < 0.2)
@@ -113,11 +113,18 @@ def case_adjoint():
     if rc != 0:
         return desc + " (forward status, skipped)", True
     gy = (rng.standard_normal(ref.shape) / ref[-1].size).astype(f32)
-    g, a0, stats, _ = adjoint_backward(px.MLPField(*w, pre=pre), t, ref, gy, return_adj_y0=True, check_status=False, **o)
-    g_ref, a_ref, st_ref, _, rc = xo.dopri5_mlp_adjoint(om, t, ref, gy, **o)
+    want_gt = rng.random() < 0.4  # the t_requires_grad branch: grad_t_span, the g_t slot in the controller norm
+    gt = torch.zeros(t.size, device="cuda") if want_gt else None
+    gt_ref = np.zeros(t.size, f32) if want_gt else None
+    desc += f" grad_t={want_gt}"
+    g, a0, stats, _ = adjoint_backward(px.MLPField(*w, pre=pre), t, ref, gy, return_adj_y0=True, check_status=False,
+                                       out_grad_t=gt, **o)
+    g_ref, a_ref, st_ref, _, rc = xo.dopri5_mlp_adjoint(om, t, ref, gy, grad_t=gt_ref, **o)
     s = stats.read()
     scale = max(np.abs(g_ref).max(), 1e-30)
     checks = {"status": s.status == rc, "attempts": s.n_attempts == int(st_ref.n_attempts.sum()),
+              "grad_t": (not want_gt) or rc != 0 or np.allclose(gt.cpu().numpy(), gt_ref, rtol=1e-5,
+                                                                   atol=3e-5 * max(np.abs(gt_ref).max(), 1e-30)),
               "adj_state": np.array_equal(a0.cpu().numpy(), a_ref, equal_nan=True),
               # random-sign cotangents at every output time cancel across the batch, and the two sides sum the same
               # per-evaluation contributions in different fp32 orders (oracle: g_theta as fp32 Runge-Kutta state;
@@ -131,6 +138,87 @@ def case_adjoint():
                 f"{int(st_ref.n_attempts.sum())} max|dg|/max|g|={np.abs(gd - g_ref).max() / scale:.2e} " \
                 f"n_adj_state_diff={int((a0.cpu().numpy() != a_ref).sum())}"
     return desc, ok
+
+
+def case_adjoint_tile():
+    """odeint_adjoint's backward for large states (csrc/xde_adj_tile.cu)"""
+    d, h = TILE[rng.integers(len(TILE))]; pre = PRES[rng.integers(3)]
+    B = int(rng.integers(1, 150)); w = weights(d, h, rng.uniform(0.5, 2.5))
+    o = dict(rtol=float(10.0 ** rng.uniform(-6.5, -4))); o["atol"] = o["rtol"] * 1e-2
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32); t = tspan(int(rng.integers(2, 5)), rng.uniform(0.2, 1.5), rng.random() < 0.2)
+    desc = f"adjoint tile d={d} h={h} pre={pre} B={B} T={t.size} {o}"
+    om = xo.MLP(*w, pre=pre)
+    ref, _, _, rc = xo.dopri5_mlp(om, y0, t, **o)
+    if rc != 0:
+        return desc + " (forward status, skipped)", True
+    gy = (rng.standard_normal(ref.shape) / ref[-1].size).astype(f32)
+    g, a0, stats, _ = adjoint_backward(px.MLPField(*w, pre=pre), t, ref, gy, return_adj_y0=True, check_status=False, **o)
+    g_ref, a_ref, st_ref, _, rc = xo.dopri5_mlp_adjoint(om, t, ref, gy, **o)
+    s = stats.read()
+    scale = max(np.abs(g_ref).max(), 1e-30)
+    checks = {"status": s.status == rc, "attempts": s.n_attempts == int(st_ref.n_attempts.sum()),
+              "accepted": s.n_accepted == int(st_ref.n_accepted.sum()),
+              "adj_state": np.array_equal(a0.cpu().numpy(), a_ref, equal_nan=True),
+              "grads": rc != 0 or np.allclose(g.cpu().numpy(), g_ref, rtol=1e-5, atol=3e-5 * scale)}
+    ok = all(checks.values())
+    if not ok:
+        desc += f" failed={[k for k, v in checks.items() if not v]} max|dg|/max|g|={np.abs(g.cpu().numpy() - g_ref).max() / scale:.2e}"
+    return desc, ok
+
+
+def case_adjoint_batch():
+    """controller='batch' (the reference's default configuration): the whole sequence and g_theta bit for bit"""
+    d = [1, 2, 4][rng.integers(3)]; h = int(rng.integers(2, 65)); pre = PRES[rng.integers(3)]
+    B = int(rng.integers(1, 3000)); w = weights(d, h, rng.uniform(0.5, 2.5))
+    o = dict(rtol=float(10.0 ** rng.uniform(-7, -4))); o["atol"] = o["rtol"] * 1e-2
+    norm = ["mixed", "seminorm"][rng.integers(2)]
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32); t = tspan(int(rng.integers(2, 6)), rng.uniform(0.2, 2), rng.random() < 0.2)
+    desc = f"adjoint batch {norm} d={d} h={h} pre={pre} B={B} T={t.size} {o}"
+    om = xo.MLP(*w, pre=pre)
+    ref, _, _, rc = xo.dopri5_mlp(om, y0, t, controller="batch", **o)
+    if rc != 0:
+        return desc + " (forward status, skipped)", True
+    gy = (rng.standard_normal(ref.shape) / ref[-1].size).astype(f32)
+    g, a0, stats, log = adjoint_backward(px.MLPField(*w, pre=pre), t, ref, gy, return_adj_y0=True, check_status=False,
+                                         controller="batch", adj_norm=norm, log_attempts=2048, **o)
+    g_ref, a_ref, st_ref, lg, rc = xo.dopri5_mlp_adjoint(om, t, ref, gy, controller="batch", adj_norm=norm, **o)
+    s = stats.read()
+    rec, cnt = log.read()
+    n = min(int(cnt[0]), 2048)
+    checks = {"status": s.status == rc, "log_len": int(cnt[0]) == len(lg),
+              "sequence": rec[0, :n].tobytes() == lg[:n].tobytes(),
+              "adj_state": rc != 0 or np.array_equal(a0.cpu().numpy(), a_ref, equal_nan=True),
+              "g_theta": rc != 0 or np.array_equal(g.cpu().numpy(), g_ref, equal_nan=True)}
+    ok = all(checks.values())
+    if not ok:
+        desc += f" failed={[k for k, v in checks.items() if not v]}"
+    return desc, ok
+
+
+def case_fixed_grid():
+    """FixedSolver(step_size=): len(t) - 1 steps on the constructed grid + linear_interp at t[i]"""
+    solver = ["Euler", "RK4", "Midpoint"][rng.integers(3)]
+    d, h = (TILE[rng.integers(len(TILE))] if rng.random() < 0.3 else (int(rng.integers(1, 9)), int(rng.integers(2, 60))))
+    pre = PRES[rng.integers(3)]; B = int(rng.integers(1, 200)); w = weights(d, h, rng.uniform(0.5, 2.0))
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32)
+    T = int(rng.integers(2, 8)); t = np.linspace(0, rng.uniform(0.3, 1.0), T).astype(f32)
+    step = float((t[-1] - t[0]) / (T - 1) / rng.uniform(1.5, 6.0))
+    niters = int(np.ceil(np.float32((t[-1] - t[0]) / np.float32(step)) + np.float32(1.0)))
+    grid = np.arange(0, niters, dtype=f32) * np.float32(step) + t[0]
+    grid[-1] = t[-1]
+    desc = f"{solver} step_size={step:.4f} d={d} h={h} pre={pre} B={B} T={T}"
+    g = np.ascontiguousarray(grid[:T])
+    if not np.all(np.diff(g) > 0):
+        return desc + " (degenerate grid, skipped)", True
+    y = xo.fixed_mlp(solver.lower(), xo.MLP(*w, pre=pre), y0, g)
+    ref = np.empty_like(y); ref[:, 0] = y[:, 0]
+    for i in range(1, T):
+        if t[i] == g[i - 1]: ref[:, i] = y[:, i - 1]
+        elif t[i] == g[i]: ref[:, i] = y[:, i]
+        else: ref[:, i] = y[:, i - 1] + np.float32(np.float32(t[i] - g[i - 1]) / np.float32(g[i] - g[i - 1])) * (y[:, i] - y[:, i - 1])
+    sol = px.odeint(px.MLPField(*w, pre=pre), torch.from_numpy(y0).cuda().reshape(B, 1, d), t, getattr(px, solver),
+                    options={"math": "fp32", "step_size": step}).cpu().numpy()
+    return desc, np.array_equal(sol, ref, equal_nan=True)
 
 
 def case_fixed():
@@ -152,13 +240,15 @@ def case_fixed():
 def case_sde():
     scheme = ["em", "milstein"][rng.integers(2)]
     d = int(rng.integers(1, 9)); h = int(rng.integers(2, 50)); B = int(rng.integers(1, 300))
+    if rng.random() < 0.3:  # the FP32 tiles (Milstein included since round 2)
+        d, h = [(32, 64), (32, 128), (16, 64), (64, 128), (64, 64)][rng.integers(5)]
     wf, wg = weights(d, h, 1.0), weights(d, h, 0.7)
     pf, pg = PRES[rng.integers(3)], PRES[rng.integers(3)]
     y0 = rng.uniform(-1, 1, (B, d)).astype(f32); t = tspan(int(rng.integers(2, 10)), 1.0, False)
     dW = (0.2 * rng.standard_normal((t.size - 1, B, d))).astype(f32)
     desc = f"sde {scheme} d={d} h={h} pre={pf}/{pg} B={B} T={t.size}"
     sol = px.sdeint(px.MLPField(*wf, pre=pf), px.MLPField(*wg, pre=pg), torch.from_numpy(y0).cuda().reshape(B, 1, d), t,
-                    px.Euler, options={"bm_increments": torch.from_numpy(dW).cuda(), "scheme": scheme}).cpu().numpy()
+                    px.Euler, options={"bm_increments": torch.from_numpy(dW).cuda(), "scheme": scheme, "math": "fp32"}).cpu().numpy()
     ref = xo.sde_mlp(scheme, xo.MLP(*wf, pre=pf), xo.MLP(*wg, pre=pg), y0, t, dW)
     return desc, np.array_equal(sol, ref, equal_nan=True)
 
@@ -286,7 +376,8 @@ def case_tensor():
 
 
 CASES = [case_dopri5_small, case_dopri5_tile, case_other_tableaux, case_adjoint, case_fixed, case_sde, case_gather,
-         case_batch_controller, case_grid_points, case_sde_adjoint, case_tensor]
+         case_batch_controller, case_grid_points, case_sde_adjoint, case_tensor, case_adjoint_tile, case_adjoint_batch,
+         case_fixed_grid]
 counts = {c.__name__: [0, 0] for c in CASES}
 t_end = time.time() + budget
 i = int(sys.argv[3]) if ONE else 0
