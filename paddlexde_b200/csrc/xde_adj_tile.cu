@@ -243,42 +243,43 @@ __global__ void __launch_bounds__(kTileThreads, 1) adjoint_tile_kernel(const Adj
       }
     }
     // ---- dH = A W2^T: sequential-d fma chain per hidden unit (orc_mlp_vjp); dZ = dH (1 - h^2) -> sDZ ----
-    // packed over ROW pairs (the two rows are adjacent components of the operand fetch): per element the same chain
     {
-      f32x2 acc[R1 / 2][C1];
+      float acc[R1][C1];
 #pragma unroll
-      for (int r = 0; r < R1 / 2; ++r)
+      for (int r = 0; r < R1; ++r)
 #pragma unroll
-        for (int c = 0; c < C1; ++c) acc[r][c] = pk1(0.0f);
+        for (int c = 0; c < C1; ++c) acc[r][c] = 0.0f;
       const float4 *a4 = reinterpret_cast<const float4 *>(sA + rg1 * R1);
 #pragma unroll 2
       for (int d = 0; d < D; d += 4) {
-        f32x2 ar[4][2];
+        float ar[4][4];
 #pragma unroll
         for (int dd = 0; dd < 4; ++dd) {
           const float4 av = a4[(d + dd) * (TM / 4)];
-          ar[dd][0] = pk(av.x, av.y);
-          ar[dd][1] = pk(av.z, av.w);
+          ar[dd][0] = av.x;
+          ar[dd][1] = av.y;
+          ar[dd][2] = av.z;
+          ar[dd][3] = av.w;
         }
 #pragma unroll
         for (int c = 0; c < C1; ++c) {
           const float4 wv = *reinterpret_cast<const float4 *>(sW2 + (cg1 * C1 + c) * D + d);
           const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-          for (int dd = 0; dd < 4; ++dd) {
-            acc[0][c] = fma2(ar[dd][0], pk1(wr[dd]), acc[0][c]);
-            acc[1][c] = fma2(ar[dd][1], pk1(wr[dd]), acc[1][c]);
-          }
+          for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+            for (int r = 0; r < R1; ++r) acc[r][c] = fmaf(ar[dd][r], wr[dd], acc[r][c]);
         }
       }
 #pragma unroll
       for (int c = 0; c < C1; ++c) {
         const int j = cg1 * C1 + c;
         const float4 hv = *reinterpret_cast<const float4 *>(sH + j * TM + rg1 * R1);
-        float d0, d1, d2, d3;
-        upk(mul2(acc[0][c], one_minus_sq2(pk(hv.x, hv.y))), d0, d1);
-        upk(mul2(acc[1][c], one_minus_sq2(pk(hv.z, hv.w))), d2, d3);
-        *reinterpret_cast<float4 *>(sDZ + j * TM + rg1 * R1) = make_float4(d0, d1, d2, d3);
+        const float hr[4] = {hv.x, hv.y, hv.z, hv.w};
+        float dz[4];
+#pragma unroll
+        for (int r = 0; r < R1; ++r) dz[r] = acc[r][c] * fmaf(-hr[r], hr[r], 1.0f);
+        *reinterpret_cast<float4 *>(sDZ + j * TM + rg1 * R1) = make_float4(dz[0], dz[1], dz[2], dz[3]);
       }
     }
     if (theta_only) return;
@@ -422,32 +423,31 @@ __global__ void __launch_bounds__(kTileThreads, 1) adjoint_tile_kernel(const Adj
       const float *sJ = half ? sH : sDZ;  // [H][TM]
 #pragma unroll 1
       for (int kh = 0; kh < KB; kh += KBH) {
-        // (sum over the even rows of a 4-row chunk | sum over the odd rows) packed: one FFMA2 per two products
-        f32x2 acc[KBH][JB];
+        float acc[KBH][JB];
 #pragma unroll
         for (int kq = 0; kq < KBH; ++kq)
 #pragma unroll
-          for (int jq = 0; jq < JB; ++jq) acc[kq][jq] = pk1(0.0f);
+          for (int jq = 0; jq < JB; ++jq) acc[kq][jq] = 0.0f;
 #pragma unroll 1
         for (int b = 0; b < TM; b += 4) {
           const float4 wv = *reinterpret_cast<const float4 *>(sWt + b);
-          const f32x2 w01 = pk(wv.x, wv.y), w23 = pk(wv.z, wv.w);
-          f32x2 kv[KBH][2];
+          float kv[KBH][4];
 #pragma unroll
           for (int kq = 0; kq < KBH; ++kq) {
             const float4 x = *reinterpret_cast<const float4 *>(sK + (kb0 + kh + kq) * TM + b);
-            kv[kq][0] = mul2(pk(x.x, x.y), w01);
-            kv[kq][1] = mul2(pk(x.z, x.w), w23);
+            kv[kq][0] = x.x * wv.x;
+            kv[kq][1] = x.y * wv.y;
+            kv[kq][2] = x.z * wv.z;
+            kv[kq][3] = x.w * wv.w;
           }
 #pragma unroll
           for (int jq = 0; jq < JB; ++jq) {
             const float4 x = *reinterpret_cast<const float4 *>(sJ + (jb0 + jq) * TM + b);
-            const f32x2 j01 = pk(x.x, x.y), j23 = pk(x.z, x.w);
+            const float jv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-            for (int kq = 0; kq < KBH; ++kq) {
-              acc[kq][jq] = fma2(kv[kq][0], j01, acc[kq][jq]);
-              acc[kq][jq] = fma2(kv[kq][1], j23, acc[kq][jq]);
-            }
+            for (int z = 0; z < 4; ++z)
+#pragma unroll
+              for (int kq = 0; kq < KBH; ++kq) acc[kq][jq] = fmaf(kv[kq][z], jv[z], acc[kq][jq]);
           }
         }
         // add to the running sums in TMEM
@@ -460,11 +460,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) adjoint_tile_kernel(const Adj
             tmem_ld<4>(col, t4);
             tmem_wait_ld();
 #pragma unroll
-            for (int z = 0; z < 4; ++z) {
-              float ev, od;
-              upk(acc[kq][jq + z], ev, od);
-              t4[z] += ev + od;
-            }
+            for (int z = 0; z < 4; ++z) t4[z] += acc[kq][jq + z];
             tmem_st<4>(col, t4);
           }
       }

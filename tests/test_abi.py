@@ -120,3 +120,64 @@ def test_sort_tvals_single_point_on_a_decreasing_span():
     assert AdaptiveRKSolver._sort_tvals([0.5, 0.75, 9.0], t, like).tolist() == [0.75, 0.5]
     assert AdaptiveRKSolver._sort_tvals([0.5, 0.25, -1.0], t[::-1].copy(), like).tolist() == [0.25, 0.5]
     assert AdaptiveRKSolver._sort_tvals([9.0], t, like) is None
+
+
+def test_default_controller_selection(monkeypatch):
+    """The controller granularity when the caller does not choose: per trajectory (north star), announced once;
+    PADDLEXDE_B200_CONTROLLER flips it globally without a warning."""
+    import warnings
+
+    import paddlexde_b200.solver.adaptive_solver as A
+
+    monkeypatch.delenv("PADDLEXDE_B200_CONTROLLER", raising=False)
+    A._warned_default = False
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        assert A.default_controller(64) == "trajectory"
+        assert A.default_controller(64) == "trajectory"
+    assert sum(issubclass(r.category, A.ControllerDefaultWarning) for r in rec) == 1
+    A._warned_default = False
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        assert A.default_controller(1) == "trajectory"  # B = 1: both controllers coincide, nothing to announce
+    assert not rec
+    monkeypatch.setenv("PADDLEXDE_B200_CONTROLLER", "batch")
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        assert A.default_controller(64) == "batch"
+    assert not rec
+    monkeypatch.setenv("PADDLEXDE_B200_CONTROLLER", "nonsense")
+    with pytest.raises(ValueError):
+        A.default_controller(64)
+
+
+def test_fixed_solver_time_grid_follows_the_reference():
+    """_grid_constructor_from_step_size (base_fixed_solver.py:66-89): arange(niters) * step + start with the last point
+    replaced by t[-1]; the solver uses its first len(t_span) points; the reference's end-point asserts."""
+    import paddlexde_b200 as px
+
+    class X:
+        kind = "ode"
+
+    t = np.linspace(0, 1, 5).astype(np.float32)
+    s = px.RK4(xde=X(), y0=None, rtol=1, atol=1, step_size=0.1)
+    g = s._time_grid(t)
+    assert g.dtype == np.float32 and g.size == t.size
+    assert np.array_equal(g, (np.arange(5, dtype=np.float32) * np.float32(0.1)).astype(np.float32))
+    s = px.RK4(xde=X(), y0=None, rtol=1, atol=1, grid_constructor=lambda y, tt: np.array([0, 0.3, 0.5, 0.6, 0.9, 1.0]))
+    assert np.array_equal(s._time_grid(t), np.array([0, 0.3, 0.5, 0.6, 0.9], np.float32))
+    with pytest.raises(AssertionError):
+        px.RK4(xde=X(), y0=None, rtol=1, atol=1, grid_constructor=lambda y, tt: np.array([0.1, 0.5, 1.0]))._time_grid(t)
+    with pytest.raises(ValueError):  # fewer grid points than steps to take
+        px.RK4(xde=X(), y0=None, rtol=1, atol=1, step_size=0.5)._time_grid(t)
+    with pytest.raises(NotImplementedError):
+        px.RK4(xde=X(), y0=None, rtol=1, atol=1, step_size=0.1, interp="cubic")
+
+
+def test_shard_rows_and_hooks_without_a_process_group():
+    from paddlexde_b200 import distributed as pxd
+
+    assert [pxd.shard_rows(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert pxd.init_from_env() == (0, 1, 0)
+    g = np.ones(3, np.float32)
+    assert pxd.grad_allreduce()(g) is g  # a single process: nothing to sum

@@ -253,7 +253,9 @@ def main(args, ClockSampler, peaks):
                "e2e": {"value": e2e_units * args.steps / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": int(h2d_bytes),
                        "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e / args.steps},
                "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(out))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        print(json.dumps(out), flush=True)
+    if world > 1:  # no teardown (see bench.py): every collective is done, leave with exit code 0
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
