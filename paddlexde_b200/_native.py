@@ -154,6 +154,15 @@ class DeviceArray:
 _keepalive: dict = {}
 
 
+def release_exports() -> int:
+    """Drop the references that keep DLPack-exported DeviceArrays alive (the C deleter of a borrowed capsule cannot call
+    back into Python, so an exported array otherwise lives until the process ends).  Call it only when every consumer
+    of those capsules is gone.  -> number of references dropped."""
+    n = len(_keepalive)
+    _keepalive.clear()
+    return n
+
+
 def asarray(x, dtype=np.float32) -> DeviceArray:
     if isinstance(x, DeviceArray):
         if x.dtype != np.dtype(dtype):

@@ -300,3 +300,105 @@ def test_oracle_exact_batch_sum_is_order_independent_and_correctly_rounded(oracl
     assert fx([np.float32(2.0 ** -60), np.float32(-2.0 ** -60)]) == 0.0 and fx([np.float32(2.0 ** -61)] * 8) == 0.0
     assert fx([np.float32(3 * 2.0 ** -60)]) == np.float32(2.0 ** -59)
     assert np.isnan(fx([np.float32(2.0 ** 40)])) and np.isnan(fx([np.float32(np.inf), 1.0])) and fx([np.float32(2.0 ** 39)]) == 2.0 ** 39
+
+
+def test_batch_adjoint_c_equals_an_independent_restatement_of_the_exact_sum(oracle):
+    """The order-independent batch sum of the arithmetic specification (round 2), restated independently in exact
+    rational arithmetic: 32-trajectory fp32 fma chains (fma = one rounding of the exact a*b + c), addends truncated toward
+    zero to the 2^-59 grid, added exactly, one rounding to fp32.  Driving the literal NumPy solver (oracle_np) with this
+    VJP must reproduce the C oracle's batch-controller adjoint -- the reference's default mixed-norm configuration --
+    bit for bit: gradients, dL/dy0 and every dt of the step sequence."""
+    import ctypes as C
+    from fractions import Fraction
+
+    def rn32(fr):  # exact rational -> fp32, round to nearest even
+        if fr == 0:
+            return f32(0.0)
+        c = f32(float(fr))
+        cands = sorted({np.nextafter(c, f32(-np.inf)), c, np.nextafter(c, f32(np.inf))}, key=float)
+        return f32(min(cands, key=lambda v: (abs(Fraction(float(v)) - fr), int(f32(v).view(np.uint32)) & 1)))
+
+    def fma32(a, b, c):
+        return rn32(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
+
+    GRID = 2 ** 59
+
+    def exact_total(addends):
+        tot = 0
+        for x in addends:
+            fr = Fraction(float(x)) * GRID
+            tot += int(fr) if fr >= 0 else -int(-fr)  # truncation toward zero
+        return rn32(Fraction(tot, GRID))
+
+    rng = np.random.default_rng(11)
+    d, h, B = 2, 6, 40  # two chain blocks: 32 + 8 trajectories
+    w = [(rng.standard_normal((d, h)) / np.sqrt(d)).astype(f32), (0.1 * rng.standard_normal(h)).astype(f32),
+         (rng.standard_normal((h, d)) / np.sqrt(h)).astype(f32), (0.1 * rng.standard_normal(d)).astype(f32)]
+    mlp = oracle.MLP(*w, pre="id")
+    lib = oracle.lib()
+
+    def vjp_exact(t, y, c):
+        y, c = np.ascontiguousarray(y, f32).reshape(-1, d), np.ascontiguousarray(c, f32).reshape(-1, d)
+        n = y.shape[0]
+        f, dy = np.empty_like(y), np.empty_like(y)
+        per = []  # per trajectory: (u, dz, h, cot) from the C field evaluation (that part is covered by other tests)
+        m = mlp.c()
+        for b in range(n):
+            g1 = np.zeros(mlp.n_params, f32)
+            gw1, gb1, gw2, gb2 = mlp.split(g1)
+            lib.orc_mlp_vjp(C.byref(m), y[b].ctypes.data_as(C.c_void_p), c[b].ctypes.data_as(C.c_void_p),
+                            f[b].ctypes.data_as(C.c_void_p), dy[b].ctypes.data_as(C.c_void_p),
+                            gw1.ctypes.data_as(C.c_void_p), gb1.ctypes.data_as(C.c_void_p),
+                            gw2.ctypes.data_as(C.c_void_p), gb2.ctypes.data_as(C.c_void_p))
+            hb = np.empty(h, f32)
+            ftmp = np.empty(d, f32)
+            lib.orc_mlp_eval(C.byref(m), y[b].ctypes.data_as(C.c_void_p), ftmp.ctypes.data_as(C.c_void_p),
+                             hb.ctypes.data_as(C.c_void_p))
+            per.append((y[b].copy(), gb1.copy(), hb, c[b].copy()))  # pre = id: u = y;  gb1 of one trajectory = dz
+        if n == 1:
+            g1 = np.zeros(mlp.n_params, f32)
+            u, dz, hb, cot = per[0]
+            return f, dy, [np.outer(u, dz).astype(f32), dz, np.outer(hb, cot).astype(f32), cot]
+        gW1, gb1t, gW2, gb2t = np.zeros((d, h), f32), np.zeros(h, f32), np.zeros((h, d), f32), np.zeros(d, f32)
+        blocks = [per[i:i + 32] for i in range(0, n, 32)]
+        for k in range(d):
+            for j in range(h):
+                chains = []
+                for blk in blocks:
+                    X = f32(0.0)
+                    for (u, dz, hb, cot) in blk:
+                        X = fma32(u[k], dz[j], X)
+                    chains.append(X)
+                gW1[k, j] = exact_total(chains)
+        for j in range(h):
+            chains = []
+            for blk in blocks:
+                X = f32(0.0)
+                for (u, dz, hb, cot) in blk:
+                    X = fma32(f32(1.0), dz[j], X)
+                chains.append(X)
+            gb1t[j] = exact_total(chains)
+            for dd in range(d):
+                chains = []
+                for blk in blocks:
+                    X = f32(0.0)
+                    for (u, dz, hb, cot) in blk:
+                        X = fma32(cot[dd], hb[j], X)
+                    chains.append(X)
+                gW2[j, dd] = exact_total(chains)
+        for dd in range(d):
+            gb2t[dd] = exact_total([cot[dd] for (_, _, _, cot) in per])
+        return f, dy, [gW1, gb1t, gW2, gb2t]
+
+    y0 = rng.uniform(-1, 1, (B, d)).astype(f32)
+    t = np.array([0.0, 0.4, 1.0], f32)
+    kw = dict(rtol=1e-6, atol=1e-8)
+    out, _, _, rc = oracle.dopri5_mlp(mlp, y0, t, controller="batch", **kw)
+    assert rc == 0
+    gy = (rng.standard_normal(out.shape) / out[0].size).astype(f32)
+    g, a0, st, log, rc = oracle.dopri5_mlp_adjoint(mlp, t, out, gy, controller="batch", adj_norm="mixed", **kw)
+    assert rc == 0
+    ps, a, logs = onp.odeint_adjoint_backward(mlp, t, out, gy, seminorm=False, vjp=vjp_exact, **kw)
+    assert np.array_equal(np.concatenate([p.ravel() for p in ps]), g)
+    assert np.array_equal(a, a0)
+    assert np.array_equal(np.concatenate([np.array(l.dt, f32) for l in logs]), log.dt)
