@@ -103,11 +103,11 @@ def ptr(t) -> C.c_void_p:
 
 
 def stream(like=None) -> C.c_void_p:
-    """The stream the call is ordered on: torch's current stream for torch buffers, the default stream otherwise."""
-    if torch is not None and (like is None or is_torch(like)) and torch.cuda.is_available():
-        if like is None or is_torch(like):
-            return C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    return C.c_void_p(0)
+    """The stream the call is ordered on: torch's current stream when the buffers are torch tensors (or when no buffer
+    is named and torch is there), the default stream for DeviceArrays."""
+    if isinstance(like, DeviceArray) or torch is None or not torch.cuda.is_available():
+        return C.c_void_p(0)
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def like_input(result, template):

@@ -56,10 +56,16 @@ class MLPField:
         tr = self.weight_layout == "out_in"
         w1, b1, w2, b2 = self._src
         self.w1, self.b1, self.w2, self.b2 = dev(w1, tr), dev(b1, False), dev(w2, tr), dev(b2, False)
+        self._versions = self._src_versions()
+
+    def _src_versions(self):
+        # torch bumps `_version` on every in-place update (optimizer.step()): lets c_struct() notice stale device copies
+        return tuple(getattr(a, "_version", None) for a in self._src)
 
     def refresh(self):
-        """Re-read the caller's parameter tensors (after an optimizer step; device tensors in the [in, out]
-        layout are shared, everything else is copied)."""
+        """Re-read the caller's parameter tensors.  torch tensors are re-read automatically when an in-place update
+        (optimizer.step()) has bumped their version counter; call this after changing numpy / DeviceArray sources
+        (those are copied at construction) or after rebinding `.data`."""
         self._load()
         return self
 
@@ -86,6 +92,8 @@ class MLPField:
         return out
 
     def c_struct(self) -> MlpFieldC:
+        if self._src_versions() != self._versions:  # the caller's tensors were updated in place since the last load
+            self._load()
         return MlpFieldC(self.d, self.h, PRE[self.pre], 0, self.w1.data_ptr(), self.b1.data_ptr(),
                          self.w2.data_ptr(), self.b2.data_ptr())
 
