@@ -9,9 +9,12 @@ tests/interpolation/test_interpolation.py) can pin it.  The C oracle (xde_oracle
 algorithm specialised to the fused MLP field; tests check the two agree bit for bit when this
 module is handed the C field evaluation.
 
-PARITY STATUS: Paddle is not installable here and the reference at HEAD is not runnable, so
-accept/reject sequences, adjoint gradients, SDE results, HistoryIndex.backward and B>1 behaviour
-are "parity unpinned" -- defined by this restatement, not by reference outputs.
+PARITY STATUS: Paddle is not installable here.  Since round 2 the reference's own forward-solver files run in this
+container on a NumPy stand-in for `paddle` (oracle/ref_shim/, tools/make_reference_golden.py) and the C oracle must
+reproduce their solutions and attempt logs bit for bit (tests/test_reference_run_golden.py): accept/reject sequences
+and B>1 behaviour of the forward solvers are pinned to reference outputs.  Adjoint gradients, SDE results and
+HistoryIndex.backward remain "parity unpinned" -- defined by this restatement (the reference's code for them does not
+run: repairs R2-R6).
 """
 from __future__ import annotations
 

@@ -1,0 +1,297 @@
+"""A NumPy stand-in for the handful of `paddle` operations the reference's hot-path modules use.
+
+TEST INFRASTRUCTURE ONLY (lives under oracle/): PaddlePaddle cannot be installed in the build container, so the
+reference (pure Python on Paddle eager ops) could not be run -- and the oracle's restatement of its control flow could
+only be pinned to the closed-form fixtures of the reference's tests.  With this module on `sys.path` the reference's OWN,
+UNMODIFIED source files (`paddlexde/solver/base_adaptive_solver*.py`, `solver/adaptive_solver/*.py`,
+`solver/base_fixed_solver.py`, `solver/fixed_solver/{euler,midpoint,rk4}.py`, `utils/ode_utils.py`,
+`xde/base_{xde,ode}.py`, `interpolation/functional/interp_fn.py`) import and run here
+(`tools/make_reference_golden.py`), which turns "the oracle restates the reference" into "the oracle reproduces what the
+reference's code computes", bit for bit, for step sequences, batched (B > 1) behaviour, every tableau, `step_t` /
+`jump_t`, the fixed solvers and `step_size` grids.
+
+What is an operation of THIS module and not of the reference: how an eager op rounds.  Paddle's CPU kernels do not
+document their summation orders, so every op here follows the repository's arithmetic specification (DESIGN.md
+section 2) -- fp32 elementwise ops, `sum(axis)` left to right in fp32, `mean()` accumulated sequentially in fp64 with
+`sqrt()` of that mean taken in fp64 and rounded once to fp32, `x ** (1/p)` through the specification's `rootp`.  What the
+golden vectors therefore pin is everything ABOVE the op level: the reference's formulas, their order, its control flow.
+"""
+from __future__ import annotations
+
+import builtins
+import ctypes as C
+import os
+
+import numpy as np
+
+float32, float64, int32, int64 = np.float32, np.float64, np.int32, np.int64
+bool = np.bool_  # noqa: A001  (paddle.bool)
+
+_ORC = None
+
+
+def _oracle():
+    global _ORC
+    if _ORC is None:
+        here = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        _ORC = C.CDLL(os.path.join(here, "libxde_oracle.so"))
+        _ORC.orc_rootpf.restype = C.c_float
+        _ORC.orc_rootpf.argtypes = [C.c_float, C.c_int32]
+    return _ORC
+
+
+def _np(x):
+    return x.a if isinstance(x, Tensor) else x
+
+
+class Tensor:
+    """An eager tensor: a NumPy array plus the methods the reference calls."""
+    __array_priority__ = 1000
+
+    def __init__(self, a, wide=False):
+        self.a = np.asarray(a)
+        self.stop_gradient = True
+        self._wide = wide  # an fp64 mean on its way into sqrt() (the RMS norm of the specification)
+
+    # ---- metadata ----
+    @property
+    def dtype(self):
+        return self.a.dtype.type
+
+    @property
+    def shape(self):
+        return list(self.a.shape)
+
+    def __len__(self):
+        return self.a.shape[0]
+
+    def __iter__(self):
+        for i in range(self.a.shape[0]):
+            yield Tensor(self.a[i])
+
+    def __bool__(self):
+        return builtins_bool(self.a)
+
+    def __float__(self):
+        return float(self.a)
+
+    def __repr__(self):
+        return f"Tensor({self.a!r})"
+
+    def item(self):
+        return self.a.item()
+
+    def tolist(self):
+        return self.a.tolist()
+
+    def numpy(self):
+        return self.a
+
+    def astype(self, dtype=None):
+        return Tensor(self.a.astype(dtype))
+
+    cast = astype
+
+    def reshape(self, shape):
+        return Tensor(self.a.reshape(shape))
+
+    def flip(self, axis):
+        return Tensor(np.flip(self.a, axis))
+
+    def unsqueeze(self, axis):
+        return Tensor(np.expand_dims(self.a, axis))
+
+    # ---- indexing ----
+    def __getitem__(self, idx):
+        idx = _np(idx) if not isinstance(idx, tuple) else tuple(_np(i) for i in idx)
+        return Tensor(self.a[idx])
+
+    def __setitem__(self, idx, value):
+        idx = _np(idx) if not isinstance(idx, tuple) else tuple(_np(i) for i in idx)
+        self.a[idx] = _np(value)
+
+    # ---- arithmetic: a Python scalar takes the tensor's dtype (as in Paddle), results keep fp32 ----
+    def _other(self, o):
+        if isinstance(o, Tensor):
+            return o.a
+        if isinstance(o, (int, float)) and self.a.dtype.kind == "f":
+            return self.a.dtype.type(o)
+        return o
+
+    def __add__(self, o): return Tensor(self.a + self._other(o))
+    def __radd__(self, o): return Tensor(self._other(o) + self.a)
+    def __sub__(self, o): return Tensor(self.a - self._other(o))
+    def __rsub__(self, o): return Tensor(self._other(o) - self.a)
+    def __mul__(self, o): return Tensor(self.a * self._other(o))
+    def __rmul__(self, o): return Tensor(self._other(o) * self.a)
+    def __truediv__(self, o): return Tensor(self.a / self._other(o))
+    def __rtruediv__(self, o): return Tensor(self._other(o) / self.a)
+    def __neg__(self): return Tensor(-self.a)
+
+    def __pow__(self, e):
+        """x ** e.  e = 1/p (the step-size controller and select_initial_step): the specification's rootp for finite
+        positive x, x itself otherwise (inf ** (1/p) = inf, 0 ** (1/p) = 0, NaN stays NaN)."""
+        ev = float(_np(e))
+        if ev == 2.0:
+            return Tensor(self.a * self.a)
+        p = round(1.0 / ev) if ev != 0 else 0
+        if p not in (2, 3, 5, 8) or builtins.abs(ev * p - 1.0) > 1e-6 or self.a.dtype != np.float32:
+            raise NotImplementedError(f"paddle shim: x ** {ev}")
+        flat = self.a.reshape(-1)
+        out = np.array([_oracle().orc_rootpf(float(v), p) if (v > 0 and np.isfinite(v)) else v for v in flat], np.float32)
+        return Tensor(out.reshape(self.a.shape))
+
+    # ---- comparisons ----
+    def __lt__(self, o): return Tensor(self.a < self._other(o))
+    def __le__(self, o): return Tensor(self.a <= self._other(o))
+    def __gt__(self, o): return Tensor(self.a > self._other(o))
+    def __ge__(self, o): return Tensor(self.a >= self._other(o))
+    def __eq__(self, o): return Tensor(self.a == self._other(o))  # noqa: E704
+    def __ne__(self, o): return Tensor(self.a != self._other(o))
+    def __and__(self, o): return Tensor(self.a & _np(o))
+    __hash__ = None
+
+    # ---- methods ----
+    def abs(self):
+        return Tensor(np.abs(self.a), wide=self._wide)
+
+    def pow(self, e):
+        return self.__pow__(e)
+
+    def mean(self):
+        """fp64, accumulated sequentially over the flattened tensor (oracle: rms_f64)."""
+        flat = self.a.reshape(-1).astype(np.float64)
+        acc = np.float64(0.0)
+        for v in flat:
+            acc = acc + v
+        return Tensor(acc / np.float64(flat.size), wide=True)
+
+    def sqrt(self):
+        if self._wide:
+            return Tensor(np.float32(np.sqrt(self.a)))  # (float) sqrt(acc / n)
+        return Tensor(np.sqrt(self.a))
+
+    def max(self):
+        return Tensor(self.a.max())
+
+    def all(self):
+        return Tensor(self.a.all())
+
+    def any(self):
+        return Tensor(self.a.any())
+
+    def clip(self, lo=None, hi=None):
+        return Tensor(np.clip(self.a, _np(lo), _np(hi)))
+
+    def reciprocal(self):
+        return Tensor(self.a.dtype.type(1.0) / self.a)
+
+
+builtins_bool = builtins.bool
+
+
+def to_tensor(x, dtype=None, **_):
+    return Tensor(np.array(_np(x), dtype=dtype))
+
+
+def empty(shape, dtype=float32):
+    return Tensor(np.zeros([int(s) for s in shape], dtype=dtype))
+
+
+zeros = empty
+
+
+def abs(x):  # noqa: A001
+    return Tensor(np.abs(_np(x)))
+
+
+def sum(x, axis=None):  # noqa: A001
+    """Left-to-right fp32 accumulation along `axis` (arithmetic specification: the stage sums)."""
+    a = _np(x)
+    a = np.moveaxis(a, axis, -1)
+    s = a[..., 0].copy()
+    for j in range(1, a.shape[-1]):
+        s = s + a[..., j]
+    return Tensor(s)
+
+
+def concat(xs, axis=0):
+    return Tensor(np.concatenate([_np(v) for v in xs], axis=axis))
+
+
+def fmax(a, b):
+    x, y = np.asarray(_np(a)), np.asarray(_np(b))
+    dt = x.dtype if x.dtype.kind == "f" else y.dtype
+    return Tensor(np.fmax(x.astype(dt), y.astype(dt)))
+
+
+def fmin(a, b):
+    x, y = np.asarray(_np(a)), np.asarray(_np(b))
+    dt = x.dtype if x.dtype.kind == "f" else y.dtype
+    return Tensor(np.fmin(x.astype(dt), y.astype(dt)))
+
+
+def max(a, b=None):  # noqa: A001
+    if b is None:
+        return Tensor(np.max(_np(a)))
+    return Tensor(np.maximum(_np(a), _np(b)))  # the degenerate branch of select_initial_step
+
+
+def sort(x):
+    return Tensor(np.sort(_np(x)))
+
+
+def isfinite(x):
+    return Tensor(np.isfinite(_np(x)))
+
+
+def numel(x):
+    return Tensor(np.int64(_np(x).size))
+
+
+def equal_all(a, b):
+    return Tensor(np.array_equal(_np(a), _np(b)))
+
+
+def ceil(x):
+    return Tensor(np.ceil(_np(x)))
+
+
+def arange(start, end=None, step=1, dtype=None):
+    return Tensor(np.arange(_np(start), _np(end), _np(step), dtype=dtype))
+
+
+def linspace(a, b, n, dtype=float32):
+    return Tensor(np.linspace(a, b, int(n), dtype=dtype))
+
+
+def promote_types(a, b):
+    return np.promote_types(a, b).type
+
+
+class no_grad:
+    def __call__(self, fn):
+        return fn
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class _Ctx:
+    pass
+
+
+class _PyLayer:
+    @classmethod
+    def apply(cls, *args, **kwargs):
+        return cls.forward(_Ctx(), *args, **kwargs)
+
+
+class autograd:
+    PyLayer = _PyLayer
+
+
+from . import nn  # noqa: E402,F401  (`import paddle.nn as nn`, `from paddle import nn`)

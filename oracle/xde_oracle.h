@@ -10,9 +10,18 @@
  * R1-R7).  This oracle is therefore a *restatement* of the reference algorithm with a fully defined
  * fp32 arithmetic order (DESIGN.md "Arithmetic specification").  It is pinned against every
  * known-answer fixture the reference's tests hold for this path (closed-form Sine/Linear/Constant
- * ODE fixtures, interpolation ramp/sin fixtures; see tests/test_oracle_fixtures.py).  What those
- * fixtures do NOT pin (accept/reject sequences, adjoint gradients, SDE results, HistoryIndex
- * backward, B>1) is "parity unpinned": parity there is defined against this oracle.
+ * ODE fixtures, interpolation ramp/sin fixtures; see tests/test_oracle_fixtures.py).
+ * Round 2: it is also pinned against OUTPUTS OF THE REFERENCE'S OWN CODE run in the build container: the
+ * reference's unmodified solver files (solver/base_adaptive_solver*.py, solver/adaptive_solver/*.py,
+ * solver/base_fixed_solver.py, solver/fixed_solver/{euler,midpoint,rk4}.py, utils/ode_utils.py, xde/base_{xde,ode}.py,
+ * interpolation/functional/interp_fn.py) execute on a NumPy stand-in for `paddle` (oracle/ref_shim/) whose eager ops
+ * round as the arithmetic specification says; tools/make_reference_golden.py commits their solutions and attempt logs
+ * to tests/golden/reference_run_vectors.npz and tests/test_reference_run_golden.py requires this oracle to reproduce
+ * them bit for bit (26 cases: five tableaux, options, min_step, step_t / jump_t, B = 1 and B > 1, fixed solvers,
+ * step_size / grid_constructor grids).  Step sequences and batched behaviour of the FORWARD solvers are thereby pinned.
+ * Still "parity unpinned" (the reference's code for them cannot run: repairs R2-R6, autograd): adjoint gradients,
+ * SDE results, HistoryIndex backward -- parity there is defined against this oracle and cross-checked against fp64
+ * autograd / finite differences.
  *
  * Each function cites the reference file:line it follows (paths relative to /root/reference).
  */
