@@ -72,8 +72,12 @@ def load():
     fixed = _load("paddlexde.solver.base_fixed_solver", os.path.join(root, "solver", "base_fixed_solver.py"))
     _pkg("paddlexde.solver.adaptive_solver", os.path.join(root, "solver", "adaptive_solver"))
     _pkg("paddlexde.solver.fixed_solver", os.path.join(root, "solver", "fixed_solver"))
+    utils.misc = _load("paddlexde.utils.misc", os.path.join(root, "utils", "misc.py"))
+    _pkg("paddlexde.functional", os.path.join(root, "functional"))
+    f_odeint = _load("paddlexde.functional.odeint", os.path.join(root, "functional", "odeint.py"))
+    f_adjoint = _load("paddlexde.functional.odeint_adjoint", os.path.join(root, "functional", "odeint_adjoint.py"))
     ns = types.SimpleNamespace(paddle=paddle, ode_utils=ode_utils, BaseODE=base_ode.BaseODE, rk=rk, fixed=fixed,
-                               interp_fn=interp_fn)
+                               interp_fn=interp_fn, odeint_mod=f_odeint, adjoint_mod=f_adjoint)
     for mod, cls in (("dopri5", "Dopri5"), ("bosh3", "Bosh3"), ("fehlberg2", "Fehlberg2"), ("adaptive_heun", "AdaptiveHeun"),
                      ("dopri8", "Dopri8")):
         m = _load(f"paddlexde.solver.adaptive_solver.{mod}", os.path.join(root, "solver", "adaptive_solver", mod + ".py"))

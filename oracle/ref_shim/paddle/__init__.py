@@ -186,8 +186,42 @@ class Tensor:
     def reciprocal(self):
         return Tensor(self.a.dtype.type(1.0) / self.a)
 
+    def detach(self):
+        return Tensor(self.a)
+
+    def dot(self, o):
+        """1-D dot product: products rounded, summed left to right in fp32 (the oracle's grad_t_span terms)."""
+        x, y = self.a.reshape(-1), _np(o).reshape(-1)
+        acc = x[0] * y[0]
+        for i in range(1, x.size):
+            acc = acc + x[i] * y[i]
+        return Tensor(acc)
+
+    @property
+    def trainable(self):
+        return True
+
 
 builtins_bool = builtins.bool
+
+
+def zeros_like(x):
+    return Tensor(np.zeros_like(_np(x)))
+
+
+def assign(x):
+    return Tensor(np.array(_np(x)))
+
+
+class set_grad_enabled:
+    def __init__(self, mode):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def to_tensor(x, dtype=None, **_):
@@ -281,17 +315,39 @@ class no_grad:
 
 
 class _Ctx:
-    pass
+    def save_for_backward(self, *tensors):
+        self._saved = tensors
+
+    def saved_tensor(self):
+        return self._saved
 
 
 class _PyLayer:
+    """`apply` runs `forward` and leaves the context on the result (`._ctx`), so that a test can call the layer's own
+    `backward(ctx, grad)` -- there is no tape in the stand-in."""
+
     @classmethod
     def apply(cls, *args, **kwargs):
-        return cls.forward(_Ctx(), *args, **kwargs)
+        ctx = _Ctx()
+        out = cls.forward(ctx, *args, **kwargs)
+        out._ctx = ctx
+        return out
 
 
 class autograd:
     PyLayer = _PyLayer
+
+    @staticmethod
+    def grad(outputs, inputs, grad_outputs=None, allow_unused=False, retain_graph=False):
+        """The one use the reference makes of autograd (functional/odeint_adjoint.py:108-114): the vector-Jacobian
+        product of the caller's field.  `outputs` must come from a field that attached its VJP (`_vjp`: cotangent ->
+        gradients in the order of `inputs`, None where the output does not depend on the input)."""
+        vjp = getattr(outputs, "_vjp", None)
+        if vjp is None:
+            raise NotImplementedError("paddle shim: autograd.grad of a tensor without an attached VJP")
+        grads = vjp(grad_outputs)
+        assert len(grads) == len(inputs)
+        return list(grads)
 
 
 from . import nn  # noqa: E402,F401  (`import paddle.nn as nn`, `from paddle import nn`)

@@ -936,26 +936,20 @@ float orc_fx_sum(const float *x, int64_t n) {
   return fx_to_float(&a);
 }
 
-/* augmented_dynamics (functional/odeint_adjoint.py:89-124) */
-static void adj_rhs(void *ctx, float t, const float *Y, float *dY) {
-  (void)t;
-  adj_ctx_t *c = (adj_ctx_t *)ctx;
-  const orc_mlp_t *m = c->m;
+/* paddle.autograd.grad(f(y), (y, *params), grad_outputs=c) for a BATCH of Bm trajectories: per-trajectory f and vjp_y,
+ * parameter gradients summed over the batch by the order-independent specification above (one trajectory: the plain
+ * products).  y, c, f, dy: [Bm, D]; gparams: [P] = (gW1, gb1, gW2, gb2), overwritten. */
+void orc_mlp_vjp_batch(const orc_mlp_t *m, const float *y, const float *c, int64_t Bm, float *f, float *dy,
+                       float *gparams) {
   const int D = m->d, H = m->h;
-  const int64_t Bm = c->Bm;
   const int64_t P = adj_nparams(m);
-  const float *y = Y + 1, *a = Y + 1 + Bm * D;
-  float *fy = dY + 1, *fa = dY + 1 + Bm * D;
-  float *gw1 = dY + 1 + 2 * Bm * D;
+  float *gw1 = gparams;
   float *gb1 = gw1 + (size_t)D * H;
   float *gw2 = gb1 + H;
   float *gb2 = gw2 + (size_t)H * D;
-  dY[0] = 0.0f; /* vjp_t: the field ignores t -> allow_unused zero (:116-118) */
-  memset(gw1, 0, sizeof(float) * P);
-  float cot[ORC_MAX_D];
+  memset(gparams, 0, sizeof(float) * P);
   if (Bm == 1) { /* one trajectory: every sum has one term */
-    for (int e = 0; e < D; ++e) cot[e] = -a[e]; /* grad_outputs=-adj_y */
-    orc_mlp_vjp(m, y, cot, fy, fa, gw1, gb1, gw2, gb2);
+    orc_mlp_vjp(m, y, c, f, dy, gw1, gb1, gw2, gb2);
     return;
   }
   fx128_t *tot = (fx128_t *)calloc((size_t)P, sizeof(fx128_t));
@@ -966,11 +960,10 @@ static void adj_rhs(void *ctx, float t, const float *Y, float *dY) {
     float *xw1 = X, *xb1 = X + (size_t)D * H, *xw2 = xb1 + H;
     for (int64_t i = 0; i < P; ++i) X[i] = 0.0f;
     for (int64_t b = b0; b < b1; ++b) {
-      const float *yb = y + b * D;
-      for (int e = 0; e < D; ++e) cot[e] = -a[b * D + e];
+      const float *yb = y + b * D, *cot = c + b * D;
       /* f, dy exactly as orc_mlp_vjp; the parameter terms enter the block chains */
       for (int k = 0; k < D; ++k) u[k] = pre_act(m->pre, yb[k]);
-      orc_mlp_eval(m, yb, fy + b * D, h);
+      orc_mlp_eval(m, yb, f + b * D, h);
       for (int j = 0; j < H; ++j) {
         float acc = cot[0] * m->w2[(size_t)j * D];
         for (int d = 1; d < D; ++d) acc = fmaf(cot[d], m->w2[(size_t)j * D + d], acc);
@@ -978,7 +971,7 @@ static void adj_rhs(void *ctx, float t, const float *Y, float *dY) {
         dz[j] = acc * sd;
       }
       for (int k = 0; k < D; ++k)
-        fa[b * D + k] = chain2_dot(dz, m->w1 + (size_t)k * H, 1, H) * pre_act_grad(m->pre, yb[k]);
+        dy[b * D + k] = chain2_dot(dz, m->w1 + (size_t)k * H, 1, H) * pre_act_grad(m->pre, yb[k]);
       for (int k = 0; k < D; ++k)
         for (int j = 0; j < H; ++j) xw1[(size_t)k * H + j] = fmaf(u[k], dz[j], xw1[(size_t)k * H + j]);
       for (int j = 0; j < H; ++j) xb1[j] = fmaf(1.0f, dz[j], xb1[j]);
@@ -988,9 +981,24 @@ static void adj_rhs(void *ctx, float t, const float *Y, float *dY) {
     }
     for (int64_t i = 0; i < (int64_t)D * H + H + (int64_t)H * D; ++i) fx_add_float(&tot[i], X[i]);
   }
-  for (int64_t i = 0; i < P; ++i) gw1[i] = fx_to_float(&tot[i]);
+  for (int64_t i = 0; i < P; ++i) gparams[i] = fx_to_float(&tot[i]);
   free(X);
   free(tot);
+}
+
+/* augmented_dynamics (functional/odeint_adjoint.py:89-124) */
+static void adj_rhs(void *ctx, float t, const float *Y, float *dY) {
+  (void)t;
+  adj_ctx_t *c = (adj_ctx_t *)ctx;
+  const orc_mlp_t *m = c->m;
+  const int D = m->d;
+  const int64_t Bm = c->Bm;
+  const float *y = Y + 1, *a = Y + 1 + Bm * D;
+  dY[0] = 0.0f; /* vjp_t: the field ignores t -> allow_unused zero (:116-118) */
+  float *cot = (float *)malloc(sizeof(float) * (size_t)Bm * D);
+  for (int64_t i = 0; i < Bm * D; ++i) cot[i] = -a[i]; /* grad_outputs=-adj_y */
+  orc_mlp_vjp_batch(m, y, cot, Bm, dY + 1, dY + 1 + Bm * D, dY + 1 + 2 * Bm * D);
+  free(cot);
 }
 
 /* default_adjoint_norm / adjoint_seminorm (functional/odeint_adjoint.py:284-309) with

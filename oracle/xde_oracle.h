@@ -12,7 +12,8 @@
  * known-answer fixture the reference's tests hold for this path (closed-form Sine/Linear/Constant
  * ODE fixtures, interpolation ramp/sin fixtures; see tests/test_oracle_fixtures.py).
  * Round 2: it is also pinned against OUTPUTS OF THE REFERENCE'S OWN CODE run in the build container: the
- * reference's unmodified solver files (solver/base_adaptive_solver*.py, solver/adaptive_solver/*.py,
+ * reference's unmodified solver files (solver/base_adaptive_solver.py, base_adaptive_solver_rk.py, the five tableau
+ * modules under solver/adaptive_solver/,
  * solver/base_fixed_solver.py, solver/fixed_solver/{euler,midpoint,rk4}.py, utils/ode_utils.py, xde/base_{xde,ode}.py,
  * interpolation/functional/interp_fn.py) execute on a NumPy stand-in for `paddle` (oracle/ref_shim/) whose eager ops
  * round as the arithmetic specification says; tools/make_reference_golden.py commits their solutions and attempt logs
@@ -150,6 +151,11 @@ int orc_dopri5_mlp_adjoint(const orc_mlp_t *m, const float *t_span, int32_t T, c
                            int32_t controller, int32_t adj_norm, float *out_gparams,
                            float *out_adj_y0, float *out_grad_t, orc_stats_t *stats, orc_attempt_t *log,
                            int64_t log_cap, int64_t log_traj, int64_t *log_len, int32_t nthreads);
+
+/* The batch form of orc_mlp_vjp: y, c, f, dy [Bm, D]; gparams [P] = (gW1, gb1, gW2, gb2) summed over the batch with the
+ * order-independent specification (32-trajectory fma chains + exact fixed-point total, one rounding). */
+void orc_mlp_vjp_batch(const orc_mlp_t *m, const float *y, const float *c, int64_t Bm, float *f, float *dy,
+                       float *gparams);
 
 /* Order-independent batch sum of the arithmetic specification (see adj_rhs in the .c file): the n fp32 addends are
  * truncated toward zero to a grid of 2^-59, added exactly in 128-bit fixed point, and the total is rounded once to

@@ -128,6 +128,16 @@ class MLP:
                               _p(gw1), _p(gb1), _p(gw2), _p(gb2))
         return f, dy, [gw1, gb1, gw2, gb2]
 
+    def vjp_batch(self, y, c):
+        """paddle.autograd.grad(f(y), (y, *params), grad_outputs=c) over a batch: y, c [B, D] -> (f, dy, [gW1, gb1, gW2,
+        gb2]) with the parameter gradients summed over the batch by the order-independent specification."""
+        y, c = _f32(y).reshape(-1, self.d), _f32(c).reshape(-1, self.d)
+        f, dy = np.empty_like(y), np.empty_like(y)
+        g = np.zeros(self.n_params, np.float32)
+        m = self.c()
+        lib().orc_mlp_vjp_batch(C.byref(m), _p(y), _p(c), C.c_int64(y.shape[0]), _p(f), _p(dy), _p(g))
+        return f, dy, self.split(g)
+
 
 def make_opts(rtol=1e-7, atol=1e-9, min_step=0.0, max_step=float("inf"), first_step=None, safety=0.9,
               ifactor=10.0, dfactor=0.2, max_num_steps=2**31 - 1):
