@@ -66,6 +66,10 @@ def load():
     sys.modules["paddlexde.interpolation.functional"].linear_interp = interp_fn.linear_interp
     sys.modules["paddlexde.interpolation.functional"].cubic_hermite_interp = interp_fn.cubic_hermite_interp
     interp.functional = sys.modules["paddlexde.interpolation.functional"]
+    _load("paddlexde.interpolation.interpolate_base", os.path.join(root, "interpolation", "interpolate_base.py"))
+    interp.interpolate = _load("paddlexde.interpolation.interpolate", os.path.join(root, "interpolation", "interpolate.py"))
+    base_dde = _load("paddlexde.xde.base_dde", os.path.join(root, "xde", "base_dde.py"))
+    xde.BaseDDE = base_dde.BaseDDE
     _pkg("paddlexde.solver", os.path.join(root, "solver"))
     _load("paddlexde.solver.base_adaptive_solver", os.path.join(root, "solver", "base_adaptive_solver.py"))
     rk = _load("paddlexde.solver.base_adaptive_solver_rk", os.path.join(root, "solver", "base_adaptive_solver_rk.py"))
@@ -76,8 +80,10 @@ def load():
     _pkg("paddlexde.functional", os.path.join(root, "functional"))
     f_odeint = _load("paddlexde.functional.odeint", os.path.join(root, "functional", "odeint.py"))
     f_adjoint = _load("paddlexde.functional.odeint_adjoint", os.path.join(root, "functional", "odeint_adjoint.py"))
+    f_ddeint = _load("paddlexde.functional.ddeint", os.path.join(root, "functional", "ddeint.py"))
     ns = types.SimpleNamespace(paddle=paddle, ode_utils=ode_utils, BaseODE=base_ode.BaseODE, rk=rk, fixed=fixed,
-                               interp_fn=interp_fn, odeint_mod=f_odeint, adjoint_mod=f_adjoint)
+                               interp_fn=interp_fn, odeint_mod=f_odeint, adjoint_mod=f_adjoint, interpolate=interp.interpolate,
+                               base_dde=base_dde, ddeint=f_ddeint.ddeint)
     for mod, cls in (("dopri5", "Dopri5"), ("bosh3", "Bosh3"), ("fehlberg2", "Fehlberg2"), ("adaptive_heun", "AdaptiveHeun"),
                      ("dopri8", "Dopri8")):
         m = _load(f"paddlexde.solver.adaptive_solver.{mod}", os.path.join(root, "solver", "adaptive_solver", mod + ".py"))

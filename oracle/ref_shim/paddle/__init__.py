@@ -101,6 +101,18 @@ class Tensor:
     def unsqueeze(self, axis):
         return Tensor(np.expand_dims(self.a, axis))
 
+    def squeeze(self, axis=None):
+        return Tensor(np.squeeze(self.a, axis))
+
+    def __matmul__(self, o):
+        """[..., n, k] @ [..., k, m] (broadcast over the leading dims): every product rounded to fp32, summed left to
+        right over k in fp32 -- no fused multiply-add (the interpolation weights ts @ H @ ps, interpolate_base.py:92)."""
+        x, y = self.a, _np(o)
+        acc = x[..., :, 0:1] * y[..., 0:1, :]
+        for j in range(1, x.shape[-1]):
+            acc = acc + x[..., :, j:j + 1] * y[..., j:j + 1, :]
+        return Tensor(acc)
+
     # ---- indexing ----
     def __getitem__(self, idx):
         idx = _np(idx) if not isinstance(idx, tuple) else tuple(_np(i) for i in idx)
@@ -134,6 +146,8 @@ class Tensor:
         ev = float(_np(e))
         if ev == 2.0:
             return Tensor(self.a * self.a)
+        if ev == 3.0:  # the Hermite / Bezier monomials (interpolation/interpolate.py:186,280): (x * x) * x
+            return Tensor((self.a * self.a) * self.a)
         p = round(1.0 / ev) if ev != 0 else 0
         if p not in (2, 3, 5, 8) or builtins.abs(ev * p - 1.0) > 1e-6 or self.a.dtype != np.float32:
             raise NotImplementedError(f"paddle shim: x ** {ev}")
@@ -209,6 +223,47 @@ def zeros_like(x):
     return Tensor(np.zeros_like(_np(x)))
 
 
+def ones_like(x):
+    return Tensor(np.ones_like(_np(x)))
+
+
+def get_default_dtype():
+    return float32
+
+
+def cast(x, dtype=None):
+    return Tensor(np.asarray(_np(x)).astype(dtype))
+
+
+def stack(xs, axis=0):
+    return Tensor(np.stack([_np(v) for v in xs], axis=axis))
+
+
+def bucketize(x, sorted_sequence, right=False):
+    """#{s < x} (right=False): numpy's searchsorted(side='left')."""
+    return Tensor(np.searchsorted(_np(sorted_sequence), _np(x), side="right" if right else "left").astype(np.int64))
+
+
+def index_select(x, index, axis=0):
+    return Tensor(np.take(_np(x), _np(index), axis=axis))
+
+
+class _SparseCoo:
+    def __init__(self, indices, values, shape):
+        self._dense = np.zeros(shape, np.float32)
+        for r, c, v in zip(indices[0], indices[1], values):
+            self._dense[r, c] = np.float32(v)
+
+    def to_dense(self):
+        return Tensor(self._dense)
+
+
+class sparse:  # noqa: N801  (paddle.sparse)
+    @staticmethod
+    def sparse_coo_tensor(indices, values, shape):
+        return _SparseCoo(indices, values, shape)
+
+
 def assign(x):
     return Tensor(np.array(_np(x)))
 
@@ -242,6 +297,17 @@ def abs(x):  # noqa: A001
 def sum(x, axis=None):  # noqa: A001
     """Left-to-right fp32 accumulation along `axis` (arithmetic specification: the stage sums)."""
     a = _np(x)
+    if isinstance(axis, (list, tuple)):
+        # several axes at once (HistoryIndex.backward, xde/base_dde.py:126): the kept axes first, the reduced ones
+        # flattened in row-major order and accumulated sequentially in fp64, one rounding to fp32 (oracle:
+        # orc_history_gather_bwd)
+        red = [ax % a.ndim for ax in axis]
+        keep = [ax for ax in range(a.ndim) if ax not in red]
+        flat = np.transpose(a, keep + red).reshape([a.shape[ax] for ax in keep] + [-1]).astype(np.float64)
+        acc = np.zeros(flat.shape[:-1], np.float64)
+        for j in range(flat.shape[-1]):
+            acc = acc + flat[..., j]
+        return Tensor(acc.astype(np.float32))
     a = np.moveaxis(a, axis, -1)
     s = a[..., 0].copy()
     for j in range(1, a.shape[-1]):

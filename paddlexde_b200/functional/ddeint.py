@@ -1,5 +1,7 @@
 from __future__ import annotations
 
+import numpy as np
+
 from .. import _tensor as T
 from .._tensor import torch
 from ..utils.ode_utils import _rms_norm
@@ -12,21 +14,23 @@ _two_thirds = 2 / 3
 
 def _step(method, xde, t0, t1, y0):
     """FixedSolver.step of the reference driven through xde.move / xde.fuse
-    (fixed_solver/euler.py:7-11, midpoint.py:7-18, rk4.py:7-10 -> rk4_alt_step_func base_fixed_solver.py:166-197)."""
-    dt = t1 - t0
+    (fixed_solver/euler.py:7-11, midpoint.py:7-18, rk4.py:7-10 -> rk4_alt_step_func base_fixed_solver.py:166-197).
+    The time arithmetic is the reference's: fp32 tensors (`dt * _one_third` is an fp32 product of two fp32 values)."""
+    t0, t1 = np.float32(t0), np.float32(t1)
+    dt = np.float32(t1 - t0)
     if method == "euler":
         dy = xde.move(t0, dt, y0)
         return xde.fuse(dy, dt, y0), dy
     if method == "midpoint":
-        half_dt = 0.5 * dt
+        half_dt = np.float32(0.5) * dt
         y_half = xde.fuse(xde.move(t0, half_dt, y0), half_dt, y0)
         dy = xde.move(t0 + half_dt, dt, y_half)
         return xde.fuse(dy, dt, y0), dy
     if method == "rk4":
         k1 = xde.move(t0, dt, y0)
-        dt3 = dt * _one_third
+        dt3 = dt * np.float32(_one_third)
         k2 = xde.move(t0 + dt3, dt3, xde.fuse(k1, dt3, y0))
-        k3 = xde.move(t0 + dt * _two_thirds, dt3, xde.fuse(k1 - k2 * _one_third, dt, y0))
+        k3 = xde.move(t0 + dt * np.float32(_two_thirds), dt3, xde.fuse(k1 - k2 * _one_third, dt, y0))
         k4 = xde.move(t1, t0 + dt3, xde.fuse(k1 - k2 + k3, dt, y0))
         y1 = (xde.fuse(k1, dt, y0) + 3 * xde.fuse(k2, dt, y0) + 3 * xde.fuse(k3, dt, y0) + xde.fuse(k4, dt, y0)) * 0.125
         return y1, k1

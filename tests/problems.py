@@ -36,3 +36,9 @@ def spiral_truth(n=1000):
     A = np.array([[-0.1, 2.0], [-2.0, -0.1]], np.float32)
     t = np.linspace(0.0, 25.0, n).astype(np.float32)
     return t, A
+
+
+def dde_field_coefficients():
+    """The stand-in delay field of the reference-run ddeint vectors: dy = 0.5 * y_lags - 0.25 * y, elementwise fp32 (two
+    rounded products and one rounded difference: the same bits from NumPy, the paddle stand-in and torch eager)."""
+    return np.float32(0.5), np.float32(0.25)

@@ -142,3 +142,50 @@ def test_per_trajectory_adjoint_kernels_reproduce_the_reference_run_at_b1(px, na
     if gt is not None:
         gt_ref = ZA[f"{name}/grad_t"]
         np.testing.assert_allclose(gt, gt_ref, rtol=1e-5, atol=3e-5 * np.abs(gt_ref).max())
+
+
+# ------------------------------------------------------------------------------------------------
+# the delay path against vectors produced by the reference's own interpolation / base_dde / ddeint code
+# (tools/make_reference_dde_golden.py; CPU twin: tests/test_reference_run_dde_golden.py)
+# ------------------------------------------------------------------------------------------------
+ZD = np.load(os.path.join(ROOT, "tests", "golden", "reference_run_dde_vectors.npz"), allow_pickle=False)
+GATHER = sorted({k.split("/")[1] for k in ZD.files if k.startswith("gather/")})
+DDEINT = sorted({k.split("/")[1] for k in ZD.files if k.startswith("ddeint/") and k.count("/") == 2})
+
+
+@pytest.mark.parametrize("kind", ["linear", "cubic", "bez"])
+@pytest.mark.parametrize("name", GATHER)
+def test_gather_kernel_reproduces_the_reference_interpolants(px, name, kind):
+    from paddlexde_b200.xde.base_dde import history_gather
+
+    v, d = history_gather(ZD[f"gather/{name}/lags"], ZD[f"gather/{name}/his"], ZD[f"gather/{name}/span"], kind)
+    assert np.array_equal(v.cpu().numpy(), ZD[f"gather/{name}/{kind}/val"]), "evaluate"
+    assert np.array_equal(d.cpu().numpy(), ZD[f"gather/{name}/{kind}/der"]), "derivative"
+
+
+def test_history_index_reproduces_the_reference_forward_and_backward(px):
+    import torch
+
+    lags = torch.tensor(ZD["index/lags"], device="cuda", requires_grad=True)
+    y_lags = px.xde.base_dde.HistoryIndex.apply(lags, torch.from_numpy(ZD["index/his"]).cuda(),
+                                                torch.from_numpy(ZD["index/span"]).cuda())
+    assert np.array_equal(y_lags.detach().cpu().numpy(), ZD["index/y_lags"])
+    y_lags.backward(torch.from_numpy(ZD["index/grad_y"]).cuda())
+    ref = ZD["index/grad_lags"]  # the kernel reduces in another order: rtol 1e-5 (as test_history_gather_cfg5)
+    np.testing.assert_allclose(lags.grad.cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name", DDEINT)
+def test_ddeint_reproduces_the_reference_run(px, name):
+    import torch
+    from tests.problems import dde_field_coefficients
+
+    ca, cb = (float(c) for c in dde_field_coefficients())
+    func = lambda y_lags, y: y_lags * ca - y * cb  # noqa: E731  (elementwise fp32: the bits of the NumPy field)
+    sol, y_lags = px.ddeint(func, torch.from_numpy(ZD["ddeint/y0"]).cuda(), ZD[f"ddeint/{name}/t"],
+                            torch.from_numpy(ZD["index/lags"]).cuda(), torch.from_numpy(ZD["index/his"]).cuda(),
+                            torch.from_numpy(ZD["index/span"]).cuda(), getattr(px, name.split("_")[0].capitalize() if
+                                                                                 not name.startswith("rk4") else "RK4"),
+                            fixed_solver_interp=str(ZD[f"ddeint/{name}/interp"]))
+    assert np.array_equal(y_lags.cpu().numpy(), ZD["index/y_lags"])
+    assert np.array_equal(sol.cpu().numpy(), ZD[f"ddeint/{name}/sol"])
