@@ -131,7 +131,15 @@ def cpu_baseline(target_s=12.0):
     Bs = 1 << int(np.floor(np.log2(Bs)))
     w, y0, t = workload(Bs)
     n, dt = oracle_pass(xo, om, y0, t, cores)
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    try:  # cfg1 (BASELINE configs[0]: the reference's own CPU-runnable case): one ode_demo call, batch 20, on one core
+        w1, y1, t1 = workload(20)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            xo.dopri5_mlp(om, y1, t1, controller="batch", nthreads=1)
+        cfg1_ms = (time.perf_counter() - t0) / 20 * 1e3
+    except Exception:
+        cfg1_ms = None
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port", "cfg1_call_ms_one_core": cfg1_ms,
             "sample": f"first {Bs} trajectories of the cfg2 batch (2^20), forward+adjoint, OpenMP over {cores} threads, "
                       f"{dt:.1f} s; Paddle CPU reference not installable offline -> C oracle port of the reference algorithm"}
 
@@ -276,6 +284,10 @@ def secondary_configs():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_configs as bc
         res = []
+        try:  # cfg1 (BASELINE configs[0]) is a 20-trajectory call: its latency, reported beside the throughput configs
+            res.append(bc.cfg1_latency())
+        except Exception as e:
+            res.append({"config": "cfg1 latency", "error": f"{type(e).__name__}: {e}"})
         for fn, kw in ((bc.cfg2_batch, {"norm": "mixed"}), (bc.cfg3, {"math": "tensor"}), (bc.cfg3, {"math": "fp32"}),
                        (bc.cfg4, {"math": "tensor", "B": 1 << 22}), (bc.cfg4, {"math": "fp32"}),
                        (bc.cfg4, {"math": "tensor", "generated": True, "B": 1 << 22}), (bc.cfg5, {}),

@@ -5,15 +5,20 @@ reference (pure Python on Paddle eager ops) could not be run -- and the oracle's
 only be pinned to the closed-form fixtures of the reference's tests.  With this module on `sys.path` the reference's OWN,
 UNMODIFIED source files (`paddlexde/solver/base_adaptive_solver*.py`, `solver/adaptive_solver/*.py`,
 `solver/base_fixed_solver.py`, `solver/fixed_solver/{euler,midpoint,rk4}.py`, `utils/ode_utils.py`,
-`xde/base_{xde,ode}.py`, `interpolation/functional/interp_fn.py`) import and run here
-(`tools/make_reference_golden.py`), which turns "the oracle restates the reference" into "the oracle reproduces what the
+`xde/base_{xde,ode}.py`, `interpolation/functional/interp_fn.py`; and, with the additions below,
+`functional/odeint_adjoint.py`, `interpolation/interpolate_base.py`, `interpolation/interpolate.py`, `xde/base_dde.py`,
+`functional/ddeint.py`) import and run here (`tools/make_reference_golden.py`, `make_reference_adjoint_golden.py`,
+`make_reference_dde_golden.py`), which turns "the oracle restates the reference" into "the oracle reproduces what the
 reference's code computes", bit for bit, for step sequences, batched (B > 1) behaviour, every tableau, `step_t` /
 `jump_t`, the fixed solvers and `step_size` grids.
 
 What is an operation of THIS module and not of the reference: how an eager op rounds.  Paddle's CPU kernels do not
 document their summation orders, so every op here follows the repository's arithmetic specification (DESIGN.md
 section 2) -- fp32 elementwise ops, `sum(axis)` left to right in fp32, `mean()` accumulated sequentially in fp64 with
-`sqrt()` of that mean taken in fp64 and rounded once to fp32, `x ** (1/p)` through the specification's `rootp`.  What the
+`sqrt()` of that mean taken in fp64 and rounded once to fp32, `x ** (1/p)` through the specification's `rootp`,
+`x ** 3 = (x * x) * x`, `a @ b` = rounded products summed left to right in fp32 (no fused multiply-add), `sum` over
+several axes accumulated sequentially in fp64 and rounded once, `autograd.grad` = the vector-Jacobian product the
+caller's field attached to its output (there is no tape).  What the
 golden vectors therefore pin is everything ABOVE the op level: the reference's formulas, their order, its control flow.
 """
 from __future__ import annotations

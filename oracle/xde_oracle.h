@@ -20,9 +20,20 @@
  * to tests/golden/reference_run_vectors.npz and tests/test_reference_run_golden.py requires this oracle to reproduce
  * them bit for bit (26 cases: five tableaux, options, min_step, step_t / jump_t, B = 1 and B > 1, fixed solvers,
  * step_size / grid_constructor grids).  Step sequences and batched behaviour of the FORWARD solvers are thereby pinned.
- * Still "parity unpinned" (the reference's code for them cannot run: repairs R2-R6, autograd): adjoint gradients,
- * SDE results, HistoryIndex backward -- parity there is defined against this oracle and cross-checked against fp64
- * autograd / finite differences.
+ * The ADJOINT is pinned the same way (tools/make_reference_adjoint_golden.py, tests/test_reference_run_adjoint_golden.py):
+ * the reference's unmodified functional/odeint_adjoint.py -- option defaulting, handle_adjoint_norm_,
+ * OdeintAdjointMethod.forward / backward, augmented_dynamics, the segment loop, the t_requires_grad branch -- drives the
+ * reference's Dopri5 on the stand-in (the four-line functional/odeint.py is supplied from outside with repairs R1, R4-R6;
+ * the field's vector-Jacobian product is the caller's, here this oracle's orc_mlp_vjp_batch); 20 cases, parameter
+ * gradients, dL/dy0, grad_t_span and every backward attempt log reproduced bit for bit.  So is the DELAY path
+ * (tools/make_reference_dde_golden.py, tests/test_reference_run_dde_golden.py): interpolation/interpolate_base.py,
+ * interpolate.py, xde/base_dde.py (HistoryIndex forward and backward, the damped fuse) and functional/ddeint.py run
+ * unmodified and unrepaired; evaluate / derivative of the three interpolants, the lag gradients and whole ddeint solves
+ * (Euler / Midpoint / RK4) reproduced bit for bit.
+ * Still "parity unpinned": everything SDE (the reference's BaseSDE cannot be instantiated and its fuse is a placeholder:
+ * repairs R2 / R3; sdeint_adjoint is a stub) and Milstein (an extension) -- defined against this oracle and cross-checked
+ * against fp64 autograd.  And in every pinned case the ROUNDING OF AN EAGER OP is the stand-in's (the arithmetic
+ * specification), not Paddle's: what is pinned is everything above the op level.
  *
  * Each function cites the reference file:line it follows (paths relative to /root/reference).
  */

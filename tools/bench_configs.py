@@ -121,6 +121,29 @@ def cfg5_real_size(kind="cubic"):
                     "overhead (two allocations + one ctypes call), not by HBM"}
 
 
+def cfg1_latency():
+    """cfg1 = BASELINE configs[0]: example/ode_demo.py's training call, odeint(func, batch_y0 [20, 2], batch_t [10],
+    Dopri5) with the 2-50-2 field at rtol 1e-7 -- 20 trajectories: pure latency.  One call through the public API from
+    device-resident inputs to a synchronised result (host wall clock), and the kernel alone (20 queued solves between
+    two events); with the reference's global controller and with one controller per trajectory."""
+    from tests.problems import cfg2_tspan, cfg2_y0, spiral_weights
+    field = px.MLPField(*spiral_weights(), pre="cube")
+    y0 = torch.from_numpy(cfg2_y0(20)).cuda()
+    t = cfg2_tspan(10)
+    out = {"config": "cfg1 ode_demo call: dopri5 rtol 1e-7, MLP 2-50-2, batch 20, 10 output times (latency)"}
+    for ctrl in ("batch", "trajectory"):
+        call = lambda: px.odeint(field, y0, t, px.Dopri5, options={"controller": ctrl, "check_status": False})  # noqa: E731
+        NB = 20
+        ms = timeit(lambda: [call() for _ in range(NB)]) / NB
+        t0 = time.perf_counter()
+        for _ in range(100):
+            call()
+            torch.cuda.synchronize()
+        out[f"us_per_call_gpu_queued_{ctrl}"] = ms * 1e3
+        out[f"us_per_call_host_wall_synchronised_{ctrl}"] = (time.perf_counter() - t0) / 100 * 1e6
+    return out
+
+
 def cfg2_batch(B=1 << 20, norm="mixed"):
     """cfg2 with the REFERENCE-FAITHFUL controller: one global RMS norm and dt for the whole batch
     (utils/ode_utils.py:8-9), adjoint with the reference's default mixed norm or the seminorm."""
