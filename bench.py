@@ -169,7 +169,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(Bs, 1, "host"),
+        # the B200 arm's config (the contract: "on your arm's config"); what one reference step really integrates is the
+        # bounded sample named in cpu_baseline.sample / reference_sample -- the rate is per trajectory-step
+        "config": config_dict(args.batch // max(args.gpus, 1) if args.scaling == "strong" else args.batch,
+                              max(args.gpus, 1), "device", args),
+        "reference_sample": {"trajectories_per_step": Bs, "of": args.batch, "where": "host cores, no GPU"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))

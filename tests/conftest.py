@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+    if os.environ.get("XDE_DRY_RUN") == "1":  # host-layer dry run without a GPU: see tests/host_dry_run.py
+        from tests import host_dry_run
+
+        config._xde_dry_run = host_dry_run.install()
 
 
 @pytest.fixture(scope="session")

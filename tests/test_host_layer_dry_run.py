@@ -1,0 +1,58 @@
+"""The Python host layer, executed on the CPU: the GPU-marked test files run in a subprocess with two test doubles
+(tests/host_dry_run.py): the C ABI is answered by the CPU oracle on the same raw pointers and CUDA placement is sent to
+the CPU.  This checks what lives ABOVE the C ABI -- argument marshalling against include/xde_b200.h, layouts, option
+routing, the autograd adapters, status / attempt-log decoding -- and that the GPU tests themselves are executable.  It
+says nothing about the kernels (both sides are the oracle's numbers by construction); the parity tests proper are the
+same files under `-m gpu` on a B200.  Deselected: tests of the tensor-core entries, the Philox generator and the SDE
+adjoint (no double), of shape refusals / status words raised by the kernels, and the slow large-state / full-size cases."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SKIP = ("tensor", "generated", "brownian", "sde_adjoint", "sdeint_adjoint", "full_size", "status", "milstein",
+        "test_midpoint_fixed_solver", "tiled_sde_cfg4", "baseline_size", "large_state")
+
+
+def test_gpu_test_files_run_against_the_host_layer_doubles():
+    env = dict(os.environ, XDE_DRY_RUN="1", PYTHONPATH=ROOT)
+    cmd = [sys.executable, "-m", "pytest", "tests/test_zz_reference_run_gpu.py", "tests/test_gpu_round2.py",
+           "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+           "-k", " and ".join(f"not {s}" for s in SKIP)]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join(r.stdout.splitlines()[-25:])
+    assert r.returncode == 0, tail + "\n" + r.stderr[-2000:]
+    assert " passed" in tail and "failed" not in tail, tail
+
+
+def _run(code, timeout=900):
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-2000:] + "\n" + r.stderr[-3000:]
+    return r.stdout
+
+
+def test_smoke_runs_against_the_host_layer_doubles():
+    out = _run("from tests import host_dry_run; host_dry_run.install()\n"
+               "import __graft_entry__ as g; g.smoke()")
+    assert "smoke ok" in out
+
+
+def test_bench_line_schema_against_the_host_layer_doubles():
+    """bench.py end to end on the doubles (a small batch, no secondary configs): the JSON line carries every key the
+    contract names.  The numbers are meaningless here (host wall clock around the CPU oracle)."""
+    import json
+
+    out = _run("import sys\n"
+               "from tests import host_dry_run; host_dry_run.install()\n"
+               "sys.argv = ['bench.py', '--steps', '2', '--warmup', '1', '--batch', '2048', '--no-secondary', '--cpu-seconds', '0.3']\n"
+               "import bench; bench.main()")
+    line = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["config"]["workload"].startswith("cfg2") and line["dtype"] == "f32" and line["vs_baseline"] is None
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["gpu_launches"] > 0 and line["steps"] == 2
