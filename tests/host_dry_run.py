@@ -365,8 +365,10 @@ def install():
     torch.cuda.set_device = lambda *a, **k: None
     torch.cuda.empty_cache = lambda: None
 
-    from paddlexde_b200 import _lib, _tensor
+    from paddlexde_b200 import _lib, _tensor, distributed
 
+    init_from_env = distributed.init_from_env
+    distributed.init_from_env = lambda backend=None: init_from_env("gloo")  # no NCCL without GPUs
     _tensor.device = lambda: torch.device("cpu")  # autograd's backward thread runs outside the function mode
     _lib._lib = FakeLib()
     return mode

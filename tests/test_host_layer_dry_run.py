@@ -56,3 +56,53 @@ def test_bench_line_schema_against_the_host_layer_doubles():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["gpu_launches"] > 0 and line["steps"] == 2
+
+
+def _free_port():
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_bench_two_ranks_under_torchrun_on_gloo():
+    """The driver's N > 1 launch (`python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N`) on the
+    doubles with `gloo`: both ranks leave with exit code 0 (the round-2 exit path: no process-group teardown), rank 0
+    prints ONE line, weak scaling doubles the global batch and strong scaling splits it."""
+    import json
+
+    for scaling, per_gpu, total in (("weak", 512, 1024), ("strong", 256, 512)):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+               "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "_dry_run_bench.py"),
+               "--gpus", "2", "--steps", "1", "--warmup", "1", "--batch", "512", "--scaling", scaling]
+        r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + "\n" + r.stderr[-3000:]
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        assert len(lines) == 1, lines
+        line = json.loads(lines[0])
+        assert line["n_gpus"] == 2 and line["scaling"] == scaling
+        assert line["config"]["batch_per_gpu"] == per_gpu and line["config"]["global_batch"] == total
+        assert "cpu_baseline" not in line  # rank 0 at N = 1 only
+
+
+def test_reference_arm_line_and_its_torchrun_launch():
+    """`bench.py --impl reference` needs no GPU: rank 0 times the oracle port on the host cores and prints the line (the
+    B200 arm's metric / unit / config, `impl`, `cpu_baseline`, zero-copy `e2e`), every other rank exits 0 without work."""
+    import json
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "1", "--ref-batch", "512"]
+    r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + "\n" + r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "trajectory-steps/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["batch_per_gpu"] == 1 << 20 and line["config"]["parallelism"] == "batch-sharded x2"
+    assert line["reference_sample"]["trajectories_per_step"] == 512
