@@ -518,11 +518,26 @@ def run_b200(args):
     torch.cuda.synchronize()
     ffma_tflops = nfl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
+    ms_cfg3 = 0.0
+    if world > 1 and not args.no_secondary:
+        # BASELINE config 3 is "8xB200 batch-sharded": at N > 1 every rank also integrates ITS 2^17-trajectory share of the
+        # cfg3 ensemble (RK4, 64-256-64, 100 steps, tcgen05) -- no communication on that path; the share's kernel time
+        # joins the max-over-ranks reduction below (no extra collective).  A failure is reported as 0, never raised:
+        # an exception on one rank would leave the others waiting in the reduction.
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs as bc
+            ms_cfg3 = float(bc.cfg3(B=args.cfg3_share, math="tensor")["ms"])
+        except Exception:
+            ms_cfg3 = 0.0
     if world > 1:
-        tt = torch.tensor([ms, ms_e2e, ms_fwd, ms_adj, ms_e2e_sync, ms_e2e_graph or 0.0], device=dev, dtype=torch.float64)
+        tt = torch.tensor([ms, ms_e2e, ms_fwd, ms_adj, ms_e2e_sync, ms_e2e_graph or 0.0, ms_cfg3,
+                           -ms_cfg3 if ms_cfg3 > 0 else -1e30], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_fwd, ms_adj, ms_e2e_sync, mg = tt.tolist()
+        ms, ms_e2e, ms_fwd, ms_adj, ms_e2e_sync, mg, ms_cfg3, neg_min_cfg3 = tt.tolist()
         ms_e2e_graph = mg if ms_e2e_graph else None
+        if neg_min_cfg3 <= -1e29:  # some rank could not measure its share
+            ms_cfg3 = 0.0
         cnt = torch.tensor([n_traj_steps, fwd_stats.n_attempts, adj_stats.n_attempts], device=dev, dtype=torch.int64)
         cnt_local = cnt.clone()
         dist.all_reduce(cnt)
@@ -605,6 +620,14 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if world > 1 and ms_cfg3 > 0:
+            out["cfg3_sharded"] = {
+                "config": f"cfg3: RK4 3/8 rule, MLP 64-256-64, 100 steps, {args.cfg3_share} trajectories per GPU x {world} GPUs "
+                          f"(global {world * args.cfg3_share}; BASELINE: 2^20 on 8 GPUs), tcgen05 field, batch-sharded, "
+                          "no collective",
+                "ms_max_over_ranks": ms_cfg3, "traj_steps_per_s": world * args.cfg3_share * 100 / (ms_cfg3 * 1e-3),
+                "timing": "CUDA events around the solve on each rank (median of 5 after 2 warm-up solves, device-resident "
+                          "inputs), max over ranks through the same all-reduce as the headline timings"}
         if not args.no_cpu and world == 1:  # the CPU leg is timed at N = 1 only (rank 0)
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         if world == 1 and not args.no_secondary:
@@ -631,6 +654,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the cfg3/cfg4 kernel timings")
+    ap.add_argument("--cfg3-share", type=int, default=1 << 17,
+                    help="trajectories per GPU of the cfg3 ensemble share measured at N > 1 (BASELINE: 2^20 over 8 GPUs)")
     ap.add_argument("--graph-e2e", action="store_true", help="capture the e2e step in a CUDA graph at N > 1 as well")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch trajectories per GPU; strong: --batch trajectories in total, split across the GPUs")

@@ -77,7 +77,7 @@ def test_bench_two_ranks_under_torchrun_on_gloo():
     for scaling, per_gpu, total in (("weak", 512, 1024), ("strong", 256, 512)):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "_dry_run_bench.py"),
-               "--gpus", "2", "--steps", "1", "--warmup", "1", "--batch", "512", "--scaling", scaling]
+               "--gpus", "2", "--steps", "1", "--warmup", "1", "--batch", "512", "--scaling", scaling, "--cfg3-share", "16"]
         r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-1500:] + "\n" + r.stderr[-3000:]
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
@@ -86,6 +86,7 @@ def test_bench_two_ranks_under_torchrun_on_gloo():
         assert line["n_gpus"] == 2 and line["scaling"] == scaling
         assert line["config"]["batch_per_gpu"] == per_gpu and line["config"]["global_batch"] == total
         assert "cpu_baseline" not in line  # rank 0 at N = 1 only
+        assert line["cfg3_sharded"]["ms_max_over_ranks"] > 0  # BASELINE config 3's share per rank, max over ranks
 
 
 def test_reference_arm_line_and_its_torchrun_launch():
