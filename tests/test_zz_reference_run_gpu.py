@@ -189,3 +189,34 @@ def test_ddeint_reproduces_the_reference_run(px, name):
                             fixed_solver_interp=str(ZD[f"ddeint/{name}/interp"]))
     assert np.array_equal(y_lags.cpu().numpy(), ZD["index/y_lags"])
     assert np.array_equal(sol.cpu().numpy(), ZD[f"ddeint/{name}/sol"])
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's assertions (tools/make_reference_error_golden.py; CPU twin: tests/test_reference_run_error_golden.py)
+# ------------------------------------------------------------------------------------------------
+ZE = np.load(os.path.join(ROOT, "tests", "golden", "reference_run_errors.npz"), allow_pickle=False)
+ERR_NAMES = sorted({k.split("/")[0] for k in ZE.files})
+ERR_CODE = {"max_num_steps exceeded": 3, "non-finite values in state `y`": 2, "underflow in dt": 1}
+
+
+@pytest.mark.parametrize("name", ERR_NAMES)
+def test_kernels_raise_the_reference_assertions(px, name):
+    import torch
+
+    meta = ast.literal_eval(str(ZE[f"{name}/meta"]))
+    field = px.MLPField(ZE[f"{name}/w1"], ZE[f"{name}/b1"], ZE[f"{name}/w2"], ZE[f"{name}/b2"], pre=meta.pop("pre"))
+    y0, t = torch.from_numpy(ZE[f"{name}/y0"]).cuda(), ZE[f"{name}/t"]
+    msg = str(ZE[f"{name}/message"])
+    (prefix, code), = [(p, c) for p, c in ERR_CODE.items() if msg.startswith(p)]
+    done = int(ZE[f"{name}/adaptive_step_calls"]) - (0 if code == 3 else 1)
+    B = y0.shape[0]
+    for controller in (("batch", "trajectory") if B == 1 else ("batch",)):  # the reference's controller is the global one
+        xde = px.xde.BaseODE(field, y0, t)
+        kw = {"rtol": 1e-7, "atol": 1e-9, **meta}
+        with pytest.raises(AssertionError) as e:
+            px.Dopri5(xde=xde, y0=xde.y0, controller=controller, **kw).integrate(t)
+        assert str(e.value).startswith(prefix), (controller, str(e.value))
+        s = px.Dopri5(xde=xde, y0=xde.y0, controller=controller, check_status=False, **kw)
+        s.integrate(t)
+        st = s.read_stats()
+        assert st.status == code and st.n_attempts == done * B, (controller, st)
