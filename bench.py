@@ -288,6 +288,7 @@ def secondary_configs():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_configs as bc
         res = []
+        t_start = time.perf_counter()
         try:  # cfg1 (BASELINE configs[0]) is a 20-trajectory call: its latency, reported beside the throughput configs
             res.append(bc.cfg1_latency())
         except Exception as e:
@@ -296,7 +297,13 @@ def secondary_configs():
                        (bc.cfg4, {"math": "tensor", "B": 1 << 22}), (bc.cfg4, {"math": "fp32"}),
                        (bc.cfg4, {"math": "tensor", "generated": True, "B": 1 << 22}), (bc.cfg5, {}),
                        (bc.cfg5_real_size, {})):
-            res.append(fn(**kw))
+            if time.perf_counter() - t_start > 150.0:  # the default run must end within minutes
+                res.append({"config": f"{fn.__name__} {kw}", "skipped": "secondary time budget (150 s) spent"})
+                continue
+            try:  # one failing configuration must not take the others (or the headline) with it
+                res.append(fn(**kw))
+            except Exception as e:
+                res.append({"config": f"{fn.__name__} {kw}", "error": f"{type(e).__name__}: {e}"})
             torch.cuda.empty_cache()
         return res
     except Exception as e:  # never lose the headline line over a secondary measurement
