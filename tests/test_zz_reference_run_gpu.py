@@ -144,6 +144,32 @@ def test_per_trajectory_adjoint_kernels_reproduce_the_reference_run_at_b1(px, na
         np.testing.assert_allclose(gt, gt_ref, rtol=1e-5, atol=3e-5 * np.abs(gt_ref).max())
 
 
+@pytest.mark.parametrize("name", ["b1_cfg2_default_mixed", "batch_cfg1_default_mixed", "batch_d4_options",
+                                  "batch_d4_seminorm_rejections"])
+def test_odeint_adjoint_entry_point_reproduces_the_reference_run(px, name):
+    """The same vectors through the PUBLIC entry point, called the way the reference was called by the generator:
+    `odeint_adjoint(func, y0, t, rtol=, atol=, solver=Dopri5, options={"norm": _rms_norm, **solver options},
+    adjoint_options=None | {"norm": "seminorm", ...})` then `sol.backward(grad_y)` -- the option defaulting of
+    functional/odeint_adjoint.py:194-238 (backward tolerances and solver options inherited from the forward ones, mixed
+    norm unless "seminorm") has to route everything to the two kernels.  `controller="batch"` = the reference's."""
+    import torch
+
+    meta = ast.literal_eval(str(ZA[f"{name}/meta"]))
+    pre, adj_norm = meta.pop("pre"), meta.pop("adj_norm")
+    rtol, atol = meta.pop("rtol", 1e-7), meta.pop("atol", 1e-9)
+    params = [torch.tensor(ZA[f"{name}/{k}"], device="cuda", requires_grad=True) for k in ("w1", "b1", "w2", "b2")]
+    field = px.MLPField(*params, pre=pre)
+    sol = px.odeint_adjoint(field, torch.from_numpy(ZA[f"{name}/y0"]).cuda(), ZA[f"{name}/t"], rtol=rtol, atol=atol,
+                            solver=px.Dopri5, options={"norm": px.utils._rms_norm, "controller": "batch", **meta},
+                            adjoint_options=({"norm": "seminorm", "controller": "batch", **meta} if adj_norm == "seminorm"
+                                             else None))
+    assert np.array_equal(sol.detach().cpu().numpy(), ZA[f"{name}/sol"])
+    sol.backward(torch.from_numpy(ZA[f"{name}/grad_y"]).cuda())
+    assert px.odeint_adjoint.last["adj_norm"] == adj_norm
+    for p, k in zip(params, ("gw1", "gb1", "gw2", "gb2")):
+        assert np.array_equal(p.grad.cpu().numpy(), ZA[f"{name}/{k}"]), k
+
+
 # ------------------------------------------------------------------------------------------------
 # the delay path against vectors produced by the reference's own interpolation / base_dde / ddeint code
 # (tools/make_reference_dde_golden.py; CPU twin: tests/test_reference_run_dde_golden.py)
