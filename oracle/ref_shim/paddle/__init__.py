@@ -217,6 +217,14 @@ class Tensor:
     def detach(self):
         return Tensor(self.a)
 
+    # ---- raw-buffer surface (integration/b200.py binds a C ABI with these) ----
+    def contiguous(self):
+        return self if self.a.flags["C_CONTIGUOUS"] else Tensor(np.ascontiguousarray(self.a))
+
+    def data_ptr(self):
+        assert self.a.flags["C_CONTIGUOUS"]
+        return self.a.ctypes.data
+
     def dot(self, o):
         """1-D dot product: products rounded, summed left to right in fp32 (the oracle's grad_t_span terms)."""
         x, y = self.a.reshape(-1), _np(o).reshape(-1)
@@ -235,6 +243,21 @@ builtins_bool = builtins.bool
 
 def zeros_like(x):
     return Tensor(np.zeros_like(_np(x)))
+
+
+def split(x, sizes, axis=0):
+    return [Tensor(p) for p in np.split(_np(x), np.cumsum(sizes)[:-1], axis=axis)]
+
+
+class _CurrentStream:
+    cuda_stream = 0
+
+
+class device:  # noqa: N801  (paddle.device.cuda.current_stream().cuda_stream)
+    class cuda:  # noqa: N801
+        @staticmethod
+        def current_stream():
+            return _CurrentStream()
 
 
 def ones_like(x):
