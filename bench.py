@@ -279,7 +279,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # secondary configs (not the headline): BASELINE.json configs[2] (cfg3) and [3] (cfg4), device-resident
 # ---------------------------------------------------------------------------------------------------
-def secondary_configs():
+def secondary_configs(ffma_tflops=None):
     """Kernel timings of the large-state fixed-grid paths, tensor-core (tcgen05) and FP32, with the
     roofline fractions of SURVEY 8(d).  Reported next to the headline, never instead of it."""
     try:
@@ -287,6 +287,8 @@ def secondary_configs():
 
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_configs as bc
+        if ffma_tflops:  # the FP32 fractions of the secondary entries use THIS run's probe, not a pasted constant
+            bc.FFMA = float(ffma_tflops)
         res = []
         t_start = time.perf_counter()
         try:  # cfg1 (BASELINE configs[0]) is a 20-trajectory call: its latency, reported beside the throughput configs
@@ -638,7 +640,7 @@ def run_b200(args):
         if not args.no_cpu and world == 1:  # the CPU leg is timed at N = 1 only (rank 0)
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         if world == 1 and not args.no_secondary:
-            out["secondary"] = secondary_configs()
+            out["secondary"] = secondary_configs(ffma_tflops)
         print(json.dumps(out), flush=True)
     if world > 1:
         # Every collective of the run is behind us (the last one is the all-reduce of the timings above).  Leave without

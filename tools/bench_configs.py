@@ -11,7 +11,7 @@ _PEAKS = os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")
 _P = json.load(open(_PEAKS)) if os.path.exists(_PEAKS) else {}
 HBM = _P.get("hbm_gbs", 6650.0)
 TENSOR = _P.get("bf16_tflops_sustained", 1371.6)  # dense 16-bit tensor TFLOP/s (the tensor path runs kind::f16)
-FFMA = 72.3  # TFLOP/s, measured by tools/probe_fp32.py on this pool
+FFMA = 72.3  # TFLOP/s: tools/probe_fp32.py on this pool; bench.py overwrites it with the probe it timed in the same run
 
 
 def timeit(fn, n=5, warm=2):
