@@ -358,6 +358,7 @@ def install():
     torch.cuda.CUDAGraph = _no_graph
     torch.cuda.get_device_properties = lambda *a, **k: types.SimpleNamespace(
         uuid="host-dry-run", multi_processor_count=148, name="host dry run", total_memory=180 << 30)
+    torch.cuda.is_current_stream_capturing = lambda: False  # asked by torch.optim before every step
     torch.cuda.is_available = lambda: True
     torch.cuda.current_device = lambda: 0
     torch.cuda.current_stream = lambda *a, **k: _Stream()

@@ -107,3 +107,19 @@ def test_reference_arm_line_and_its_torchrun_launch():
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["batch_per_gpu"] == 1 << 20 and line["config"]["parallelism"] == "batch-sharded x2"
     assert line["reference_sample"]["trajectories_per_step"] == 512
+
+
+def test_training_example_runs_and_the_field_follows_the_optimizer():
+    """examples/ode_demo.py (the reference's example/ode_demo.py flow through the public API) on the doubles: the loss is
+    finite, every parameter moves, and the solves see the optimizer's in-place updates (MLPField re-reads the caller's
+    tensors when their version counters change: without that the loss sequence would not react to the steps)."""
+    out = _run("from tests import host_dry_run; host_dry_run.install()\n"
+               "import runpy, numpy as np\n"
+               "m = runpy.run_path('examples/ode_demo.py')\n"
+               "a, pa = m['main'](['--steps', '12', '--lr', '0.01'])\n"
+               "b, pb = m['main'](['--steps', '12', '--lr', '0.0'])\n"
+               "assert all(np.isfinite(a)) and all(np.isfinite(b))\n"
+               "assert a[0] == b[0] and a[1:] != b[1:], 'the solves ignore the optimizer steps'\n"
+               "assert np.mean(a[-4:]) < np.mean(b[-4:]), (a, b)\n"
+               "print('example ok', a[0], a[-1], b[-1])")
+    assert "example ok" in out
