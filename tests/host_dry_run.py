@@ -249,6 +249,42 @@ class FakeLib:
         _arr(out, (B, len(idx), D))[:] = y[:, idx]
         return 0
 
+    def xde_brownian_increments_f32(self, seed, traj_offset, t_span, T, B, D, dW, stream):
+        from oracle import philox_np
+
+        self._launches += 1
+        _arr(dW, (T - 1, B, D))[:] = philox_np.brownian_increments(int(seed), _arr(t_span, (T,)), B, D, int(traj_offset))
+        return 0
+
+    def xde_sde_mlp_philox_f32(self, scheme, math, drift, diffusion, y0, B, t_span, T, seed, traj_offset, out_stride_t,
+                               out, status, stream):
+        from oracle import philox_np
+
+        if math == 1 and scheme != 0:
+            self._err = "the tensor-core SDE kernel integrates Euler-Maruyama only"
+            return -2
+        if _addr(status):
+            _arr(status, (1,), np.int32)[0] = 0
+        dW = philox_np.brownian_increments(int(seed), _arr(t_span, (T,)), B, self._field(drift).d, int(traj_offset))
+        return self.xde_sde_mlp_f32(scheme, drift, diffusion, y0, B, t_span, T, C.c_void_p(dW.ctypes.data), out_stride_t,
+                                    out, stream)
+
+    def xde_sde_mlp_adjoint_f32(self, drift, diffusion, t_span, T, y_all, grad_y, B, dW, seed, traj_offset, out_gf, out_gg,
+                                out_a0, stream):
+        from oracle import philox_np
+
+        self._launches += 1
+        f, g = self._field(drift), self._field(diffusion)
+        D = f.d
+        ta = _arr(t_span, (T,))
+        table = _arr(dW, (T - 1, B, D)) if _addr(dW) else philox_np.brownian_increments(int(seed), ta, B, D, int(traj_offset))
+        gf, gg, a0 = self.xo.sde_mlp_adjoint(f, g, ta, _arr(y_all, (B, T, D)), _arr(grad_y, (B, T, D)), table)
+        _arr(out_gf, (f.n_params,))[:] = gf
+        _arr(out_gg, (g.n_params,))[:] = gg
+        if _addr(out_a0):
+            _arr(out_a0, (B, D))[:] = a0
+        return 0
+
     # ---- delay path ----
     def xde_history_gather_f32(self, kind, his, R, Th, D, span, lags, L, out_val, out_der, stream):
         self._launches += 1
