@@ -147,16 +147,28 @@ class FakeLib:
         jt_a = np.ascontiguousarray(sgn * _arr(jump_t, (n_jump,))) if n_jump else None
         ns = B if ctrl == "trajectory" else 1
         st = np.zeros(ns, xo.STATS_DTYPE)
-        for lt in (range(B) if (want and ctrl == "trajectory") else [0]):
-            rec = np.zeros(100000 if want else 0, xo.ATTEMPT_DTYPE)
-            n = C.c_int64(0)
-            rc = xo.lib().orc_adaptive_rk_mlp_grid(
-                C.c_int32(xo.RK[RK_NAME[method]]), C.byref(m), xo._p(y0a), C.c_int64(B), xo._p(ta), C.c_int32(T),
-                C.byref(o), C.c_int32(xo.CTRL[ctrl]), xo._p(st_a), C.c_int32(n_step),
-                xo._p(jt_a), C.c_int32(n_jump), xo._p(outa), xo._p(st), xo._p(rec) if want else None,
-                C.c_int64(rec.size), C.c_int64(lt), C.byref(n), C.c_int32(0))
-            if want:
-                rows[lt] = rec[:n.value].view(np.recarray)
+
+        cap = (_obj(log).cap + 8) if want else 0  # the oracle keeps counting past the capacity, like the kernels
+        rec = np.zeros(cap if (want and ctrl == "batch") else 0, xo.ATTEMPT_DTYPE)
+        n = C.c_int64(0)
+        rc = xo.lib().orc_adaptive_rk_mlp_grid(
+            C.c_int32(xo.RK[RK_NAME[method]]), C.byref(m), xo._p(y0a), C.c_int64(B), xo._p(ta), C.c_int32(T),
+            C.byref(o), C.c_int32(xo.CTRL[ctrl]), xo._p(st_a), C.c_int32(n_step), xo._p(jt_a), C.c_int32(n_jump),
+            xo._p(outa), xo._p(st), xo._p(rec) if rec.size else None, C.c_int64(rec.size), C.c_int64(0), C.byref(n),
+            C.c_int32(0))
+        if want and ctrl == "batch":
+            rows[0] = rec[:n.value].view(np.recarray)
+        elif want:  # one controller per trajectory: every trajectory is its own solve, so its log is that of a B = 1 run
+            for b in range(B):
+                rec = np.zeros(cap, xo.ATTEMPT_DTYPE)
+                n = C.c_int64(0)
+                st1, out1 = np.zeros(1, xo.STATS_DTYPE), np.empty((T, 1, D), np.float32)
+                yb = np.ascontiguousarray(y0a[b:b + 1])
+                xo.lib().orc_adaptive_rk_mlp_grid(
+                    C.c_int32(xo.RK[RK_NAME[method]]), C.byref(m), xo._p(yb), C.c_int64(1), xo._p(ta), C.c_int32(T),
+                    C.byref(o), C.c_int32(xo.CTRL[ctrl]), xo._p(st_a), C.c_int32(n_step), xo._p(jt_a), C.c_int32(n_jump),
+                    xo._p(out1), xo._p(st1), xo._p(rec), C.c_int64(rec.size), C.c_int64(0), C.byref(n), C.c_int32(0))
+                rows[b] = rec[:n.value].view(np.recarray)
         self._write_stats(stats, st.view(np.recarray), rc, B, ctrl)
         self._write_log(log, rows)
         return 0
@@ -186,12 +198,18 @@ class FakeLib:
         gt = np.zeros(T, np.float32) if _addr(out_gt) else None
         want = _obj(log) is not None
         rows = {}
-        for lt in (range(B) if (want and ctrl == "trajectory") else [0]):
-            g, a0, st, lg, rc = xo.dopri5_mlp_adjoint(om, ta, ya, ga, controller=ctrl, adj_norm=norm,
-                                                      log_traj=lt if want else None,
-                                                      grad_t=None if gt is None else gt, **kw)
-            if want:
-                rows[lt] = lg
+        cap = (_obj(log).cap + 8) if want else 8
+        g, a0, st, lg, rc = xo.dopri5_mlp_adjoint(om, ta, ya, ga, controller=ctrl, adj_norm=norm, log_cap=cap,
+                                                  log_traj=0 if (want and ctrl == "batch") else None,
+                                                  grad_t=None if gt is None else gt, **kw)
+        if want and ctrl == "batch":
+            rows[0] = lg
+        elif want:  # per-trajectory controller: the log of trajectory b is the log of its own B = 1 solve
+            for b in range(B):
+                _, _, _, lgb, _ = xo.dopri5_mlp_adjoint(om, ta, ya[:, b:b + 1], ga[:, b:b + 1], controller=ctrl,
+                                                        adj_norm=norm, log_traj=0, log_cap=cap,
+                                                        grad_t=None if gt is None else np.zeros(T, np.float32), **kw)
+                rows[b] = lgb
         _arr(out_g, (om.n_params,))[:] = g
         if _addr(out_a0):
             _arr(out_a0, (B, D))[:] = a0

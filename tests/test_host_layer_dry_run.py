@@ -4,21 +4,22 @@ the CPU.  This checks what lives ABOVE the C ABI -- argument marshalling against
 routing, the autograd adapters, status / attempt-log decoding -- and that the GPU tests themselves are executable.  It
 says nothing about the kernels (both sides are the oracle's numbers by construction); the parity tests proper are the
 same files under `-m gpu` on a B200.  Deselected: tests that measure the tensor-core entries' own accuracy (their double
-is the FP32 oracle), tests of shape refusals / status words raised by the kernels, and the slow large-state / full-size
-cases."""
+is the FP32 oracle), tests of shape refusals / status words raised by the kernels, and the full-size cases."""
 import os
 import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SKIP = ("tensor", "full_size", "status", "test_midpoint_fixed_solver", "tiled_sde_cfg4", "baseline_size", "large_state")
+SKIP = ("tensor", "full_size", "status", "test_midpoint_fixed_solver", "tiled_sde_cfg4", "baseline_size")
+DESELECT = ("tests/test_gpu_parity.py::test_other_tableaux_large_state[16-64-square-33-Bosh3-1e-05]",)  # ends with a refusal
 
 
 def test_gpu_test_files_run_against_the_host_layer_doubles():
-    env = dict(os.environ, XDE_DRY_RUN="1", PYTHONPATH=ROOT)
+    # the oracle's OpenMP team spins between the many short calls: a few threads are much faster than all cores here
+    env = dict(os.environ, XDE_DRY_RUN="1", PYTHONPATH=ROOT, OMP_NUM_THREADS="4", OMP_WAIT_POLICY="passive")
     cmd = [sys.executable, "-m", "pytest", "tests/test_zz_reference_run_gpu.py", "tests/test_gpu_round2.py",
            "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
-           "-k", " and ".join(f"not {s}" for s in SKIP)]
+           "-k", " and ".join(f"not {s}" for s in SKIP)] + [f"--deselect={d}" for d in DESELECT]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = "\n".join(r.stdout.splitlines()[-25:])
     assert r.returncode == 0, tail + "\n" + r.stderr[-2000:]
@@ -26,7 +27,7 @@ def test_gpu_test_files_run_against_the_host_layer_doubles():
 
 
 def _run(code, timeout=900):
-    env = dict(os.environ, PYTHONPATH=ROOT)
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="4", OMP_WAIT_POLICY="passive")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout[-2000:] + "\n" + r.stderr[-3000:]
     return r.stdout
