@@ -541,11 +541,11 @@ def run_b200(args):
             ms_cfg3 = 0.0
     if world > 1:
         tt = torch.tensor([ms, ms_e2e, ms_fwd, ms_adj, ms_e2e_sync, ms_e2e_graph or 0.0, ms_cfg3,
-                           -ms_cfg3 if ms_cfg3 > 0 else -1e30], device=dev, dtype=torch.float64)
+                           0.0 if ms_cfg3 > 0 else 1.0], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_fwd, ms_adj, ms_e2e_sync, mg, ms_cfg3, neg_min_cfg3 = tt.tolist()
+        ms, ms_e2e, ms_fwd, ms_adj, ms_e2e_sync, mg, ms_cfg3, cfg3_missing = tt.tolist()
         ms_e2e_graph = mg if ms_e2e_graph else None
-        if neg_min_cfg3 <= -1e29:  # some rank could not measure its share
+        if cfg3_missing > 0:  # some rank could not measure its share: report nothing rather than a partial maximum
             ms_cfg3 = 0.0
         cnt = torch.tensor([n_traj_steps, fwd_stats.n_attempts, adj_stats.n_attempts], device=dev, dtype=torch.int64)
         cnt_local = cnt.clone()
